@@ -1,0 +1,195 @@
+// db_prepare.h — host-side preparation of an `.mxy` file for the device: section bounds (mxy_reader.h), one-time
+// validation, and the small derived indexes that sit beside the unchanged sections in HBM (device_fns.cuh DbView).
+// Pure C++ (no CUDA) so that tests/host_emulation can build the very same view over host memory.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_fns.cuh"
+#include "mxy_reader.h"
+
+namespace mgpu {
+
+struct PslTable {
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> vals;
+  std::vector<uint8_t> pool;
+  uint32_t mask = 0, max_len = 0;
+};
+
+// lines().map(trim).filter(non-empty, not "//…") — matchy-extractor/src/lib.rs:1552-1563
+inline bool build_psl(const uint8_t* text, size_t len, PslTable& t, std::string& err) {
+  std::vector<std::pair<size_t, uint32_t>> ent;
+  auto ws = [](uint8_t ch) { return ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n' || ch == '\f' || ch == '\v'; };
+  size_t i = 0;
+  while (i < len) {
+    size_t e = i;
+    while (e < len && text[e] != '\n') e++;
+    size_t s0 = i, s1 = e;
+    while (s0 < s1 && ws(text[s0])) s0++;
+    while (s1 > s0 && ws(text[s1 - 1])) s1--;
+    if (s1 > s0 && !(s1 - s0 >= 2 && text[s0] == '/' && text[s0 + 1] == '/')) {
+      if (s1 - s0 > 255) { err = "PSL entry longer than 255 bytes"; return false; }
+      // the device relies on this: a PSL-validated domain can never parse as an IP address (database.rs:760)
+      size_t ld = s1;
+      while (ld > s0 && text[ld - 1] != '.') ld--;
+      bool all_digit = true;
+      for (size_t k = ld; k < s1; k++) all_digit &= text[k] >= '0' && text[k] <= '9';
+      if (all_digit) { err = "PSL entry with an all-numeric last label is not supported"; return false; }
+      ent.push_back({s0, (uint32_t)(s1 - s0)});
+    }
+    i = e + 1;
+  }
+  if (ent.empty()) { err = "empty PSL"; return false; }
+  uint32_t cap = 1024;
+  while (cap < ent.size() * 3) cap <<= 1;
+  t.keys.assign(cap, 0); t.vals.assign(cap, 0); t.pool.clear(); t.mask = cap - 1; t.max_len = 0;
+  for (auto& en : ent) {
+    const uint8_t* s = text + en.first;
+    uint64_t h = MGPU_FNV_BASIS;
+    for (uint32_t k = en.second; k-- > 0;) h = psl_step(h, s[k]);
+    if (h == 0) h = 1;
+    uint32_t slot = (uint32_t)(h >> 17) & t.mask;
+    bool dup = false;
+    while (t.keys[slot] != 0) {
+      if (t.keys[slot] == h && (t.vals[slot] & 0xFF) == en.second && memcmp(t.pool.data() + (t.vals[slot] >> 8), s, en.second) == 0) { dup = true; break; }
+      slot = (slot + 1) & t.mask;
+    }
+    if (dup) continue;
+    t.keys[slot] = h;
+    t.vals[slot] = ((uint32_t)t.pool.size() << 8) | en.second;
+    t.pool.insert(t.pool.end(), s, s + en.second);
+    t.max_len = std::max(t.max_len, en.second);
+  }
+  return true;
+}
+
+struct PreparedDb {
+  mxy::Layout L;
+  DbView view;                     // scalar members set; section pointers are the caller's business
+  std::vector<uint32_t> lh_index;  // pattern_id -> data_offset
+  std::vector<uint32_t> aclh;      // literal id -> (abs offset, count)
+  uint32_t ac_node_count = 0;
+};
+
+inline uint32_t prep_le32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& err) {
+  mxy::Layout& L = P.L;
+  if (!mxy::locate_sections(d, n, L, err)) return false;
+  DbView& db = P.view;
+  memset(&db, 0, sizeof db);
+  db.node_count = L.node_count; db.record_bits = L.record_bits; db.ip_version = L.ip_version;
+  db.match_mode = L.match_mode;
+  db.has_ip = 1;  // the reference sets ip_header for every MMDB-format file (database.rs:664-700)
+  // --- tree: validate once so that the per-lookup error paths of the reference cannot trigger
+  {
+    const uint64_t data_len = n - L.data_start;
+    const size_t nb = L.record_bits == 24 ? 6 : L.record_bits == 28 ? 7 : 8;
+    auto rec = [&](uint32_t node, int side) -> uint32_t {
+      const uint8_t* b = d + (size_t)node * nb;
+      if (L.record_bits == 24) { b += side * 3; return ((uint32_t)b[0] << 16) | ((uint32_t)b[1] << 8) | b[2]; }
+      if (L.record_bits == 28) return side == 0 ? (((uint32_t)(b[3] >> 4) << 24) | ((uint32_t)b[0] << 16) | ((uint32_t)b[1] << 8) | b[2])
+                                                 : (((uint32_t)(b[3] & 15) << 24) | ((uint32_t)b[4] << 16) | ((uint32_t)b[5] << 8) | b[6]);
+      b += side * 4; return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    };
+    for (uint32_t i = 0; i < L.node_count; i++)
+      for (int s = 0; s < 2; s++) {
+        uint32_t r = rec(i, s);
+        if (r > L.node_count && ((uint64_t)r < (uint64_t)L.node_count + 16 || (uint64_t)r - L.node_count - 16 >= data_len)) {
+          err = "corrupt IP search tree: record is neither a node, the empty marker nor a data pointer";
+          return false;
+        }
+      }
+    uint32_t node = 0;
+    if (L.ip_version == 6 && L.node_count > 0) {  // find_ipv4_start_node, once (tree.rs:258-277)
+      for (int k = 0; k < 96; k++) { uint32_t r = rec(node, 0); if (r >= L.node_count) break; node = r; }
+    }
+    db.v4_start_node = node;
+    if (L.node_count == 0) db.has_ip = 0;
+  }
+  // --- literal hash
+  if (L.has_literal) {
+    const uint8_t* lh = d + L.lit_off;
+    uint64_t len = L.lit_len;
+    uint32_t strings_offset = prep_le32(lh + 16), strings_size = prep_le32(lh + 20), num_shards = prep_le32(lh + 24);
+    if (num_shards == 0 || 32 + ((uint64_t)num_shards + 1) * 4 > len) { err = "literal hash: bad shard table"; return false; }
+    uint64_t maps = (uint64_t)strings_offset + strings_size;
+    if (maps + 4 <= len) {  // pattern_id -> data_offset, first entry wins (== the reference's linear scan, lib.rs:560-572)
+      uint64_t cnt = prep_le32(lh + maps);
+      if (maps + 4 + cnt * 8 > len) cnt = (len - maps - 4) / 8;  // the scan stops at the first out-of-bounds entry
+      uint32_t max_id = 0; bool any = false;
+      for (uint64_t k = 0; k < cnt; k++) { uint32_t id = prep_le32(lh + maps + 4 + k * 8); if (id != NONE32) { max_id = std::max(max_id, id); any = true; } }
+      if (any) {
+        if (max_id > 0x10000000u) { err = "literal hash: pattern ids too sparse"; return false; }
+        P.lh_index.assign((size_t)max_id + 1, NONE32);
+        for (uint64_t k = 0; k < cnt; k++) {
+          uint32_t id = prep_le32(lh + maps + 4 + k * 8), off = prep_le32(lh + maps + 8 + k * 8);
+          if (id <= max_id && P.lh_index[id] == NONE32) P.lh_index[id] = off;
+        }
+      }
+    }
+    db.lh_len = len; db.has_literal = 1;
+    db.lh_num_shards = num_shards; db.lh_strings_offset = strings_offset; db.lh_table_start = 32 + (num_shards + 1) * 4;
+    db.lh_data_index_n = (uint32_t)P.lh_index.size();
+  }
+  // --- paraglob
+  if (L.has_glob) {
+    const uint8_t* pg = d + L.pg_off;
+    uint32_t pg_len = (uint32_t)L.pg_len;
+    db.ac_start = prep_le32(pg + 20); db.ac_size = prep_le32(pg + 24);
+    if ((uint64_t)db.ac_start + db.ac_size > pg_len) { err = "paraglob: AC buffer out of range"; return false; }
+    P.ac_node_count = prep_le32(pg + 16);
+    db.patterns_offset = prep_le32(pg + 36);
+    uint64_t un = (uint64_t)prep_le32(pg + 40) + prep_le32(pg + 44);
+    db.wild_off = (uint32_t)(un + (8 - un % 8) % 8);
+    db.wild_count = prep_le32(pg + 60);
+    db.glob_segments_offset = prep_le32(pg + 104);
+    uint32_t pattern_count = prep_le32(pg + 32);
+    // ACLH -> dense literal-id index over every occupied slot (keeps the unpinned FxHash off the read side)
+    uint32_t ao = prep_le32(pg + 96), acnt = prep_le32(pg + 100);
+    if (ao != 0 && acnt != 0 && (uint64_t)ao + 24 <= pg_len && memcmp(pg + ao, "ACLH", 4) == 0 && prep_le32(pg + ao + 4) == 1) {
+      uint32_t table_size = prep_le32(pg + ao + 12), lists = prep_le32(pg + ao + 16);
+      uint32_t max_id = 0; bool any = false;
+      for (uint32_t s = 0; s < table_size; s++) {
+        uint64_t eo = (uint64_t)ao + 24 + (uint64_t)s * 16;
+        if (eo + 16 > pg_len) break;
+        uint32_t id = prep_le32(pg + eo);
+        if (id != NONE32) { max_id = std::max(max_id, id); any = true; }
+      }
+      if (any) {
+        if (max_id > 0x10000000u) { err = "paraglob: AC literal ids too sparse"; return false; }
+        P.aclh.assign(((size_t)max_id + 1) * 2, 0);
+        std::vector<uint8_t> seen((size_t)max_id + 1, 0);
+        for (uint32_t s = 0; s < table_size; s++) {
+          uint64_t eo = (uint64_t)ao + 24 + (uint64_t)s * 16;
+          if (eo + 16 > pg_len) break;
+          uint32_t id = prep_le32(pg + eo);
+          if (id == NONE32 || seen[id]) continue;
+          seen[id] = 1;
+          uint64_t abs = (uint64_t)ao + lists + prep_le32(pg + eo + 4);
+          uint32_t cnt = prep_le32(pg + eo + 8);
+          if (abs + (uint64_t)cnt * 4 > pg_len) continue;  // read_pattern_list -> None -> no candidates
+          P.aclh[2 * (size_t)id] = (uint32_t)abs; P.aclh[2 * (size_t)id + 1] = cnt;
+        }
+      }
+    }
+    // glob segments: the device matcher keeps one frame per '*'
+    uint32_t gso = db.glob_segments_offset;
+    for (uint32_t pid = 0; pid < pattern_count; pid++) {
+      uint64_t io = (uint64_t)gso + (uint64_t)pid * 8;
+      if (io + 8 > pg_len) break;
+      uint32_t first = prep_le32(pg + io), cnt = (uint32_t)pg[io + 4] | ((uint32_t)pg[io + 5] << 8), stars = 0;
+      for (uint32_t s = 0; s < cnt; s++) { uint64_t so = (uint64_t)first + (uint64_t)s * 12; if (so + 12 > pg_len) break; if (pg[so] == 1) stars++; }
+      if (stars > MGPU_GLOB_MAX_STARS) { err = "glob pattern with more than 24 '*' segments is not supported on the device"; return false; }
+    }
+    db.pg_len = pg_len; db.has_glob = 1;
+    db.aclh_n = (uint32_t)(P.aclh.size() / 2);
+    db.glob_data_n = (uint32_t)L.map_count;
+  }
+  return true;
+}
+
+}  // namespace mgpu

@@ -1,0 +1,605 @@
+// device_fns.cuh — per-token device functions of the scan path: token validation (the second half of the
+// extractor), IP-trie walk, literal-hash probe, Aho-Corasick walk + ACLH map + glob verification.
+//
+// Everything here is a plain function of byte pointers into the UNCHANGED .mxy sections as uploaded to HBM
+// (plus a few derived, result-neutral indexes built at upload, see DbView).  The functions are MGPU_HD so that
+// tests/host_emulation can compile the very same code with g++ and check it against the oracle without a GPU;
+// the product only ever runs them inside CUDA kernels (engine.cu).
+//
+// Reference behaviour restated (crates/… paths relative to the reference root):
+//   try_parse_ipv4                matchy-extractor/src/lib.rs:813-869
+//   extract_domains_chunk/is_valid_domain/find_valid_tld_suffix_bytes   :537-689, 1671-1692
+//   extract_email_at              :891-950
+//   extract_ipv6_chunk (+ core::net::parser Ipv6Addr::from_str)  :1044-1116, 1425-1456
+//   SearchTree::lookup_v4/v6      matchy-format/src/mmdb/tree.rs:46-277
+//   LiteralHash::lookup           matchy-literal-hash/src/lib.rs:467-575
+//   Paraglob::find_all & co       matchy-paraglob/src/paraglob_offset.rs:1028-1639
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define MGPU_HD __host__ __device__ __forceinline__
+#define MGPU_HDN __host__ __device__
+#else
+#define MGPU_HD inline
+#define MGPU_HDN inline
+#endif
+
+namespace mgpu {
+
+static const uint32_t NONE32 = 0xFFFFFFFFu;
+
+// View of one uploaded database.  Raw sections are byte-identical to the file; "derived" members are small
+// indexes computed once at upload that return exactly what the reference's slower lookup would.
+struct DbView {
+  // --- IP search tree (file offset 0) ---
+  const uint8_t* tree;
+  uint32_t node_count, record_bits, ip_version, has_ip;
+  uint32_t v4_start_node;  // derived: result of find_ipv4_start_node (tree.rs:258-277), identical for every query
+  // --- literal hash section ("LHSH") ---
+  const uint8_t* lh;
+  uint64_t lh_len;
+  uint32_t has_literal, lh_num_shards, lh_strings_offset, lh_table_start;
+  const uint32_t* lh_data_index;  // derived: pattern_id -> data_offset of the FIRST mapping entry with that id (== linear scan :560-572)
+  uint32_t lh_data_index_n;
+  // --- paraglob buffer ("PARAGLOB") ---
+  const uint8_t* pg;
+  uint32_t pg_len, has_glob;
+  uint32_t ac_start, ac_size, patterns_offset, wild_off, wild_count, glob_segments_offset;
+  const uint32_t* aclh_index;     // derived: literal_id -> {abs offset of its pattern list in pg, count} (2 words each)
+  uint32_t aclh_n;
+  const uint32_t* glob_data;      // [data_offset × count] array that follows the paraglob buffer (database.rs:212-228)
+  uint32_t glob_data_n;
+  uint32_t match_mode;            // 0 case-sensitive, 1 case-insensitive (ASCII folding)
+  // --- Public Suffix List as an open-addressing set (derived from the reference's PSL text) ---
+  const uint64_t* psl_keys;       // 0 = empty
+  const uint32_t* psl_vals;       // pool offset << 8 | length
+  const uint8_t* psl_pool;
+  uint32_t psl_mask, psl_max_len;
+};
+
+MGPU_HD uint32_t ld32(const uint8_t* p) {  // little-endian, 4-byte aligned
+  return *reinterpret_cast<const uint32_t*>(p);
+}
+MGPU_HD uint32_t ld32u(const uint8_t* p) {  // unaligned
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+MGPU_HD uint64_t ld64u(const uint8_t* p) { return (uint64_t)ld32u(p) | ((uint64_t)ld32u(p + 4) << 32); }
+MGPU_HD uint8_t lc(uint8_t c, bool fold) { return (fold && c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
+
+// ---- character classes (matchy-extractor/src/lib.rs:1568-1717) ----
+MGPU_HD bool is_digit(uint8_t b) { return (uint8_t)(b - '0') < 10; }
+MGPU_HD bool is_alpha(uint8_t b) { return (uint8_t)((b | 32) - 'a') < 26; }
+MGPU_HD bool is_hex(uint8_t b) { return is_digit(b) || (uint8_t)((b | 32) - 'a') < 6; }
+MGPU_HD bool is_boundary(uint8_t b) {
+  switch (b) {
+    case ' ': case '\t': case '\n': case '\r': case '/': case ',': case ';': case ':': case '(': case ')':
+    case '[': case ']': case '{': case '}': case '<': case '>': case '"': case '\'': case '@': case '=':
+      return true;
+    default: return false;
+  }
+}
+MGPU_HD bool is_domain_ascii(uint8_t b) { return is_digit(b) || is_alpha(b) || b == '-' || b == '.'; }
+MGPU_HD bool is_domain_fast(uint8_t b) { return is_domain_ascii(b) || b >= 0x80; }
+MGPU_HD bool is_local_char(uint8_t b) { return is_digit(b) || is_alpha(b) || b == '.' || b == '-' || b == '_' || b == '+'; }
+
+// ---- XXH64, seed 0 (public specification) ----
+#define MGPU_P1 11400714785074694791ULL
+#define MGPU_P2 14029467366897019727ULL
+#define MGPU_P3 1609587929392839161ULL
+#define MGPU_P4 9650029242287828579ULL
+#define MGPU_P5 2870177450012600261ULL
+MGPU_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+MGPU_HD uint64_t xx_round(uint64_t acc, uint64_t in) { acc += in * MGPU_P2; acc = rotl64(acc, 31); return acc * MGPU_P1; }
+MGPU_HD uint64_t xx_merge(uint64_t acc, uint64_t v) { v = xx_round(0, v); acc ^= v; return acc * MGPU_P1 + MGPU_P4; }
+MGPU_HD uint64_t rd64f(const uint8_t* p, bool fold) {
+  uint64_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) v |= (uint64_t)lc(p[k], fold) << (8 * k);
+  return v;
+}
+MGPU_HDN uint64_t xxh64_fold(const uint8_t* p, size_t len, bool fold) {
+  const uint8_t* end = p + len;
+  uint64_t h;
+  if (len >= 32) {
+    uint64_t v1 = MGPU_P1 + MGPU_P2, v2 = MGPU_P2, v3 = 0, v4 = 0ULL - MGPU_P1;
+    const uint8_t* lim = end - 32;
+    do {
+      v1 = xx_round(v1, rd64f(p, fold)); v2 = xx_round(v2, rd64f(p + 8, fold));
+      v3 = xx_round(v3, rd64f(p + 16, fold)); v4 = xx_round(v4, rd64f(p + 24, fold));
+      p += 32;
+    } while (p <= lim);
+    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = xx_merge(h, v1); h = xx_merge(h, v2); h = xx_merge(h, v3); h = xx_merge(h, v4);
+  } else {
+    h = MGPU_P5;
+  }
+  h += (uint64_t)len;
+  while (p + 8 <= end) { h ^= xx_round(0, rd64f(p, fold)); h = rotl64(h, 27) * MGPU_P1 + MGPU_P4; p += 8; }
+  if (p + 4 <= end) {
+    uint32_t w = (uint32_t)lc(p[0], fold) | ((uint32_t)lc(p[1], fold) << 8) | ((uint32_t)lc(p[2], fold) << 16) | ((uint32_t)lc(p[3], fold) << 24);
+    h ^= (uint64_t)w * MGPU_P1; h = rotl64(h, 23) * MGPU_P2 + MGPU_P3; p += 4;
+  }
+  while (p < end) { h ^= (uint64_t)lc(*p, fold) * MGPU_P5; h = rotl64(h, 11) * MGPU_P1; p++; }
+  h ^= h >> 33; h *= MGPU_P2; h ^= h >> 29; h *= MGPU_P3; h ^= h >> 32;
+  return h;
+}
+
+// ---- UTF-8 (Rust str::from_utf8) ----
+MGPU_HDN bool valid_utf8(const uint8_t* s, size_t n) {
+  size_t i = 0;
+  while (i < n) {
+    uint8_t c = s[i];
+    if (c < 0x80) { i++; continue; }
+    if (c >= 0xC2 && c <= 0xDF) {
+      if (i + 1 >= n || (s[i + 1] & 0xC0) != 0x80) return false;
+      i += 2;
+    } else if (c >= 0xE0 && c <= 0xEF) {
+      if (i + 2 >= n) return false;
+      uint8_t c1 = s[i + 1], c2 = s[i + 2];
+      if ((c1 & 0xC0) != 0x80 || (c2 & 0xC0) != 0x80) return false;
+      if (c == 0xE0 && c1 < 0xA0) return false;
+      if (c == 0xED && c1 > 0x9F) return false;
+      i += 3;
+    } else if (c >= 0xF0 && c <= 0xF4) {
+      if (i + 3 >= n) return false;
+      uint8_t c1 = s[i + 1], c2 = s[i + 2], c3 = s[i + 3];
+      if ((c1 & 0xC0) != 0x80 || (c2 & 0xC0) != 0x80 || (c3 & 0xC0) != 0x80) return false;
+      if (c == 0xF0 && c1 < 0x90) return false;
+      if (c == 0xF4 && c1 > 0x8F) return false;
+      i += 4;
+    } else return false;
+  }
+  return true;
+}
+MGPU_HD uint32_t utf8_len(uint8_t c) { return c < 0x80 ? 1u : c < 0xE0 ? 2u : c < 0xF0 ? 3u : 4u; }
+MGPU_HD uint32_t utf8_decode(const uint8_t* t, uint32_t n, uint32_t pos, uint32_t& cp) {  // t is valid UTF-8
+  uint8_t c = t[pos];
+  if (c < 0x80) { cp = c; return 1; }
+  if (c < 0xE0 && pos + 1 < n) { cp = ((c & 0x1Fu) << 6) | (t[pos + 1] & 0x3Fu); return 2; }
+  if (c < 0xF0 && pos + 2 < n) { cp = ((c & 0x0Fu) << 12) | ((t[pos + 1] & 0x3Fu) << 6) | (t[pos + 2] & 0x3Fu); return 3; }
+  if (pos + 3 < n) { cp = ((c & 0x07u) << 18) | ((t[pos + 1] & 0x3Fu) << 12) | ((t[pos + 2] & 0x3Fu) << 6) | (t[pos + 3] & 0x3Fu); return 4; }
+  cp = c; return 1;
+}
+
+// =================================================================================================
+// Public Suffix List membership.  Key = 64-bit FNV-1a over the suffix bytes taken RIGHT TO LEFT, so one
+// backward pass over a token yields the key of every dot-suffix.  Hits are confirmed byte-for-byte.
+// =================================================================================================
+#define MGPU_FNV_BASIS 0xcbf29ce484222325ULL
+#define MGPU_FNV_PRIME 0x100000001b3ULL
+MGPU_HD uint64_t psl_step(uint64_t h, uint8_t b) { return (h ^ b) * MGPU_FNV_PRIME; }
+MGPU_HDN bool psl_contains(const DbView& db, uint64_t key, const uint8_t* suffix, uint32_t len) {
+  if (key == 0) key = 1;
+  uint32_t slot = (uint32_t)(key >> 17) & db.psl_mask;
+  for (;;) {
+    uint64_t k = db.psl_keys[slot];
+    if (k == 0) return false;
+    if (k == key) {
+      uint32_t v = db.psl_vals[slot];
+      if ((v & 0xFF) == len) {
+        const uint8_t* e = db.psl_pool + (v >> 8);
+        bool eq = true;
+        for (uint32_t i = 0; i < len; i++) if (e[i] != suffix[i]) { eq = false; break; }
+        if (eq) return true;
+      }
+    }
+    slot = (slot + 1) & db.psl_mask;
+  }
+}
+// find_valid_tld_suffix_bytes(...).is_some(): does ANY dot-suffix of d[0..n) belong to the PSL?  (lib.rs:1671-1692)
+MGPU_HDN bool psl_any_suffix(const DbView& db, const uint8_t* d, uint32_t n) {
+  uint64_t h = MGPU_FNV_BASIS;
+  for (uint32_t k = n; k-- > 0;) {
+    uint8_t b = d[k];
+    if (b == '.') {
+      uint32_t sl = n - k - 1;
+      if (sl > db.psl_max_len) return false;  // longer suffixes cannot be entries either
+      if (sl > 0 && psl_contains(db, h, d + k + 1, sl)) return true;
+    }
+    h = psl_step(h, b);
+  }
+  return false;
+}
+
+// =================================================================================================
+// Token validation (second half of the extractor; candidates come from the tokenizer kernel)
+// =================================================================================================
+// try_parse_ipv4 on a whole boundary-delimited word w[0..n): all of it must be consumed.
+MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) {
+  if (n < 7 || n > 15) return false;
+  uint32_t pos = 0, addr = 0;
+  for (int k = 0; k < 4; k++) {
+    uint32_t v = 0, digits = 0, st = pos;
+    while (pos < n && is_digit(w[pos]) && digits < 3) { v = v * 10 + (uint32_t)(w[pos] - '0'); pos++; digits++; }
+    if (digits == 0 || v > 255) return false;
+    if (digits > 1 && w[st] == '0') return false;
+    addr = (addr << 8) | v;
+    if (k < 3) { if (pos >= n || w[pos] != '.') return false; pos++; }
+  }
+  if (pos != n) return false;  // the byte after the address must be a boundary == end of the word
+  addr_out = addr;
+  return true;
+}
+
+// A boundary-delimited word made only of domain characters (incl. bytes >= 0x80) that contains a '.':
+// is it a domain?  labels non-empty and not starting/ending with '-', >= 2 labels (implied by the dot),
+// some dot-suffix in the PSL, valid UTF-8.  (lib.rs:537-689)
+MGPU_HDN bool validate_domain_word(const DbView& db, const uint8_t* w, uint32_t n) {
+  if (n < 3) return false;
+  if (w[0] == '.' || w[0] == '-' || w[n - 1] == '.' || w[n - 1] == '-') return false;
+  // one backward pass: label structure, PSL probe (shortest suffix first), high-byte detection
+  uint64_t h = MGPU_FNV_BASIS;
+  bool psl_hit = false, psl_open = true, high = false;
+  for (uint32_t k = n; k-- > 0;) {
+    uint8_t b = w[k];
+    if (b == '.') {
+      // k is neither 0 nor n-1 here
+      if (w[k + 1] == '-' || w[k + 1] == '.' || w[k - 1] == '-') return false;
+      if (psl_open && !psl_hit) {
+        uint32_t sl = n - k - 1;
+        if (sl > db.psl_max_len) psl_open = false;
+        else psl_hit = psl_contains(db, h, w + k + 1, sl);
+      }
+    }
+    high |= b >= 0x80;
+    h = psl_step(h, b);
+  }
+  if (!psl_hit) return false;
+  if (high && !valid_utf8(w, n)) return false;
+  return true;
+}
+
+// extract_email_at: buf[lo..n) is the chunk, at = position of '@'.
+MGPU_HDN bool email_at(const DbView& db, const uint8_t* buf, size_t lo, size_t n, size_t at, size_t& s_out, size_t& e_out) {
+  size_t start = at;
+  while (start > lo && is_local_char(buf[start - 1])) start--;
+  if (start == at) return false;
+  if (start > lo && !is_boundary(buf[start - 1])) return false;
+  size_t end = at + 1;
+  while (end < n && is_domain_ascii(buf[end])) end++;
+  if (end == at + 1) return false;
+  if (end < n && !is_boundary(buf[end])) return false;
+  bool has_letter = false;
+  for (size_t k = start; k < at; k++) {
+    if (buf[k] == '.' && k + 1 < at && buf[k + 1] == '.') return false;
+    has_letter |= is_alpha(buf[k]);
+  }
+  if (!has_letter) return false;
+  // "domain part contains a dot" is implied by a PSL suffix hit
+  if (end - at - 1 > 0xFFFFFFFFull) return false;
+  if (!psl_any_suffix(db, buf + at + 1, (uint32_t)(end - at - 1))) return false;
+  s_out = start; e_out = end;
+  return true;
+}
+
+// core::net::parser Ipv6Addr::from_str for inputs made of hex digits and ':' only.
+MGPU_HD uint32_t v6_read_groups(const uint8_t* s, uint32_t n, uint32_t& pos, uint16_t* groups, uint32_t limit) {
+  for (uint32_t i = 0; i < limit; i++) {
+    uint32_t p = pos;
+    if (i > 0) { if (p < n && s[p] == ':') p++; else return i; }
+    uint32_t v = 0, digits = 0;
+    while (p < n) {
+      uint8_t c = s[p]; uint32_t d;
+      if (is_digit(c)) d = c - '0';
+      else if ((uint8_t)((c | 32) - 'a') < 6) d = (c | 32) - 'a' + 10;
+      else break;
+      v = v * 16 + d; digits++; p++;
+      if (digits > 4) return i;
+    }
+    if (digits == 0) return i;
+    groups[i] = (uint16_t)v;
+    pos = p;
+  }
+  return limit;
+}
+MGPU_HDN bool parse_ipv6_run(const uint8_t* s, uint32_t n, uint16_t out[8]) {
+  uint32_t pos = 0;
+  uint16_t head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t hs = v6_read_groups(s, n, pos, head, 8);
+  if (hs == 8) {
+    if (pos != n) return false;
+  } else {
+    if (!(pos + 1 < n && s[pos] == ':' && s[pos + 1] == ':')) return false;
+    pos += 2;
+    uint16_t tail[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t limit = 8 - (hs + 1);
+    uint32_t ts = v6_read_groups(s, n, pos, tail, limit);
+    if (pos != n) return false;
+    for (uint32_t k = 0; k < ts; k++) head[8 - ts + k] = tail[k];
+  }
+  for (int k = 0; k < 8; k++) out[k] = head[k];
+  return true;
+}
+// extract_ipv6_chunk for the "::" whose first colon is at `at`.  Returns true with the run span and address.
+MGPU_HDN bool ipv6_at(const uint8_t* buf, size_t lo, size_t n, size_t at, size_t& s_out, size_t& e_out, uint16_t segs[8]) {
+  // maximal [0-9A-Fa-f:] run around the anchor; a valid address is at most 39 bytes, longer runs cannot parse
+  size_t start = at;
+  while (start > lo && at - start <= 40) { uint8_t c = buf[start - 1]; if (!is_hex(c) && c != ':') break; start--; }
+  if (at - start > 40) return false;
+  size_t end = at + 2;
+  while (end < n && end - at <= 42) { uint8_t c = buf[end]; if (!is_hex(c) && c != ':') break; end++; }
+  uint32_t len = (uint32_t)(end - start);
+  if (len > 39 || len < 8) return false;
+  const uint8_t* c = buf + start;
+  if ((c[0] == ':' && c[1] == ':') || (c[len - 2] == ':' && c[len - 1] == ':')) return false;
+  if ((c[0] | 32) == 'f' && (c[1] | 32) == 'e') {  // link-local fe80::/10 by text prefix (lib.rs:1425-1456)
+    uint8_t t = c[2] | 32;
+    if (c[2] == '8' || c[2] == '9' || t == 'a' || t == 'b') return false;
+  }
+  if (!parse_ipv6_run(c, len, segs)) return false;
+  s_out = start; e_out = end;
+  return true;
+}
+
+// =================================================================================================
+// IP search tree — tree.rs:46-277.  Tree validity (every record < node_count, == node_count or >= node_count+16)
+// is checked at upload, so the Err paths of the reference cannot occur here.
+// =================================================================================================
+MGPU_HD uint32_t tree_record(const DbView& db, uint32_t node, uint32_t side) {
+  if (db.record_bits == 24) {
+    const uint8_t* p = db.tree + (size_t)node * 6 + side * 3;
+    return ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | p[2];
+  } else if (db.record_bits == 28) {
+    const uint8_t* b = db.tree + (size_t)node * 7;
+    if (side == 0) return ((uint32_t)(b[3] >> 4) << 24) | ((uint32_t)b[0] << 16) | ((uint32_t)b[1] << 8) | b[2];
+    return ((uint32_t)(b[3] & 15) << 24) | ((uint32_t)b[4] << 16) | ((uint32_t)b[5] << 8) | b[6];
+  } else {
+    const uint8_t* p = db.tree + (size_t)node * 8 + side * 4;
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  }
+}
+MGPU_HDN bool trie_lookup_v4(const DbView& db, uint32_t bits, uint32_t& data_off, uint8_t& prefix) {
+  uint32_t node = db.ip_version == 6 ? db.v4_start_node : 0;
+  for (uint32_t bi = 0; bi < 32; bi++) {
+    uint32_t rec = tree_record(db, node, (bits >> (31 - bi)) & 1);
+    if (rec == db.node_count) return false;
+    if (rec < db.node_count) { node = rec; continue; }
+    data_off = rec - db.node_count - 16;
+    prefix = (uint8_t)(bi + 1);  // depth counts one per address bit in both tree kinds (96 is subtracted again, tree.rs:76-80)
+    return true;
+  }
+  return false;
+}
+MGPU_HDN bool trie_lookup_v6(const DbView& db, const uint16_t seg[8], uint32_t& data_off, uint8_t& prefix) {
+  uint32_t node = 0;
+  for (uint32_t bi = 0; bi < 128; bi++) {
+    uint32_t rec = tree_record(db, node, (seg[bi >> 4] >> (15 - (bi & 15))) & 1);
+    if (rec == db.node_count) return false;
+    if (rec < db.node_count) { node = rec; continue; }
+    data_off = rec - db.node_count - 16;
+    prefix = (uint8_t)(bi + 1);
+    return true;
+  }
+  return false;
+}
+
+// =================================================================================================
+// Literal hash — matchy-literal-hash/src/lib.rs:467-575
+// =================================================================================================
+MGPU_HDN bool lh_lookup(const DbView& db, const uint8_t* q, uint32_t n, uint32_t& pattern_id) {
+  bool fold = db.match_mode == 1;
+  uint64_t h = xxh64_fold(q, n, fold);
+  uint32_t shard = (uint32_t)(h % db.lh_num_shards);
+  uint32_t s0 = ld32(db.lh + 32 + (size_t)shard * 4), s1 = ld32(db.lh + 32 + (size_t)shard * 4 + 4);
+  uint32_t cap = s1 - s0;
+  if (cap == 0) return false;
+  uint32_t mask = cap - 1;
+  uint32_t slot = s0 + ((uint32_t)h & mask);
+  for (uint32_t it = 0; it < cap; it++) {
+    uint64_t eo = (uint64_t)db.lh_table_start + (uint64_t)slot * 16;
+    if (eo + 16 > db.lh_len) return false;
+    const uint8_t* e = db.lh + eo;
+    uint32_t so = ld32(e + 8);
+    if (so == NONE32) return false;
+    uint64_t eh = (uint64_t)ld32(e) | ((uint64_t)ld32(e + 4) << 32);
+    if (eh == h) {
+      uint64_t abs = (uint64_t)db.lh_strings_offset + so;
+      if (abs + 2 <= db.lh_len) {
+        uint32_t sl = (uint32_t)db.lh[abs] | ((uint32_t)db.lh[abs + 1] << 8);
+        if (abs + 2 + sl <= db.lh_len && sl == n) {
+          // (stored strings are valid UTF-8 — checked at upload — so read_string cannot fail here)
+          const uint8_t* sp = db.lh + abs + 2;
+          bool eq = true;
+          for (uint32_t i = 0; i < n; i++) if (sp[i] != lc(q[i], fold)) { eq = false; break; }
+          if (eq) { pattern_id = ld32(e + 12); return true; }
+        }
+      }
+    }
+    slot = s0 + ((slot + 1 - s0) & mask);
+  }
+  return false;
+}
+MGPU_HD bool lh_data_offset(const DbView& db, uint32_t pattern_id, uint32_t& off) {
+  if (pattern_id >= db.lh_data_index_n) return false;
+  uint32_t v = db.lh_data_index[pattern_id];
+  // NONE32 doubles as "no mapping entry"; a genuine data offset of 0xFFFFFFFF cannot exist in a < 4 GiB file
+  if (v == NONE32) return false;
+  off = v;
+  return true;
+}
+
+// =================================================================================================
+// Paraglob — paraglob_offset.rs:1028-1639
+// =================================================================================================
+// find_ac_transition :1271-1353.  `ac` = AC buffer base (pg + ac_start); offsets are relative to it.
+MGPU_HD bool ac_transition(const uint8_t* ac, uint32_t acn, uint32_t node_off, uint8_t ch, uint32_t& next) {
+  if ((uint64_t)node_off + 20 > acn) return false;
+  const uint8_t* nd = ac + node_off;
+  uint32_t w0 = ld32(nd);
+  uint32_t kind = w0 & 0xFF;
+  if (kind == 1) {
+    if (((w0 >> 8) & 0xFF) == ch) { next = ld32(nd + 12); return true; }
+    return false;
+  }
+  if (kind == 2) {
+    uint32_t eo = ld32(nd + 12), cnt = (w0 >> 16) & 0xFF;
+    if ((uint64_t)eo + (uint64_t)cnt * 8 > acn) return false;
+    for (uint32_t i = 0; i < cnt; i++) {
+      uint8_t ec = ac[eo + i * 8];
+      if (ec == ch) { next = ld32(ac + eo + i * 8 + 4); return true; }
+      if (ec > ch) return false;
+    }
+    return false;
+  }
+  if (kind == 3) {
+    uint64_t to = (uint64_t)ld32(nd + 12) + (uint64_t)ch * 4;
+    if (to + 4 > acn) return false;
+    uint32_t t = ld32(ac + to);
+    if (t != 0) { next = t; return true; }
+    return false;
+  }
+  return false;
+}
+
+// match_segments_impl :1402-1639 as an explicit-stack machine.  Every reference call (including failed ones and
+// the calls a Star makes for each candidate position) decrements the 100 000-step budget exactly once.
+#define MGPU_GLOB_MAX_STARS 24  // patterns with more '*' segments are refused at upload
+MGPU_HDN bool glob_match(const DbView& db, uint32_t pattern_id, const uint8_t* text, uint32_t tn) {
+  uint64_t io = (uint64_t)db.glob_segments_offset + (uint64_t)pattern_id * 8;
+  if (io + 8 > db.pg_len) return false;
+  const uint32_t first = ld32(db.pg + io);
+  const uint32_t count = (uint32_t)db.pg[io + 4] | ((uint32_t)db.pg[io + 5] << 8);
+  const bool ci = db.match_mode == 1;
+  uint32_t steps = 100000;
+  uint32_t st_idx[MGPU_GLOB_MAX_STARS], st_pos[MGPU_GLOB_MAX_STARS];
+  int sp = 0;
+  uint32_t pos = 0, idx = 0;
+  for (;;) {
+    bool result;
+    // ---- one call of match_segments_impl(pos, idx) ----
+    for (;;) {
+      if (steps == 0) { result = false; break; }
+      steps--;
+      if (idx >= count) { result = pos >= tn; break; }
+      uint64_t so = (uint64_t)first + (uint64_t)idx * 12;
+      if (so + 12 > db.pg_len) { result = false; break; }
+      const uint8_t* sh = db.pg + so;
+      uint32_t stype = sh[0], sflags = sh[1], dlen = ld32(sh + 4), doff = ld32(sh + 8);
+      if (stype == 0) {
+        if ((uint64_t)doff + dlen > db.pg_len) { result = false; break; }
+        const uint8_t* lit = db.pg + doff;
+        uint32_t adv;
+        bool m;
+        if (!ci) {
+          m = tn - pos >= dlen;
+          for (uint32_t i = 0; m && i < dlen; i++) m = text[pos + i] == lit[i];
+          adv = dlen;
+        } else {  // chars of literal vs chars of text, ASCII-insensitive (:1456-1478)
+          uint32_t lp = 0, tp = pos;
+          m = true;
+          while (tp < tn && lp < dlen) {
+            uint32_t lcp, tcp;
+            uint32_t ll = utf8_decode(lit, dlen, lp, lcp), tl = utf8_decode(text, tn, tp, tcp);
+            bool eq = (lcp < 128 && tcp < 128) ? lc((uint8_t)lcp, true) == lc((uint8_t)tcp, true) : lcp == tcp;
+            if (!eq) { m = false; break; }
+            lp += ll; tp += tl;
+          }
+          if (m && lp < dlen) m = false;
+          adv = tp - pos;
+        }
+        if (!m) { result = false; break; }
+        pos += adv; idx++;
+        continue;  // tail call
+      } else if (stype == 1) {
+        if (idx + 1 >= count) { result = true; break; }
+        if (sp >= MGPU_GLOB_MAX_STARS) { result = false; break; }  // unreachable: checked at upload
+        st_idx[sp] = idx; st_pos[sp] = pos; sp++;
+        idx++;
+        continue;  // first candidate position: call (pos, idx+1)
+      } else if (stype == 2) {
+        if (pos >= tn) { result = false; break; }
+        pos += utf8_len(text[pos]); idx++;
+        continue;
+      } else if (stype == 3) {
+        if (pos >= tn) { result = false; break; }
+        uint32_t ch;
+        uint32_t l = utf8_decode(text, tn, pos, ch);
+        if (ci && ch < 128) ch = lc((uint8_t)ch, true);
+        if ((uint64_t)doff + dlen > db.pg_len) { result = false; break; }
+        uint32_t items = dlen / 12;
+        bool in_class = false;
+        for (uint32_t i = 0; i < items; i++) {
+          const uint8_t* it = db.pg + doff + i * 12;
+          uint32_t c1 = ld32(it + 4), c2 = ld32(it + 8);
+          bool v1 = c1 <= 0x10FFFF && !(c1 >= 0xD800 && c1 <= 0xDFFF), v2 = c2 <= 0x10FFFF && !(c2 >= 0xD800 && c2 <= 0xDFFF);
+          if (ci && c1 < 128) c1 = lc((uint8_t)c1, true);
+          if (ci && c2 < 128) c2 = lc((uint8_t)c2, true);
+          bool mi = false;
+          if (it[0] == 0) mi = v1 && ch == c1;
+          else if (it[0] == 1) mi = v1 && v2 && ch >= c1 && ch <= c2;
+          if (mi) { in_class = true; break; }
+        }
+        if (((sflags & 1) != 0) == in_class) { result = false; break; }
+        pos += l; idx++;
+        continue;
+      } else { result = false; break; }
+    }
+    // ---- unwind: the innermost call returned `result` ----
+    for (;;) {
+      if (result || sp == 0) return result;  // a true result propagates through every enclosing Star
+      uint32_t p = st_pos[sp - 1];
+      if (p >= tn) { sp--; continue; }  // this Star is exhausted -> it returns false to its caller
+      p += utf8_len(text[p]);
+      st_pos[sp - 1] = p;
+      pos = p; idx = st_idx[sp - 1] + 1;
+      break;  // next candidate position for the innermost Star
+    }
+  }
+}
+
+// Visit every glob id find_all would return for `text` (before sort+dedup; duplicates possible).
+// run_ac_matching_into_static :1186-1266 + ACLH map + verification :1136-1171, pure wildcards :1096-1134.
+template <typename F>
+MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn, F&& emit) {
+  if (db.pg_len < 112) return;
+  // pure wildcards are tested on every query
+  for (uint32_t i = 0; i < db.wild_count; i++) {
+    uint64_t wo = (uint64_t)db.wild_off + (uint64_t)i * 8;
+    if (wo + 8 > db.pg_len) continue;
+    uint32_t pid = ld32(db.pg + wo);
+    if ((uint64_t)db.patterns_offset + (uint64_t)pid * 16 + 16 > db.pg_len) continue;
+    if (glob_match(db, pid, text, tn)) emit(pid);
+  }
+  if (db.ac_size == 0 || tn == 0) return;
+  const uint8_t* ac = db.pg + db.ac_start;
+  const uint32_t acn = db.ac_size;
+  const bool fold = db.match_mode == 1;
+  uint32_t cur = 0;
+  for (uint32_t i = 0; i < tn; i++) {
+    uint8_t ch = lc(text[i], fold);
+    for (;;) {
+      uint32_t nx;
+      if (ac_transition(ac, acn, cur, ch, nx)) { cur = nx; break; }
+      if (cur == 0) break;
+      if ((uint64_t)cur + 20 > acn) break;
+      cur = ld32(ac + cur + 8);
+    }
+    if ((uint64_t)cur + 20 > acn) continue;
+    uint32_t pc = ac[cur + 3];
+    if (pc == 0) continue;
+    uint32_t po = ld32(ac + cur + 16);
+    if ((uint64_t)po + (uint64_t)pc * 4 > acn) continue;
+    for (uint32_t k = 0; k < pc; k++) {
+      uint32_t lit = ld32(ac + po + k * 4);
+      if (lit >= db.aclh_n) continue;
+      uint32_t lo = db.aclh_index[2 * lit], lcnt = db.aclh_index[2 * lit + 1];
+      for (uint32_t j = 0; j < lcnt; j++) {
+        uint32_t pid = ld32(db.pg + lo + j * 4);
+        uint64_t eo = (uint64_t)db.patterns_offset + (uint64_t)pid * 16;
+        if (eo + 16 > db.pg_len) continue;
+        uint32_t entry_id = ld32(db.pg + eo);
+        if (db.pg[eo + 4] == 0) emit(entry_id);                 // literal-type pattern: accepted on the AC hit alone
+        else if (glob_match(db, entry_id, text, tn)) emit(entry_id);
+      }
+    }
+  }
+}
+MGPU_HD bool glob_data_offset(const DbView& db, uint32_t pid, uint32_t& off) {
+  if (pid >= db.glob_data_n) return false;
+  off = db.glob_data[pid];
+  return true;
+}
+
+}  // namespace mgpu

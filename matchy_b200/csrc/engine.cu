@@ -1,0 +1,1104 @@
+// engine.cu — the B200 log-scan engine: CUDA kernels + host driver + C ABI (include/matchy_b200.h).
+//
+// Replaces the body of processing::Worker::process_bytes (crates/matchy/src/processing/mod.rs:353-448):
+//   tokenize_kernel  (K1)  candidates: words / '@' / "::" anchors          extractor lib.rs:409-488 (first half)
+//   validate_kernel  (K2)  candidate -> typed token (IPv4/IPv6/domain/e-mail/hash)   (second half)
+//   iptrie_kernel    (K3)  SearchTree::lookup per IP token + record emission      mmdb/tree.rs:46-125
+//   lithash_kernel   (K4)  LiteralHash::lookup per string token                    matchy-literal-hash lib.rs:467-575
+//   acglob_kernel    (K5)  Paraglob::find_all per string token + record emission   paraglob_offset.rs:1028-1182
+// Records are appended with aggregated atomics (the "stream compaction" step) and sorted on the host.
+// sm_100a only.  No CPU fallback: every entry point fails when there is no CUDA device.
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/matchy_b200.h"
+#include "db_prepare.h"
+#include "mxy_reader.h"
+#include "tokenize.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mgpu {
+
+struct Cand { uint32_t start, len; };
+struct StrTok { uint32_t start, len, type; };
+struct IpTok { uint32_t start, len, type, pad; uint32_t w[4]; };  // v4: w[0]; v6: w[k] = seg[2k] << 16 | seg[2k+1]
+
+struct DevCounters {
+  uint32_t q_count[Q_COUNT];  // slots handed out per candidate queue (includes invalidated padding)
+  uint32_t n_str, n_ip, n_rec, n_ids;
+  uint32_t overflow;          // bit q: queue q, 8: str tokens, 9: ip tokens, 10: records, 11: ids
+  uint32_t pad[3];
+  unsigned long long lines;
+  unsigned long long by_type[12];
+  unsigned long long matches;
+};
+
+struct ScanArgs {
+  const uint8_t* buf;  // 16-byte aligned, readable up to round_up(n, 1024); the chunk is buf[lo .. n)
+  uint64_t lo;         // 0..15: bytes before the chunk (alignment padding, treated like a chunk edge)
+  uint64_t n;          // end of the chunk relative to buf
+  uint64_t base;       // absolute log offset of buf[0]
+  uint32_t flags;
+  DbView db;
+  Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2;
+  uint32_t cap_q[Q_COUNT];
+  StrTok* str; uint32_t cap_str;
+  IpTok* ip; uint32_t cap_ip;
+  uint32_t* lh_res;
+  mgpu_match* recs; uint32_t cap_rec;
+  mgpu_id_pair* ids; uint32_t cap_ids;
+  DevCounters* ctr;
+};
+
+static const int K1_THREADS = 512;
+static const uint32_t RESERVE = 512;  // queue slots a warp takes per atomic
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 tokenize
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t gather_mask(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t k) {
+  uint32_t s = k | ((4u + k) << 4);
+  return __byte_perm(__byte_perm(a0, a1, s), __byte_perm(a2, a3, s), 0x5410);
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= (uint32_t)d) v += t;
+  }
+  return v;
+}
+
+struct QueueCursor { uint32_t base, left; };
+
+__device__ __forceinline__ void q_invalidate(const ScanArgs& a, int q, uint32_t from, uint32_t count, uint32_t lane) {
+  for (uint32_t i = lane; i < count; i += 32) {
+    uint32_t s = from + i;
+    if (s >= a.cap_q[q]) break;
+    if (q == Q_DOTTED) a.q_dotted[s].start = NONE32;
+    else if (q == Q_HASH) a.q_hash[s].start = NONE32;
+    else if (q == Q_AT) a.q_at[s] = NONE32;
+    else a.q_c2[s] = NONE32;
+  }
+}
+
+// Slots for `total` new entries of queue q (warp-uniform).  NONE32 = dropped, overflow flagged.
+__device__ __forceinline__ uint32_t warp_reserve(const ScanArgs& a, int q, uint32_t total, uint32_t lane, QueueCursor& c) {
+  if (total <= c.left) { uint32_t b = c.base; c.base += total; c.left -= total; return b; }
+  q_invalidate(a, q, c.base, c.left, lane);
+  uint32_t sz = total > RESERVE ? total : RESERVE;
+  uint32_t b = 0;
+  if (lane == 0) b = atomicAdd(&a.ctr->q_count[q], sz);
+  b = __shfl_sync(0xFFFFFFFFu, b, 0);
+  if ((uint64_t)b + sz > a.cap_q[q]) {
+    if (lane == 0) atomicOr(&a.ctr->overflow, 1u << q);
+    if (b < a.cap_q[q]) q_invalidate(a, q, b, a.cap_q[q] - b, lane);
+    c.base = 0; c.left = 0;
+    return NONE32;
+  }
+  c.base = b + total; c.left = sz - total;
+  return b;
+}
+
+__global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  // class table replicated per lane: entry (b, lane) at b*256 + lane*8 -> every LDS.64 of a warp is conflict-free
+  uint2* lut = reinterpret_cast<uint2*>(smem);
+  uint32_t* sB_all = reinterpret_cast<uint32_t*>(smem + 256 * 32 * 8);
+  for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+    uint32_t c = class_bits((uint8_t)(i >> 5));
+    uint2 e;
+    e.x = (c & 1u) | (((c >> 1) & 1u) << 8) | (((c >> 2) & 1u) << 16) | (((c >> 3) & 1u) << 24);
+    e.y = ((c >> 4) & 1u) | (((c >> 5) & 1u) << 8) | (((c >> 6) & 1u) << 16) | (((c >> 7) & 1u) << 24);
+    lut[i] = e;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* sB = sB_all + warp * 32;
+  const uint8_t* lut_lane = smem + lane * 8;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const uint64_t tiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
+  const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
+  const uint64_t t0 = w * tpw;
+  uint64_t t1 = t0 + tpw;
+  if (t1 > tiles) t1 = tiles;
+  if (t0 >= t1) return;
+
+  TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
+  QueueCursor qc[Q_COUNT];
+#pragma unroll
+  for (int q = 0; q < Q_COUNT; q++) { qc[q].base = 0; qc[q].left = 0; }
+  uint32_t lines = 0;
+  const bool want_dot = (a.flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
+  const bool want_hash = (a.flags & MGPU_X_HASHES) != 0;
+  const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
+  const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
+
+  for (uint64_t t = t0; t < t1; t++) {
+    const uint64_t tile_base = t * TILE_BYTES;
+    const uint64_t p = tile_base + (uint64_t)lane * SLICE_BYTES;
+    uint4 v0 = ld_stream(a.buf + p), v1 = ld_stream(a.buf + p + 16);
+    uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t off = __byte_perm(wds[j], 0, 0x4404u | ((uint32_t)k << 4));  // byte k of the word, times 256
+        uint2 e = *reinterpret_cast<const uint2*>(lut_lane + off);
+        const uint32_t sh = (uint32_t)((j & 1) * 4 + k);
+        accLo[j >> 1] += e.x << sh;
+        accHi[j >> 1] += e.y << sh;
+      }
+    }
+    LaneMasks m;
+    m.B = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 0);
+    m.DOT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 1);
+    m.AT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 2);
+    m.CL = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 3);
+    m.NL = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 0);
+    m.DM = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 1);
+    m.HX = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 2);
+    if (tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
+      uint64_t valid = a.n > p ? a.n - p : 0;
+      uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
+      if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
+      m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep;
+    }
+    if (!cy.pT) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
+    lines += __popc(m.NL);
+    sB[lane] = m.B;
+    __syncwarp();
+
+    const uint32_t T = ~m.B;
+    uint32_t pT = __shfl_up_sync(0xFFFFFFFFu, T >> 31, 1);
+    uint32_t pCL = __shfl_up_sync(0xFFFFFFFFu, m.CL >> 30, 1);  // bit 1: byte -1 is ':', bit 0: byte -2 is ':'
+    if (lane == 0) { pT = cy.pT; pCL = cy.pCL; }  // lane 0 looks into the previous tile
+    const uint32_t S = T & ~((T << 1) | pT);
+
+    uint32_t A_DM, A_DN, A_HX;
+    {
+      uint32_t g, pr, co;
+      uint32_t G = m.DM, Sg = S & G;
+      gp_bits(G, Sg, g, pr);
+      uint32_t cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cDM, co);
+      A_DM = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B);
+      cy.cDM = co;
+      G = m.DM & ~m.DOT; Sg = S & G;
+      gp_bits(G, Sg, g, pr);
+      cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cDN, co);
+      A_DN = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B);
+      cy.cDN = co;
+      G = m.HX; Sg = S & G;
+      gp_bits(G, Sg, g, pr);
+      cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cHX, co);
+      A_HX = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B);
+      cy.cHX = co;
+    }
+    uint32_t candDot = want_dot ? (A_DM & ~A_DN) : 0u;
+    // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
+    uint32_t candHex = (want_hash && pT) ? (A_HX & (m.B & (0u - m.B))) : 0u;
+    uint32_t candAt = want_at ? m.AT : 0u;
+    // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
+    uint32_t cl1 = (m.CL << 1) | (pCL >> 1), cl2 = (m.CL << 2) | pCL;
+    uint32_t candC2 = want_c2 ? (m.CL & cl1 & ~cl2) : 0u;
+
+    // ---- emission ----
+    if (__any_sync(0xFFFFFFFFu, candDot != 0)) {
+      uint32_t cnt = __popc(candDot), incl = warp_incl_scan(cnt, lane);
+      uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      uint32_t b = warp_reserve(a, Q_DOTTED, total, lane, qc[Q_DOTTED]);
+      if (b != NONE32) {
+        uint32_t idx = b + incl - cnt, mm = candDot;
+        while (mm) {
+          uint32_t bit = __ffs(mm) - 1; mm &= mm - 1;
+          uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
+          a.q_dotted[idx++] = Cand{(uint32_t)s, (uint32_t)(e - s)};
+        }
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, candHex != 0)) {
+      bool keep = false; Cand c{0, 0};
+      if (candHex) {
+        uint32_t bit = __ffs(candHex) - 1;
+        uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
+        keep = is_hash_len(e - s);
+        c.start = (uint32_t)s; c.len = (uint32_t)(e - s);
+      }
+      uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+      if (bal) {
+        uint32_t b = warp_reserve(a, Q_HASH, __popc(bal), lane, qc[Q_HASH]);
+        if (b != NONE32 && keep) a.q_hash[b + __popc(bal & ((1u << lane) - 1u))] = c;
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, candAt != 0)) {
+      uint32_t cnt = __popc(candAt), incl = warp_incl_scan(cnt, lane);
+      uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      uint32_t b = warp_reserve(a, Q_AT, total, lane, qc[Q_AT]);
+      if (b != NONE32) {
+        uint32_t idx = b + incl - cnt, mm = candAt;
+        while (mm) { uint32_t bit = __ffs(mm) - 1; mm &= mm - 1; a.q_at[idx++] = (uint32_t)(p + bit); }
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, candC2 != 0)) {
+      uint32_t cnt = __popc(candC2), incl = warp_incl_scan(cnt, lane);
+      uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      uint32_t b = warp_reserve(a, Q_COLON2, total, lane, qc[Q_COLON2]);
+      if (b != NONE32) {
+        uint32_t idx = b + incl - cnt, mm = candC2;
+        while (mm) { uint32_t bit = __ffs(mm) - 1; mm &= mm - 1; a.q_c2[idx++] = (uint32_t)(p + bit - 1); }
+      }
+    }
+
+    // ---- carry into the next tile ----
+    uint32_t hasB = __ballot_sync(0xFFFFFFFFu, m.B != 0);
+    if (hasB) {
+      uint32_t ll = 31u - (uint32_t)__clz((int)hasB);
+      uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
+      cy.open_start = tile_base + (uint64_t)ll * 32 + (31u - (uint32_t)__clz((int)Bl)) + 1;
+    }
+    cy.pT = __shfl_sync(0xFFFFFFFFu, T >> 31, 31);
+    cy.pCL = __shfl_sync(0xFFFFFFFFu, m.CL >> 30, 31);
+    __syncwarp();
+  }
+#pragma unroll
+  for (int q = 0; q < Q_COUNT; q++) q_invalidate(a, q, qc[q].base, qc[q].left, lane);
+  for (int d = 16; d; d >>= 1) lines += __shfl_down_sync(0xFFFFFFFFu, lines, d);
+  if (lane == 0 && lines) atomicAdd(&a.ctr->lines, (unsigned long long)lines);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 validate: candidate -> token.  One thread per candidate, block-aggregated appends.
+// ---------------------------------------------------------------------------------------------------------
+static const int K2_THREADS = 256;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+  // v in {0,1,2}; returns the exclusive prefix within the block
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = warp_incl_scan(v, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+  for (uint32_t k = 0; k < (blockDim.x >> 5); k++) { uint32_t x = s_warp[k]; if (k < warp) off += x; tot += x; }
+  __syncthreads();
+  total = tot;
+  return off + incl - v;
+}
+
+__global__ void __launch_bounds__(K2_THREADS) validate_kernel(ScanArgs a) {
+  __shared__ uint32_t s_warp[K2_THREADS / 32];
+  __shared__ uint32_t s_base[2];
+  __shared__ unsigned int s_type[12];
+  if (threadIdx.x < 12) s_type[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t nD = min(a.ctr->q_count[Q_DOTTED], a.cap_q[Q_DOTTED]);
+  const uint32_t nH = min(a.ctr->q_count[Q_HASH], a.cap_q[Q_HASH]);
+  const uint32_t nA = min(a.ctr->q_count[Q_AT], a.cap_q[Q_AT]);
+  const uint32_t nC = min(a.ctr->q_count[Q_COLON2], a.cap_q[Q_COLON2]);
+  const uint64_t total = (uint64_t)nD + nH + nA + nC;
+  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < total; i0 += step) {
+    const uint64_t i = i0 + threadIdx.x;
+    bool ws = false, wi = false;
+    StrTok st{0, 0, 0};
+    IpTok it{0, 0, 0, 0, {0, 0, 0, 0}};
+    if (i < total) {
+      if (i < nD) {
+        Cand c = a.q_dotted[i];
+        if (c.start != NONE32 && (uint64_t)c.start + c.len <= a.n) {
+          const uint8_t* wp = a.buf + c.start;
+          uint32_t addr;
+          if ((a.flags & MGPU_X_IPV4) && parse_ipv4_word(wp, c.len, addr)) {
+            wi = true; it.start = c.start; it.len = c.len; it.type = MGPU_T_IPV4; it.w[0] = addr;
+          }
+          if ((a.flags & MGPU_X_DOMAINS) && validate_domain_word(a.db, wp, c.len)) {
+            ws = true; st.start = c.start; st.len = c.len; st.type = MGPU_T_DOMAIN;
+          }
+        }
+      } else if (i < (uint64_t)nD + nH) {
+        Cand c = a.q_hash[i - nD];
+        if (c.start != NONE32 && (uint64_t)c.start + c.len <= a.n) {
+          ws = true; st.start = c.start; st.len = c.len;
+          st.type = c.len == 32 ? MGPU_T_MD5 : c.len == 40 ? MGPU_T_SHA1 : c.len == 64 ? MGPU_T_SHA256 : c.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
+        }
+      } else if (i < (uint64_t)nD + nH + nA) {
+        uint32_t at = a.q_at[i - nD - nH];
+        size_t s, e;
+        if (at != NONE32 && at < a.n && email_at(a.db, a.buf, (size_t)a.lo, (size_t)a.n, at, s, e)) {
+          ws = true; st.start = (uint32_t)s; st.len = (uint32_t)(e - s); st.type = MGPU_T_EMAIL;
+        }
+      } else {
+        uint32_t at = a.q_c2[i - nD - nH - nA];
+        size_t s, e; uint16_t seg[8];
+        if (at != NONE32 && (uint64_t)at + 2 <= a.n && ipv6_at(a.buf, (size_t)a.lo, (size_t)a.n, at, s, e, seg)) {
+          wi = true; it.start = (uint32_t)s; it.len = (uint32_t)(e - s); it.type = MGPU_T_IPV6;
+          for (int k = 0; k < 4; k++) it.w[k] = ((uint32_t)seg[2 * k] << 16) | seg[2 * k + 1];
+        }
+      }
+    }
+    uint32_t ts, ti;
+    uint32_t es = block_excl_scan(ws ? 1u : 0u, s_warp, ts);
+    uint32_t ei = block_excl_scan(wi ? 1u : 0u, s_warp, ti);
+    if (threadIdx.x == 0) {
+      s_base[0] = ts ? atomicAdd(&a.ctr->n_str, ts) : 0;
+      s_base[1] = ti ? atomicAdd(&a.ctr->n_ip, ti) : 0;
+    }
+    __syncthreads();
+    if (ws) {
+      uint32_t k = s_base[0] + es;
+      if (k < a.cap_str) a.str[k] = st; else atomicOr(&a.ctr->overflow, 1u << 8);
+      atomicAdd(&s_type[st.type], 1u);
+    }
+    if (wi) {
+      uint32_t k = s_base[1] + ei;
+      if (k < a.cap_ip) a.ip[k] = it; else atomicOr(&a.ctr->overflow, 1u << 9);
+      atomicAdd(&s_type[it.type], 1u);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x < 12 && s_type[threadIdx.x]) atomicAdd(&a.ctr->by_type[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// record emission (aggregated across the currently active lanes)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t agg_add(uint32_t* ctr, uint32_t v) {
+  cg::coalesced_group g = cg::coalesced_threads();
+  uint32_t incl = cg::inclusive_scan(g, v);
+  uint32_t base = 0;
+  if (g.thread_rank() == g.size() - 1) base = atomicAdd(ctr, incl);
+  base = g.shfl(base, g.size() - 1);
+  return base + incl - v;
+}
+
+// K3: IP tokens
+__global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
+  const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
+  if (!a.db.has_ip) return;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    IpTok t = a.ip[i];
+    uint32_t off = 0; uint8_t pl = 0; bool hit;
+    if (t.type == MGPU_T_IPV4) hit = trie_lookup_v4(a.db, t.w[0], off, pl);
+    else {
+      uint16_t seg[8];
+      for (int k = 0; k < 4; k++) { seg[2 * k] = (uint16_t)(t.w[k] >> 16); seg[2 * k + 1] = (uint16_t)t.w[k]; }
+      hit = trie_lookup_v6(a.db, seg, off, pl);
+    }
+    if (!hit) continue;
+    uint32_t k = agg_add(&a.ctr->n_rec, 1u);
+    if (k >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); continue; }
+    mgpu_match r;
+    r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_IP; r.prefix_len = pl; r.reserved = 0;
+    r.n_ids = 0; r.ids_index = 0; r.data_offset = off; r.pad = 0;
+    a.recs[k] = r;
+  }
+}
+
+// K4: literal hash probe per string token
+__global__ void __launch_bounds__(256) lithash_kernel(ScanArgs a) {
+  const uint32_t n = min(a.ctr->n_str, a.cap_str);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    StrTok t = a.str[i];
+    uint32_t pid = NONE32;
+    if (!lh_lookup(a.db, a.buf + t.start, t.len, pid)) pid = NONE32;
+    a.lh_res[i] = pid;
+  }
+}
+
+// K5: Aho-Corasick walk + glob verification per string token, merge with the literal result, emit
+__global__ void __launch_bounds__(256) acglob_kernel(ScanArgs a) {
+  const uint32_t n = min(a.ctr->n_str, a.cap_str);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    StrTok t = a.str[i];
+    const uint8_t* text = a.buf + t.start;
+    uint32_t lit_pid = a.db.has_literal ? a.lh_res[i] : NONE32, lit_off = 0;
+    bool lit_ok = lit_pid != NONE32 && lh_data_offset(a.db, lit_pid, lit_off);
+    uint32_t cnt = 0;
+    if (a.db.has_glob) find_all_visit(a.db, text, t.len, [&](uint32_t) { cnt++; });
+    if (!lit_ok && cnt == 0) continue;
+    uint32_t total = cnt + (lit_ok ? 1u : 0u);
+    uint32_t b = agg_add(&a.ctr->n_ids, total);
+    if ((uint64_t)b + total > a.cap_ids) { atomicOr(&a.ctr->overflow, 1u << 11); continue; }
+    uint32_t k = b;
+    if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
+    const uint32_t g0 = k;
+    if (cnt) {
+      find_all_visit(a.db, text, t.len, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
+      // sort_unstable + dedup (paraglob_offset.rs:1173-1181)
+      for (uint32_t x = g0 + 1; x < k; x++) {
+        uint32_t v = a.ids[x].pattern_id, y = x;
+        while (y > g0 && a.ids[y - 1].pattern_id > v) { a.ids[y].pattern_id = a.ids[y - 1].pattern_id; y--; }
+        a.ids[y].pattern_id = v;
+      }
+      uint32_t u = g0;
+      for (uint32_t x = g0; x < k; x++) if (x == g0 || a.ids[x].pattern_id != a.ids[u - 1].pattern_id) a.ids[u++].pattern_id = a.ids[x].pattern_id;
+      k = u;
+      for (uint32_t x = g0; x < k; x++) {
+        uint32_t off;
+        a.ids[x].data_offset = glob_data_offset(a.db, a.ids[x].pattern_id, off) ? off : MGPU_NO_DATA;
+      }
+    }
+    uint32_t r_i = agg_add(&a.ctr->n_rec, 1u);
+    if (r_i >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); continue; }
+    mgpu_match r;
+    r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_PATTERN; r.prefix_len = 0; r.reserved = 0;
+    r.n_ids = k - b; r.ids_index = b; r.data_offset = MGPU_NO_DATA; r.pad = 0;
+    a.recs[r_i] = r;
+  }
+}
+
+// position just after the first '\n' at or after `from` (or n): where a newline-aligned cut may be made
+__global__ void cut_kernel(const uint8_t* buf, uint64_t n, const uint64_t* from, uint64_t* out, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint64_t p = from[i];
+  while (p < n && buf[p] != '\n') p++;
+  out[i] = p < n ? p + 1 : n;
+}
+
+// position just after the LAST '\n' in buf[lo, hi), or 0 if there is none (one block)
+__global__ void rfind_nl_kernel(const uint8_t* buf, uint64_t lo, uint64_t hi, uint64_t* out) {
+  __shared__ unsigned long long best;
+  uint64_t end = hi;
+  while (end > lo) {
+    uint64_t beg = end - lo > 8192 ? end - 8192 : lo;
+    if (threadIdx.x == 0) best = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (uint64_t i = beg + threadIdx.x; i < end; i += blockDim.x) if (buf[i] == '\n') mine = i + 1;
+    if (mine) atomicMax(&best, mine);
+    __syncthreads();
+    unsigned long long b = best;
+    __syncthreads();
+    if (b) { if (threadIdx.x == 0) *out = b; return; }
+    end = beg;
+  }
+  if (threadIdx.x == 0) *out = 0;
+}
+
+__global__ void fill_kernel(uint4* p, size_t n16, uint32_t v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(v, v, v, v);
+}
+
+// single-query lookups through the same device functions (Database::lookup / lookup_ip)
+__global__ void query_string_kernel(ScanArgs a, uint32_t len, uint32_t* out_n) {
+  uint32_t n = 0;
+  uint32_t pid, off;
+  if (a.db.has_literal && lh_lookup(a.db, a.buf, len, pid) && lh_data_offset(a.db, pid, off)) { if (n < a.cap_ids) { a.ids[n].pattern_id = pid; a.ids[n].data_offset = off; } n++; }
+  uint32_t g0 = n;
+  if (a.db.has_glob) find_all_visit(a.db, a.buf, len, [&](uint32_t p) { if (n < a.cap_ids) a.ids[n].pattern_id = p; n++; });
+  uint32_t k = n < a.cap_ids ? n : a.cap_ids;
+  for (uint32_t x = g0 + 1; x < k; x++) {
+    uint32_t v = a.ids[x].pattern_id, y = x;
+    while (y > g0 && a.ids[y - 1].pattern_id > v) { a.ids[y].pattern_id = a.ids[y - 1].pattern_id; y--; }
+    a.ids[y].pattern_id = v;
+  }
+  uint32_t u = g0;
+  for (uint32_t x = g0; x < k; x++) if (x == g0 || a.ids[x].pattern_id != a.ids[u - 1].pattern_id) a.ids[u++].pattern_id = a.ids[x].pattern_id;
+  for (uint32_t x = g0; x < u; x++) { uint32_t o; a.ids[x].data_offset = glob_data_offset(a.db, a.ids[x].pattern_id, o) ? o : MGPU_NO_DATA; }
+  *out_n = (n > a.cap_ids) ? NONE32 : u;
+}
+__global__ void query_ip_kernel(ScanArgs a, int is_v6, uint32_t* out3) {
+  uint32_t off = 0; uint8_t pl = 0; bool hit = false;
+  if (a.db.has_ip) {
+    if (!is_v6) hit = trie_lookup_v4(a.db, ((uint32_t)a.buf[0] << 24) | ((uint32_t)a.buf[1] << 16) | ((uint32_t)a.buf[2] << 8) | a.buf[3], off, pl);
+    else {
+      uint16_t seg[8];
+      for (int k = 0; k < 8; k++) seg[k] = (uint16_t)(((uint32_t)a.buf[2 * k] << 8) | a.buf[2 * k + 1]);
+      hit = trie_lookup_v6(a.db, seg, off, pl);
+    }
+  }
+  out3[0] = hit; out3[1] = off; out3[2] = pl;
+}
+
+}  // namespace mgpu
+
+// =========================================================================================================
+// Host side
+// =========================================================================================================
+using namespace mgpu;
+
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+      return MGPU_E_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+struct mgpu_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t chunk_bytes = 0;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_k[MGPU_K_COUNT + 1] = {};
+  // log staging (double buffered) and pinned bounce buffers for pageable callers
+  uint8_t* d_log[2] = {nullptr, nullptr};
+  uint8_t* h_pin[2] = {nullptr, nullptr};
+  // work buffers
+  ScanArgs args;  // device pointers + capacities (buf/n/base/flags filled per chunk)
+  DevCounters* h_ctr = nullptr;  // pinned
+  uint64_t* d_cut = nullptr; uint64_t* h_cut = nullptr;
+  uint8_t* d_small = nullptr; uint32_t* d_small_out = nullptr;
+  void* d_flush = nullptr;
+  // database
+  bool db_loaded = false;
+  std::vector<void*> db_allocs;
+  mxy::Layout layout;
+  mgpu_db_info info{};
+  // PSL
+  std::vector<uint8_t> psl_text;
+  void* d_psl_keys = nullptr; void* d_psl_vals = nullptr; void* d_psl_pool = nullptr;
+  // results of the last scan
+  std::vector<mgpu_match> recs;
+  std::vector<mgpu_id_pair> ids;
+  mgpu_counters counters{};
+  mgpu_timing timing{};
+  bool keep_results = true;
+  std::vector<StrTok> x_str; std::vector<IpTok> x_ip;  // extraction-only capture
+  bool capture_tokens = false;
+};
+
+static int launch_grid(mgpu_ctx* c, int per_sm) { return c->sm_count * per_sm; }
+
+extern "C" {
+
+const char* mgpu_last_error(void) { return g_err.c_str(); }
+
+static void free_db(mgpu_ctx* c) {
+  for (void* p : c->db_allocs) cudaFree(p);
+  c->db_allocs.clear();
+  c->db_loaded = false;
+}
+
+void mgpu_destroy(mgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_db(c);
+  for (int s = 0; s < 2; s++) {
+    if (c->d_log[s]) cudaFree(c->d_log[s]);
+    if (c->h_pin[s]) cudaFreeHost(c->h_pin[s]);
+    if (c->ev_copied[s]) cudaEventDestroy(c->ev_copied[s]);
+    if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
+  }
+  for (auto& e : c->ev_k) if (e) cudaEventDestroy(e);
+  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.str, c->args.ip, c->args.lh_res,
+                  c->args.recs, c->args.ids, c->args.ctr, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool};
+  for (void* p : bufs) if (p) cudaFree(p);
+  if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  if (c->h_cut) cudaFreeHost(c->h_cut);
+  if (c->compute) cudaStreamDestroy(c->compute);
+  if (c->copy) cudaStreamDestroy(c->copy);
+  delete c;
+}
+
+static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_err("no such CUDA device"); return MGPU_E_PARAM; }
+  c->device = device;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_err("matchy_b200 needs an sm_100-class GPU"); return MGPU_E_CUDA; }
+  c->sm_count = prop.multiProcessorCount;
+  if (chunk_bytes == 0) chunk_bytes = (size_t)256 << 20;
+  chunk_bytes = (chunk_bytes + TILE_BYTES - 1) / TILE_BYTES * TILE_BYTES;
+  if (chunk_bytes > ((size_t)2 << 30)) chunk_bytes = (size_t)2 << 30;
+  if (chunk_bytes < (size_t)64 << 10) chunk_bytes = (size_t)64 << 10;
+  c->chunk_bytes = chunk_bytes;
+  CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++) {
+    CK(cudaEventCreateWithFlags(&c->ev_copied[s], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming));
+    CK(cudaMalloc(&c->d_log[s], chunk_bytes + TILE_BYTES));
+    CK(cudaMallocHost(&c->h_pin[s], std::min(chunk_bytes, (size_t)64 << 20)));
+  }
+  for (auto& e : c->ev_k) CK(cudaEventCreate(&e));
+  ScanArgs& a = c->args;
+  memset(&a, 0, sizeof a);
+  auto cap32 = [](size_t v) { return (uint32_t)std::min<size_t>(v, 0x7FFFFFFFu); };
+  a.cap_q[Q_DOTTED] = cap32(chunk_bytes / 8 + 4 * RESERVE);
+  a.cap_q[Q_HASH] = cap32(chunk_bytes / 33 + 64 * RESERVE);
+  a.cap_q[Q_AT] = cap32(chunk_bytes / 16 + 4 * RESERVE);
+  a.cap_q[Q_COLON2] = cap32(chunk_bytes / 16 + 4 * RESERVE);
+  a.cap_str = cap32(chunk_bytes / 8 + 1024);
+  a.cap_ip = cap32(chunk_bytes / 8 + 1024);
+  a.cap_rec = cap32(chunk_bytes / 16 + 4096);
+  a.cap_ids = cap32(chunk_bytes / 8 + 8192);
+  CK(cudaMalloc(&a.q_dotted, (size_t)a.cap_q[Q_DOTTED] * sizeof(Cand)));
+  CK(cudaMalloc(&a.q_hash, (size_t)a.cap_q[Q_HASH] * sizeof(Cand)));
+  CK(cudaMalloc(&a.q_at, (size_t)a.cap_q[Q_AT] * 4));
+  CK(cudaMalloc(&a.q_c2, (size_t)a.cap_q[Q_COLON2] * 4));
+  CK(cudaMalloc(&a.str, (size_t)a.cap_str * sizeof(StrTok)));
+  CK(cudaMalloc(&a.ip, (size_t)a.cap_ip * sizeof(IpTok)));
+  CK(cudaMalloc(&a.lh_res, (size_t)a.cap_str * 4));
+  CK(cudaMalloc(&a.recs, (size_t)a.cap_rec * sizeof(mgpu_match)));
+  CK(cudaMalloc(&a.ids, (size_t)a.cap_ids * sizeof(mgpu_id_pair)));
+  CK(cudaMalloc(&a.ctr, sizeof(DevCounters)));
+  CK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters)));
+  CK(cudaMalloc(&c->d_cut, 64 * sizeof(uint64_t) * 2));
+  CK(cudaMallocHost(&c->h_cut, 64 * sizeof(uint64_t) * 2));
+  CK(cudaMalloc(&c->d_small, 65536 + TILE_BYTES));
+  CK(cudaMalloc(&c->d_small_out, 64));
+  CK(cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8 + (K1_THREADS / 32) * 32 * 4));
+  return MGPU_OK;
+}
+
+mgpu_ctx* mgpu_create(int device, size_t chunk_bytes) {
+  mgpu_ctx* c = new mgpu_ctx();
+  if (create_impl(c, device, chunk_bytes) != MGPU_OK) { std::string keep = g_err; mgpu_destroy(c); g_err = keep; return nullptr; }
+  return c;
+}
+
+void mgpu_set_keep_results(mgpu_ctx* c, int keep) { c->keep_results = keep != 0; }
+
+// ---- PSL ------------------------------------------------------------------------------------------------
+int mgpu_set_psl(mgpu_ctx* c, const uint8_t* text, size_t len) {
+  CK(cudaSetDevice(c->device));
+  PslTable t;
+  std::string err;
+  if (!build_psl(text, len, t, err)) { set_err(err); return MGPU_E_FORMAT; }
+  if (c->d_psl_keys) { cudaFree(c->d_psl_keys); cudaFree(c->d_psl_vals); cudaFree(c->d_psl_pool); }
+  CK(cudaMalloc(&c->d_psl_keys, t.keys.size() * 8));
+  CK(cudaMalloc(&c->d_psl_vals, t.vals.size() * 4));
+  CK(cudaMalloc(&c->d_psl_pool, t.pool.size() + 16));
+  CK(cudaMemcpy(c->d_psl_keys, t.keys.data(), t.keys.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_psl_vals, t.vals.data(), t.vals.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_psl_pool, t.pool.data(), t.pool.size(), cudaMemcpyHostToDevice));
+  DbView& db = c->args.db;
+  db.psl_keys = (const uint64_t*)c->d_psl_keys; db.psl_vals = (const uint32_t*)c->d_psl_vals; db.psl_pool = (const uint8_t*)c->d_psl_pool;
+  db.psl_mask = t.mask; db.psl_max_len = t.max_len;
+  return MGPU_OK;
+}
+
+// ---- database upload ------------------------------------------------------------------------------------
+static int dev_copy(mgpu_ctx* c, const void* src, size_t len, size_t align_off, size_t align, void** out_base) {
+  // device copy of [src, src+len) placed so that (address % align) == align_off
+  void* raw = nullptr;
+  CK(cudaMalloc(&raw, len + align + 64));
+  c->db_allocs.push_back(raw);
+  uintptr_t p = (uintptr_t)raw;
+  uintptr_t q = (p + align - 1) / align * align + align_off;
+  if (len) CK(cudaMemcpy((void*)q, src, len, cudaMemcpyHostToDevice));
+  CK(cudaMemset((uint8_t*)q + len, 0, 32));
+  *out_base = (void*)q;
+  return MGPU_OK;
+}
+
+int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
+  CK(cudaSetDevice(c->device));
+  free_db(c);
+  std::string err;
+  PreparedDb P;
+  if (!prepare_db(d, n, P, err)) { set_err(err); return MGPU_E_FORMAT; }
+  const mxy::Layout& L = P.L;
+  DbView db = P.view;  // scalar fields filled; pointers below
+  db.psl_keys = c->args.db.psl_keys; db.psl_vals = c->args.db.psl_vals; db.psl_pool = c->args.db.psl_pool;
+  db.psl_mask = c->args.db.psl_mask; db.psl_max_len = c->args.db.psl_max_len;
+  void* p;
+  int rc = dev_copy(c, d, (size_t)L.tree_size, 0, 256, &p);
+  if (rc) return rc;
+  db.tree = (const uint8_t*)p;
+  if (L.has_literal) {
+    // the slot table starts at 4 (mod 16) inside the section: base = 12 (mod 16) makes every 16-byte entry aligned
+    rc = dev_copy(c, d + L.lit_off, (size_t)L.lit_len, 12, 256, &p);
+    if (rc) return rc;
+    db.lh = (const uint8_t*)p;
+    rc = dev_copy(c, P.lh_index.data(), P.lh_index.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.lh_data_index = (const uint32_t*)p;
+  }
+  if (L.has_glob) {
+    rc = dev_copy(c, d + L.pg_off, (size_t)L.pg_len, 0, 256, &p);
+    if (rc) return rc;
+    db.pg = (const uint8_t*)p;
+    rc = dev_copy(c, P.aclh.data(), P.aclh.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.aclh_index = (const uint32_t*)p;
+    rc = dev_copy(c, d + L.map_off, (size_t)L.map_count * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.glob_data = (const uint32_t*)p;
+  }
+  c->args.db = db;
+  c->layout = L;
+  c->db_loaded = true;
+  mgpu_db_info& I = c->info;
+  I.node_count = L.node_count; I.record_bits = L.record_bits; I.ip_version = L.ip_version; I.match_mode = L.match_mode;
+  I.has_ip = db.has_ip; I.has_literal = db.has_literal; I.has_glob = db.has_glob;
+  I.literal_count = L.literal_count; I.glob_count = L.glob_count; I.ac_node_count = P.ac_node_count;
+  I.tree_bytes = L.tree_size; I.literal_bytes = L.lit_len; I.paraglob_bytes = L.pg_len; I.file_bytes = n;
+  return MGPU_OK;
+}
+
+int mgpu_db_info_get(mgpu_ctx* c, mgpu_db_info* out) {
+  if (!c->db_loaded) { set_err("no database uploaded"); return MGPU_E_NODB; }
+  *out = c->info;
+  return MGPU_OK;
+}
+
+uint32_t mgpu_default_flags(mgpu_ctx* c) {
+  uint32_t f = 0;
+  if (!c->db_loaded) return 0;
+  if (c->args.db.has_ip) f |= MGPU_X_IPV4 | MGPU_X_IPV6;
+  if (c->args.db.has_literal || c->args.db.has_glob) f |= MGPU_X_DOMAINS | MGPU_X_EMAILS | MGPU_X_HASHES;
+  return f;
+}
+
+// ---- scanning -------------------------------------------------------------------------------------------
+static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, bool lookups) {
+  ScanArgs a = c->args;
+  a.buf = d_buf; a.lo = lo; a.n = n; a.base = base; a.flags = flags;
+  cudaStream_t st = c->compute;
+  CK(cudaMemsetAsync(a.ctr, 0, sizeof(DevCounters), st));
+  CK(cudaEventRecord(c->ev_k[0], st));
+  {
+    uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
+    int warps_per_block = K1_THREADS / 32;
+    uint64_t want_blocks = (tiles + warps_per_block - 1) / warps_per_block;
+    int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 2));
+    if (grid < 1) grid = 1;
+    size_t smem = 256 * 32 * 8 + (size_t)warps_per_block * 32 * 4;
+    tokenize_kernel<<<grid, K1_THREADS, smem, st>>>(a);
+  }
+  CK(cudaEventRecord(c->ev_k[1], st));
+  validate_kernel<<<launch_grid(c, 8), K2_THREADS, 0, st>>>(a);
+  CK(cudaEventRecord(c->ev_k[2], st));
+  if (lookups) {
+    iptrie_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
+    CK(cudaEventRecord(c->ev_k[3], st));
+    if (a.db.has_literal) lithash_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
+    CK(cudaEventRecord(c->ev_k[4], st));
+    if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
+    CK(cudaEventRecord(c->ev_k[5], st));
+  } else {
+    for (int k = 3; k <= 5; k++) CK(cudaEventRecord(c->ev_k[k], st));
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(c->h_ctr, a.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < MGPU_K_COUNT; k++) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev_k[k], c->ev_k[k + 1]));
+    c->timing.kernel_ms[k] += ms;
+  }
+  c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_VALIDATE]++;
+  if (lookups) {
+    c->timing.launches[MGPU_K_IPTRIE]++;
+    if (a.db.has_literal) c->timing.launches[MGPU_K_LITHASH]++;
+    if (a.db.has_literal || a.db.has_glob) c->timing.launches[MGPU_K_ACGLOB]++;
+  }
+  float tot = 0;
+  CK(cudaEventElapsedTime(&tot, c->ev_k[0], c->ev_k[MGPU_K_COUNT]));
+  c->timing.total_ms += tot;
+  c->timing.chunks++;
+  return MGPU_OK;
+}
+
+// first newline-aligned cut point at or after each of `from` inside dev[0..n)
+static int find_cuts(mgpu_ctx* c, const uint8_t* dev, uint64_t n, const std::vector<uint64_t>& from, std::vector<uint64_t>& out) {
+  int cnt = (int)from.size();
+  if (cnt > 64) { set_err("too many cuts"); return MGPU_E_PARAM; }
+  for (int k = 0; k < cnt; k++) c->h_cut[k] = from[k];
+  CK(cudaMemcpyAsync(c->d_cut, c->h_cut, cnt * 8, cudaMemcpyHostToDevice, c->compute));
+  cut_kernel<<<1, 64, 0, c->compute>>>(dev, n, c->d_cut, c->d_cut + 64, cnt);
+  CK(cudaMemcpyAsync(c->h_cut + 64, c->d_cut + 64, cnt * 8, cudaMemcpyDeviceToHost, c->compute));
+  CK(cudaStreamSynchronize(c->compute));
+  out.assign(c->h_cut + 64, c->h_cut + 64 + cnt);
+  return MGPU_OK;
+}
+
+// Process the resident piece dev[pos, end) (dev 16-byte aligned; the piece may start anywhere).  On buffer
+// exhaustion split it at newlines and retry the parts.  `base` = absolute log offset of dev[0].
+static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t end, uint64_t base, uint32_t flags, bool lookups, int depth) {
+  if (end <= pos) return MGPU_OK;
+  const uint64_t al = pos & ~(uint64_t)15;
+  int rc = run_kernels(c, dev + al, pos - al, end - al, base + al, flags, lookups);
+  if (rc) return rc;
+  DevCounters& h = *c->h_ctr;
+  if (h.overflow) {
+    if (depth >= 6 || end - pos < 4096) { set_err("result buffers exhausted (match density too high for the configured chunk size)"); return MGPU_E_OVERFLOW; }
+    std::vector<uint64_t> from, cuts;
+    for (int k = 1; k < 8; k++) from.push_back(pos + (end - pos) / 8 * k);
+    rc = find_cuts(c, dev, end, from, cuts);
+    if (rc) return rc;
+    uint64_t prev = pos;
+    cuts.push_back(end);
+    for (uint64_t cut : cuts) {
+      if (cut <= prev) continue;
+      rc = scan_piece(c, dev, prev, cut, base, flags, lookups, depth + 1);
+      if (rc) return rc;
+      prev = cut;
+    }
+    return MGPU_OK;
+  }
+  // collect
+  c->counters.lines += h.lines;
+  c->counters.bytes += end - pos;
+  for (int k = 0; k < 12; k++) { c->counters.by_type[k] += h.by_type[k]; c->counters.candidates += h.by_type[k]; }
+  c->counters.matches += h.n_rec;
+  if (c->capture_tokens) {
+    size_t s0 = c->x_str.size(), i0 = c->x_ip.size();
+    c->x_str.resize(s0 + h.n_str); c->x_ip.resize(i0 + h.n_ip);
+    if (h.n_str) CK(cudaMemcpy(c->x_str.data() + s0, c->args.str, (size_t)h.n_str * sizeof(StrTok), cudaMemcpyDeviceToHost));
+    if (h.n_ip) CK(cudaMemcpy(c->x_ip.data() + i0, c->args.ip, (size_t)h.n_ip * sizeof(IpTok), cudaMemcpyDeviceToHost));
+    for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);  // extraction is limited to < 4 GiB inputs
+    for (size_t k = i0; k < c->x_ip.size(); k++) c->x_ip[k].start += (uint32_t)(base + al);
+  }
+  if (c->keep_results && h.n_rec) {
+    size_t r0 = c->recs.size(), i0 = c->ids.size();
+    c->recs.resize(r0 + h.n_rec);
+    CK(cudaMemcpyAsync(c->recs.data() + r0, c->args.recs, (size_t)h.n_rec * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->compute));
+    if (h.n_ids) {
+      c->ids.resize(i0 + h.n_ids);
+      CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids, (size_t)h.n_ids * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
+    }
+    CK(cudaStreamSynchronize(c->compute));
+    for (size_t k = r0; k < c->recs.size(); k++) if (c->recs[k].kind == MGPU_KIND_PATTERN) c->recs[k].ids_index += (uint32_t)i0;
+  }
+  return MGPU_OK;
+}
+
+static void begin_scan(mgpu_ctx* c) {
+  c->recs.clear(); c->ids.clear();
+  c->x_str.clear(); c->x_ip.clear();
+  memset(&c->counters, 0, sizeof c->counters);
+  memset(&c->timing, 0, sizeof c->timing);
+}
+
+static void finish_scan(mgpu_ctx* c) {
+  // deterministic order: (offset, item_type, len).  Pairs stay where they are; ids_index still points at them.
+  std::sort(c->recs.begin(), c->recs.end(), [](const mgpu_match& x, const mgpu_match& y) {
+    if (x.offset != y.offset) return x.offset < y.offset;
+    if (x.item_type != y.item_type) return x.item_type < y.item_type;
+    return x.len < y.len;
+  });
+}
+
+static int check_ready(mgpu_ctx* c, uint32_t flags) {
+  if (!c) { set_err("null context"); return MGPU_E_PARAM; }
+  if (!c->db_loaded) { set_err("no database uploaded"); return MGPU_E_NODB; }
+  if (flags & ~MGPU_X_SUPPORTED) { set_err("bitcoin/ethereum/monero extractors are not available on the device path"); return MGPU_E_PARAM; }
+  if ((flags & (MGPU_X_DOMAINS | MGPU_X_EMAILS)) && !c->args.db.psl_keys) { set_err("Public Suffix List not set (mgpu_set_psl)"); return MGPU_E_PARAM; }
+  return MGPU_OK;
+}
+
+// dev[0..len) resident in HBM: pieces of at most chunk_bytes, each ending just after a newline
+// (FileReader::next_batch, processing/mod.rs:206-251: cut at the last '\n' of the window; the tail goes last)
+static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_t base, uint32_t flags, bool lookups) {
+  if (((uintptr_t)dev & 15) != 0) { set_err("device buffer must be 16-byte aligned"); return MGPU_E_PARAM; }
+  uint64_t pos = 0;
+  const uint64_t window = c->chunk_bytes - 16;  // run_kernels realigns the start downwards by up to 15 bytes
+  while (pos < len) {
+    uint64_t end = std::min<uint64_t>(len, pos + window);
+    if (end < len) {
+      rfind_nl_kernel<<<1, 256, 0, c->compute>>>(dev, pos, end, c->d_cut);
+      CK(cudaMemcpyAsync(c->h_cut, c->d_cut, 8, cudaMemcpyDeviceToHost, c->compute));
+      CK(cudaStreamSynchronize(c->compute));
+      if (c->h_cut[0] == 0) { set_err("a single line is longer than the scan chunk; raise chunk_bytes"); return MGPU_E_OVERFLOW; }
+      end = c->h_cut[0];
+    }
+    int rc = scan_piece(c, dev, pos, end, base, flags, lookups, 0);
+    if (rc) return rc;
+    pos = end;
+  }
+  return MGPU_OK;
+}
+
+int mgpu_scan_device(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_t base, uint32_t flags) {
+  int rc = check_ready(c, flags);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  begin_scan(c);
+  rc = scan_device_impl(c, dev, len, base, flags, true);
+  if (rc) return rc;
+  finish_scan(c);
+  return MGPU_OK;
+}
+
+static int scan_host_impl(mgpu_ctx* c, const uint8_t* host, size_t len, uint64_t base, uint32_t flags, bool lookups) {
+  // FileReader::next_batch semantics (processing/mod.rs:206-251): pieces end just after a '\n', the tail goes last.
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  size_t pos = 0;
+  int slot = 0;
+  struct Piece { size_t pos, len; int slot; };
+  auto stage = [&](size_t p, size_t l, int s) -> int {
+    // H2D of piece [p, p+l) into d_log[s] on the copy stream; waits until the kernels that last read d_log[s] are done
+    CK(cudaStreamWaitEvent(c->copy, c->ev_free[s], 0));
+    if (pinned) CK(cudaMemcpyAsync(c->d_log[s], host + p, l, cudaMemcpyHostToDevice, c->copy));
+    else {
+      size_t bounce = std::min(c->chunk_bytes, (size_t)64 << 20);
+      for (size_t o = 0; o < l; o += bounce) {
+        size_t m = std::min(bounce, l - o);
+        CK(cudaStreamSynchronize(c->copy));  // the bounce buffer is reused
+        memcpy(c->h_pin[s], host + p + o, m);
+        CK(cudaMemcpyAsync(c->d_log[s] + o, c->h_pin[s], m, cudaMemcpyHostToDevice, c->copy));
+      }
+    }
+    CK(cudaEventRecord(c->ev_copied[s], c->copy));
+    return MGPU_OK;
+  };
+  auto next_piece = [&](size_t p, size_t& l) -> int {
+    size_t want = std::min(len - p, c->chunk_bytes);
+    if (p + want < len) {
+      const uint8_t* q = (const uint8_t*)memrchr(host + p, '\n', want);
+      if (!q) { set_err("a single line is longer than the scan chunk; raise chunk_bytes"); return MGPU_E_OVERFLOW; }
+      want = (size_t)(q - (host + p)) + 1;
+    }
+    l = want;
+    return MGPU_OK;
+  };
+  if (len == 0) return MGPU_OK;
+  Piece cur{0, 0, 0};
+  int rc = next_piece(0, cur.len);
+  if (rc) return rc;
+  rc = stage(cur.pos, cur.len, cur.slot);
+  if (rc) return rc;
+  pos = cur.len;
+  while (true) {
+    Piece nxt{pos, 0, cur.slot ^ 1};
+    bool have_next = pos < len;
+    if (have_next) {
+      rc = next_piece(pos, nxt.len);
+      if (rc) return rc;
+      rc = stage(nxt.pos, nxt.len, nxt.slot);  // overlaps with the kernels of `cur`
+      if (rc) return rc;
+      pos += nxt.len;
+    }
+    CK(cudaStreamWaitEvent(c->compute, c->ev_copied[cur.slot], 0));
+    rc = scan_piece(c, c->d_log[cur.slot], 0, cur.len, base + cur.pos, flags, lookups, 0);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev_free[cur.slot], c->compute));
+    if (!have_next) break;
+    cur = nxt;
+  }
+  (void)slot;
+  return MGPU_OK;
+}
+
+int mgpu_scan(mgpu_ctx* c, const uint8_t* host, size_t len, uint64_t base, uint32_t flags) {
+  int rc = check_ready(c, flags);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  begin_scan(c);
+  rc = scan_host_impl(c, host, len, base, flags, true);
+  if (rc) return rc;
+  finish_scan(c);
+  return MGPU_OK;
+}
+
+int mgpu_results(mgpu_ctx* c, const mgpu_match** recs, size_t* n_recs, const mgpu_id_pair** ids, size_t* n_ids) {
+  *recs = c->recs.data(); *n_recs = c->recs.size(); *ids = c->ids.data(); *n_ids = c->ids.size();
+  return MGPU_OK;
+}
+int mgpu_counters_get(mgpu_ctx* c, mgpu_counters* out) { *out = c->counters; return MGPU_OK; }
+int mgpu_timing_get(mgpu_ctx* c, mgpu_timing* out) { *out = c->timing; return MGPU_OK; }
+
+int64_t mgpu_extract(mgpu_ctx* c, const uint8_t* host, size_t len, uint32_t flags, uint64_t* out, size_t cap) {
+  if (!c) { set_err("null context"); return MGPU_E_PARAM; }
+  if (flags & ~MGPU_X_SUPPORTED) { set_err("unsupported extractor flags"); return MGPU_E_PARAM; }
+  if ((flags & (MGPU_X_DOMAINS | MGPU_X_EMAILS)) && !c->args.db.psl_keys) { set_err("Public Suffix List not set"); return MGPU_E_PARAM; }
+  if (len >= ((size_t)1 << 32)) { set_err("mgpu_extract is limited to inputs < 4 GiB"); return MGPU_E_PARAM; }
+  if (cudaSetDevice(c->device) != cudaSuccess) { set_err("cudaSetDevice failed"); return MGPU_E_CUDA; }
+  begin_scan(c);
+  c->capture_tokens = true;
+  int rc = scan_host_impl(c, host, len, 0, flags, false);
+  c->capture_tokens = false;
+  if (rc) return rc;
+  std::vector<std::array<uint64_t, 3>> items;
+  for (auto& t : c->x_str) items.push_back({t.type, t.start, (uint64_t)t.start + t.len});
+  for (auto& t : c->x_ip) items.push_back({t.type, t.start, (uint64_t)t.start + t.len});
+  std::sort(items.begin(), items.end(), [](auto& x, auto& y) { return x[1] != y[1] ? x[1] < y[1] : x[0] < y[0]; });
+  for (size_t k = 0; k < items.size() && k < cap; k++) { out[3 * k] = items[k][0]; out[3 * k + 1] = items[k][1]; out[3 * k + 2] = items[k][2]; }
+  return (int64_t)items.size();
+}
+
+int mgpu_lookup_string(mgpu_ctx* c, const uint8_t* q, size_t len, mgpu_id_pair* out, size_t cap) {
+  if (!c || !c->db_loaded) { set_err("no database uploaded"); return MGPU_E_NODB; }
+  if (len > 65536) { set_err("query too long"); return MGPU_E_PARAM; }
+  CK(cudaSetDevice(c->device));
+  ScanArgs a = c->args;
+  CK(cudaMemcpyAsync(c->d_small, q, len, cudaMemcpyHostToDevice, c->compute));
+  a.buf = c->d_small; a.n = len;
+  query_string_kernel<<<1, 1, 0, c->compute>>>(a, (uint32_t)len, c->d_small_out);
+  uint32_t n = 0;
+  CK(cudaMemcpyAsync(&n, c->d_small_out, 4, cudaMemcpyDeviceToHost, c->compute));
+  CK(cudaStreamSynchronize(c->compute));
+  if (n == NONE32) { set_err("too many matching patterns"); return MGPU_E_OVERFLOW; }
+  std::vector<mgpu_id_pair> tmp(n);
+  if (n) CK(cudaMemcpy(tmp.data(), a.ids, (size_t)n * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < n && k < cap; k++) out[k] = tmp[k];
+  return (int)n;
+}
+
+int mgpu_lookup_ip(mgpu_ctx* c, const uint8_t ip16[16], int is_v6, uint32_t* data_offset, uint8_t* prefix_len) {
+  if (!c || !c->db_loaded) { set_err("no database uploaded"); return MGPU_E_NODB; }
+  CK(cudaSetDevice(c->device));
+  ScanArgs a = c->args;
+  CK(cudaMemcpyAsync(c->d_small, ip16, 16, cudaMemcpyHostToDevice, c->compute));
+  a.buf = c->d_small; a.n = 16;
+  query_ip_kernel<<<1, 1, 0, c->compute>>>(a, is_v6, c->d_small_out);
+  uint32_t r[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(r, c->d_small_out, 12, cudaMemcpyDeviceToHost, c->compute));
+  CK(cudaStreamSynchronize(c->compute));
+  *data_offset = r[1]; *prefix_len = (uint8_t)r[2];
+  return (int)r[0];
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------------------
+void* mgpu_dev_alloc(mgpu_ctx* c, size_t bytes) {
+  if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes + 2 * TILE_BYTES) != cudaSuccess) { set_err("cudaMalloc failed"); return nullptr; }
+  return p;
+}
+void mgpu_dev_free(mgpu_ctx* c, void* p) { cudaSetDevice(c->device); cudaFree(p); }
+int mgpu_dev_upload(mgpu_ctx* c, void* dst, const void* src, size_t bytes) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return MGPU_OK;
+}
+void* mgpu_host_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { set_err("cudaMallocHost failed"); return nullptr; }
+  return p;
+}
+void mgpu_host_free_pinned(void* p) { cudaFreeHost(p); }
+int mgpu_flush_l2(mgpu_ctx* c) {
+  // overwrite a buffer larger than the 126 MB L2
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)256 << 20;
+  if (!c->d_flush) CK(cudaMalloc(&c->d_flush, bytes));
+  fill_kernel<<<c->sm_count * 4, 256, 0, c->compute>>>((uint4*)c->d_flush, bytes / 16, 0x0A0A0A0Au);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->compute));
+  return MGPU_OK;
+}
+
+}  // extern "C"

@@ -876,6 +876,8 @@ struct mxyb_builder {
   std::string err;
 };
 
+mxy::DatabaseBuilder& mxyb_inner(mxyb_builder* h) { return h->b; }  // for the synthetic generators (synth.cpp)
+
 extern "C" {
 
 mxyb_builder* mxyb_new(int case_insensitive) {

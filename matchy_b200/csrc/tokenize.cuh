@@ -1,0 +1,114 @@
+// tokenize.cuh — first half of the extractor: find every candidate token in a log chunk.
+//
+// Restates, as bit-parallel mask arithmetic, what the reference does with per-anchor byte loops
+// (crates/matchy-extractor/src/lib.rs):
+//   find_word_boundaries_into :1742-1782   words = maximal runs of non-boundary bytes (BOUNDARY_LOOKUP :1568-1593)
+//   hashes   :1212-1250   word of length 32/40/64/96/128, all hex
+//   domains  :537-628     maximal run of DOMAIN_CHAR_LOOKUP bytes that holds a '.', boundary (or chunk edge) both sides
+//                         == a WORD made only of domain bytes with a '.' in it
+//   IPv4     :1120-1179   maximal [0-9.] run with boundaries both sides == a word of digits and dots (subset of the above)
+//   e-mail   :1182-1196   anchored at every '@'
+//   IPv6     :1044-1116   anchored at every "::"
+// The tokenizer emits CANDIDATES (exact word extents / anchor positions, conservative class filters); the
+// validate kernel (device_fns.cuh) applies the remaining rules.  Layout: one warp owns a contiguous range of
+// 1 KiB tiles and walks it front to back; lane L owns bytes [32L, 32L+32) of the tile and holds one bit per byte
+// in 32-bit class masks.  A word belongs to the lane that holds the boundary byte FOLLOWING it, so all state
+// flows forward: lane → lane by shuffle/ballot carry resolution, tile → tile in registers.
+#pragma once
+#include "device_fns.cuh"
+
+namespace mgpu {
+
+enum { CLS_B = 0, CLS_DOT = 1, CLS_AT = 2, CLS_CL = 3, CLS_NL = 4, CLS_DM = 5, CLS_HX = 6 };
+enum { Q_DOTTED = 0, Q_HASH = 1, Q_AT = 2, Q_COLON2 = 3, Q_COUNT = 4 };
+static const uint32_t TILE_BYTES = 1024;
+static const uint32_t SLICE_BYTES = 32;
+
+MGPU_HD uint32_t class_bits(uint8_t b) {
+  uint32_t c = 0;
+  if (is_boundary(b)) c |= 1u << CLS_B;
+  if (b == '.') c |= 1u << CLS_DOT;
+  if (b == '@') c |= 1u << CLS_AT;
+  if (b == ':') c |= 1u << CLS_CL;
+  if (b == '\n') c |= 1u << CLS_NL;
+  if (is_domain_fast(b)) c |= 1u << CLS_DM;
+  if (is_hex(b)) c |= 1u << CLS_HX;
+  return c;
+}
+
+struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX; };
+
+// State carried into a tile (identical in all lanes of the warp).
+struct TileCarry {
+  uint32_t pT;          // previous byte is a word byte
+  uint32_t pCL;         // bit 1: previous byte is ':', bit 0: the byte before that is ':'
+  uint32_t cDM, cDN, cHX;  // the open word so far is all domain bytes / all dot-less domain bytes / all hex
+  uint64_t open_start;  // chunk offset where the open word starts (valid when pT)
+};
+
+// carry generate/propagate of (G + Sg) for one lane
+MGPU_HD void gp_bits(uint32_t G, uint32_t Sg, uint32_t& g, uint32_t& p) {
+  uint64_t s0 = (uint64_t)G + Sg;
+  g = (uint32_t)(s0 >> 32);
+  p = (uint32_t)(((s0 + 1) >> 32) & 1u) & ~g;
+}
+// Given per-lane generate/propagate ballots and the carry into lane 0, the carry into every lane (bit i) and
+// out of lane 31: c[i+1] = g[i] | (p[i] & c[i]) is exactly the carry chain of (g|p) + g + c0.
+MGPU_HD uint32_t carry_chain(uint32_t gen, uint32_t prop, uint32_t c0, uint32_t& cout) {
+  uint64_t a = (uint64_t)(gen | prop), b = (uint64_t)gen;
+  uint64_t x = a + b + c0;
+  uint64_t c = x ^ a ^ b;
+  cout = (uint32_t)(c >> 32) & 1u;
+  return (uint32_t)c;
+}
+// Bits where a word made only of class-G bytes ends: bit i set <=> byte i is a boundary, byte i-1 is the last byte of
+// a word, and every byte of that word is in G.  (carry injected at word starts ripples through G and must land on B)
+MGPU_HD uint32_t all_class_ends(uint32_t G, uint32_t Sg, uint32_t cin, uint32_t B) {
+  uint64_t x = (uint64_t)G + Sg + cin;
+  uint32_t carry_into = (uint32_t)x ^ G ^ Sg;
+  return carry_into & ~G & B;
+}
+
+// Start (chunk offset) of the word that ends at boundary bit `bit` of lane `lane`.
+// sB[j] = boundary mask of lane j of this tile.
+MGPU_HD uint64_t word_start(const uint32_t* sB, uint32_t lane, uint32_t bit, uint64_t tile_base, uint64_t open_start) {
+  uint32_t below = bit ? (sB[lane] & (0xFFFFFFFFu >> (32 - bit))) : 0u;
+  int j = (int)lane;
+  while (below == 0) {
+    if (--j < 0) return open_start;
+    below = sB[j];
+  }
+#ifdef __CUDA_ARCH__
+  uint32_t hi = 31u - (uint32_t)__clz((int)below);
+#else
+  uint32_t hi = 31u - (uint32_t)__builtin_clz(below);
+#endif
+  return tile_base + (uint64_t)j * 32 + hi + 1;
+}
+
+MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len == 64 || len == 96 || len == 128; }
+
+// Carry state for a range that starts at offset `a` of a chunk whose first byte is at `lo`: look back over the
+// word that is open there.
+MGPU_HDN TileCarry range_prologue(const uint8_t* buf, uint64_t lo, uint64_t a) {
+  TileCarry c;
+  c.pT = 0; c.pCL = 0; c.cDM = 0; c.cDN = 0; c.cHX = 0; c.open_start = a;
+  if (a <= lo) return c;
+  uint8_t prev = buf[a - 1];
+  c.pCL = (prev == ':' ? 2u : 0u) | ((a >= lo + 2 && buf[a - 2] == ':') ? 1u : 0u);
+  if (is_boundary(prev)) return c;
+  c.pT = 1;
+  uint32_t dm = 1, dn = 1, hx = 1;
+  uint64_t s = a;
+  while (s > lo) {
+    uint8_t b = buf[s - 1];
+    if (is_boundary(b)) break;
+    bool d = is_domain_fast(b);
+    dm &= d; dn &= (d && b != '.'); hx &= is_hex(b);
+    s--;
+  }
+  c.cDM = dm; c.cDN = dn; c.cHX = hx; c.open_start = s;
+  return c;
+}
+
+}  // namespace mgpu

@@ -1,0 +1,282 @@
+// emu.cpp — HOST EMULATION OF THE DEVICE LOGIC.  TEST INFRASTRUCTURE ONLY, never part of the product.
+//
+// There is no GPU in the development container, so the kernel logic is written as host/device functions
+// (matchy_b200/csrc/device_fns.cuh, tokenize.cuh, db_prepare.h) and this file re-wires the kernels of engine.cu
+// around them with plain loops: a "warp" is a loop over 32 lanes, ballots and shuffles are arrays.  The CPU test
+// suite (-m "not gpu") checks this emulation against the oracle so that logic bugs are found before GPU time is
+// spent; the -m gpu suite then checks the real kernels.  Nothing under matchy_b200/ loads or links this file,
+// and the product has no CPU execution path: libmatchy_b200.so fails without a CUDA device.
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/matchy_b200.h"
+#include "../../matchy_b200/csrc/db_prepare.h"
+#include "../../matchy_b200/csrc/tokenize.cuh"
+
+using namespace mgpu;
+
+struct Cand { uint32_t start, len; };
+struct StrTok { uint32_t start, len, type; };
+struct IpTok { uint32_t start, len, type; uint32_t w[4]; };
+
+struct emu_ctx {
+  std::vector<uint8_t> file;
+  PreparedDb P;
+  PslTable psl;
+  DbView db;
+  bool loaded = false;
+  std::vector<mgpu_match> recs;
+  std::vector<mgpu_id_pair> ids;
+  mgpu_counters counters;
+  std::vector<StrTok> str;
+  std::vector<IpTok> ip;
+  std::string err;
+};
+
+// ---- K1: tokenize_kernel, one "warp" per range of tiles -------------------------------------------------
+static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t flags, uint64_t nwarps,
+                         std::vector<Cand>& qd, std::vector<Cand>& qh, std::vector<uint32_t>& qa, std::vector<uint32_t>& qc,
+                         uint64_t& lines) {
+  const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
+  const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
+  const bool want_dot = (flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0, want_hash = (flags & MGPU_X_HASHES) != 0;
+  const bool want_at = (flags & MGPU_X_EMAILS) != 0, want_c2 = (flags & MGPU_X_IPV6) != 0;
+  for (uint64_t w = 0; w < nwarps; w++) {
+    uint64_t t0 = w * tpw, t1 = std::min(t0 + tpw, tiles);
+    if (t0 >= t1) continue;
+    TileCarry cy = range_prologue(buf, lo, t0 * TILE_BYTES);
+    for (uint64_t t = t0; t < t1; t++) {
+      const uint64_t tile_base = t * TILE_BYTES;
+      LaneMasks m[32];
+      uint32_t sB[32];
+      for (uint32_t lane = 0; lane < 32; lane++) {
+        uint64_t p = tile_base + (uint64_t)lane * 32;
+        LaneMasks x{0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t i = 0; i < 32; i++) {
+          uint64_t q = p + i;
+          uint32_t c = (q >= lo && q < n) ? class_bits(buf[q]) : (1u << CLS_B);
+          x.B |= ((c >> CLS_B) & 1u) << i; x.DOT |= ((c >> CLS_DOT) & 1u) << i; x.AT |= ((c >> CLS_AT) & 1u) << i;
+          x.CL |= ((c >> CLS_CL) & 1u) << i; x.NL |= ((c >> CLS_NL) & 1u) << i; x.DM |= ((c >> CLS_DM) & 1u) << i;
+          x.HX |= ((c >> CLS_HX) & 1u) << i;
+        }
+        m[lane] = x; sB[lane] = x.B;
+        lines += (uint64_t)__builtin_popcount(x.NL);
+      }
+      if (!cy.pT) cy.open_start = tile_base;
+      uint32_t pT[32], pCL[32], S[32];
+      for (uint32_t lane = 0; lane < 32; lane++) {
+        pT[lane] = lane ? (~m[lane - 1].B) >> 31 : cy.pT;
+        pCL[lane] = lane ? m[lane - 1].CL >> 30 : cy.pCL;
+        uint32_t T = ~m[lane].B;
+        S[lane] = T & ~((T << 1) | pT[lane]);
+      }
+      uint32_t A[3][32];
+      for (int cls = 0; cls < 3; cls++) {
+        uint32_t gen = 0, prop = 0, G[32], Sg[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+          G[lane] = cls == 0 ? m[lane].DM : cls == 1 ? (m[lane].DM & ~m[lane].DOT) : m[lane].HX;
+          Sg[lane] = S[lane] & G[lane];
+          uint32_t g, p;
+          gp_bits(G[lane], Sg[lane], g, p);
+          gen |= g << lane; prop |= p << lane;
+        }
+        uint32_t& c0 = cls == 0 ? cy.cDM : cls == 1 ? cy.cDN : cy.cHX;
+        uint32_t co, cv = carry_chain(gen, prop, c0, co);
+        for (uint32_t lane = 0; lane < 32; lane++) A[cls][lane] = all_class_ends(G[lane], Sg[lane], (cv >> lane) & 1u, m[lane].B);
+        c0 = co;
+      }
+      for (uint32_t lane = 0; lane < 32; lane++) {
+        uint64_t p = tile_base + (uint64_t)lane * 32;
+        uint32_t candDot = want_dot ? (A[0][lane] & ~A[1][lane]) : 0u;
+        uint32_t candHex = (want_hash && pT[lane]) ? (A[2][lane] & (m[lane].B & (0u - m[lane].B))) : 0u;
+        uint32_t candAt = want_at ? m[lane].AT : 0u;
+        uint32_t cl1 = (m[lane].CL << 1) | (pCL[lane] >> 1), cl2 = (m[lane].CL << 2) | pCL[lane];
+        uint32_t candC2 = want_c2 ? (m[lane].CL & cl1 & ~cl2) : 0u;
+        for (uint32_t mm = candDot; mm; mm &= mm - 1) {
+          uint32_t bit = (uint32_t)__builtin_ctz(mm);
+          uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
+          qd.push_back(Cand{(uint32_t)s, (uint32_t)(e - s)});
+        }
+        if (candHex) {
+          uint32_t bit = (uint32_t)__builtin_ctz(candHex);
+          uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
+          if (is_hash_len(e - s)) qh.push_back(Cand{(uint32_t)s, (uint32_t)(e - s)});
+        }
+        for (uint32_t mm = candAt; mm; mm &= mm - 1) qa.push_back((uint32_t)(p + (uint32_t)__builtin_ctz(mm)));
+        for (uint32_t mm = candC2; mm; mm &= mm - 1) qc.push_back((uint32_t)(p + (uint32_t)__builtin_ctz(mm) - 1));
+      }
+      uint32_t hasB = 0;
+      for (uint32_t lane = 0; lane < 32; lane++) hasB |= (m[lane].B != 0 ? 1u : 0u) << lane;
+      if (hasB) {
+        uint32_t ll = 31u - (uint32_t)__builtin_clz(hasB);
+        cy.open_start = tile_base + (uint64_t)ll * 32 + (31u - (uint32_t)__builtin_clz(m[ll].B)) + 1;
+      }
+      cy.pT = (~m[31].B) >> 31;
+      cy.pCL = m[31].CL >> 30;
+    }
+  }
+}
+
+static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, uint64_t nwarps, bool lookups) {
+  std::vector<Cand> qd, qh;
+  std::vector<uint32_t> qa, qc;
+  uint64_t lines = 0;
+  emu_tokenize(buf, lo, n, flags, nwarps, qd, qh, qa, qc, lines);
+  const DbView& db = c->db;
+  size_t s0 = c->str.size(), i0 = c->ip.size();
+  // K2 validate
+  for (auto& cd : qd) {
+    const uint8_t* wp = buf + cd.start;
+    uint32_t addr;
+    if ((flags & MGPU_X_IPV4) && parse_ipv4_word(wp, cd.len, addr)) c->ip.push_back(IpTok{cd.start, cd.len, MGPU_T_IPV4, {addr, 0, 0, 0}});
+    if ((flags & MGPU_X_DOMAINS) && validate_domain_word(db, wp, cd.len)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
+  }
+  for (auto& cd : qh) {
+    uint32_t ty = cd.len == 32 ? MGPU_T_MD5 : cd.len == 40 ? MGPU_T_SHA1 : cd.len == 64 ? MGPU_T_SHA256 : cd.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
+    c->str.push_back(StrTok{cd.start, cd.len, ty});
+  }
+  for (uint32_t at : qa) {
+    size_t s, e;
+    if (email_at(db, buf, (size_t)lo, (size_t)n, at, s, e)) c->str.push_back(StrTok{(uint32_t)s, (uint32_t)(e - s), MGPU_T_EMAIL});
+  }
+  for (uint32_t at : qc) {
+    size_t s, e; uint16_t seg[8];
+    if ((uint64_t)at + 2 <= n && ipv6_at(buf, (size_t)lo, (size_t)n, at, s, e, seg)) {
+      IpTok t{(uint32_t)s, (uint32_t)(e - s), MGPU_T_IPV6, {0, 0, 0, 0}};
+      for (int k = 0; k < 4; k++) t.w[k] = ((uint32_t)seg[2 * k] << 16) | seg[2 * k + 1];
+      c->ip.push_back(t);
+    }
+  }
+  c->counters.lines += lines;
+  c->counters.bytes += n - lo;
+  for (size_t k = s0; k < c->str.size(); k++) { c->counters.by_type[c->str[k].type]++; c->counters.candidates++; }
+  for (size_t k = i0; k < c->ip.size(); k++) { c->counters.by_type[c->ip[k].type]++; c->counters.candidates++; }
+  if (lookups) {
+    // K3
+    for (size_t k = i0; k < c->ip.size() && db.has_ip; k++) {
+      const IpTok& t = c->ip[k];
+      uint32_t off = 0; uint8_t pl = 0; bool hit;
+      if (t.type == MGPU_T_IPV4) hit = trie_lookup_v4(db, t.w[0], off, pl);
+      else {
+        uint16_t seg[8];
+        for (int j = 0; j < 4; j++) { seg[2 * j] = (uint16_t)(t.w[j] >> 16); seg[2 * j + 1] = (uint16_t)t.w[j]; }
+        hit = trie_lookup_v6(db, seg, off, pl);
+      }
+      if (!hit) continue;
+      mgpu_match r{};
+      r.offset = base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_IP; r.prefix_len = pl;
+      r.data_offset = off;
+      c->recs.push_back(r);
+    }
+    // K4 + K5
+    for (size_t k = s0; k < c->str.size(); k++) {
+      const StrTok& t = c->str[k];
+      const uint8_t* text = buf + t.start;
+      uint32_t lit_pid = NONE32, lit_off = 0;
+      if (db.has_literal && !lh_lookup(db, text, t.len, lit_pid)) lit_pid = NONE32;
+      bool lit_ok = lit_pid != NONE32 && lh_data_offset(db, lit_pid, lit_off);
+      std::vector<uint32_t> g;
+      if (db.has_glob) find_all_visit(db, text, t.len, [&](uint32_t pid) { g.push_back(pid); });
+      if (!lit_ok && g.empty()) continue;
+      std::sort(g.begin(), g.end());
+      g.erase(std::unique(g.begin(), g.end()), g.end());
+      mgpu_match r{};
+      r.offset = base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_PATTERN;
+      r.ids_index = (uint32_t)c->ids.size(); r.data_offset = MGPU_NO_DATA;
+      if (lit_ok) c->ids.push_back(mgpu_id_pair{lit_pid, lit_off});
+      for (uint32_t pid : g) { uint32_t off; c->ids.push_back(mgpu_id_pair{pid, glob_data_offset(db, pid, off) ? off : MGPU_NO_DATA}); }
+      r.n_ids = (uint32_t)c->ids.size() - r.ids_index;
+      c->recs.push_back(r);
+    }
+  }
+  for (size_t k = s0; k < c->str.size(); k++) c->str[k].start += (uint32_t)base;
+  for (size_t k = i0; k < c->ip.size(); k++) c->ip[k].start += (uint32_t)base;
+}
+
+extern "C" {
+
+emu_ctx* emu_create(const uint8_t* psl, size_t psl_len) {
+  auto* c = new emu_ctx();
+  if (!build_psl(psl, psl_len, c->psl, c->err)) { fprintf(stderr, "emu: %s\n", c->err.c_str()); delete c; return nullptr; }
+  return c;
+}
+void emu_destroy(emu_ctx* c) { delete c; }
+const char* emu_error(emu_ctx* c) { return c->err.c_str(); }
+
+int emu_db_upload(emu_ctx* c, const uint8_t* mxy, size_t len) {
+  c->file.assign(mxy, mxy + len);
+  c->file.resize(len + 64, 0);
+  if (!prepare_db(c->file.data(), len, c->P, c->err)) return MGPU_E_FORMAT;
+  c->db = c->P.view;
+  const mxy::Layout& L = c->P.L;
+  c->db.tree = c->file.data();
+  if (L.has_literal) { c->db.lh = c->file.data() + L.lit_off; c->db.lh_data_index = c->P.lh_index.data(); }
+  if (L.has_glob) {
+    c->db.pg = c->file.data() + L.pg_off; c->db.aclh_index = c->P.aclh.data();
+    c->db.glob_data = reinterpret_cast<const uint32_t*>(c->file.data() + L.map_off);
+  }
+  c->db.psl_keys = c->psl.keys.data(); c->db.psl_vals = c->psl.vals.data(); c->db.psl_pool = c->psl.pool.data();
+  c->db.psl_mask = c->psl.mask; c->db.psl_max_len = c->psl.max_len;
+  c->loaded = true;
+  return MGPU_OK;
+}
+
+uint32_t emu_default_flags(emu_ctx* c) {
+  uint32_t f = 0;
+  if (c->db.has_ip) f |= MGPU_X_IPV4 | MGPU_X_IPV6;
+  if (c->db.has_literal || c->db.has_glob) f |= MGPU_X_DOMAINS | MGPU_X_EMAILS | MGPU_X_HASHES;
+  return f;
+}
+
+// chunk_bytes: the scan is cut into newline-aligned pieces of at most this size, the way mgpu_scan does;
+// nwarps: how many tile ranges each piece is divided into; misalign: 0..15 alignment padding in front of the data.
+int emu_scan(emu_ctx* c, const uint8_t* data, size_t len, uint64_t base, uint32_t flags, size_t chunk_bytes, uint64_t nwarps, uint32_t misalign,
+             int lookups) {
+  c->recs.clear(); c->ids.clear(); c->str.clear(); c->ip.clear();
+  memset(&c->counters, 0, sizeof c->counters);
+  if (!c->loaded && lookups) return MGPU_E_NODB;
+  if (chunk_bytes == 0) chunk_bytes = len ? len : 1;
+  size_t pos = 0;
+  while (pos < len) {
+    size_t want = std::min(len - pos, chunk_bytes);
+    if (pos + want < len) {
+      const uint8_t* q = (const uint8_t*)memrchr(data + pos, '\n', want);
+      if (!q) return MGPU_E_OVERFLOW;
+      want = (size_t)(q - (data + pos)) + 1;
+    }
+    // private padded copy: [misalign garbage][piece][garbage up to the tile boundary]
+    std::vector<uint8_t> buf(misalign + want + 2 * TILE_BYTES, 'x');
+    memcpy(buf.data() + misalign, data + pos, want);
+    emu_piece(c, buf.data(), misalign, misalign + want, base + pos - misalign, flags, nwarps ? nwarps : 1, lookups != 0);
+    pos += want;
+  }
+  c->counters.matches = c->recs.size();
+  std::sort(c->recs.begin(), c->recs.end(), [](const mgpu_match& x, const mgpu_match& y) {
+    if (x.offset != y.offset) return x.offset < y.offset;
+    if (x.item_type != y.item_type) return x.item_type < y.item_type;
+    return x.len < y.len;
+  });
+  return MGPU_OK;
+}
+
+int emu_results(emu_ctx* c, const mgpu_match** recs, size_t* n_recs, const mgpu_id_pair** ids, size_t* n_ids) {
+  *recs = c->recs.data(); *n_recs = c->recs.size(); *ids = c->ids.data(); *n_ids = c->ids.size();
+  return 0;
+}
+int emu_counters_get(emu_ctx* c, mgpu_counters* out) { *out = c->counters; return 0; }
+
+int64_t emu_tokens(emu_ctx* c, uint64_t* out, size_t cap) {
+  std::vector<std::array<uint64_t, 3>> items;
+  for (auto& t : c->str) items.push_back({t.type, t.start, (uint64_t)t.start + t.len});
+  for (auto& t : c->ip) items.push_back({t.type, t.start, (uint64_t)t.start + t.len});
+  std::sort(items.begin(), items.end(), [](auto& x, auto& y) { return x[1] != y[1] ? x[1] < y[1] : x[0] < y[0]; });
+  for (size_t k = 0; k < items.size() && k < cap; k++) { out[3 * k] = items[k][0]; out[3 * k + 1] = items[k][1]; out[3 * k + 2] = items[k][2]; }
+  return (int64_t)items.size();
+}
+
+}  // extern "C"
