@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — `matchy match` log-scan throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A "step" is one pass of the whole hot path (tokenize → validate → IP-trie / literal-hash / AC+glob → records)
+over one batch of synthetic log resident in HBM.  At N=1 the workload is BASELINE.json configs[1]
+(100 K globs + 1 M literal domains over 10 GB of DNS/proxy log lines).  With N>1 every rank scans its own
+10 GB shard of the same deterministic stream (byte-range sharding, database replicated per GPU, no data-path
+collective; only the summary counters are all-reduced over NCCL) — weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C] [--gb G]
+
+`--impl reference` times the CPU restatement of the reference matcher (oracle/, kind "port": the Rust reference
+cannot be compiled in this environment) on the box's host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    1: "cfg1: 10K-indicator CSV-shaped DB (IPs, CIDRs, literal domains, *.evil globs, hashes) over synthetic nginx access log",
+    2: "cfg2: 100K paraglob globs + 1M literal domains over synthetic DNS/proxy log (AC-walk heavy)",
+    3: "cfg3: 1M IPv4/IPv6 CIDR prefixes over synthetic firewall/netflow log (ip-trie LPM heavy)",
+    4: "cfg4: 5M MD5/SHA1/SHA256 hashes over synthetic EDR/process log (literal-hash probe heavy)",
+    5: "cfg5: mixed 5M-indicator threat DB over synthetic multi-source log",
+}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_throughput(db, cfg, scale, threads, target_seconds=12.0, offset_blocks=0):
+    """Oracle (CPU port of the reference matcher) on all host cores over a bounded sample; returns (GB/s, sample_bytes, cores, counters)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from matchy_b200 import synth
+    orc = oracle_lib.Oracle(db)
+    cores = threads or os.cpu_count() or 1
+    probe = synth.gen_log(cfg, 64 << 20, scale, offset=offset_blocks * 65536)
+    t0 = time.perf_counter()
+    orc.scan_mt(probe, threads=cores)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    rate = probe.size / dt
+    nbytes = int(min(max(rate * target_seconds, 64 << 20), 4 << 30)) // 65536 * 65536
+    sample = probe if nbytes <= probe.size else synth.gen_log(cfg, nbytes, scale, offset=offset_blocks * 65536)
+    t0 = time.perf_counter()
+    cnt = orc.scan_mt(sample, threads=cores)
+    dt = time.perf_counter() - t0
+    return sample.size / dt / 1e9, int(sample.size), cores, cnt
+
+
+def run_reference(args):
+    """The reference arm: CPU matcher on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    g.build()
+    from matchy_b200 import synth
+    cfg, scale = args.config, args.scale
+    db = synth.build_db(cfg, scale)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    orc = oracle_lib.Oracle(db)
+    cores = os.cpu_count() or 1
+    # size one step at ~6 s of CPU work
+    probe = synth.gen_log(cfg, 64 << 20, scale)
+    t0 = time.perf_counter(); orc.scan_mt(probe, threads=cores); rate = probe.size / max(time.perf_counter() - t0, 1e-6)
+    nbytes = int(min(max(rate * 6.0, 64 << 20), 2 << 30)) // 65536 * 65536
+    sample = probe if nbytes <= probe.size else synth.gen_log(cfg, nbytes, scale)
+    times, cnt = [], None
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cnt = orc.scan_mt(sample, threads=cores)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    gbs = sample.size * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": "log_scan_throughput", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "sample_bytes_per_step": int(sample.size)},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": "%d MiB of the cfg%d stream per step, one thread per newline-aligned shard, 128 KiB reads" % (sample.size >> 20, cfg)},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lines_per_s": cnt[0] * len(times) / total, "matches_per_s": cnt[3] * len(times) / total,
+        "note": "CPU restatement (oracle/oracle.cpp) of matchy v1.2.2's matcher; the Rust reference cannot be built here (no cargo/rustc)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--gb", type=float, default=10.0, help="log bytes per GPU per step, in GB (1e9)")
+    ap.add_argument("--scale", type=float, default=1.0, help="database size scale (1.0 = the BASELINE.json counts)")
+    ap.add_argument("--chunk-mb", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if dist:
+        dist.barrier()
+    from matchy_b200 import Engine, synth
+
+    cfg, scale = args.config, args.scale
+    nbytes = int(args.gb * 1e9) // 65536 * 65536
+    db = synth.build_db(cfg, scale)
+    eng = Engine(local_rank, chunk_bytes=args.chunk_mb << 20)
+    eng.upload(db)
+    info = eng.db_info()
+    flags = eng.default_flags()
+
+    # this rank's shard of the stream: blocks [rank*nblocks, (rank+1)*nblocks); generated on the host into pinned memory
+    import ctypes as C
+    import numpy as np
+    from matchy_b200 import _native as N
+    pinned = N.lib().mgpu_host_alloc_pinned(nbytes)
+    if not pinned:
+        raise RuntimeError("pinned allocation failed")
+    host = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    synth.gen_log(cfg, nbytes, scale, offset=rank * nbytes, out=host)
+    dev = eng.dev_alloc(nbytes)
+    eng.dev_upload(dev, host)
+
+    def sync_all():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- HBM-resident timing ("value") ----
+    eng.set_keep_results(True)
+    for _ in range(args.warmup):
+        eng.scan_device(dev, nbytes, flags, base=rank * nbytes)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    step_ms, kern = [], {}
+    launches = 0
+    counters = None
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.scan_device(dev, nbytes, flags, base=rank * nbytes)  # inputs (10 GB) are far larger than the 126 MB L2
+        t = eng.timing()
+        step_ms.append(t["scan_ms"])
+        for k, v in t["kernel_ms"].items():
+            kern.setdefault(k, [0.0, 0])
+            kern[k][0] += v; kern[k][1] += t["launches"][k]
+        launches += sum(t["launches"].values()) + t["aux_launches"]
+        counters = eng.counters()
+    sync_all()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_s = sum(step_ms) / 1000.0
+    if dist:
+        tt = torch.tensor([dev_s, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s, wall_s = float(tt[0]), float(tt[1])
+        ct = torch.tensor([counters["lines"], counters["bytes"], counters["candidates"], counters["matches"]] + counters["by_type"],
+                          dtype=torch.int64, device="cuda")
+        dist.all_reduce(ct, op=dist.ReduceOp.SUM)  # the only collective of the path: summary counters over NVLink
+        tot = [int(x) for x in ct.tolist()]
+    else:
+        tot = [counters["lines"], counters["bytes"], counters["candidates"], counters["matches"]] + counters["by_type"]
+    total_bytes = nbytes * world * args.steps
+    value = total_bytes / dev_s / 1e9
+
+    # ---- end to end through the C ABI with host buffers ("e2e") ----
+    e2e = None
+    if not args.no_e2e:
+        eng.scan(host, flags, base=rank * nbytes)  # warm-up
+        sync_all()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            recs, ids = eng.scan(host, flags, base=rank * nbytes)
+            d2h += recs.nbytes + ids.nbytes + 192
+        sync_all()
+        e_s = time.perf_counter() - t0
+        if dist:
+            tt = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_s = float(tt[0])
+        e2e = {"value": total_bytes / e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h // args.steps,
+               "timed": "wall clock around mgpu_scan (pinned host buffer -> double-buffered H2D -> kernels -> D2H of records), max over ranks"}
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peak()
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms, dom_launches = kern[dom]
+    bytes_per_launch = nbytes * args.steps / max(dom_launches, 1)  # 1 algorithmic byte per log byte scanned
+    achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
+                "whole_path_frac": (nbytes * args.steps / dev_s / 1e9) / peak if world == 1 else None}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gbs, sample_bytes, cores, _ = cpu_port_throughput(db, cfg, scale, 0)
+        cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+               "sample": "%d MiB of the same stream, one thread per newline-aligned shard, 128 KiB reads" % (sample_bytes >> 20)}
+
+    if rank == 0:
+        line = {
+            "metric": "log_scan_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "log_bytes_per_gpu": nbytes, "chunk_bytes": args.chunk_mb << 20,
+                       "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (nbytes / 1e9),
+                       "db": {k: info[k] for k in ("node_count", "literal_count", "glob_count", "ac_node_count", "file_bytes")},
+                       "parallelism": "byte-range shards x%d, database replicated" % world},
+            "lines_per_s": tot[0] * args.steps / dev_s, "matches_per_s": tot[3] * args.steps / dev_s,
+            "counters": {"lines": tot[0], "bytes": tot[1], "candidates": tot[2], "matches": tot[3]},
+            "wall_s_timed_region": wall_s,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        }
+        print(json.dumps(line))
+    eng.dev_free(dev)
+    N.lib().mgpu_host_free_pinned(C.c_void_p(pinned))
+    eng.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

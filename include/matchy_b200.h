@@ -83,7 +83,14 @@ typedef struct mgpu_counters { uint64_t lines, bytes, candidates, matches, by_ty
 #define MGPU_K_LITHASH 3
 #define MGPU_K_ACGLOB 4
 #define MGPU_K_COUNT 5
-typedef struct mgpu_timing { float kernel_ms[MGPU_K_COUNT]; uint32_t launches[MGPU_K_COUNT]; float total_ms; uint32_t chunks; } mgpu_timing;
+typedef struct mgpu_timing {
+  float kernel_ms[MGPU_K_COUNT];    /* summed over the chunks of the scan */
+  uint32_t launches[MGPU_K_COUNT];
+  float total_ms;                   /* sum of per-chunk kernel spans */
+  uint32_t chunks;
+  float scan_ms;                    /* first kernel of the scan to last, inter-chunk gaps included */
+  uint32_t aux_launches;            /* helper kernels (newline cut search) */
+} mgpu_timing;
 
 typedef struct mgpu_db_info {
   uint32_t node_count, record_bits, ip_version, match_mode;

@@ -27,7 +27,8 @@ class MgpuCounters(C.Structure):
 
 
 class MgpuTiming(C.Structure):
-    _fields_ = [("kernel_ms", C.c_float * 5), ("launches", C.c_uint32 * 5), ("total_ms", C.c_float), ("chunks", C.c_uint32)]
+    _fields_ = [("kernel_ms", C.c_float * 5), ("launches", C.c_uint32 * 5), ("total_ms", C.c_float), ("chunks", C.c_uint32),
+                ("scan_ms", C.c_float), ("aux_launches", C.c_uint32)]
 
 
 class MgpuDbInfo(C.Structure):

@@ -176,6 +176,32 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         }
       }
     }
+    // The device walks the automaton without per-step bounds/alignment checks (the reference checks bounds on every
+    // access and tolerates any alignment).  Verify every offset once here instead; builder-written files always pass.
+    {
+      const uint8_t* ac = pg + db.ac_start;
+      const uint64_t acn = db.ac_size;
+      if (acn != 0 && (acn < 20 || (uint64_t)P.ac_node_count * 20 > acn)) { err = "paraglob: AC node table out of range"; return false; }
+      const uint64_t nodes = P.ac_node_count;
+      bool ok = true;
+      auto node_ref = [&](uint32_t off) { if ((off % 20) != 0 || (uint64_t)off / 20 >= nodes) ok = false; };
+      for (uint64_t i = 0; i < nodes && ok; i++) {
+        const uint8_t* nd = ac + i * 20;
+        uint32_t kind = nd[0], cnt = nd[2], pc = nd[3], eo = prep_le32(nd + 12), po = prep_le32(nd + 16);
+        node_ref(prep_le32(nd + 8));
+        if (pc && ((po & 3) || (uint64_t)po + (uint64_t)pc * 4 > acn)) ok = false;
+        if (kind == 1) { node_ref(eo); if (eo == 0) ok = false; }
+        else if (kind == 2) {
+          if ((eo & 3) || (uint64_t)eo + (uint64_t)cnt * 8 > acn) { ok = false; break; }
+          for (uint32_t k = 0; k < cnt; k++) { uint32_t t = prep_le32(ac + eo + k * 8 + 4); node_ref(t); if (t == 0) ok = false; }
+        } else if (kind == 3) {
+          if ((eo & 3) || (uint64_t)eo + 1024 > acn) { ok = false; break; }
+          for (uint32_t k = 0; k < 256; k++) { uint32_t t = prep_le32(ac + eo + k * 4); if (t) node_ref(t); }
+        } else if (kind != 0) ok = false;
+      }
+      for (size_t k = 0; k + 1 < P.aclh.size(); k += 2) if (P.aclh[k] & 3) ok = false;
+      if (!ok) { err = "paraglob automaton with out-of-range or unaligned offsets is not supported on the device"; return false; }
+    }
     // glob segments: the device matcher keeps one frame per '*'
     uint32_t gso = db.glob_segments_offset;
     for (uint32_t pid = 0; pid < pattern_count; pid++) {
@@ -186,6 +212,12 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
       if (stars > MGPU_GLOB_MAX_STARS) { err = "glob pattern with more than 24 '*' segments is not supported on the device"; return false; }
     }
     db.pg_len = pg_len; db.has_glob = 1;
+    db.pg_align = (uint32_t)(L.pg_off & 3);
+    // the device reads these with aligned 32-bit loads (the reference tolerates any alignment here: raw pointer reads)
+    if ((db.ac_start & 3) || (db.patterns_offset & 3) || (db.wild_off & 3) || (ao & 3) || (db.pg_align != 0)) {
+      err = "paraglob section with unaligned tables is not supported on the device";
+      return false;
+    }
     db.aclh_n = (uint32_t)(P.aclh.size() / 2);
     db.glob_data_n = (uint32_t)L.map_count;
   }

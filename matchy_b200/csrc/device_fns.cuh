@@ -46,6 +46,8 @@ struct DbView {
   // --- paraglob buffer ("PARAGLOB") ---
   const uint8_t* pg;
   uint32_t pg_len, has_glob;
+  uint32_t pg_align;              // (file offset of the PARAGLOB buffer) & 3: the reference reads glob structs through
+                                  // zerocopy::Ref, which fails on misaligned addresses (page-aligned mmap + file offset)
   uint32_t ac_start, ac_size, patterns_offset, wild_off, wild_count, glob_segments_offset;
   const uint32_t* aclh_index;     // derived: literal_id -> {abs offset of its pattern list in pg, count} (2 words each)
   uint32_t aclh_n;
@@ -59,8 +61,12 @@ struct DbView {
   uint32_t psl_mask, psl_max_len;
 };
 
-MGPU_HD uint32_t ld32(const uint8_t* p) {  // little-endian, 4-byte aligned
+MGPU_HD uint32_t ld32(const uint8_t* p) {  // little-endian; 4-byte aligned on the device (layout chosen at upload)
+#ifdef __CUDA_ARCH__
   return *reinterpret_cast<const uint32_t*>(p);
+#else
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);  // host emulation: any alignment
+#endif
 }
 MGPU_HD uint32_t ld32u(const uint8_t* p) {  // unaligned
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
@@ -93,7 +99,30 @@ MGPU_HD bool is_local_char(uint8_t b) { return is_digit(b) || is_alpha(b) || b =
 MGPU_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 MGPU_HD uint64_t xx_round(uint64_t acc, uint64_t in) { acc += in * MGPU_P2; acc = rotl64(acc, 31); return acc * MGPU_P1; }
 MGPU_HD uint64_t xx_merge(uint64_t acc, uint64_t v) { v = xx_round(0, v); acc ^= v; return acc * MGPU_P1 + MGPU_P4; }
+// Unaligned little-endian loads built from aligned 32-bit loads + funnel shifts (3 loads instead of 8 byte loads).
+// They may touch up to 4 bytes past the value: every buffer the scan reads from has at least 16 bytes of slack.
+MGPU_HD uint64_t ldu64_fast(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(a & 3) * 8;
+  uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+  return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+#else
+  return ld64u(p);
+#endif
+}
+MGPU_HD uint32_t ldu32_fast(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  return __funnelshift_r(q[0], q[1], (uint32_t)(a & 3) * 8);
+#else
+  return ld32u(p);
+#endif
+}
 MGPU_HD uint64_t rd64f(const uint8_t* p, bool fold) {
+  if (!fold) return ldu64_fast(p);
   uint64_t v = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) v |= (uint64_t)lc(p[k], fold) << (8 * k);
@@ -118,7 +147,8 @@ MGPU_HDN uint64_t xxh64_fold(const uint8_t* p, size_t len, bool fold) {
   h += (uint64_t)len;
   while (p + 8 <= end) { h ^= xx_round(0, rd64f(p, fold)); h = rotl64(h, 27) * MGPU_P1 + MGPU_P4; p += 8; }
   if (p + 4 <= end) {
-    uint32_t w = (uint32_t)lc(p[0], fold) | ((uint32_t)lc(p[1], fold) << 8) | ((uint32_t)lc(p[2], fold) << 16) | ((uint32_t)lc(p[3], fold) << 24);
+    uint32_t w = fold ? ((uint32_t)lc(p[0], fold) | ((uint32_t)lc(p[1], fold) << 8) | ((uint32_t)lc(p[2], fold) << 16) | ((uint32_t)lc(p[3], fold) << 24))
+                      : ldu32_fast(p);
     h ^= (uint64_t)w * MGPU_P1; h = rotl64(h, 23) * MGPU_P2 + MGPU_P3; p += 4;
   }
   while (p < end) { h ^= (uint64_t)lc(*p, fold) * MGPU_P5; h = rotl64(h, 11) * MGPU_P1; p++; }
@@ -391,9 +421,15 @@ MGPU_HDN bool lh_lookup(const DbView& db, const uint8_t* q, uint32_t n, uint32_t
     uint64_t eo = (uint64_t)db.lh_table_start + (uint64_t)slot * 16;
     if (eo + 16 > db.lh_len) return false;
     const uint8_t* e = db.lh + eo;
-    uint32_t so = ld32(e + 8);
+#ifdef __CUDA_ARCH__
+    const uint4 ent = *reinterpret_cast<const uint4*>(e);  // entries are 16-byte aligned in the device copy
+    const uint32_t so = ent.z, e_pid = ent.w;
+    const uint64_t eh = (uint64_t)ent.x | ((uint64_t)ent.y << 32);
+#else
+    const uint32_t so = ld32u(e + 8), e_pid = ld32u(e + 12);
+    const uint64_t eh = ld64u(e);
+#endif
     if (so == NONE32) return false;
-    uint64_t eh = (uint64_t)ld32(e) | ((uint64_t)ld32(e + 4) << 32);
     if (eh == h) {
       uint64_t abs = (uint64_t)db.lh_strings_offset + so;
       if (abs + 2 <= db.lh_len) {
@@ -403,7 +439,7 @@ MGPU_HDN bool lh_lookup(const DbView& db, const uint8_t* q, uint32_t n, uint32_t
           const uint8_t* sp = db.lh + abs + 2;
           bool eq = true;
           for (uint32_t i = 0; i < n; i++) if (sp[i] != lc(q[i], fold)) { eq = false; break; }
-          if (eq) { pattern_id = ld32(e + 12); return true; }
+          if (eq) { pattern_id = e_pid; return true; }
         }
       }
     }
@@ -423,42 +459,15 @@ MGPU_HD bool lh_data_offset(const DbView& db, uint32_t pattern_id, uint32_t& off
 // =================================================================================================
 // Paraglob — paraglob_offset.rs:1028-1639
 // =================================================================================================
-// find_ac_transition :1271-1353.  `ac` = AC buffer base (pg + ac_start); offsets are relative to it.
-MGPU_HD bool ac_transition(const uint8_t* ac, uint32_t acn, uint32_t node_off, uint8_t ch, uint32_t& next) {
-  if ((uint64_t)node_off + 20 > acn) return false;
-  const uint8_t* nd = ac + node_off;
-  uint32_t w0 = ld32(nd);
-  uint32_t kind = w0 & 0xFF;
-  if (kind == 1) {
-    if (((w0 >> 8) & 0xFF) == ch) { next = ld32(nd + 12); return true; }
-    return false;
-  }
-  if (kind == 2) {
-    uint32_t eo = ld32(nd + 12), cnt = (w0 >> 16) & 0xFF;
-    if ((uint64_t)eo + (uint64_t)cnt * 8 > acn) return false;
-    for (uint32_t i = 0; i < cnt; i++) {
-      uint8_t ec = ac[eo + i * 8];
-      if (ec == ch) { next = ld32(ac + eo + i * 8 + 4); return true; }
-      if (ec > ch) return false;
-    }
-    return false;
-  }
-  if (kind == 3) {
-    uint64_t to = (uint64_t)ld32(nd + 12) + (uint64_t)ch * 4;
-    if (to + 4 > acn) return false;
-    uint32_t t = ld32(ac + to);
-    if (t != 0) { next = t; return true; }
-    return false;
-  }
-  return false;
-}
-
 // match_segments_impl :1402-1639 as an explicit-stack machine.  Every reference call (including failed ones and
 // the calls a Star makes for each candidate position) decrements the 100 000-step budget exactly once.
 #define MGPU_GLOB_MAX_STARS 24  // patterns with more '*' segments are refused at upload
 MGPU_HDN bool glob_match(const DbView& db, uint32_t pattern_id, const uint8_t* text, uint32_t tn) {
   uint64_t io = (uint64_t)db.glob_segments_offset + (uint64_t)pattern_id * 8;
   if (io + 8 > db.pg_len) return false;
+  // zerocopy::Ref::from_prefix needs 4-byte alignment for GlobSegmentIndex / GlobSegmentHeader / CharClassItemEncoded
+  // (offset_format.rs:391-431); a misaligned read is an Err, which `?` carries out of the whole match => not a match.
+  if (((db.pg_align + io) & 3) != 0) return false;
   const uint32_t first = ld32(db.pg + io);
   const uint32_t count = (uint32_t)db.pg[io + 4] | ((uint32_t)db.pg[io + 5] << 8);
   const bool ci = db.match_mode == 1;
@@ -475,6 +484,7 @@ MGPU_HDN bool glob_match(const DbView& db, uint32_t pattern_id, const uint8_t* t
       if (idx >= count) { result = pos >= tn; break; }
       uint64_t so = (uint64_t)first + (uint64_t)idx * 12;
       if (so + 12 > db.pg_len) { result = false; break; }
+      if (((db.pg_align + so) & 3) != 0) return false;  // Err("Invalid GlobSegmentHeader")
       const uint8_t* sh = db.pg + so;
       uint32_t stype = sh[0], sflags = sh[1], dlen = ld32(sh + 4), doff = ld32(sh + 8);
       if (stype == 0) {
@@ -519,6 +529,7 @@ MGPU_HDN bool glob_match(const DbView& db, uint32_t pattern_id, const uint8_t* t
         if (ci && ch < 128) ch = lc((uint8_t)ch, true);
         if ((uint64_t)doff + dlen > db.pg_len) { result = false; break; }
         uint32_t items = dlen / 12;
+        if (items && ((db.pg_align + doff) & 3) != 0) return false;  // Err("Invalid CharClassItemEncoded")
         bool in_class = false;
         for (uint32_t i = 0; i < items; i++) {
           const uint8_t* it = db.pg + doff + i * 12;
@@ -549,10 +560,37 @@ MGPU_HDN bool glob_match(const DbView& db, uint32_t pattern_id, const uint8_t* t
   }
 }
 
+// Automaton node held in registers: the 20-byte ACNodeHot minus one_target (== edges_offset for kind One).
+struct AcNode { uint32_t w0, fail, eo, po; };
+MGPU_HD AcNode ac_fetch(const uint8_t* ac, uint32_t off) {
+  AcNode n;
+  n.w0 = ld32(ac + off); n.fail = ld32(ac + off + 8); n.eo = ld32(ac + off + 12); n.po = ld32(ac + off + 16);
+  return n;
+}
+// goto function of node `nd` on byte ch (find_ac_transition :1271-1353); 0 = no transition (offset 0 is the root and is
+// never a goto target).  Offsets were bounds- and alignment-checked at upload (db_prepare.h), so no per-step checks.
+MGPU_HD uint32_t ac_goto(const uint8_t* ac, const AcNode& nd, uint8_t ch) {
+  uint32_t kind = nd.w0 & 0xFF;
+  if (kind == 1) return ((nd.w0 >> 8) & 0xFF) == ch ? nd.eo : 0u;
+  if (kind == 2) {
+    uint32_t cnt = (nd.w0 >> 16) & 0xFF;
+    for (uint32_t i = 0; i < cnt; i++) {
+      uint32_t e0 = ld32(ac + nd.eo + i * 8);
+      uint8_t ec = (uint8_t)e0;
+      if (ec == ch) return ld32(ac + nd.eo + i * 8 + 4);
+      if (ec > ch) return 0u;
+    }
+    return 0u;
+  }
+  if (kind == 3) return ld32(ac + nd.eo + (uint32_t)ch * 4);
+  return 0u;
+}
+
 // Visit every glob id find_all would return for `text` (before sort+dedup; duplicates possible).
 // run_ac_matching_into_static :1186-1266 + ACLH map + verification :1136-1171, pure wildcards :1096-1134.
+// root_tab: the root's 256-entry dense table (possibly a shared-memory copy) or nullptr when the root is not dense.
 template <typename F>
-MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn, F&& emit) {
+MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn, const uint32_t* root_tab, F&& emit) {
   if (db.pg_len < 112) return;
   // pure wildcards are tested on every query
   for (uint32_t i = 0; i < db.wild_count; i++) {
@@ -562,27 +600,25 @@ MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn,
     if ((uint64_t)db.patterns_offset + (uint64_t)pid * 16 + 16 > db.pg_len) continue;
     if (glob_match(db, pid, text, tn)) emit(pid);
   }
-  if (db.ac_size == 0 || tn == 0) return;
+  if (db.ac_size < 20 || tn == 0) return;
   const uint8_t* ac = db.pg + db.ac_start;
-  const uint32_t acn = db.ac_size;
   const bool fold = db.match_mode == 1;
+  const AcNode root = ac_fetch(ac, 0);
   uint32_t cur = 0;
+  AcNode nd = root;
   for (uint32_t i = 0; i < tn; i++) {
     uint8_t ch = lc(text[i], fold);
     for (;;) {
-      uint32_t nx;
-      if (ac_transition(ac, acn, cur, ch, nx)) { cur = nx; break; }
-      if (cur == 0) break;
-      if ((uint64_t)cur + 20 > acn) break;
-      cur = ld32(ac + cur + 8);
+      uint32_t nx = (cur == 0 && root_tab) ? root_tab[ch] : ac_goto(ac, nd, ch);
+      if (nx) { cur = nx; nd = ac_fetch(ac, cur); break; }
+      if (cur == 0) break;  // at the root: stay
+      cur = nd.fail;
+      nd = cur ? ac_fetch(ac, cur) : root;
     }
-    if ((uint64_t)cur + 20 > acn) continue;
-    uint32_t pc = ac[cur + 3];
+    uint32_t pc = nd.w0 >> 24;
     if (pc == 0) continue;
-    uint32_t po = ld32(ac + cur + 16);
-    if ((uint64_t)po + (uint64_t)pc * 4 > acn) continue;
     for (uint32_t k = 0; k < pc; k++) {
-      uint32_t lit = ld32(ac + po + k * 4);
+      uint32_t lit = ld32(ac + nd.po + k * 4);
       if (lit >= db.aclh_n) continue;
       uint32_t lo = db.aclh_index[2 * lit], lcnt = db.aclh_index[2 * lit + 1];
       for (uint32_t j = 0; j < lcnt; j++) {
@@ -595,6 +631,13 @@ MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn,
       }
     }
   }
+}
+// the root's dense table, if the root is a Dense state
+MGPU_HD const uint32_t* ac_root_table(const DbView& db) {
+  if (!db.has_glob || db.ac_size < 20) return nullptr;
+  const uint8_t* ac = db.pg + db.ac_start;
+  if ((ld32(ac) & 0xFF) != 3) return nullptr;
+  return reinterpret_cast<const uint32_t*>(ac + ld32(ac + 12));
 }
 MGPU_HD bool glob_data_offset(const DbView& db, uint32_t pid, uint32_t& off) {
   if (pid >= db.glob_data_n) return false;

@@ -285,12 +285,26 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K2 validate: candidate -> token.  One thread per candidate, block-aggregated appends.
+// Token bytes: a warp handles 32 consecutive queue entries, which lie close together in the log (queues are filled
+// in log order per tokenizer warp).  The warp copies the covering window into shared memory with coalesced 16-byte
+// loads, and every lane then reads its token from there instead of issuing 32 scattered sector requests per byte.
 // ---------------------------------------------------------------------------------------------------------
-static const int K2_THREADS = 256;
+static const uint32_t WIN_BYTES = 4096;
+static const int KT_THREADS = 256;  // validate / lithash / acglob block size
+static const int KT_WARPS = KT_THREADS / 32;
+
+// Returns p with p[pos] readable for pos in [lo, hi + 16).  Falls back to the global buffer for wide windows.
+__device__ __forceinline__ const uint8_t* stage_window(const uint8_t* buf, uint8_t* win, uint32_t lo, uint32_t hi, uint32_t lane) {
+  if (lo >= hi) return buf;
+  const uint32_t alo = lo & ~15u, ahi = (hi + 31u) & ~15u;
+  if (ahi - alo > WIN_BYTES) return buf;
+  __syncwarp();
+  for (uint32_t o = alo + lane * 16; o < ahi; o += 512) *reinterpret_cast<uint4*>(win + (o - alo)) = *reinterpret_cast<const uint4*>(buf + o);
+  __syncwarp();
+  return win - alo;
+}
 
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
-  // v in {0,1,2}; returns the exclusive prefix within the block
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = warp_incl_scan(v, lane);
   if (lane == 31) s_warp[warp] = incl;
@@ -302,24 +316,45 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
   return off + incl - v;
 }
 
-__global__ void __launch_bounds__(K2_THREADS) validate_kernel(ScanArgs a) {
-  __shared__ uint32_t s_warp[K2_THREADS / 32];
+// ---------------------------------------------------------------------------------------------------------
+// K2 validate: candidate -> token.  One thread per candidate, block-aggregated appends.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KT_THREADS) validate_kernel(ScanArgs a) {
+  __shared__ __align__(16) uint8_t s_win[KT_WARPS][WIN_BYTES + 32];
+  __shared__ uint32_t s_warp[KT_WARPS];
   __shared__ uint32_t s_base[2];
-  __shared__ unsigned int s_type[12];
-  if (threadIdx.x < 12) s_type[threadIdx.x] = 0;
-  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nD = min(a.ctr->q_count[Q_DOTTED], a.cap_q[Q_DOTTED]);
   const uint32_t nH = min(a.ctr->q_count[Q_HASH], a.cap_q[Q_HASH]);
   const uint32_t nA = min(a.ctr->q_count[Q_AT], a.cap_q[Q_AT]);
   const uint32_t nC = min(a.ctr->q_count[Q_COLON2], a.cap_q[Q_COLON2]);
   const uint64_t total = (uint64_t)nD + nH + nA + nC;
   const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t n_dom = 0, n_mail = 0, n_v4 = 0, n_v6 = 0, n_md5 = 0, n_sha1 = 0, n_sha256 = 0, n_sha384 = 0, n_sha512 = 0;
   for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < total; i0 += step) {
     const uint64_t i = i0 + threadIdx.x;
+    const uint64_t w0 = i0 + warp * 32;  // first entry of this warp
     bool ws = false, wi = false;
     StrTok st{0, 0, 0};
     IpTok it{0, 0, 0, 0, {0, 0, 0, 0}};
-    if (i < total) {
+    if (w0 + 32 <= nD) {
+      // a full warp of dotted words: stage their window
+      Cand c = a.q_dotted[i];
+      bool ok = c.start != NONE32 && (uint64_t)c.start + c.len <= a.n;
+      uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, ok ? c.start : 0xFFFFFFFFu);
+      uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, ok ? c.start + c.len : 0u);
+      const uint8_t* p = stage_window(a.buf, s_win[warp], lo, hi, lane);
+      if (ok) {
+        const uint8_t* wp = p + c.start;
+        uint32_t addr;
+        if ((a.flags & MGPU_X_IPV4) && parse_ipv4_word(wp, c.len, addr)) {
+          wi = true; it.start = c.start; it.len = c.len; it.type = MGPU_T_IPV4; it.w[0] = addr;
+        }
+        if ((a.flags & MGPU_X_DOMAINS) && validate_domain_word(a.db, wp, c.len)) {
+          ws = true; st.start = c.start; st.len = c.len; st.type = MGPU_T_DOMAIN;
+        }
+      }
+    } else if (i < total) {
       if (i < nD) {
         Cand c = a.q_dotted[i];
         if (c.start != NONE32 && (uint64_t)c.start + c.len <= a.n) {
@@ -364,17 +399,23 @@ __global__ void __launch_bounds__(K2_THREADS) validate_kernel(ScanArgs a) {
     if (ws) {
       uint32_t k = s_base[0] + es;
       if (k < a.cap_str) a.str[k] = st; else atomicOr(&a.ctr->overflow, 1u << 8);
-      atomicAdd(&s_type[st.type], 1u);
+      n_dom += st.type == MGPU_T_DOMAIN; n_mail += st.type == MGPU_T_EMAIL; n_md5 += st.type == MGPU_T_MD5; n_sha1 += st.type == MGPU_T_SHA1;
+      n_sha256 += st.type == MGPU_T_SHA256; n_sha384 += st.type == MGPU_T_SHA384; n_sha512 += st.type == MGPU_T_SHA512;
     }
     if (wi) {
       uint32_t k = s_base[1] + ei;
       if (k < a.cap_ip) a.ip[k] = it; else atomicOr(&a.ctr->overflow, 1u << 9);
-      atomicAdd(&s_type[it.type], 1u);
+      n_v4 += it.type == MGPU_T_IPV4; n_v6 += it.type == MGPU_T_IPV6;
     }
     __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x < 12 && s_type[threadIdx.x]) atomicAdd(&a.ctr->by_type[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+  // per-type candidate counters (WorkerStats): warp-reduce, one atomic per warp and type
+  uint32_t cnt[9] = {n_dom, n_mail, n_v4, n_v6, n_md5, n_sha1, n_sha256, n_sha384, n_sha512};
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cnt[t]);
+    if (lane == 0 && v) atomicAdd(&a.ctr->by_type[t], (unsigned long long)v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -412,27 +453,55 @@ __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
   }
 }
 
+// tokens of one warp iteration -> staged window pointer
+__device__ __forceinline__ const uint8_t* stage_tokens(const ScanArgs& a, uint8_t* win, bool valid, const StrTok& t, uint32_t lane) {
+  uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, valid ? t.start : 0xFFFFFFFFu);
+  uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, valid ? t.start + t.len : 0u);
+  return stage_window(a.buf, win, lo, hi, lane);
+}
+
 // K4: literal hash probe per string token
-__global__ void __launch_bounds__(256) lithash_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(KT_THREADS) lithash_kernel(ScanArgs a) {
+  __shared__ __align__(16) uint8_t s_win[KT_WARPS][WIN_BYTES + 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    StrTok t = a.str[i];
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    StrTok t{0, 0, 0};
+    if (valid) t = a.str[i];
+    const uint8_t* p = stage_tokens(a, s_win[warp], valid, t, lane);
+    if (!valid) continue;
     uint32_t pid = NONE32;
-    if (!lh_lookup(a.db, a.buf + t.start, t.len, pid)) pid = NONE32;
+    if (!lh_lookup(a.db, p + t.start, t.len, pid)) pid = NONE32;
     a.lh_res[i] = pid;
   }
 }
 
 // K5: Aho-Corasick walk + glob verification per string token, merge with the literal result, emit
-__global__ void __launch_bounds__(256) acglob_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
+  __shared__ __align__(16) uint8_t s_win[KT_WARPS][WIN_BYTES + 32];
+  __shared__ uint32_t s_root[256];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t* root_tab = ac_root_table(a.db);
+  if (root_tab) {  // hot state in shared memory: every token byte that does not continue a literal goes through the root
+    s_root[threadIdx.x] = root_tab[threadIdx.x];
+    __syncthreads();
+    root_tab = s_root;
+  }
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    StrTok t = a.str[i];
-    const uint8_t* text = a.buf + t.start;
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    StrTok t{0, 0, 0};
+    if (valid) t = a.str[i];
+    const uint8_t* p = stage_tokens(a, s_win[warp], valid, t, lane);
+    if (!valid) continue;
+    const uint8_t* text = p + t.start;
     uint32_t lit_pid = a.db.has_literal ? a.lh_res[i] : NONE32, lit_off = 0;
     bool lit_ok = lit_pid != NONE32 && lh_data_offset(a.db, lit_pid, lit_off);
     uint32_t cnt = 0;
-    if (a.db.has_glob) find_all_visit(a.db, text, t.len, [&](uint32_t) { cnt++; });
+    if (a.db.has_glob) find_all_visit(a.db, text, t.len, root_tab, [&](uint32_t) { cnt++; });
     if (!lit_ok && cnt == 0) continue;
     uint32_t total = cnt + (lit_ok ? 1u : 0u);
     uint32_t b = agg_add(&a.ctr->n_ids, total);
@@ -441,7 +510,7 @@ __global__ void __launch_bounds__(256) acglob_kernel(ScanArgs a) {
     if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
     const uint32_t g0 = k;
     if (cnt) {
-      find_all_visit(a.db, text, t.len, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
+      find_all_visit(a.db, text, t.len, root_tab, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
       // sort_unstable + dedup (paraglob_offset.rs:1173-1181)
       for (uint32_t x = g0 + 1; x < k; x++) {
         uint32_t v = a.ids[x].pattern_id, y = x;
@@ -504,7 +573,7 @@ __global__ void query_string_kernel(ScanArgs a, uint32_t len, uint32_t* out_n) {
   uint32_t pid, off;
   if (a.db.has_literal && lh_lookup(a.db, a.buf, len, pid) && lh_data_offset(a.db, pid, off)) { if (n < a.cap_ids) { a.ids[n].pattern_id = pid; a.ids[n].data_offset = off; } n++; }
   uint32_t g0 = n;
-  if (a.db.has_glob) find_all_visit(a.db, a.buf, len, [&](uint32_t p) { if (n < a.cap_ids) a.ids[n].pattern_id = p; n++; });
+  if (a.db.has_glob) find_all_visit(a.db, a.buf, len, ac_root_table(a.db), [&](uint32_t p) { if (n < a.cap_ids) a.ids[n].pattern_id = p; n++; });
   uint32_t k = n < a.cap_ids ? n : a.cap_ids;
   for (uint32_t x = g0 + 1; x < k; x++) {
     uint32_t v = a.ids[x].pattern_id, y = x;
@@ -554,6 +623,7 @@ struct mgpu_ctx {
   cudaStream_t compute = nullptr, copy = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_k[MGPU_K_COUNT + 1] = {};
+  cudaEvent_t ev_scan[2] = {nullptr, nullptr};
   // log staging (double buffered) and pinned bounce buffers for pageable callers
   uint8_t* d_log[2] = {nullptr, nullptr};
   uint8_t* h_pin[2] = {nullptr, nullptr};
@@ -605,6 +675,7 @@ void mgpu_destroy(mgpu_ctx* c) {
     if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
   }
   for (auto& e : c->ev_k) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
   void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.str, c->args.ip, c->args.lh_res,
                   c->args.recs, c->args.ids, c->args.ctr, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool};
   for (void* p : bufs) if (p) cudaFree(p);
@@ -639,6 +710,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
     CK(cudaMallocHost(&c->h_pin[s], std::min(chunk_bytes, (size_t)64 << 20)));
   }
   for (auto& e : c->ev_k) CK(cudaEventCreate(&e));
+  for (auto& e : c->ev_scan) CK(cudaEventCreate(&e));
   ScanArgs& a = c->args;
   memset(&a, 0, sizeof a);
   auto cap32 = [](size_t v) { return (uint32_t)std::min<size_t>(v, 0x7FFFFFFFu); };
@@ -786,14 +858,14 @@ static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t 
     tokenize_kernel<<<grid, K1_THREADS, smem, st>>>(a);
   }
   CK(cudaEventRecord(c->ev_k[1], st));
-  validate_kernel<<<launch_grid(c, 8), K2_THREADS, 0, st>>>(a);
+  validate_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
   CK(cudaEventRecord(c->ev_k[2], st));
   if (lookups) {
     iptrie_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
     CK(cudaEventRecord(c->ev_k[3], st));
-    if (a.db.has_literal) lithash_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
+    if (a.db.has_literal) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
     CK(cudaEventRecord(c->ev_k[4], st));
-    if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
+    if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
     CK(cudaEventRecord(c->ev_k[5], st));
   } else {
     for (int k = 3; k <= 5; k++) CK(cudaEventRecord(c->ev_k[k], st));
@@ -826,6 +898,7 @@ static int find_cuts(mgpu_ctx* c, const uint8_t* dev, uint64_t n, const std::vec
   for (int k = 0; k < cnt; k++) c->h_cut[k] = from[k];
   CK(cudaMemcpyAsync(c->d_cut, c->h_cut, cnt * 8, cudaMemcpyHostToDevice, c->compute));
   cut_kernel<<<1, 64, 0, c->compute>>>(dev, n, c->d_cut, c->d_cut + 64, cnt);
+  c->timing.aux_launches++;
   CK(cudaMemcpyAsync(c->h_cut + 64, c->d_cut + 64, cnt * 8, cudaMemcpyDeviceToHost, c->compute));
   CK(cudaStreamSynchronize(c->compute));
   out.assign(c->h_cut + 64, c->h_cut + 64 + cnt);
@@ -888,15 +961,31 @@ static void begin_scan(mgpu_ctx* c) {
   c->x_str.clear(); c->x_ip.clear();
   memset(&c->counters, 0, sizeof c->counters);
   memset(&c->timing, 0, sizeof c->timing);
+  cudaEventRecord(c->ev_scan[0], c->compute);
 }
 
 static void finish_scan(mgpu_ctx* c) {
-  // deterministic order: (offset, item_type, len).  Pairs stay where they are; ids_index still points at them.
+  cudaEventRecord(c->ev_scan[1], c->compute);
+  cudaEventSynchronize(c->ev_scan[1]);
+  cudaEventElapsedTime(&c->timing.scan_ms, c->ev_scan[0], c->ev_scan[1]);
+  // deterministic output: records by (offset, item_type, len), id pairs re-packed in record order (the device appends
+  // both with atomics, so their raw order varies from run to run)
   std::sort(c->recs.begin(), c->recs.end(), [](const mgpu_match& x, const mgpu_match& y) {
     if (x.offset != y.offset) return x.offset < y.offset;
     if (x.item_type != y.item_type) return x.item_type < y.item_type;
     return x.len < y.len;
   });
+  if (!c->ids.empty()) {
+    std::vector<mgpu_id_pair> packed;
+    packed.reserve(c->ids.size());
+    for (auto& r : c->recs) {
+      if (r.kind != MGPU_KIND_PATTERN) continue;
+      uint32_t at = (uint32_t)packed.size();
+      packed.insert(packed.end(), c->ids.begin() + r.ids_index, c->ids.begin() + r.ids_index + r.n_ids);
+      r.ids_index = at;
+    }
+    c->ids.swap(packed);
+  }
 }
 
 static int check_ready(mgpu_ctx* c, uint32_t flags) {
@@ -917,6 +1006,7 @@ static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_
     uint64_t end = std::min<uint64_t>(len, pos + window);
     if (end < len) {
       rfind_nl_kernel<<<1, 256, 0, c->compute>>>(dev, pos, end, c->d_cut);
+      c->timing.aux_launches++;
       CK(cudaMemcpyAsync(c->h_cut, c->d_cut, 8, cudaMemcpyDeviceToHost, c->compute));
       CK(cudaStreamSynchronize(c->compute));
       if (c->h_cut[0] == 0) { set_err("a single line is longer than the scan chunk; raise chunk_bytes"); return MGPU_E_OVERFLOW; }

@@ -115,7 +115,7 @@ class Engine:
         _check(self.L.mgpu_timing_get(self.h, C.byref(t)), "mgpu_timing_get")
         return {"kernel_ms": {KERNEL_NAMES[k]: float(t.kernel_ms[k]) for k in range(5)},
                 "launches": {KERNEL_NAMES[k]: int(t.launches[k]) for k in range(5)},
-                "total_ms": float(t.total_ms), "chunks": int(t.chunks)}
+                "total_ms": float(t.total_ms), "chunks": int(t.chunks), "scan_ms": float(t.scan_ms), "aux_launches": int(t.aux_launches)}
 
     def set_keep_results(self, keep: bool):
         self.L.mgpu_set_keep_results(self.h, 1 if keep else 0)

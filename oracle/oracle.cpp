@@ -799,6 +799,8 @@ struct Db {
   // paraglob (paraglob_offset.rs) + mappings (database.rs:1315-1394)
   bool has_glob = false;
   const uint8_t* pg = nullptr; size_t pg_len = 0;
+  size_t pg_file_off = 0;             // file offset of the PARAGLOB buffer; with the page-aligned mmap of Database::open it
+                                      // decides whether zerocopy's alignment checks pass (see aligned4 below)
   size_t map_off = 0, map_count = 0;  // absolute offset of u32 data offsets
   std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> aclh;  // literal id → (abs offset in pg, count)
   Psl psl;
@@ -852,7 +854,7 @@ struct Db {
         if (pend + 4 > n) { error = "mappings truncated"; return false; }
         size_t cnt = rd32(d + pend);
         if (pend + 4 + cnt * 4 > n) { error = "mappings out of bounds"; return false; }
-        pg = d + pstart; pg_len = pg_size; map_off = pend + 4; map_count = cnt; has_glob = true;
+        pg = d + pstart; pg_len = pg_size; pg_file_off = pstart; map_off = pend + 4; map_count = cnt; has_glob = true;
         if (pg_len < 112 || memcmp(pg, "PARAGLOB", 8) != 0) { error = "bad paraglob magic"; return false; }
         load_aclh();
       }
@@ -1102,6 +1104,10 @@ struct Db {
   static uint32_t lower_cp(uint32_t c) { return (c >= 'A' && c <= 'Z') ? c + 32 : c; }
   static bool valid_scalar(uint32_t c) { return c <= 0x10FFFF && !(c >= 0xD800 && c <= 0xDFFF); }
 
+  // zerocopy::Ref::<_, T>::from_prefix fails unless the slice is aligned for T (all three glob structs hold u32s and are
+  // not `Unaligned`, offset_format.rs:391-431).  The file is mmap'd page-aligned, so alignment follows from file offsets.
+  bool aligned4(size_t pg_offset) const { return ((pg_file_off + pg_offset) & 3) == 0; }
+
   // match_segments_impl :1402-1639.  Returns 1 true, 0 false, -1 Err (propagates like `?`)
   int match_segments(const uint8_t* text, size_t tn, size_t first_seg, size_t seg_count, size_t tpos, size_t seg_idx,
                      size_t& steps) const {
@@ -1110,6 +1116,7 @@ struct Db {
     if (seg_idx >= seg_count) return tpos >= tn ? 1 : 0;
     size_t so = first_seg + seg_idx * 12;
     if (so + 12 > pg_len) return 0;
+    if (!aligned4(so)) return -1;  // "Invalid GlobSegmentHeader" :1432-1435
     const uint8_t* sh = pg + so;
     uint8_t stype = sh[0], sflags = sh[1];
     size_t data_len = rd32(sh + 4), data_off = rd32(sh + 8);
@@ -1167,6 +1174,7 @@ struct Db {
         if (data_off + data_len > pg_len) return 0;
         bool negated = sflags & 1, in_class = false;
         for (size_t i = 0; i < item_count; i++) {
+          if (!aligned4(data_off + i * 12)) return -1;  // "Invalid CharClassItemEncoded" :1572-1577
           const uint8_t* it = pg + data_off + i * 12;
           uint8_t itype = it[0];
           uint32_t c1 = rd32(it + 4), c2 = rd32(it + 8);
@@ -1194,6 +1202,7 @@ struct Db {
     size_t gso = rd32(pg + 104);
     size_t io = gso + (size_t)pattern_id * 8;
     if (io + 8 > pg_len) return false;
+    if (!aligned4(io)) return false;  // Err("Invalid GlobSegmentIndex") is not Ok(true)
     size_t first = rd32(pg + io), count = rd16(pg + io + 4);
     size_t steps = 100000;
     return match_segments(text, tn, first, count, 0, 0, steps) == 1;

@@ -181,7 +181,7 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
       if (db.has_literal && !lh_lookup(db, text, t.len, lit_pid)) lit_pid = NONE32;
       bool lit_ok = lit_pid != NONE32 && lh_data_offset(db, lit_pid, lit_off);
       std::vector<uint32_t> g;
-      if (db.has_glob) find_all_visit(db, text, t.len, [&](uint32_t pid) { g.push_back(pid); });
+      if (db.has_glob) find_all_visit(db, text, t.len, ac_root_table(db), [&](uint32_t pid) { g.push_back(pid); });
       if (!lit_ok && g.empty()) continue;
       std::sort(g.begin(), g.end());
       g.erase(std::unique(g.begin(), g.end()), g.end());

@@ -1,0 +1,154 @@
+"""CPU suite: the C-ABI library loads and exports everything include/matchy_b200.h declares; host-side pieces
+(writer, section locator, NDJSON renderer, generators, API mirror) behave; no compute calls need a GPU."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from matchy_b200 import _native as N
+    hdr = open(os.path.join(ROOT, "include", "matchy_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b((?:mgpu|mxyr|mxyb|mgen)_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 45
+    lib = C.CDLL(N.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device engine creation fails loudly (this container has none)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from matchy_b200 import Engine, EngineError
+    with pytest.raises(EngineError):
+        Engine(0)
+
+
+def test_product_does_not_import_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "matchy_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                assert "oracle_lib" not in text and "liboracle" not in text and "host_emulation" not in text.replace("tests/host_emulation can", ""), f
+
+
+def test_writer_layout_and_metadata(built):
+    from matchy_b200 import DatabaseBuilder
+    b = DatabaseBuilder(build_epoch=1700000000)
+    b.add_entry("10.0.0.0/8", {"threat_level": "low", "score": 1})
+    b.add_entry("evil.com", {"threat_level": "high", "score": 5})
+    b.add_entry("*.evil.com", {"threat_level": "high", "score": 5})  # same data -> deduplicated offset
+    db = b.build()
+    assert db[-2000:].count(b"\xab\xcd\xefMaxMind.com") == 1
+    assert b"MMDB_PATTERN\0\0\0\0" in db and b"MMDB_LITERAL\0\0\0\0" in db and b"PARAGLOB" in db and b"LHSH" in db and b"ACLH" in db
+    o = O.Oracle(db)
+    lit, glob = o.lookup_string(b"evil.com"), o.lookup_string(b"x.evil.com")
+    assert lit[0][1] == glob[0][1]
+    assert json.loads(o.data_json(lit[0][1])) == {"score": 5, "threat_level": "high"}
+    assert b.stats() == {"ip_entries": 1, "literal_entries": 1, "glob_entries": 1}
+
+
+def test_entry_type_detection(built):
+    """mmdb_builder.rs:392-429."""
+    from matchy_b200 import DatabaseBuilder
+    b = DatabaseBuilder(build_epoch=1)
+    for key in ("1.2.3.4", "10.0.0.0/8", "2001:db8::/32", "ip:9.9.9.9"):
+        b.add_entry(key, {})
+    for key in ("*.example.com", "file[0-9].txt", "glob:no-wildcards.com"):
+        b.add_entry(key, {})
+    for key in ("evil.com", "literal:*.not-a-glob.com", "[unclosed", "1.2.3.4/33"):
+        b.add_entry(key, {})
+    assert b.stats() == {"ip_entries": 4, "literal_entries": 4, "glob_entries": 3}
+    with pytest.raises(ValueError):
+        b.add_entry("glob:[unclosed", {})
+    with pytest.raises(ValueError):
+        b.add_entry("ip:not-an-ip", {})
+
+
+def test_24bit_record_overflow_is_refused(built):
+    """The reference silently truncates records that do not fit (matchy-ip-trie/src/lib.rs:467-475); the writer refuses."""
+    from matchy_b200 import DatabaseBuilder
+    b = DatabaseBuilder(build_epoch=1)
+    big = "x" * 4000
+    for i in range(4300):
+        b.add_entry("10.%d.%d.0/24" % (i // 256, i % 256), {"blob": big + str(i)})
+    with pytest.raises(ValueError):
+        b.build()
+
+
+def test_ndjson_renderer_matches_oracle(small_dbs):
+    """mxyr_ndjson (product, host) == oracle NDJSON for the same records."""
+    import numpy as np
+    from matchy_b200 import Engine, RecordFormatter
+    for cfg in (1, 3, 5):
+        db, log = small_dbs[cfg]
+        log = log[:300000] + b"src=2001:d00::1 ::ffff:1.2.3.4 x\n"
+        orc = O.Oracle(db)
+        recs, _ = orc.scan(log, chunk_size=128 * 1024)
+        r = np.zeros(len(recs), Engine.REC_DTYPE)
+        ids = []
+        for k, (off, ln, ty, kind, pl, doff, pairs) in enumerate(recs):
+            r[k] = (off, ln, ty, kind, pl, 0, len(pairs), len(ids), doff, 0)
+            ids.extend(pairs)
+        i = np.array(ids, Engine.ID_DTYPE) if ids else np.zeros(0, Engine.ID_DTYPE)
+        got = RecordFormatter(db).ndjson(r, i, log, 0, 'we"ird\\src.log')
+        orc.scan(log, chunk_size=128 * 1024)
+        assert sorted(got.splitlines()) == sorted(orc.ndjson(log, 'we"ird\\src.log').splitlines())
+        for line in got.splitlines()[:50]:
+            obj = json.loads(line)
+            assert list(obj) == sorted(obj) and obj["timestamp"] == "0.000"
+
+
+def test_generators_are_deterministic_and_block_addressable(built):
+    from matchy_b200 import synth
+    a = synth.gen_log(2, 4 * 65536, 0.01)
+    b = synth.gen_log(2, 2 * 65536, 0.01, offset=2 * 65536)
+    assert bytes(a[2 * 65536:]) == bytes(b)
+    assert bytes(synth.gen_log(2, 4 * 65536, 0.01, threads=3)) == bytes(a)
+    assert a[-1] == 10 and a[65535] == 10
+    c = synth.gen_log(3, 100000, 0.01)
+    assert c[-1] == 10
+    assert synth.build_db(1, 0.01) == synth.build_db(1, 0.01)
+
+
+def test_file_reader_next_batch(tmp_path):
+    """FileReader::next_batch (processing/mod.rs:206-251): every batch ends at a newline except the tail."""
+    from matchy_b200.processing import FileReader
+    p = tmp_path / "x.log"
+    lines = [b"line %d 1.2.3.%d\n" % (i, i % 250) for i in range(1000)]
+    p.write_bytes(b"".join(lines) + b"tail-without-newline")
+    fr = FileReader(p, chunk_size=1000)
+    got = [b.data for b in fr.batches()]
+    assert b"".join(got) == p.read_bytes()
+    assert all(g.endswith(b"\n") for g in got[:-1]) and got[-1] == b"tail-without-newline"
+    assert max(len(g) for g in got) <= 1000 + 30
+
+
+def test_csv_loader_value_typing(tmp_path, built):
+    """match_cmd.rs:77-97: i64 -> Int32, f64 -> Double, true/false -> Bool, else String; empty cells skipped."""
+    from matchy_b200 import builder
+    p = tmp_path / "db.csv"
+    p.write_text("entry,score,ratio,active,note\n1.2.3.4,7,0.5,true,hello\nevil.com,,,false,\n*.bad.org,-3,x,TRUE,y z\n")
+    db = builder.build_from_csv(str(p), build_epoch=1)
+    o = O.Oracle(db)
+    rc, off, pl = o.lookup_ip4(0x01020304)
+    assert json.loads(o.data_json(off)) == {"active": True, "note": "hello", "ratio": 0.5, "score": 7}
+    assert json.loads(o.data_json(o.lookup_string(b"evil.com")[0][1])) == {"active": False}
+    assert json.loads(o.data_json(o.lookup_string(b"a.bad.org")[0][1])) == {"active": "TRUE", "note": "y z", "ratio": "x", "score": -3}
+
+
+def test_oracle_multithreaded_counters_equal_single_thread(small_dbs):
+    db, log = small_dbs[5]
+    o = O.Oracle(db)
+    _, cnt = o.scan(log, chunk_size=128 * 1024)
+    assert o.scan_mt(log, threads=4) == cnt

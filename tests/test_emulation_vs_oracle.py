@@ -1,0 +1,86 @@
+"""CPU suite: the device logic (tokenizer bit arithmetic, validation, trie / hash / AC+glob walkers), compiled for the
+host by tests/host_emulation/emu.cpp, against the oracle.  This is how kernel logic is debugged without a GPU; the
+real kernels are checked by test_gpu_parity.py.  Nothing here is a product path."""
+import random
+
+import pytest
+
+import emu_lib as E
+import oracle_lib as O
+from test_gpu_parity import FRAGS, _fuzz_text
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_configs(small_dbs, cfg):
+    db, log = small_dbs[cfg]
+    log = log[:400000]
+    orc, emu = O.Oracle(db), E.Emu(db)
+    want = orc.scan(log, chunk_size=128 * 1024)
+    for chunk, nwarps, mis in ((0, 1, 0), (70000, 3, 5), (0, 7, 15), (150000, 64, 9)):
+        assert emu.scan(log, chunk_bytes=chunk, nwarps=nwarps, misalign=mis) == want, (chunk, nwarps, mis)
+
+
+def test_extractor_fuzz(small_dbs):
+    db, _ = small_dbs[1]
+    orc, emu = O.Oracle(db), E.Emu(db)
+    rng = random.Random(7)
+    for it in range(600):
+        data = _fuzz_text(rng, rng.randint(0, 60) if it % 10 else rng.randint(200, 900))
+        flags = rng.choice([31, 31, 31, 1, 2, 4, 8, 16, 5, 10, 21])
+        want = sorted((s, t, e) for t, s, e in orc.extract(data, flags))
+        got = sorted((s, t, e) for t, s, e in emu.tokens(data, flags, nwarps=rng.choice([1, 1, 2, 3, 5]), misalign=rng.choice([0, 0, 3, 15])))
+        assert got == want, (it, flags, data[:160])
+
+
+def test_scan_fuzz_with_hits(small_dbs):
+    db, log = small_dbs[5]
+    orc, emu = O.Oracle(db), E.Emu(db)
+    rng = random.Random(99)
+    words = [w for w in log.replace(b"=", b" ").replace(b"\"", b" ").split() if b"." in w or len(w) in (32, 40, 64)]
+    for it in range(40):
+        parts = []
+        for _ in range(rng.randint(5, 300)):
+            parts.append(rng.choice(words) if rng.random() < 0.5 else rng.choice(FRAGS))
+            parts.append(rng.choice([b" ", b"\n", b" ", b"=", b","]))
+        data = b"".join(parts)
+        assert emu.scan(data, nwarps=rng.choice([1, 2, 4])) == orc.scan(data), it
+
+
+def test_long_tokens_cross_tiles(small_dbs):
+    """Words longer than a 32-byte slice, a 1 KiB tile and a whole warp range keep exact extents."""
+    db, _ = small_dbs[5]
+    orc, emu = O.Oracle(db), E.Emu(db)
+    for n in (31, 32, 33, 63, 64, 65, 1000, 1023, 1024, 1025, 3000, 5000):
+        for data in (b"a" * n + b".com x", b"x " + b"b" * n + b".evil.org\n", b"0" * n + b" ", b"q=" + b"1" * 7 + b"." + b"c" * n + b".net",
+                     b"u" * n + b"@mail.example.com ", b"\xc3\xa9" * (n // 2) + b".fr "):
+            want = sorted((s, t, e) for t, s, e in orc.extract(data, 31))
+            for nwarps in (1, 2, 5):
+                got = sorted((s, t, e) for t, s, e in emu.tokens(data, 31, nwarps=nwarps))
+                assert got == want, (n, data[:40], nwarps)
+
+
+def test_glob_backtracking_budget(built):
+    """The 100 000-step budget of match_segments_impl is spent exactly like the reference spends it."""
+    from matchy_b200 import DatabaseBuilder
+    b = DatabaseBuilder(build_epoch=1)
+    b.add_glob("*aaa*aaa*aaa*aaa*aaa*bbb", {"x": 1})
+    b.add_glob("*.example.*", {"x": 2})
+    db = b.build()
+    orc, emu = O.Oracle(db), E.Emu(db)
+    for text in (b"a" * 60 + b".example.com", b"a" * 200 + b".example.com", b"a" * 60 + b"bbb.example.com", b"aaa" * 5 + b"bbb"):
+        data = b"host=" + text + b" \n"
+        assert emu.scan(data) == orc.scan(data), text
+
+
+def test_case_insensitive_database(built):
+    from matchy_b200 import DatabaseBuilder, MatchMode
+    b = DatabaseBuilder(MatchMode.CaseInsensitive, build_epoch=1)
+    b.add_entry("Evil.Example.COM", {"x": 1})
+    b.add_entry("*.BadSite.org", {"x": 2})
+    b.add_entry("5D41402ABC4B2A76B9719D911017C592", {"x": 3})
+    db = b.build()
+    orc, emu = O.Oracle(db), E.Emu(db)
+    data = b"a Evil.example.com b evil.EXAMPLE.com c www.badsite.ORG d 5d41402abc4b2a76b9719d911017c592 e WWW.BADSITE.org\n"
+    want = orc.scan(data)
+    assert len(want[0]) >= 4
+    assert emu.scan(data) == want

@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.  Bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines(small_dbs):
+    from matchy_b200 import Engine
+    out = {}
+    for cfg, (db, log) in small_dbs.items():
+        e = Engine(0, chunk_bytes=8 << 20)
+        e.upload(db)
+        out[cfg] = (e, O.Oracle(db), log)
+    return out
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_config_parity(engines, cfg):
+    eng, orc, log = engines[cfg]
+    eng.scan(log)
+    want, wcnt = orc.scan(log, chunk_size=128 * 1024)
+    assert eng.counters_list() == wcnt
+    assert eng.records_as_tuples() == want
+    assert len(want) > 0
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_ndjson_parity(engines, small_dbs, cfg):
+    """sorted NDJSON of the GPU path == sorted NDJSON of the oracle (the `matchy match` output contract)."""
+    from matchy_b200 import RecordFormatter
+    eng, orc, log = engines[cfg]
+    recs, ids = eng.scan(log)
+    fmt = RecordFormatter(small_dbs[cfg][0])
+    got = sorted(fmt.ndjson(recs, ids, log, 0, "test.log").splitlines())
+    orc.scan(log, chunk_size=128 * 1024)
+    want = sorted(orc.ndjson(log, "test.log").splitlines())
+    assert got == want
+
+
+def test_chunking_is_invisible(engines, small_dbs):
+    """Results do not depend on how the engine cuts the buffer (newline-aligned pieces, FileReader::next_batch)."""
+    from matchy_b200 import Engine
+    db, log = small_dbs[5]
+    ref = None
+    for chunk in (64 << 10, 200 << 10, 8 << 20):
+        e = Engine(0, chunk_bytes=chunk)
+        e.upload(db)
+        e.scan(log, base=1 << 33)
+        cur = (e.records_as_tuples(), e.counters_list())
+        if ref is None:
+            ref = cur
+        assert cur == ref
+        e.close()
+    orc = O.Oracle(db)
+    want, wcnt = orc.scan(log, base=1 << 33, chunk_size=128 * 1024)
+    assert ref == (want, wcnt)
+
+
+def test_device_resident_scan_matches_host_scan(engines):
+    eng, orc, log = engines[2]
+    eng.scan(log)
+    host = (eng.records_as_tuples(), eng.counters_list())
+    p = eng.dev_alloc(len(log))
+    try:
+        eng.dev_upload(p, log)
+        eng.scan_device(p, len(log))
+        assert (eng.records_as_tuples(), eng.counters_list()) == host
+    finally:
+        eng.dev_free(p)
+
+
+FRAGS = [b"1.2.3.4", b"10.0.0.1", b"256.1.1.1", b"1.2.3", b"1.2.3.4.5", b"01.2.3.4", b"192.168.001.1", b"evil.com", b"www.example.co.uk",
+         b"a.b", b".com", b"com.", b"-a.com", b"a-.com", b"a..com", b"EVIL.COM", b"Evil.com", b"x_y.com", b"user@example.com", b"user@.com",
+         b"a@b", b"@", b"@@", b"u.s.e.r@sub.evil.org", b"a..b@c.com", b"123@456.com", b"u+tag@ex-ample.net", b"::", b":::", b"::1",
+         b"2001:db8::1", b"fe80::1ff:fe23:4567:890a", b"2001:db8:0:0:0:0:2:1", b"2001:db8::85a3::7334", b"1:2:3:4:5:6:7::", b"12345::1:2:3",
+         b"::ffff:1.2.3.4", b"a::b:c:d:e:f:1", b"FE90::1:2:3:4", b"5d41402abc4b2a76b9719d911017c592", b"5D41402ABC4B2A76B9719D911017C59",
+         b"da39a3ee5e6b4b0d3255bfef95601890afd80709", b"e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855",
+         b"0123456789abcdef" * 6, b"0123456789abcdef" * 8, b"0123456789abcdef" * 9, b"g" * 32, b"\xc3\xa9xample.com", b"\xff\xfe.com",
+         b"caf\xc3\xa9.fr", b"\xe2\x82\xac.org", b"\xc3.com", b" ", b"\t", b"\n", b"\r\n", b"/", b",", b";", b":", b"(", b")", b"[", b"]",
+         b"{", b"}", b"<", b">", b"\"", b"'", b"=", b"&", b"?", b"-", b"_", b".", b"%", b"#", b"|", b"\\", b"*", b"!", b"~", b"http://",
+         b"key=", b"a" * 70 + b".com", b"x" * 1500 + b".org", b"b." * 600 + b"com", b"9" * 40, b"1." * 20, b"deadbeef"]
+
+
+def _fuzz_text(rng, n):
+    parts = []
+    for _ in range(n):
+        f = rng.choice(FRAGS)
+        if rng.random() < 0.1:
+            f = bytes(rng.getrandbits(8) for _ in range(rng.randint(1, 6)))
+        parts.append(f)
+        if rng.random() < 0.5:
+            parts.append(rng.choice([b" ", b" ", b"\n", b"/", b"=", b":", b"@", b"", b"."]))
+    return b"".join(parts)
+
+
+def test_extractor_fuzz(engines):
+    """Adversarial token soup: the device extractor returns exactly the oracle's (type, start, end) set."""
+    eng, orc, _ = engines[1]
+    rng = random.Random(1234)
+    for it in range(400):
+        data = _fuzz_text(rng, rng.randint(0, 60) if it % 8 else rng.randint(300, 3000))
+        flags = rng.choice([31, 31, 31, 1, 2, 4, 8, 16, 5, 10, 21])
+        want = sorted((s, t, e) for t, s, e in orc.extract(data, flags))
+        got = sorted((s, t, e) for t, s, e in eng.extract(data, flags))
+        assert got == want, (it, flags, data[:200])
+
+
+def test_scan_fuzz_with_hits(engines, small_dbs):
+    """Token soup salted with real indicators of the mixed database: same records, same counters."""
+    from matchy_b200 import synth  # noqa: F401
+    eng, orc, log = engines[5]
+    rng = random.Random(99)
+    words = [w for w in log.replace(b"=", b" ").replace(b"\"", b" ").split() if b"." in w or len(w) in (32, 40, 64)]
+    for it in range(60):
+        parts = []
+        for _ in range(rng.randint(5, 400)):
+            parts.append(rng.choice(words) if rng.random() < 0.5 else rng.choice(FRAGS))
+            parts.append(rng.choice([b" ", b"\n", b" ", b"=", b","]))
+        data = b"".join(parts)
+        eng.scan(data)
+        want, wcnt = orc.scan(data)
+        assert eng.counters_list() == wcnt, it
+        assert eng.records_as_tuples() == want, it
+
+
+@pytest.mark.parametrize("data", [b"", b"\n", b"x", b"1.2.3.4", b"evil.com", b"no newline at the end 8.8.8.8", b"\n\n\n", b" " * 5000,
+                                  b"a" * 5000, b"a." * 5000 + b"com\n", b"@" * 3000, b":" * 3000, b"." * 3000])
+def test_edge_inputs(engines, data):
+    eng, orc, _ = engines[5]
+    eng.scan(data)
+    want, wcnt = orc.scan(data)
+    assert eng.counters_list() == wcnt
+    assert eng.records_as_tuples() == want
+
+
+def test_single_lookups(engines, small_dbs):
+    """Database.lookup / lookup_ip through the device tables == the oracle's single-query helpers."""
+    eng, orc, log = engines[5]
+    toks = [w for w in log.replace(b"=", b" ").replace(b"\"", b" ").split() if b"." in w][:300]
+    for w in toks + [b"", b"nothing.example.invalid", b"a" * 300]:
+        assert eng.lookup_string(w) == orc.lookup_string(w), w
+    rng = random.Random(5)
+    for _ in range(300):
+        a = rng.getrandbits(32)
+        rc, off, pl = orc.lookup_ip4(a)
+        found, goff, gpl = eng.lookup_ip(a.to_bytes(4, "big"))
+        assert (found, goff if found else 0, gpl if found else 0) == (rc == 1, off if rc == 1 else 0, pl if rc == 1 else 0)
+
+
+def test_full_size_properties(built):
+    """At a size the oracle cannot cover quickly: splitting the log must not change the summed counters, and
+    scanning the same buffer twice is idempotent (size-independent properties)."""
+    from matchy_b200 import Engine, synth
+    db = synth.build_db(5, 0.02)
+    log = synth.gen_log(5, 256 << 20, 0.02)
+    e = Engine(0, chunk_bytes=64 << 20)
+    e.upload(db)
+    e.set_keep_results(True)
+    e.scan(log)
+    whole = e.counters_list()
+    recs_whole = e.results()[0].copy()
+    e.scan(log)
+    assert e.counters_list() == whole
+    assert np.array_equal(e.results()[0], recs_whole)
+    half = (len(log) // 2) // 65536 * 65536  # block edges are line edges
+    acc = [0] * 16
+    n = 0
+    for a, b in ((0, half), (half, len(log))):
+        e.scan(log[a:b], base=a)
+        acc = [x + y for x, y in zip(acc, e.counters_list())]
+        n += len(e.results()[0])
+    assert acc == whole
+    assert n == len(recs_whole)
+    # a 16 MiB slice against the oracle
+    orc = O.Oracle(db)
+    sl = log[:16 << 20].tobytes()
+    e.scan(sl)
+    want, wcnt = orc.scan(sl, chunk_size=128 * 1024)
+    assert e.counters_list() == wcnt
+    assert e.records_as_tuples() == want
