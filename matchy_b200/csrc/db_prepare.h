@@ -51,7 +51,7 @@ inline bool build_psl(const uint8_t* text, size_t len, PslTable& t, std::string&
     uint64_t h = MGPU_FNV_BASIS;
     for (uint32_t k = en.second; k-- > 0;) h = psl_step(h, s[k]);
     if (h == 0) h = 1;
-    uint32_t slot = (uint32_t)(h >> 17) & t.mask;
+    uint32_t slot = psl_slot(h, t.mask);
     bool dup = false;
     while (t.keys[slot] != 0) {
       if (t.keys[slot] == h && (t.vals[slot] & 0xFF) == en.second && memcmp(t.pool.data() + (t.vals[slot] >> 8), s, en.second) == 0) { dup = true; break; }
@@ -71,6 +71,10 @@ struct PreparedDb {
   DbView view;                     // scalar members set; section pointers are the caller's business
   std::vector<uint32_t> lh_index;  // pattern_id -> data_offset
   std::vector<uint32_t> aclh;      // literal id -> (abs offset, count)
+  std::vector<uint64_t> lh_bloom;  // blocked Bloom filter over the literal table's stored hashes
+  std::vector<uint32_t> gram2, gram3;  // bitmaps over the first 2 / 3 bytes of every AC literal
+  std::vector<uint64_t> pfx_keys;      // prefix map (see DbView::ac_pfx_*)
+  std::vector<uint32_t> pfx_vals;
   uint32_t ac_node_count = 0;
 };
 
@@ -130,6 +134,21 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
           if (id <= max_id && P.lh_index[id] == NONE32) P.lh_index[id] = off;
         }
       }
+    }
+    {  // Bloom filter over every occupied slot's stored hash (the same XXH64 the lookup computes): no false negatives
+      uint32_t table_size = prep_le32(lh + 12);
+      uint64_t tstart = 32 + ((uint64_t)num_shards + 1) * 4;
+      if (tstart + (uint64_t)table_size * 16 > len) table_size = (uint32_t)((len - tstart) / 16);
+      uint64_t words = 1024;
+      while (words * 4 < table_size) words <<= 1;  // >= 16 bits per slot
+      P.lh_bloom.assign((size_t)words, 0);
+      for (uint32_t k = 0; k < table_size; k++) {
+        const uint8_t* e = lh + tstart + (uint64_t)k * 16;
+        if (prep_le32(e + 8) == NONE32) continue;
+        uint64_t h; memcpy(&h, e, 8);
+        P.lh_bloom[(size_t)((uint32_t)(h >> 20) & (uint32_t)(words - 1))] |= (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63));
+      }
+      db.lh_bloom_mask = (uint32_t)(words - 1);
     }
     db.lh_len = len; db.has_literal = 1;
     db.lh_num_shards = num_shards; db.lh_strings_offset = strings_offset; db.lh_table_start = 32 + (num_shards + 1) * 4;
@@ -201,6 +220,68 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
       }
       for (size_t k = 0; k + 1 < P.aclh.size(); k += 2) if (P.aclh[k] & 3) ok = false;
       if (!ok) { err = "paraglob automaton with out-of-range or unaligned offsets is not supported on the device"; return false; }
+    }
+    // Prefix bitmaps for the anchored walk: every trie path of length 2 / 3 from the root.  The anchored walk is only
+    // exact when no literal is shorter than 3 bytes (no outputs at depth < 3) and no node list is saturated at 255.
+    {
+      const uint8_t* ac = pg + db.ac_start;
+      P.gram2.assign(65536 / 32, 0);
+      P.gram3.assign((1u << 24) / 32, 0);
+      bool anchored = P.ac_node_count > 0;
+      auto children = [&](uint32_t off, std::vector<std::pair<uint8_t, uint32_t>>& out) {
+        out.clear();
+        const uint8_t* nd = ac + off;
+        uint32_t kind = nd[0], cnt = nd[2], eo = prep_le32(nd + 12);
+        if (kind == 1) out.push_back({nd[1], eo});
+        else if (kind == 2) for (uint32_t k = 0; k < cnt; k++) out.push_back({ac[eo + k * 8], prep_le32(ac + eo + k * 8 + 4)});
+        else if (kind == 3) for (uint32_t k = 0; k < 256; k++) { uint32_t t = prep_le32(ac + eo + k * 4); if (t) out.push_back({(uint8_t)k, t}); }
+      };
+      for (uint64_t i = 0; i < P.ac_node_count; i++) if (ac[i * 20 + 3] == 255) anchored = false;
+      if (P.ac_node_count > 0) {
+        if (ac[3] != 0) anchored = false;
+        std::vector<std::pair<uint8_t, uint32_t>> c1, c2, c3;
+        children(0, c1);
+        for (auto& a1 : c1) {
+          if (ac[a1.second + 3] != 0) anchored = false;
+          children(a1.second, c2);
+          for (auto& a2 : c2) {
+            if (ac[a2.second + 3] != 0) anchored = false;
+            uint32_t g2 = ((uint32_t)a1.first << 8) | a2.first;
+            P.gram2[g2 >> 5] |= 1u << (g2 & 31);
+            children(a2.second, c3);
+            for (auto& a3 : c3) { uint32_t g3 = (g2 << 8) | a3.first; P.gram3[g3 >> 5] |= 1u << (g3 & 31); }
+          }
+        }
+      }
+      db.ac_anchored = anchored ? 1u : 0u;
+      // Prefix map: every depth-8 trie node, and every node of depth 3..7 with outputs (a literal of that length or a
+      // merged suffix literal), keyed by the path bytes.  Exact: a jump lands on the node the step-by-step walk reaches.
+      if (anchored) {
+        struct Fr { uint32_t off; uint32_t depth; uint64_t v; };
+        std::vector<Fr> st{{0, 0, 0}};
+        struct En { uint64_t v; uint32_t m, off; };
+        std::vector<En> ents;
+        std::vector<std::pair<uint8_t, uint32_t>> ch;
+        uint32_t short_lens = 0;
+        while (!st.empty()) {
+          Fr f = st.back(); st.pop_back();
+          if (f.depth >= 3 && f.depth < 8 && ac[f.off + 3] != 0) { ents.push_back({f.v, f.depth, f.off}); short_lens |= 1u << f.depth; }
+          if (f.depth == 8) { ents.push_back({f.v, 8, f.off}); continue; }
+          children(f.off, ch);
+          for (auto& c1 : ch) st.push_back({c1.second, f.depth + 1, f.v | ((uint64_t)c1.first << (8 * f.depth))});
+        }
+        uint32_t cap = 1024;
+        while ((uint64_t)cap < ents.size() * 2 + 2) cap <<= 1;
+        P.pfx_keys.assign(cap, 0);
+        P.pfx_vals.assign((size_t)cap * 2, 0);
+        for (auto& e : ents) {
+          uint32_t slot = prefix_slot(e.v, e.m, cap - 1);
+          while (P.pfx_vals[2 * (size_t)slot + 1] != 0) slot = (slot + 1) & (cap - 1);
+          P.pfx_keys[slot] = e.v; P.pfx_vals[2 * (size_t)slot] = e.off; P.pfx_vals[2 * (size_t)slot + 1] = e.m;
+        }
+        db.ac_pfx_mask = cap - 1;
+        db.ac_short_lens = short_lens;
+      }
     }
     // glob segments: the device matcher keeps one frame per '*'
     uint32_t gso = db.glob_segments_offset;

@@ -43,6 +43,8 @@ struct DbView {
   uint32_t has_literal, lh_num_shards, lh_strings_offset, lh_table_start;
   const uint32_t* lh_data_index;  // derived: pattern_id -> data_offset of the FIRST mapping entry with that id (== linear scan :560-572)
   uint32_t lh_data_index_n;
+  const uint64_t* lh_bloom;       // derived: blocked Bloom filter over the stored 64-bit hashes (no false negatives): a miss
+  uint32_t lh_bloom_mask;         //          costs one load instead of a walk over a ~38-slot probe cluster
   // --- paraglob buffer ("PARAGLOB") ---
   const uint8_t* pg;
   uint32_t pg_len, has_glob;
@@ -51,6 +53,15 @@ struct DbView {
   uint32_t ac_start, ac_size, patterns_offset, wild_off, wild_count, glob_segments_offset;
   const uint32_t* aclh_index;     // derived: literal_id -> {abs offset of its pattern list in pg, count} (2 words each)
   uint32_t aclh_n;
+  const uint32_t* ac_gram2;       // derived: bitmap over the first 2 bytes of every AC literal (2^16 bits)
+  const uint32_t* ac_gram3;       // derived: bitmap over the first 3 bytes of every AC literal (2^24 bits)
+  uint32_t ac_anchored;           // 1: every literal has >= 3 bytes and no node list is saturated -> anchored walk is exact
+  // derived: exact open-addressing map  (m, first m bytes of a trie path) -> node offset, holding every depth-8 node and
+  // every node of depth 3..7 that has outputs.  An anchored walk jumps straight to depth 8 instead of taking 8 dependent steps.
+  const uint64_t* ac_pfx_keys;    // the m bytes, little-endian, zero-padded
+  const uint32_t* ac_pfx_vals;    // 2 words per slot: node offset, m (0 = empty slot)
+  uint32_t ac_pfx_mask;
+  uint32_t ac_short_lens;         // bit m set: some node of depth m (3 <= m < 8) has outputs
   const uint32_t* glob_data;      // [data_offset × count] array that follows the paraglob buffer (database.rs:212-228)
   uint32_t glob_data_n;
   uint32_t match_mode;            // 0 case-sensitive, 1 case-insensitive (ASCII folding)
@@ -200,9 +211,14 @@ MGPU_HD uint32_t utf8_decode(const uint8_t* t, uint32_t n, uint32_t pos, uint32_
 #define MGPU_FNV_BASIS 0xcbf29ce484222325ULL
 #define MGPU_FNV_PRIME 0x100000001b3ULL
 MGPU_HD uint64_t psl_step(uint64_t h, uint8_t b) { return (h ^ b) * MGPU_FNV_PRIME; }
+// FNV-1a mixes short strings poorly in any fixed bit window; finish with a multiply-xorshift before taking slot bits
+MGPU_HD uint32_t psl_slot(uint64_t key, uint32_t mask) {
+  key ^= key >> 29; key *= 0xBF58476D1CE4E5B9ULL; key ^= key >> 32;
+  return (uint32_t)key & mask;
+}
 MGPU_HDN bool psl_contains(const DbView& db, uint64_t key, const uint8_t* suffix, uint32_t len) {
   if (key == 0) key = 1;
-  uint32_t slot = (uint32_t)(key >> 17) & db.psl_mask;
+  uint32_t slot = psl_slot(key, db.psl_mask);
   for (;;) {
     uint64_t k = db.psl_keys[slot];
     if (k == 0) return false;
@@ -253,31 +269,31 @@ MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) 
   return true;
 }
 
-// A boundary-delimited word made only of domain characters (incl. bytes >= 0x80) that contains a '.':
-// is it a domain?  labels non-empty and not starting/ending with '-', >= 2 labels (implied by the dot),
-// some dot-suffix in the PSL, valid UTF-8.  (lib.rs:537-689)
-MGPU_HDN bool validate_domain_word(const DbView& db, const uint8_t* w, uint32_t n) {
-  if (n < 3) return false;
-  if (w[0] == '.' || w[0] == '-' || w[n - 1] == '.' || w[n - 1] == '-') return false;
-  // one backward pass: label structure, PSL probe (shortest suffix first), high-byte detection
+// A boundary-delimited word made only of domain characters (incl. bytes >= 0x80), containing a '.', whose labels are
+// non-empty and neither start nor end with '-' (all of that is established by the tokenizer's mask arithmetic):
+// is it a domain?  Remaining rules: some dot-suffix is in the PSL, and the bytes are valid UTF-8.  (lib.rs:537-689)
+MGPU_HDN bool domain_word_psl_utf8(const DbView& db, const uint8_t* w, uint32_t n) {
+  // shortest suffix first; the first hit decides (any hit accepts)
   uint64_t h = MGPU_FNV_BASIS;
-  bool psl_hit = false, psl_open = true, high = false;
-  for (uint32_t k = n; k-- > 0;) {
+  bool hit = false;
+  for (uint32_t k = n; k-- > 1;) {  // a dot at index 0 cannot occur (the first label is non-empty)
     uint8_t b = w[k];
     if (b == '.') {
-      // k is neither 0 nor n-1 here
-      if (w[k + 1] == '-' || w[k + 1] == '.' || w[k - 1] == '-') return false;
-      if (psl_open && !psl_hit) {
-        uint32_t sl = n - k - 1;
-        if (sl > db.psl_max_len) psl_open = false;
-        else psl_hit = psl_contains(db, h, w + k + 1, sl);
-      }
+      uint32_t sl = n - k - 1;
+      if (sl > db.psl_max_len) break;
+      if (psl_contains(db, h, w + k + 1, sl)) { hit = true; break; }
     }
-    high |= b >= 0x80;
     h = psl_step(h, b);
   }
-  if (!psl_hit) return false;
-  if (high && !valid_utf8(w, n)) return false;
+  if (!hit) return false;
+  // any byte >= 0x80?  word-wise scan (over-reads stay inside the buffer slack)
+  uint32_t high = 0;
+  for (uint32_t k = 0; k < n; k += 4) {
+    uint32_t v = ldu32_fast(w + k);
+    if (k + 4 > n) v &= 0xFFFFFFFFu >> (8 * (k + 4 - n));
+    high |= v;
+  }
+  if ((high & 0x80808080u) && !valid_utf8(w, n)) return false;
   return true;
 }
 
@@ -411,6 +427,10 @@ MGPU_HDN bool trie_lookup_v6(const DbView& db, const uint16_t seg[8], uint32_t& 
 MGPU_HDN bool lh_lookup(const DbView& db, const uint8_t* q, uint32_t n, uint32_t& pattern_id) {
   bool fold = db.match_mode == 1;
   uint64_t h = xxh64_fold(q, n, fold);
+  if (db.lh_bloom) {
+    uint64_t need = (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63));
+    if ((db.lh_bloom[(uint32_t)(h >> 20) & db.lh_bloom_mask] & need) != need) return false;  // certainly absent
+  }
   uint32_t shard = (uint32_t)(h % db.lh_num_shards);
   uint32_t s0 = ld32(db.lh + 32 + (size_t)shard * 4), s1 = ld32(db.lh + 32 + (size_t)shard * 4 + 4);
   uint32_t cap = s1 - s0;
@@ -586,11 +606,67 @@ MGPU_HD uint32_t ac_goto(const uint8_t* ac, const AcNode& nd, uint8_t ch) {
   return 0u;
 }
 
+// slot hash of an m-byte trie path held in the low bytes of v (m <= 8)
+MGPU_HD uint32_t prefix_slot(uint64_t v, uint32_t m, uint32_t mask) {
+  uint64_t k = (v ^ ((uint64_t)m * 0x9E3779B97F4A7C15ULL)) * 0xFF51AFD7ED558CCDULL;
+  k ^= k >> 33; k *= 0xC4CEB9FE1A85EC53ULL; k ^= k >> 29;
+  return (uint32_t)k & mask;
+}
+// node reached from the root by the m bytes in v, or 0 if the map has no such path (0 is the root: never a target)
+MGPU_HD uint32_t prefix_node(const DbView& db, uint64_t v, uint32_t m) {
+  uint32_t slot = prefix_slot(v, m, db.ac_pfx_mask);
+  for (;;) {
+    uint32_t len = db.ac_pfx_vals[2 * slot + 1];
+    if (len == 0) return 0u;
+    if (len == m && db.ac_pfx_keys[slot] == v) return db.ac_pfx_vals[2 * slot];
+    slot = (slot + 1) & db.ac_pfx_mask;
+  }
+}
+MGPU_HD uint64_t load_prefix8(const uint8_t* text, uint32_t pos, bool fold) {
+  if (!fold) return ldu64_fast(text + pos);
+  uint64_t v = 0;
+  for (uint32_t k = 0; k < 8; k++) v |= (uint64_t)lc(text[pos + k], true) << (8 * k);  // may read past the token: buffer slack
+  return v;
+}
+MGPU_HD uint64_t low_bytes(uint64_t v, uint32_t m) { return m >= 8 ? v : (v & ((1ULL << (8 * m)) - 1)); }
+
+struct AcAccel {
+  const uint32_t* root_tab;  // root's 256-entry dense table (maybe a shared-memory copy), or nullptr if the root is not dense
+  const uint32_t* gram2;     // 2-byte-prefix bitmap (maybe a shared-memory copy), or nullptr
+};
+
+// candidate patterns of one literal hit -> verification -> emit (paraglob_offset.rs:1136-1171)
+template <typename F>
+MGPU_HD void ac_outputs(const DbView& db, const uint8_t* ac, const AcNode& nd, const uint8_t* text, uint32_t tn, F&& emit) {
+  uint32_t pc = nd.w0 >> 24;
+  for (uint32_t k = 0; k < pc; k++) {
+    uint32_t lit = ld32(ac + nd.po + k * 4);
+    if (lit >= db.aclh_n) continue;
+    uint32_t lo = db.aclh_index[2 * lit], lcnt = db.aclh_index[2 * lit + 1];
+    for (uint32_t j = 0; j < lcnt; j++) {
+      uint32_t pid = ld32(db.pg + lo + j * 4);
+      uint64_t eo = (uint64_t)db.patterns_offset + (uint64_t)pid * 16;
+      if (eo + 16 > db.pg_len) continue;
+      uint32_t entry_id = ld32(db.pg + eo);
+      if (db.pg[eo + 4] == 0) emit(entry_id);                 // literal-type pattern: accepted on the AC hit alone
+      else if (glob_match(db, entry_id, text, tn)) emit(entry_id);
+    }
+  }
+}
+
 // Visit every glob id find_all would return for `text` (before sort+dedup; duplicates possible).
 // run_ac_matching_into_static :1186-1266 + ACLH map + verification :1136-1171, pure wildcards :1096-1134.
-// root_tab: the root's 256-entry dense table (possibly a shared-memory copy) or nullptr when the root is not dense.
+//
+// Two result-identical ways to find the literal ids that occur in the text:
+//  * the reference's Aho-Corasick walk (goto / failure links, suffix outputs merged into every node);
+//  * ANCHORED walks (when db.ac_anchored): for every start position whose first 2 and 3 bytes begin some literal
+//    (exact bitmaps built at upload), follow goto edges only, from the root, until they stop.  A literal that occurs
+//    at [i, j) is found by the walk anchored at i; every id listed at a node reached from i is a suffix of
+//    text[i..j], hence occurs too.  Same id SET as the AC walk (duplicates differ, they are removed later anyway).
+//    Benign tokens leave the first shared-memory bitmap test at almost every position, and lanes do not diverge
+//    in failure-link loops.
 template <typename F>
-MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn, const uint32_t* root_tab, F&& emit) {
+MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn, const AcAccel& acc, F&& emit) {
   if (db.pg_len < 112) return;
   // pure wildcards are tested on every query
   for (uint32_t i = 0; i < db.wild_count; i++) {
@@ -604,32 +680,73 @@ MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn,
   const uint8_t* ac = db.pg + db.ac_start;
   const bool fold = db.match_mode == 1;
   const AcNode root = ac_fetch(ac, 0);
-  uint32_t cur = 0;
-  AcNode nd = root;
-  for (uint32_t i = 0; i < tn; i++) {
-    uint8_t ch = lc(text[i], fold);
+  if (db.ac_anchored && acc.gram2) {
+    if (tn < 3) return;  // every literal has at least 3 bytes
+    // One event per loop iteration (either test the next start position or take one goto step of the current walk), so the
+    // lanes of a warp stay in one loop instead of serialising each other's inner walks.
+    uint32_t g = ((uint32_t)lc(text[0], fold) << 8) | lc(text[1], fold);
+    uint32_t i = 0, j = 0;
+    bool walking = false;
+    AcNode nd = root;
     for (;;) {
-      uint32_t nx = (cur == 0 && root_tab) ? root_tab[ch] : ac_goto(ac, nd, ch);
-      if (nx) { cur = nx; nd = ac_fetch(ac, cur); break; }
-      if (cur == 0) break;  // at the root: stay
-      cur = nd.fail;
-      nd = cur ? ac_fetch(ac, cur) : root;
-    }
-    uint32_t pc = nd.w0 >> 24;
-    if (pc == 0) continue;
-    for (uint32_t k = 0; k < pc; k++) {
-      uint32_t lit = ld32(ac + nd.po + k * 4);
-      if (lit >= db.aclh_n) continue;
-      uint32_t lo = db.aclh_index[2 * lit], lcnt = db.aclh_index[2 * lit + 1];
-      for (uint32_t j = 0; j < lcnt; j++) {
-        uint32_t pid = ld32(db.pg + lo + j * 4);
-        uint64_t eo = (uint64_t)db.patterns_offset + (uint64_t)pid * 16;
-        if (eo + 16 > db.pg_len) continue;
-        uint32_t entry_id = ld32(db.pg + eo);
-        if (db.pg[eo + 4] == 0) emit(entry_id);                 // literal-type pattern: accepted on the AC hit alone
-        else if (glob_match(db, entry_id, text, tn)) emit(entry_id);
+      if (!walking) {
+        if (i + 2 >= tn) break;
+        uint32_t g2 = g & 0xFFFF;
+        g = (g << 8) | lc(text[i + 2], fold);
+        if ((acc.gram2[g2 >> 5] >> (g2 & 31)) & 1u) {
+          uint32_t g3 = g & 0xFFFFFF;
+          if ((db.ac_gram3[g3 >> 5] >> (g3 & 31)) & 1u) {
+            // outputs at depth 3..7, then jump to the depth-8 node
+            uint64_t v = load_prefix8(text, i, fold);
+            uint32_t avail = tn - i;
+            for (uint32_t lens = db.ac_short_lens; lens; lens &= lens - 1) {
+#ifdef __CUDA_ARCH__
+              uint32_t m = (uint32_t)__ffs((int)lens) - 1u;
+#else
+              uint32_t m = (uint32_t)__builtin_ctz(lens);
+#endif
+              if (m > avail) break;
+              uint32_t off = prefix_node(db, low_bytes(v, m), m);
+              if (off) { AcNode sn = ac_fetch(ac, off); ac_outputs(db, ac, sn, text, tn, emit); }
+            }
+            if (avail >= 8) {
+              uint32_t off = prefix_node(db, v, 8);
+              if (off) {
+                nd = ac_fetch(ac, off);
+                if (nd.w0 >> 24) ac_outputs(db, ac, nd, text, tn, emit);
+                j = i + 8;
+                walking = j < tn;
+              }
+            }
+          }
+        }
+        i++;
+      } else {
+        uint32_t nx = ac_goto(ac, nd, lc(text[j], fold));
+        if (!nx) { walking = false; continue; }
+        nd = ac_fetch(ac, nx);
+        if (nd.w0 >> 24) ac_outputs(db, ac, nd, text, tn, emit);
+        if (++j >= tn) walking = false;
       }
     }
+    return;
+  }
+  // reference formulation, one automaton event per iteration (transition, stay at root, or failure hop)
+  uint32_t cur = 0;
+  AcNode nd = root;
+  uint32_t i = 0;
+  uint8_t ch = lc(text[0], fold);
+  while (i < tn) {
+    uint32_t nx = (cur == 0 && acc.root_tab) ? acc.root_tab[ch] : ac_goto(ac, nd, ch);
+    if (!nx && cur != 0) {  // failure hop: retry the same byte from the fallback state
+      cur = nd.fail;
+      nd = cur ? ac_fetch(ac, cur) : root;
+      continue;
+    }
+    if (nx) { cur = nx; nd = ac_fetch(ac, cur); }
+    if (nd.w0 >> 24) ac_outputs(db, ac, nd, text, tn, emit);
+    i++;
+    if (i < tn) ch = lc(text[i], fold);
   }
 }
 // the root's dense table, if the root is a Dense state

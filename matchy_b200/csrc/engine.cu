@@ -176,30 +176,34 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     m.NL = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 0);
     m.DM = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 1);
     m.HX = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 2);
+    m.DASH = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 3);
     if (tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
       uint64_t valid = a.n > p ? a.n - p : 0;
       uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
       if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
-      m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep;
+      m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep; m.DASH &= keep;
     }
-    if (!cy.pT) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
+    if (!(cy.prev & PV_T)) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
     lines += __popc(m.NL);
     sB[lane] = m.B;
     __syncwarp();
 
     const uint32_t T = ~m.B;
-    uint32_t pT = __shfl_up_sync(0xFFFFFFFFu, T >> 31, 1);
-    uint32_t pCL = __shfl_up_sync(0xFFFFFFFFu, m.CL >> 30, 1);  // bit 1: byte -1 is ':', bit 0: byte -2 is ':'
-    if (lane == 0) { pT = cy.pT; pCL = cy.pCL; }  // lane 0 looks into the previous tile
+    const uint32_t my_prev = prev_bits_of(m);
+    uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, my_prev, 1);
+    if (lane == 0) pv = cy.prev;  // lane 0 looks into the previous tile
+    const uint32_t pT = pv & PV_T;
     const uint32_t S = T & ~((T << 1) | pT);
+    uint32_t bad, bad_end;
+    domain_rule_masks(m, S, pv, bad, bad_end);
 
     uint32_t A_DM, A_DN, A_HX;
     {
       uint32_t g, pr, co;
-      uint32_t G = m.DM, Sg = S & G;
+      uint32_t G = m.DM & ~bad, Sg = S & G;  // well-formed domain bytes
       gp_bits(G, Sg, g, pr);
       uint32_t cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cDM, co);
-      A_DM = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B);
+      A_DM = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B) & ~bad_end;
       cy.cDM = co;
       G = m.DM & ~m.DOT; Sg = S & G;
       gp_bits(G, Sg, g, pr);
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     uint32_t candHex = (want_hash && pT) ? (A_HX & (m.B & (0u - m.B))) : 0u;
     uint32_t candAt = want_at ? m.AT : 0u;
     // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
-    uint32_t cl1 = (m.CL << 1) | (pCL >> 1), cl2 = (m.CL << 2) | pCL;
+    uint32_t cl1 = (m.CL << 1) | ((pv >> 3) & 1u), cl2 = (m.CL << 2) | (((pv >> 3) & 1u) << 1) | ((pv >> 4) & 1u);
     uint32_t candC2 = want_c2 ? (m.CL & cl1 & ~cl2) : 0u;
 
     // ---- emission ----
@@ -274,8 +278,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
       cy.open_start = tile_base + (uint64_t)ll * 32 + (31u - (uint32_t)__clz((int)Bl)) + 1;
     }
-    cy.pT = __shfl_sync(0xFFFFFFFFu, T >> 31, 31);
-    cy.pCL = __shfl_sync(0xFFFFFFFFu, m.CL >> 30, 31);
+    cy.prev = __shfl_sync(0xFFFFFFFFu, my_prev, 31);
     __syncwarp();
   }
 #pragma unroll
@@ -294,10 +297,11 @@ static const int KT_THREADS = 256;  // validate / lithash / acglob block size
 static const int KT_WARPS = KT_THREADS / 32;
 
 // Returns p with p[pos] readable for pos in [lo, hi + 16).  Falls back to the global buffer for wide windows.
-__device__ __forceinline__ const uint8_t* stage_window(const uint8_t* buf, uint8_t* win, uint32_t lo, uint32_t hi, uint32_t lane) {
+__device__ __forceinline__ const uint8_t* stage_window(const uint8_t* buf, uint8_t* win, uint32_t lo, uint32_t hi, uint32_t lane,
+                                                       uint32_t win_bytes = WIN_BYTES) {
   if (lo >= hi) return buf;
   const uint32_t alo = lo & ~15u, ahi = (hi + 31u) & ~15u;
-  if (ahi - alo > WIN_BYTES) return buf;
+  if (ahi - alo > win_bytes) return buf;
   __syncwarp();
   for (uint32_t o = alo + lane * 16; o < ahi; o += 512) *reinterpret_cast<uint4*>(win + (o - alo)) = *reinterpret_cast<const uint4*>(buf + o);
   __syncwarp();
@@ -317,23 +321,48 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K2 validate: candidate -> token.  One thread per candidate, block-aggregated appends.
+// K2 validate: candidate -> token.  One thread per candidate.  Every warp owns a contiguous range of the candidate
+// index space, so the tokens it appends stay in log order (the lookup kernels rely on that for their windows);
+// appends go through per-warp reservations of TOK_RESERVE slots, unused slots are marked invalid.
 // ---------------------------------------------------------------------------------------------------------
+static const uint32_t TOK_RESERVE = 128;
+static const uint32_t TOK_INVALID = 0xFFu;  // StrTok.type / IpTok.type of a padding slot
+
+__device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap, uint32_t need, uint32_t lane, QueueCursor& c,
+                                                 StrTok* str, IpTok* ip, uint32_t* overflow, uint32_t ovf_bit) {
+  if (need <= c.left) { uint32_t b = c.base; c.base += need; c.left -= need; return b; }
+  for (uint32_t i = lane; i < c.left; i += 32) { if (str) str[c.base + i].type = TOK_INVALID; else ip[c.base + i].type = TOK_INVALID; }
+  uint32_t sz = need > TOK_RESERVE ? need : TOK_RESERVE;
+  uint32_t b = 0;
+  if (lane == 0) b = atomicAdd(counter, sz);
+  b = __shfl_sync(0xFFFFFFFFu, b, 0);
+  if ((uint64_t)b + sz > cap) {
+    if (lane == 0) atomicOr(overflow, ovf_bit);
+    for (uint32_t i = b + lane; i < cap; i += 32) { if (str) str[i].type = TOK_INVALID; else ip[i].type = TOK_INVALID; }
+    c.base = 0; c.left = 0;
+    return NONE32;
+  }
+  c.base = b + need; c.left = sz - need;
+  return b;
+}
+
 __global__ void __launch_bounds__(KT_THREADS) validate_kernel(ScanArgs a) {
   __shared__ __align__(16) uint8_t s_win[KT_WARPS][WIN_BYTES + 32];
-  __shared__ uint32_t s_warp[KT_WARPS];
-  __shared__ uint32_t s_base[2];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nD = min(a.ctr->q_count[Q_DOTTED], a.cap_q[Q_DOTTED]);
   const uint32_t nH = min(a.ctr->q_count[Q_HASH], a.cap_q[Q_HASH]);
   const uint32_t nA = min(a.ctr->q_count[Q_AT], a.cap_q[Q_AT]);
   const uint32_t nC = min(a.ctr->q_count[Q_COLON2], a.cap_q[Q_COLON2]);
   const uint64_t total = (uint64_t)nD + nH + nA + nC;
-  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t nwarps = (uint64_t)gridDim.x * KT_WARPS;
+  const uint64_t per = ((total + nwarps - 1) / nwarps + 31) & ~(uint64_t)31;
+  const uint64_t w_begin = ((uint64_t)blockIdx.x * KT_WARPS + warp) * per;
+  uint64_t w_end = w_begin + per;
+  if (w_end > total) w_end = total;
+  QueueCursor cs{0, 0}, ci{0, 0};
   uint32_t n_dom = 0, n_mail = 0, n_v4 = 0, n_v6 = 0, n_md5 = 0, n_sha1 = 0, n_sha256 = 0, n_sha384 = 0, n_sha512 = 0;
-  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < total; i0 += step) {
-    const uint64_t i = i0 + threadIdx.x;
-    const uint64_t w0 = i0 + warp * 32;  // first entry of this warp
+  for (uint64_t w0 = w_begin; w0 < w_end; w0 += 32) {
+    const uint64_t i = w0 + lane;
     bool ws = false, wi = false;
     StrTok st{0, 0, 0};
     IpTok it{0, 0, 0, 0, {0, 0, 0, 0}};
@@ -350,11 +379,11 @@ __global__ void __launch_bounds__(KT_THREADS) validate_kernel(ScanArgs a) {
         if ((a.flags & MGPU_X_IPV4) && parse_ipv4_word(wp, c.len, addr)) {
           wi = true; it.start = c.start; it.len = c.len; it.type = MGPU_T_IPV4; it.w[0] = addr;
         }
-        if ((a.flags & MGPU_X_DOMAINS) && validate_domain_word(a.db, wp, c.len)) {
+        if ((a.flags & MGPU_X_DOMAINS) && domain_word_psl_utf8(a.db, wp, c.len)) {
           ws = true; st.start = c.start; st.len = c.len; st.type = MGPU_T_DOMAIN;
         }
       }
-    } else if (i < total) {
+    } else if (i < w_end) {
       if (i < nD) {
         Cand c = a.q_dotted[i];
         if (c.start != NONE32 && (uint64_t)c.start + c.len <= a.n) {
@@ -363,7 +392,7 @@ __global__ void __launch_bounds__(KT_THREADS) validate_kernel(ScanArgs a) {
           if ((a.flags & MGPU_X_IPV4) && parse_ipv4_word(wp, c.len, addr)) {
             wi = true; it.start = c.start; it.len = c.len; it.type = MGPU_T_IPV4; it.w[0] = addr;
           }
-          if ((a.flags & MGPU_X_DOMAINS) && validate_domain_word(a.db, wp, c.len)) {
+          if ((a.flags & MGPU_X_DOMAINS) && domain_word_psl_utf8(a.db, wp, c.len)) {
             ws = true; st.start = c.start; st.len = c.len; st.type = MGPU_T_DOMAIN;
           }
         }
@@ -388,27 +417,23 @@ __global__ void __launch_bounds__(KT_THREADS) validate_kernel(ScanArgs a) {
         }
       }
     }
-    uint32_t ts, ti;
-    uint32_t es = block_excl_scan(ws ? 1u : 0u, s_warp, ts);
-    uint32_t ei = block_excl_scan(wi ? 1u : 0u, s_warp, ti);
-    if (threadIdx.x == 0) {
-      s_base[0] = ts ? atomicAdd(&a.ctr->n_str, ts) : 0;
-      s_base[1] = ti ? atomicAdd(&a.ctr->n_ip, ti) : 0;
+    const uint32_t bs = __ballot_sync(0xFFFFFFFFu, ws), bi = __ballot_sync(0xFFFFFFFFu, wi);
+    if (bs) {
+      uint32_t b = tok_reserve(&a.ctr->n_str, a.cap_str, __popc(bs), lane, cs, a.str, nullptr, &a.ctr->overflow, 1u << 8);
+      if (ws && b != NONE32) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
+      if (ws) {
+        n_dom += st.type == MGPU_T_DOMAIN; n_mail += st.type == MGPU_T_EMAIL; n_md5 += st.type == MGPU_T_MD5; n_sha1 += st.type == MGPU_T_SHA1;
+        n_sha256 += st.type == MGPU_T_SHA256; n_sha384 += st.type == MGPU_T_SHA384; n_sha512 += st.type == MGPU_T_SHA512;
+      }
     }
-    __syncthreads();
-    if (ws) {
-      uint32_t k = s_base[0] + es;
-      if (k < a.cap_str) a.str[k] = st; else atomicOr(&a.ctr->overflow, 1u << 8);
-      n_dom += st.type == MGPU_T_DOMAIN; n_mail += st.type == MGPU_T_EMAIL; n_md5 += st.type == MGPU_T_MD5; n_sha1 += st.type == MGPU_T_SHA1;
-      n_sha256 += st.type == MGPU_T_SHA256; n_sha384 += st.type == MGPU_T_SHA384; n_sha512 += st.type == MGPU_T_SHA512;
+    if (bi) {
+      uint32_t b = tok_reserve(&a.ctr->n_ip, a.cap_ip, __popc(bi), lane, ci, nullptr, a.ip, &a.ctr->overflow, 1u << 9);
+      if (wi && b != NONE32) a.ip[b + __popc(bi & ((1u << lane) - 1u))] = it;
+      if (wi) { n_v4 += it.type == MGPU_T_IPV4; n_v6 += it.type == MGPU_T_IPV6; }
     }
-    if (wi) {
-      uint32_t k = s_base[1] + ei;
-      if (k < a.cap_ip) a.ip[k] = it; else atomicOr(&a.ctr->overflow, 1u << 9);
-      n_v4 += it.type == MGPU_T_IPV4; n_v6 += it.type == MGPU_T_IPV6;
-    }
-    __syncthreads();
   }
+  for (uint32_t i = lane; i < cs.left; i += 32) a.str[cs.base + i].type = TOK_INVALID;
+  for (uint32_t i = lane; i < ci.left; i += 32) a.ip[ci.base + i].type = TOK_INVALID;
   // per-type candidate counters (WorkerStats): warp-reduce, one atomic per warp and type
   uint32_t cnt[9] = {n_dom, n_mail, n_v4, n_v6, n_md5, n_sha1, n_sha256, n_sha384, n_sha512};
 #pragma unroll
@@ -436,6 +461,7 @@ __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
   if (!a.db.has_ip) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     IpTok t = a.ip[i];
+    if (t.type == TOK_INVALID) continue;
     uint32_t off = 0; uint8_t pl = 0; bool hit;
     if (t.type == MGPU_T_IPV4) hit = trie_lookup_v4(a.db, t.w[0], off, pl);
     else {
@@ -454,10 +480,11 @@ __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
 }
 
 // tokens of one warp iteration -> staged window pointer
-__device__ __forceinline__ const uint8_t* stage_tokens(const ScanArgs& a, uint8_t* win, bool valid, const StrTok& t, uint32_t lane) {
+__device__ __forceinline__ const uint8_t* stage_tokens(const ScanArgs& a, uint8_t* win, bool valid, const StrTok& t, uint32_t lane,
+                                                       uint32_t win_bytes = WIN_BYTES) {
   uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, valid ? t.start : 0xFFFFFFFFu);
   uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, valid ? t.start + t.len : 0u);
-  return stage_window(a.buf, win, lo, hi, lane);
+  return stage_window(a.buf, win, lo, hi, lane, win_bytes);
 }
 
 // K4: literal hash probe per string token
@@ -467,9 +494,9 @@ __global__ void __launch_bounds__(KT_THREADS) lithash_kernel(ScanArgs a) {
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
   const uint32_t nround = (n + 31u) & ~31u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
-    const bool valid = i < n;
+    bool valid = i < n;
     StrTok t{0, 0, 0};
-    if (valid) t = a.str[i];
+    if (valid) { t = a.str[i]; valid = t.type != TOK_INVALID; }
     const uint8_t* p = stage_tokens(a, s_win[warp], valid, t, lane);
     if (!valid) continue;
     uint32_t pid = NONE32;
@@ -478,30 +505,181 @@ __global__ void __launch_bounds__(KT_THREADS) lithash_kernel(ScanArgs a) {
   }
 }
 
-// K5: Aho-Corasick walk + glob verification per string token, merge with the literal result, emit
-__global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
-  __shared__ __align__(16) uint8_t s_win[KT_WARPS][WIN_BYTES + 32];
-  __shared__ uint32_t s_root[256];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t* root_tab = ac_root_table(a.db);
-  if (root_tab) {  // hot state in shared memory: every token byte that does not continue a literal goes through the root
-    s_root[threadIdx.x] = root_tab[threadIdx.x];
-    __syncthreads();
-    root_tab = s_root;
+// K5: Paraglob::find_all per string token, merge with the literal result, emit.
+//
+// Almost every token matches nothing, so the kernel first answers, for the 32 tokens of a warp, "does ANY automaton
+// literal occur in this token?" and only flagged tokens (plus every token when the database has pure-wildcard
+// patterns) take the exact find_all path.  The filter is the anchored search of device_fns.cuh split in two so that lanes
+// stay busy:  (1) every lane scans its own token for start positions whose first 2 bytes begin some literal (bitmap in
+// shared memory) and pushes them into a warp-shared queue;  (2) the queue is dealt round-robin to the lanes, which apply
+// the exact 3-byte bitmap and the 8-byte prefix filter (L2) and then follow goto edges from the root, one step per loop
+// iteration, until a node with outputs is reached (flag the token) or the path ends.  No failure links, no per-lane
+// inner loops.
+static const uint32_t SCAN_ROUND = 8;     // positions a lane scans per round
+static const uint32_t ANCHOR_CAP = 384;   // queue A: positions that passed the 2-byte bitmap (drained above 128 entries)
+static const uint32_t WALK_CAP = 128;     // queue B: positions that also passed the 3-byte bitmap and the 8-byte prefix filter
+
+// The prefilter handles case-sensitive databases only (the reference's default and all BASELINE configs); with a
+// case-insensitive database every token takes the exact path, which folds ASCII case itself.
+
+// queue A -> queue B: exact 3-byte prefix bitmap, then the prefix map (both in L2): a node with outputs at depth 3..7 flags
+// the token at once; a depth-8 node goes into queue B as (token lane, position, node offset).  Every lane takes entries
+// lane, lane+32, ... of the slice [from, to).
+__device__ __forceinline__ void filter_anchors(const ScanArgs& a, const uint8_t* p, const uint32_t* s_start, const uint32_t* s_len,
+                                               const uint32_t* s_anchor, uint32_t from, uint32_t to, uint2* s_walk, uint32_t* s_wcnt,
+                                               uint32_t* s_hit, uint32_t lane) {
+  for (uint32_t k = from + lane; k < to; k += 32) {
+    uint32_t an = s_anchor[k];
+    uint32_t tl = an & 31u, j = an >> 5;
+    if ((*(volatile const uint32_t*)s_hit >> tl) & 1u) continue;  // already flagged: it takes the exact path anyway
+    const uint8_t* text = p + s_start[tl];
+    uint32_t g3 = ((uint32_t)text[j] << 16) | ((uint32_t)text[j + 1] << 8) | text[j + 2];
+    if (!((a.db.ac_gram3[g3 >> 5] >> (g3 & 31)) & 1u)) continue;
+    const uint32_t avail = s_len[tl] - j;
+    const uint64_t v = ldu64_fast(text + j);
+    bool hit = false;
+    for (uint32_t lens = a.db.ac_short_lens; lens && !hit; lens &= lens - 1) {
+      uint32_t m = (uint32_t)__ffs((int)lens) - 1u;
+      if (m > avail) break;
+      hit = prefix_node(a.db, low_bytes(v, m), m) != 0;  // such nodes have outputs by construction
+    }
+    if (hit) { atomicOr(s_hit, 1u << tl); continue; }
+    if (avail < 8) continue;
+    uint32_t off = prefix_node(a.db, v, 8);
+    if (!off) continue;
+    s_walk[atomicAdd(s_wcnt, 1u)] = make_uint2(an, off);
   }
+}
+
+// queue B: continue from the depth-8 node along goto edges, one step per loop iteration, until a node with outputs
+// (flag the token) or the end of the path.  Entries are dealt round-robin, so with >= 32 entries every lane walks.
+__device__ __forceinline__ void walk_anchors(const ScanArgs& a, const uint8_t* p, const uint32_t* s_start, const uint32_t* s_len,
+                                             const uint2* s_walk, uint32_t cnt, uint32_t* s_hit, uint32_t lane) {
+  const uint8_t* ac = a.db.pg + a.db.ac_start;
+  uint32_t my = lane, j = 0, tn = 0, tl = 0;
+  const uint8_t* text = nullptr;
+  bool walking = false;
+  AcNode nd{0, 0, 0, 0};
+  for (;;) {
+    if (!walking) {
+      if (my >= cnt) break;
+      uint2 e = s_walk[my];
+      my += 32;
+      tl = e.x & 31u;
+      if ((*(volatile uint32_t*)s_hit >> tl) & 1u) continue;
+      j = (e.x >> 5) + 8; tn = s_len[tl]; text = p + s_start[tl];
+      nd = ac_fetch(ac, e.y);
+      if (nd.w0 >> 24) { atomicOr(s_hit, 1u << tl); continue; }
+      walking = j < tn;
+      continue;
+    }
+    uint32_t nx = ac_goto(ac, nd, text[j]);
+    if (!nx) { walking = false; continue; }
+    nd = ac_fetch(ac, nx);
+    if (nd.w0 >> 24) { atomicOr(s_hit, 1u << tl); walking = false; continue; }
+    if (++j >= tn) walking = false;
+  }
+}
+
+__device__ __forceinline__ void drain_anchors(const ScanArgs& a, const uint8_t* p, const uint32_t* s_start,
+                                              const uint32_t* s_len, const uint32_t* s_anchor, uint32_t cnt, uint2* s_walk, uint32_t* s_wcnt,
+                                              uint32_t* s_hit, uint32_t lane) {
+  for (uint32_t from = 0; from < cnt; from += WALK_CAP) {  // a slice of A can put at most WALK_CAP entries into B
+    uint32_t to = min(from + WALK_CAP, cnt);
+    filter_anchors(a, p, s_start, s_len, s_anchor, from, to, s_walk, s_wcnt, s_hit, lane);
+    __syncwarp();
+    walk_anchors(a, p, s_start, s_len, s_walk, *(volatile uint32_t*)s_wcnt, s_hit, lane);
+    __syncwarp();
+    if (lane == 0) *s_wcnt = 0;
+    __syncwarp();
+  }
+}
+
+static const uint32_t ACG_WIN = 2048;  // token window of this kernel (smaller than WIN_BYTES: shared memory buys occupancy here)
+static const size_t ACGLOB_SMEM = KT_WARPS * (ACG_WIN + 32) + (256 + 2048 + KT_WARPS * (ANCHOR_CAP + 2 * WALK_CAP) + 2 * KT_WARPS * 32 + 3 * KT_WARPS) * 4;
+
+__global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];  // ACGLOB_SMEM bytes, carved below
+  uint8_t (*s_win)[ACG_WIN + 32] = reinterpret_cast<uint8_t (*)[ACG_WIN + 32]>(dyn_smem);
+  uint32_t* s_root = reinterpret_cast<uint32_t*>(dyn_smem + KT_WARPS * (ACG_WIN + 32));
+  uint32_t* s_gram2 = s_root + 256;
+  uint32_t (*s_anchor)[ANCHOR_CAP] = reinterpret_cast<uint32_t (*)[ANCHOR_CAP]>(s_gram2 + 2048);
+  uint2 (*s_walk)[WALK_CAP] = reinterpret_cast<uint2 (*)[WALK_CAP]>(s_gram2 + 2048 + KT_WARPS * ANCHOR_CAP);
+  uint32_t (*s_start)[32] = reinterpret_cast<uint32_t (*)[32]>(s_gram2 + 2048 + KT_WARPS * (ANCHOR_CAP + 2 * WALK_CAP));
+  uint32_t (*s_len)[32] = s_start + KT_WARPS;
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_len + KT_WARPS);
+  uint32_t* s_hit = s_cnt + KT_WARPS;
+  uint32_t* s_wcnt = s_hit + KT_WARPS;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // hot state in shared memory: the root's dense table (every walk starts there) and the 2-byte prefix bitmap that
+  // almost every token position fails
+  AcAccel acc;
+  acc.root_tab = ac_root_table(a.db);
+  acc.gram2 = nullptr;
+  if (acc.root_tab) { s_root[threadIdx.x] = acc.root_tab[threadIdx.x]; acc.root_tab = s_root; }
+  if (a.db.has_glob && a.db.ac_gram2) {
+    for (uint32_t k = threadIdx.x; k < 2048; k += blockDim.x) s_gram2[k] = a.db.ac_gram2[k];
+    acc.gram2 = s_gram2;
+  }
+  __syncthreads();
+  const bool use_filter = a.db.has_glob && a.db.ac_anchored && acc.gram2 && a.db.wild_count == 0 && a.db.ac_size >= 20 && a.db.match_mode == 0;
+  AcNode root{0, 0, 0, 0};
+  if (a.db.has_glob && a.db.ac_size >= 20) root = ac_fetch(a.db.pg + a.db.ac_start, 0);
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
   const uint32_t nround = (n + 31u) & ~31u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
-    const bool valid = i < n;
+    bool valid = i < n;
     StrTok t{0, 0, 0};
-    if (valid) t = a.str[i];
-    const uint8_t* p = stage_tokens(a, s_win[warp], valid, t, lane);
+    if (valid) { t = a.str[i]; valid = t.type != TOK_INVALID; }
+    const uint8_t* p = stage_tokens(a, s_win[warp], valid, t, lane, ACG_WIN);
+    bool exact = valid && a.db.has_glob;
+    if (use_filter) {
+      // ---- (1) anchors ----
+      s_start[warp][lane] = t.start; s_len[warp][lane] = valid ? t.len : 0u;
+      if (lane == 0) { s_cnt[warp] = 0; s_hit[warp] = 0; s_wcnt[warp] = 0; }
+      __syncwarp();
+      const uint8_t* text = p + t.start;
+      const uint32_t tn = valid ? t.len : 0u;
+      const uint32_t npos = tn >= 3 ? tn - 2 : 0u;  // start positions with at least 3 bytes left
+      uint32_t qn = 0;                              // entries in queue A (warp-uniform)
+      uint32_t g = npos ? (uint32_t)text[0] : 0u;
+      for (uint32_t pos0 = 0; __any_sync(0xFFFFFFFFu, pos0 < npos); pos0 += SCAN_ROUND) {
+        // one round: SCAN_ROUND positions per lane, branch-free; hits are collected in a register mask
+        uint32_t hits = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < SCAN_ROUND; r++) {
+          uint32_t pos = pos0 + r;
+          if (pos < npos) {
+            g = ((g << 8) | text[pos + 1]) & 0xFFFFu;  // bytes pos, pos+1
+            hits |= ((acc.gram2[g >> 5] >> (g & 31)) & 1u) << r;
+          }
+        }
+        uint32_t cnt = __popc(hits), incl = warp_incl_scan(cnt, lane);
+        uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t at = qn + incl - cnt;
+        while (hits) { uint32_t r = __ffs(hits) - 1; hits &= hits - 1; s_anchor[warp][at++] = ((pos0 + r) << 5) | lane; }
+        qn += total;
+        __syncwarp();
+        if (qn + 32 * SCAN_ROUND > ANCHOR_CAP) {  // ---- (2) filters + walks, when the next round might not fit ----
+          drain_anchors(a, p, s_start[warp], s_len[warp], s_anchor[warp], qn, s_walk[warp], &s_wcnt[warp], &s_hit[warp], lane);
+          qn = 0;
+        }
+      }
+      if (lane == 0) s_cnt[warp] = qn;
+      __syncwarp();
+      drain_anchors(a, p, s_start[warp], s_len[warp], s_anchor[warp], s_cnt[warp], s_walk[warp], &s_wcnt[warp], &s_hit[warp], lane);
+      __syncwarp();
+      exact = valid && ((s_hit[warp] >> lane) & 1u);
+      __syncwarp();
+    }
     if (!valid) continue;
     const uint8_t* text = p + t.start;
     uint32_t lit_pid = a.db.has_literal ? a.lh_res[i] : NONE32, lit_off = 0;
     bool lit_ok = lit_pid != NONE32 && lh_data_offset(a.db, lit_pid, lit_off);
+    if (!lit_ok && !exact) continue;
+    // ---- exact path (rare): every id find_all returns, sorted and deduplicated ----
     uint32_t cnt = 0;
-    if (a.db.has_glob) find_all_visit(a.db, text, t.len, root_tab, [&](uint32_t) { cnt++; });
+    if (exact) find_all_visit(a.db, text, t.len, acc, [&](uint32_t) { cnt++; });
     if (!lit_ok && cnt == 0) continue;
     uint32_t total = cnt + (lit_ok ? 1u : 0u);
     uint32_t b = agg_add(&a.ctr->n_ids, total);
@@ -510,7 +688,7 @@ __global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
     if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
     const uint32_t g0 = k;
     if (cnt) {
-      find_all_visit(a.db, text, t.len, root_tab, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
+      find_all_visit(a.db, text, t.len, acc, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
       // sort_unstable + dedup (paraglob_offset.rs:1173-1181)
       for (uint32_t x = g0 + 1; x < k; x++) {
         uint32_t v = a.ids[x].pattern_id, y = x;
@@ -573,7 +751,9 @@ __global__ void query_string_kernel(ScanArgs a, uint32_t len, uint32_t* out_n) {
   uint32_t pid, off;
   if (a.db.has_literal && lh_lookup(a.db, a.buf, len, pid) && lh_data_offset(a.db, pid, off)) { if (n < a.cap_ids) { a.ids[n].pattern_id = pid; a.ids[n].data_offset = off; } n++; }
   uint32_t g0 = n;
-  if (a.db.has_glob) find_all_visit(a.db, a.buf, len, ac_root_table(a.db), [&](uint32_t p) { if (n < a.cap_ids) a.ids[n].pattern_id = p; n++; });
+  AcAccel acc;
+  acc.root_tab = ac_root_table(a.db); acc.gram2 = a.db.ac_gram2;  // global copies: one thread, no shared-memory staging
+  if (a.db.has_glob) find_all_visit(a.db, a.buf, len, acc, [&](uint32_t p) { if (n < a.cap_ids) a.ids[n].pattern_id = p; n++; });
   uint32_t k = n < a.cap_ids ? n : a.cap_ids;
   for (uint32_t x = g0 + 1; x < k; x++) {
     uint32_t v = a.ids[x].pattern_id, y = x;
@@ -647,6 +827,7 @@ struct mgpu_ctx {
   mgpu_counters counters{};
   mgpu_timing timing{};
   bool keep_results = true;
+  bool force_ac_walk = false;
   std::vector<StrTok> x_str; std::vector<IpTok> x_ip;  // extraction-only capture
   bool capture_tokens = false;
 };
@@ -737,6 +918,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMallocHost(&c->h_cut, 64 * sizeof(uint64_t) * 2));
   CK(cudaMalloc(&c->d_small, 65536 + TILE_BYTES));
   CK(cudaMalloc(&c->d_small_out, 64));
+  CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
   CK(cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8 + (K1_THREADS / 32) * 32 * 4));
   return MGPU_OK;
 }
@@ -748,6 +930,7 @@ mgpu_ctx* mgpu_create(int device, size_t chunk_bytes) {
 }
 
 void mgpu_set_keep_results(mgpu_ctx* c, int keep) { c->keep_results = keep != 0; }
+void mgpu_set_ac_mode(mgpu_ctx* c, int mode) { c->force_ac_walk = mode == 1; }
 
 // ---- PSL ------------------------------------------------------------------------------------------------
 int mgpu_set_psl(mgpu_ctx* c, const uint8_t* text, size_t len) {
@@ -804,6 +987,9 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
     rc = dev_copy(c, P.lh_index.data(), P.lh_index.size() * 4, 0, 256, &p);
     if (rc) return rc;
     db.lh_data_index = (const uint32_t*)p;
+    rc = dev_copy(c, P.lh_bloom.data(), P.lh_bloom.size() * 8, 0, 256, &p);
+    if (rc) return rc;
+    db.lh_bloom = (const uint64_t*)p;
   }
   if (L.has_glob) {
     rc = dev_copy(c, d + L.pg_off, (size_t)L.pg_len, 0, 256, &p);
@@ -812,6 +998,20 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
     rc = dev_copy(c, P.aclh.data(), P.aclh.size() * 4, 0, 256, &p);
     if (rc) return rc;
     db.aclh_index = (const uint32_t*)p;
+    rc = dev_copy(c, P.gram2.data(), P.gram2.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.ac_gram2 = (const uint32_t*)p;
+    rc = dev_copy(c, P.gram3.data(), P.gram3.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.ac_gram3 = (const uint32_t*)p;
+    if (!P.pfx_keys.empty()) {
+      rc = dev_copy(c, P.pfx_keys.data(), P.pfx_keys.size() * 8, 0, 256, &p);
+      if (rc) return rc;
+      db.ac_pfx_keys = (const uint64_t*)p;
+      rc = dev_copy(c, P.pfx_vals.data(), P.pfx_vals.size() * 4, 0, 256, &p);
+      if (rc) return rc;
+      db.ac_pfx_vals = (const uint32_t*)p;
+    }
     rc = dev_copy(c, d + L.map_off, (size_t)L.map_count * 4, 0, 256, &p);
     if (rc) return rc;
     db.glob_data = (const uint32_t*)p;
@@ -845,6 +1045,7 @@ uint32_t mgpu_default_flags(mgpu_ctx* c) {
 static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, bool lookups) {
   ScanArgs a = c->args;
   a.buf = d_buf; a.lo = lo; a.n = n; a.base = base; a.flags = flags;
+  if (c->force_ac_walk) a.db.ac_anchored = 0;
   cudaStream_t st = c->compute;
   CK(cudaMemsetAsync(a.ctr, 0, sizeof(DevCounters), st));
   CK(cudaEventRecord(c->ev_k[0], st));
@@ -865,7 +1066,7 @@ static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t 
     CK(cudaEventRecord(c->ev_k[3], st));
     if (a.db.has_literal) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
     CK(cudaEventRecord(c->ev_k[4], st));
-    if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
+    if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, st>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
     CK(cudaEventRecord(c->ev_k[5], st));
   } else {
     for (int k = 3; k <= 5; k++) CK(cudaEventRecord(c->ev_k[k], st));
@@ -939,7 +1140,10 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
     c->x_str.resize(s0 + h.n_str); c->x_ip.resize(i0 + h.n_ip);
     if (h.n_str) CK(cudaMemcpy(c->x_str.data() + s0, c->args.str, (size_t)h.n_str * sizeof(StrTok), cudaMemcpyDeviceToHost));
     if (h.n_ip) CK(cudaMemcpy(c->x_ip.data() + i0, c->args.ip, (size_t)h.n_ip * sizeof(IpTok), cudaMemcpyDeviceToHost));
-    for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);  // extraction is limited to < 4 GiB inputs
+    // drop the padding slots of the per-warp reservations, then make offsets absolute (extraction is limited to < 4 GiB inputs)
+    c->x_str.erase(std::remove_if(c->x_str.begin() + s0, c->x_str.end(), [](const StrTok& t) { return t.type == TOK_INVALID; }), c->x_str.end());
+    c->x_ip.erase(std::remove_if(c->x_ip.begin() + i0, c->x_ip.end(), [](const IpTok& t) { return t.type == TOK_INVALID; }), c->x_ip.end());
+    for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);
     for (size_t k = i0; k < c->x_ip.size(); k++) c->x_ip[k].start += (uint32_t)(base + al);
   }
   if (c->keep_results && h.n_rec) {

@@ -19,7 +19,7 @@
 
 namespace mgpu {
 
-enum { CLS_B = 0, CLS_DOT = 1, CLS_AT = 2, CLS_CL = 3, CLS_NL = 4, CLS_DM = 5, CLS_HX = 6 };
+enum { CLS_B = 0, CLS_DOT = 1, CLS_AT = 2, CLS_CL = 3, CLS_NL = 4, CLS_DM = 5, CLS_HX = 6, CLS_DASH = 7 };
 enum { Q_DOTTED = 0, Q_HASH = 1, Q_AT = 2, Q_COLON2 = 3, Q_COUNT = 4 };
 static const uint32_t TILE_BYTES = 1024;
 static const uint32_t SLICE_BYTES = 32;
@@ -33,18 +33,31 @@ MGPU_HD uint32_t class_bits(uint8_t b) {
   if (b == '\n') c |= 1u << CLS_NL;
   if (is_domain_fast(b)) c |= 1u << CLS_DM;
   if (is_hex(b)) c |= 1u << CLS_HX;
+  if (b == '-') c |= 1u << CLS_DASH;
   return c;
 }
 
-struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX; };
+struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX, DASH; };
 
 // State carried into a tile (identical in all lanes of the warp).
 struct TileCarry {
-  uint32_t pT;          // previous byte is a word byte
-  uint32_t pCL;         // bit 1: previous byte is ':', bit 0: the byte before that is ':'
-  uint32_t cDM, cDN, cHX;  // the open word so far is all domain bytes / all dot-less domain bytes / all hex
-  uint64_t open_start;  // chunk offset where the open word starts (valid when pT)
+  uint32_t prev;        // facts about the bytes just before the tile: PV_* bits
+  uint32_t cDM, cDN, cHX;  // the open word so far is a well-formed domain prefix / all dot-less domain bytes / all hex
+  uint64_t open_start;  // chunk offset where the open word starts (valid when prev & PV_T)
 };
+// bits of the "previous bytes" word that travels lane -> lane (one shuffle) and tile -> tile
+enum { PV_T = 1, PV_DOT = 2, PV_DASH = 4, PV_CL1 = 8, PV_CL2 = 16 };  // byte -1 is a word byte / '.' / '-' / ':' ; byte -2 is ':'
+MGPU_HD uint32_t prev_bits_of(const LaneMasks& m) {  // the same facts about a slice's own last bytes, for its successor
+  return ((~m.B) >> 31) | ((m.DOT >> 31) << 1) | ((m.DASH >> 31) << 2) | ((m.CL >> 31) << 3) | (((m.CL >> 30) & 1u) << 4);
+}
+// Domain label rules as byte-adjacency facts (is_valid_domain / is_valid_label, lib.rs:637-689): no empty label ("..",
+// leading or trailing '.'), no label starting or ending with '-'.  `bad` marks bytes that break a rule when looking back;
+// `bad_end` marks boundary positions whose preceding byte may not end a domain.
+MGPU_HD void domain_rule_masks(const LaneMasks& m, uint32_t S, uint32_t pv, uint32_t& bad, uint32_t& bad_end) {
+  uint32_t prevDOT = (m.DOT << 1) | ((pv >> 1) & 1u), prevDASH = (m.DASH << 1) | ((pv >> 2) & 1u);
+  bad = (m.DOT & (prevDOT | prevDASH)) | (m.DASH & prevDOT) | (S & (m.DOT | m.DASH));
+  bad_end = prevDOT | prevDASH;
+}
 
 // carry generate/propagate of (G + Sg) for one lane
 MGPU_HD void gp_bits(uint32_t G, uint32_t Sg, uint32_t& g, uint32_t& p) {
@@ -92,21 +105,27 @@ MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len ==
 // word that is open there.
 MGPU_HDN TileCarry range_prologue(const uint8_t* buf, uint64_t lo, uint64_t a) {
   TileCarry c;
-  c.pT = 0; c.pCL = 0; c.cDM = 0; c.cDN = 0; c.cHX = 0; c.open_start = a;
+  c.prev = 0; c.cDM = 0; c.cDN = 0; c.cHX = 0; c.open_start = a;
   if (a <= lo) return c;
   uint8_t prev = buf[a - 1];
-  c.pCL = (prev == ':' ? 2u : 0u) | ((a >= lo + 2 && buf[a - 2] == ':') ? 1u : 0u);
+  c.prev = (prev == '.' ? (uint32_t)PV_DOT : 0u) | (prev == '-' ? (uint32_t)PV_DASH : 0u) | (prev == ':' ? (uint32_t)PV_CL1 : 0u) |
+           ((a >= lo + 2 && buf[a - 2] == ':') ? (uint32_t)PV_CL2 : 0u);
   if (is_boundary(prev)) return c;
-  c.pT = 1;
+  c.prev |= PV_T;
   uint32_t dm = 1, dn = 1, hx = 1;
   uint64_t s = a;
+  uint8_t right = 0;  // the byte to the right of b inside the open word (0 = none yet)
   while (s > lo) {
     uint8_t b = buf[s - 1];
     if (is_boundary(b)) break;
     bool d = is_domain_fast(b);
     dm &= d; dn &= (d && b != '.'); hx &= is_hex(b);
+    if (right == '.' && (b == '.' || b == '-')) dm = 0;  // "..", "-."
+    if (right == '-' && b == '.') dm = 0;                // ".-"
+    right = b;
     s--;
   }
+  if (right == '.' || right == '-') dm = 0;  // the word starts with '.' or '-'
   c.cDM = dm; c.cDN = dn; c.cHX = hx; c.open_start = s;
   return c;
 }

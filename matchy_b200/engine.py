@@ -120,6 +120,10 @@ class Engine:
     def set_keep_results(self, keep: bool):
         self.L.mgpu_set_keep_results(self.h, 1 if keep else 0)
 
+    def set_ac_mode(self, mode: int):
+        """0: automatic; 1: force the reference's Aho-Corasick walk instead of anchored walks (same results)."""
+        self.L.mgpu_set_ac_mode(self.h, int(mode))
+
     def extract(self, data, flags=X_SUPPORTED):
         """[(item_type, start, end), ...] sorted by (start, item_type)."""
         p, n, keep = N.as_ptr(data)

@@ -37,6 +37,8 @@ def lib():
         L.emu_error.restype = C.c_char_p
         L.emu_error.argtypes = [C.c_void_p]
         L.emu_db_upload.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.emu_set_anchored.argtypes = [C.c_void_p, C.c_int]
+        L.emu_is_anchored_exact.argtypes = [C.c_void_p]
         L.emu_default_flags.restype = C.c_uint32
         L.emu_default_flags.argtypes = [C.c_void_p]
         L.emu_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int]
@@ -69,6 +71,13 @@ class Emu:
 
     def default_flags(self):
         return self.L.emu_default_flags(self.h)
+
+    def set_anchored(self, on: bool):
+        """Choose between the anchored literal search and the Aho-Corasick formulation (both must give the oracle's answer)."""
+        self.L.emu_set_anchored(self.h, 1 if on else 0)
+
+    def anchored_exact(self):
+        return bool(self.L.emu_is_anchored_exact(self.h))
 
     def scan(self, data: bytes, flags=None, base=0, chunk_bytes=0, nwarps=1, misalign=0, lookups=True):
         if flags is None:

@@ -30,6 +30,7 @@ struct emu_ctx {
   PslTable psl;
   DbView db;
   bool loaded = false;
+  bool use_anchored = true;  // false: force the Aho-Corasick formulation (both are exercised by the tests)
   std::vector<mgpu_match> recs;
   std::vector<mgpu_id_pair> ids;
   mgpu_counters counters;
@@ -56,30 +57,31 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
       uint32_t sB[32];
       for (uint32_t lane = 0; lane < 32; lane++) {
         uint64_t p = tile_base + (uint64_t)lane * 32;
-        LaneMasks x{0, 0, 0, 0, 0, 0, 0};
+        LaneMasks x{0, 0, 0, 0, 0, 0, 0, 0};
         for (uint32_t i = 0; i < 32; i++) {
           uint64_t q = p + i;
           uint32_t c = (q >= lo && q < n) ? class_bits(buf[q]) : (1u << CLS_B);
           x.B |= ((c >> CLS_B) & 1u) << i; x.DOT |= ((c >> CLS_DOT) & 1u) << i; x.AT |= ((c >> CLS_AT) & 1u) << i;
           x.CL |= ((c >> CLS_CL) & 1u) << i; x.NL |= ((c >> CLS_NL) & 1u) << i; x.DM |= ((c >> CLS_DM) & 1u) << i;
-          x.HX |= ((c >> CLS_HX) & 1u) << i;
+          x.HX |= ((c >> CLS_HX) & 1u) << i; x.DASH |= ((c >> CLS_DASH) & 1u) << i;
         }
         m[lane] = x; sB[lane] = x.B;
         lines += (uint64_t)__builtin_popcount(x.NL);
       }
-      if (!cy.pT) cy.open_start = tile_base;
-      uint32_t pT[32], pCL[32], S[32];
+      if (!(cy.prev & PV_T)) cy.open_start = tile_base;
+      uint32_t pT[32], pv[32], S[32], bad[32], bad_end[32];
       for (uint32_t lane = 0; lane < 32; lane++) {
-        pT[lane] = lane ? (~m[lane - 1].B) >> 31 : cy.pT;
-        pCL[lane] = lane ? m[lane - 1].CL >> 30 : cy.pCL;
+        pv[lane] = lane ? prev_bits_of(m[lane - 1]) : cy.prev;
+        pT[lane] = pv[lane] & PV_T;
         uint32_t T = ~m[lane].B;
         S[lane] = T & ~((T << 1) | pT[lane]);
+        domain_rule_masks(m[lane], S[lane], pv[lane], bad[lane], bad_end[lane]);
       }
       uint32_t A[3][32];
       for (int cls = 0; cls < 3; cls++) {
         uint32_t gen = 0, prop = 0, G[32], Sg[32];
         for (uint32_t lane = 0; lane < 32; lane++) {
-          G[lane] = cls == 0 ? m[lane].DM : cls == 1 ? (m[lane].DM & ~m[lane].DOT) : m[lane].HX;
+          G[lane] = cls == 0 ? (m[lane].DM & ~bad[lane]) : cls == 1 ? (m[lane].DM & ~m[lane].DOT) : m[lane].HX;
           Sg[lane] = S[lane] & G[lane];
           uint32_t g, p;
           gp_bits(G[lane], Sg[lane], g, p);
@@ -87,7 +89,8 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         }
         uint32_t& c0 = cls == 0 ? cy.cDM : cls == 1 ? cy.cDN : cy.cHX;
         uint32_t co, cv = carry_chain(gen, prop, c0, co);
-        for (uint32_t lane = 0; lane < 32; lane++) A[cls][lane] = all_class_ends(G[lane], Sg[lane], (cv >> lane) & 1u, m[lane].B);
+        for (uint32_t lane = 0; lane < 32; lane++)
+          A[cls][lane] = all_class_ends(G[lane], Sg[lane], (cv >> lane) & 1u, m[lane].B) & (cls == 0 ? ~bad_end[lane] : 0xFFFFFFFFu);
         c0 = co;
       }
       for (uint32_t lane = 0; lane < 32; lane++) {
@@ -95,7 +98,7 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         uint32_t candDot = want_dot ? (A[0][lane] & ~A[1][lane]) : 0u;
         uint32_t candHex = (want_hash && pT[lane]) ? (A[2][lane] & (m[lane].B & (0u - m[lane].B))) : 0u;
         uint32_t candAt = want_at ? m[lane].AT : 0u;
-        uint32_t cl1 = (m[lane].CL << 1) | (pCL[lane] >> 1), cl2 = (m[lane].CL << 2) | pCL[lane];
+        uint32_t cl1 = (m[lane].CL << 1) | ((pv[lane] >> 3) & 1u), cl2 = (m[lane].CL << 2) | (((pv[lane] >> 3) & 1u) << 1) | ((pv[lane] >> 4) & 1u);
         uint32_t candC2 = want_c2 ? (m[lane].CL & cl1 & ~cl2) : 0u;
         for (uint32_t mm = candDot; mm; mm &= mm - 1) {
           uint32_t bit = (uint32_t)__builtin_ctz(mm);
@@ -116,8 +119,7 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         uint32_t ll = 31u - (uint32_t)__builtin_clz(hasB);
         cy.open_start = tile_base + (uint64_t)ll * 32 + (31u - (uint32_t)__builtin_clz(m[ll].B)) + 1;
       }
-      cy.pT = (~m[31].B) >> 31;
-      cy.pCL = m[31].CL >> 30;
+      cy.prev = prev_bits_of(m[31]);
     }
   }
 }
@@ -134,7 +136,7 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
     const uint8_t* wp = buf + cd.start;
     uint32_t addr;
     if ((flags & MGPU_X_IPV4) && parse_ipv4_word(wp, cd.len, addr)) c->ip.push_back(IpTok{cd.start, cd.len, MGPU_T_IPV4, {addr, 0, 0, 0}});
-    if ((flags & MGPU_X_DOMAINS) && validate_domain_word(db, wp, cd.len)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
+    if ((flags & MGPU_X_DOMAINS) && domain_word_psl_utf8(db, wp, cd.len)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
   }
   for (auto& cd : qh) {
     uint32_t ty = cd.len == 32 ? MGPU_T_MD5 : cd.len == 40 ? MGPU_T_SHA1 : cd.len == 64 ? MGPU_T_SHA256 : cd.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
@@ -181,7 +183,9 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
       if (db.has_literal && !lh_lookup(db, text, t.len, lit_pid)) lit_pid = NONE32;
       bool lit_ok = lit_pid != NONE32 && lh_data_offset(db, lit_pid, lit_off);
       std::vector<uint32_t> g;
-      if (db.has_glob) find_all_visit(db, text, t.len, ac_root_table(db), [&](uint32_t pid) { g.push_back(pid); });
+      AcAccel acc;
+      acc.root_tab = ac_root_table(db); acc.gram2 = c->use_anchored ? db.ac_gram2 : nullptr;
+      if (db.has_glob) find_all_visit(db, text, t.len, acc, [&](uint32_t pid) { g.push_back(pid); });
       if (!lit_ok && g.empty()) continue;
       std::sort(g.begin(), g.end());
       g.erase(std::unique(g.begin(), g.end()), g.end());
@@ -215,9 +219,12 @@ int emu_db_upload(emu_ctx* c, const uint8_t* mxy, size_t len) {
   c->db = c->P.view;
   const mxy::Layout& L = c->P.L;
   c->db.tree = c->file.data();
-  if (L.has_literal) { c->db.lh = c->file.data() + L.lit_off; c->db.lh_data_index = c->P.lh_index.data(); }
+  if (L.has_literal) { c->db.lh = c->file.data() + L.lit_off; c->db.lh_data_index = c->P.lh_index.data(); c->db.lh_bloom = c->P.lh_bloom.data(); }
   if (L.has_glob) {
     c->db.pg = c->file.data() + L.pg_off; c->db.aclh_index = c->P.aclh.data();
+    c->db.ac_gram2 = c->P.gram2.data(); c->db.ac_gram3 = c->P.gram3.data();
+    c->db.ac_pfx_keys = c->P.pfx_keys.empty() ? nullptr : c->P.pfx_keys.data();
+    c->db.ac_pfx_vals = c->P.pfx_vals.empty() ? nullptr : c->P.pfx_vals.data();
     c->db.glob_data = reinterpret_cast<const uint32_t*>(c->file.data() + L.map_off);
   }
   c->db.psl_keys = c->psl.keys.data(); c->db.psl_vals = c->psl.vals.data(); c->db.psl_pool = c->psl.pool.data();
@@ -225,6 +232,9 @@ int emu_db_upload(emu_ctx* c, const uint8_t* mxy, size_t len) {
   c->loaded = true;
   return MGPU_OK;
 }
+
+void emu_set_anchored(emu_ctx* c, int on) { c->use_anchored = on != 0; }
+int emu_is_anchored_exact(emu_ctx* c) { return (int)c->db.ac_anchored; }
 
 uint32_t emu_default_flags(emu_ctx* c) {
   uint32_t f = 0;

@@ -18,6 +18,10 @@ def test_configs(small_dbs, cfg):
     want = orc.scan(log, chunk_size=128 * 1024)
     for chunk, nwarps, mis in ((0, 1, 0), (70000, 3, 5), (0, 7, 15), (150000, 64, 9)):
         assert emu.scan(log, chunk_bytes=chunk, nwarps=nwarps, misalign=mis) == want, (chunk, nwarps, mis)
+    if cfg in (2, 5):
+        assert emu.anchored_exact()
+        emu.set_anchored(False)  # the Aho-Corasick formulation must give the same answer as the anchored walks
+        assert emu.scan(log) == want
 
 
 def test_extractor_fuzz(small_dbs):
@@ -84,3 +88,28 @@ def test_case_insensitive_database(built):
     want = orc.scan(data)
     assert len(want[0]) >= 4
     assert emu.scan(data) == want
+
+
+def test_literal_search_formulations_agree(built):
+    """Anchored walks (device default) vs Aho-Corasick walk on overlapping / nested / repeated literals; a database with a
+    2-byte literal must switch the anchored mode off."""
+    from matchy_b200 import DatabaseBuilder
+    b = DatabaseBuilder(build_epoch=1)
+    for g in ("*abcab*", "*bcabc*", "*cab*", "*.evil.com", "*evil.com*", "*l.c*", "*aaa*", "*aaaa*", "x*aaa*y", "*abc*abc*", "abcabc"):
+        b.add_glob(g, {"g": g})
+    db = b.build()
+    orc, emu = O.Oracle(db), E.Emu(db)
+    assert emu.anchored_exact()
+    texts = [b"abcabcab", b"xabcabcy", b"aaaaaaa", b"xaaay", b"www.evil.com", b"evil.com.evil.com", b"cabcabcabc.abcab", b"l.c", b"ab", b"abc"]
+    data = b" ".join(texts) + b"\n" + b"".join(b"h=" + t + b".example.com\n" for t in texts)
+    want = orc.scan(data)
+    assert len(want[0]) >= 10
+    assert emu.scan(data) == want
+    emu.set_anchored(False)
+    assert emu.scan(data) == want
+    b.add_glob("zz", {"g": "short"})  # Literal-type pattern of 2 bytes goes into the automaton
+    db2 = b.build()
+    orc2, emu2 = O.Oracle(db2), E.Emu(db2)
+    assert not emu2.anchored_exact()
+    data2 = data + b"q=buzz.example.com zz.example.org\n"
+    assert emu2.scan(data2) == orc2.scan(data2)

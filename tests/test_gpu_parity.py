@@ -184,3 +184,28 @@ def test_full_size_properties(built):
     want, wcnt = orc.scan(sl, chunk_size=128 * 1024)
     assert e.counters_list() == wcnt
     assert e.records_as_tuples() == want
+
+
+def test_literal_search_formulations_agree_on_device(engines, small_dbs):
+    """The anchored-walk fast path and the Aho-Corasick walk give identical records on the device."""
+    from matchy_b200 import DatabaseBuilder, Engine
+    for cfg in (2, 5):
+        eng, orc, log = engines[cfg]
+        eng.scan(log)
+        a = (eng.records_as_tuples(), eng.counters_list())
+        eng.set_ac_mode(1)
+        eng.scan(log)
+        b = (eng.records_as_tuples(), eng.counters_list())
+        eng.set_ac_mode(0)
+        assert a == b
+    bld = DatabaseBuilder(build_epoch=1)
+    for g in ("*abcab*", "*bcabc*", "*cab*", "*.evil.com", "*evil.com*", "*aaa*", "*aaaa*", "*abc*abc*", "abcabc", "zz"):
+        bld.add_glob(g, {"g": g})
+    db = bld.build()
+    e = Engine(0)
+    e.upload(db)
+    orc = O.Oracle(db)
+    data = b"".join(b"h=" + t + b".example.com\n" for t in [b"abcabcab", b"xabcabcy", b"aaaaaaa", b"www.evil.com", b"buzz", b"cabcabcabc.abcab"])
+    e.scan(data)
+    want, wcnt = orc.scan(data)
+    assert e.records_as_tuples() == want and e.counters_list() == wcnt and len(want) >= 5
