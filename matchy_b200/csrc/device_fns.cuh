@@ -227,7 +227,12 @@ MGPU_HDN bool psl_contains(const DbView& db, uint64_t key, const uint8_t* suffix
       if ((v & 0xFF) == len) {
         const uint8_t* e = db.psl_pool + (v >> 8);
         bool eq = true;
-        for (uint32_t i = 0; i < len; i++) if (e[i] != suffix[i]) { eq = false; break; }
+        uint32_t i = 0;
+        for (; i + 8 <= len && eq; i += 8) eq = ldu64_fast(e + i) == ldu64_fast(suffix + i);
+        if (eq && i < len) {  // 1..7 bytes left (both buffers have >= 16 bytes of slack)
+          uint64_t m = (1ULL << (8 * (len - i))) - 1;
+          eq = ((ldu64_fast(e + i) ^ ldu64_fast(suffix + i)) & m) == 0;
+        }
         if (eq) return true;
       }
     }
@@ -273,26 +278,30 @@ MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) 
 // non-empty and neither start nor end with '-' (all of that is established by the tokenizer's mask arithmetic):
 // is it a domain?  Remaining rules: some dot-suffix is in the PSL, and the bytes are valid UTF-8.  (lib.rs:537-689)
 MGPU_HDN bool domain_word_psl_utf8(const DbView& db, const uint8_t* w, uint32_t n) {
-  // shortest suffix first; the first hit decides (any hit accepts)
-  uint64_t h = MGPU_FNV_BASIS;
-  bool hit = false;
-  for (uint32_t k = n; k-- > 1;) {  // a dot at index 0 cannot occur (the first label is non-empty)
-    uint8_t b = w[k];
-    if (b == '.') {
-      uint32_t sl = n - k - 1;
-      if (sl > db.psl_max_len) break;
-      if (psl_contains(db, h, w + k + 1, sl)) { hit = true; break; }
-    }
-    h = psl_step(h, b);
-  }
-  if (!hit) return false;
-  // any byte >= 0x80?  word-wise scan (over-reads stay inside the buffer slack)
+  // any byte >= 0x80?  word-wise scan, done first while the lanes of a warp are still in step
   uint32_t high = 0;
   for (uint32_t k = 0; k < n; k += 4) {
     uint32_t v = ldu32_fast(w + k);
     if (k + 4 > n) v &= 0xFFFFFFFFu >> (8 * (k + 4 - n));
     high |= v;
   }
+  // PSL: shortest suffix first; any hit accepts.  The last label is hashed in a loop of its own so that the lanes probe
+  // the table together; longer suffixes (only needed after a miss) follow in the general loop.
+  uint64_t h = MGPU_FNV_BASIS;
+  uint32_t k = n;
+  while (k > 1 && w[k - 1] != '.') { h = psl_step(h, w[k - 1]); k--; }
+  // w[k-1] == '.' (k >= 2) or k == 1 (no dot past index 0: cannot happen for tokenizer output, handled as a miss)
+  bool hit = false;
+  while (k >= 2) {
+    uint32_t sl = n - k;  // suffix = w[k .. n)
+    if (sl > db.psl_max_len) break;
+    if (psl_contains(db, h, w + k, sl)) { hit = true; break; }
+    h = psl_step(h, '.');
+    k--;
+    while (k > 1 && w[k - 1] != '.') { h = psl_step(h, w[k - 1]); k--; }
+    if (k == 1) break;  // the remaining dot-free prefix is the first label: no further suffix
+  }
+  if (!hit) return false;
   if ((high & 0x80808080u) && !valid_utf8(w, n)) return false;
   return true;
 }
