@@ -120,8 +120,9 @@ int mgpu_results(mgpu_ctx*, const mgpu_match** recs, size_t* n_recs, const mgpu_
 int mgpu_counters_get(mgpu_ctx*, mgpu_counters* out);
 int mgpu_timing_get(mgpu_ctx*, mgpu_timing* out);
 void mgpu_set_keep_results(mgpu_ctx*, int keep); /* 0: count matches only (bench), 1: default */
-/* literal search inside Paraglob::find_all: 0 = automatic (anchored walks when provably identical), 1 = always the
- * reference's Aho-Corasick goto/failure walk.  Results are identical either way; the switch exists for tests. */
+/* String lookups: 0 = automatic (constant-time filters + sparse exact lookups when the database allows it, anchored
+ * walks when provably identical), 1 = generic kernels with the reference's Aho-Corasick goto/failure walk, 2 = generic
+ * kernels with anchored walks.  Results are identical in every mode; the switch exists for tests. */
 void mgpu_set_ac_mode(mgpu_ctx*, int mode);
 
 /* Extraction only (== Extractor::extract_from_chunk): triples (item_type, start, end) as uint64, sorted by

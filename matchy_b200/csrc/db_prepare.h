@@ -17,6 +17,7 @@ struct PslTable {
   std::vector<uint32_t> vals;
   std::vector<uint8_t> pool;
   uint32_t mask = 0, max_len = 0;
+  std::vector<uint64_t> tld;  // last-label table for tld_class(): TLD_SLOTS entries
 };
 
 // lines().map(trim).filter(non-empty, not "//…") — matchy-extractor/src/lib.rs:1552-1563
@@ -63,6 +64,33 @@ inline bool build_psl(const uint8_t* text, size_t len, PslTable& t, std::string&
     t.pool.insert(t.pool.end(), s, s + en.second);
     t.max_len = std::max(t.max_len, en.second);
   }
+  // Last-label table.  ACCEPT entries: single-label PSL entries of <= 7 bytes.  SLOW entries: labels of <= 7 bytes that end
+  // some multi-label entry without being an entry themselves.  (Longer labels always take the general walk.)
+  {
+    t.tld.assign(TLD_SLOTS, 0);
+    auto key_of = [&](const uint8_t* s, uint32_t n) { uint64_t k = 0; for (uint32_t i = 0; i < n; i++) k |= (uint64_t)s[i] << (8 * i); return k | ((uint64_t)n << 56); };
+    auto find = [&](uint64_t key) -> uint64_t* {
+      uint32_t slot = tld_slot(key);
+      while (t.tld[slot] != 0 && (t.tld[slot] & ~TLD_SLOW) != key) slot = (slot + 1) & (TLD_SLOTS - 1);
+      return &t.tld[slot];
+    };
+    size_t used = 0;
+    for (int pass = 0; pass < 2; pass++)
+      for (auto& en : ent) {
+        const uint8_t* s = text + en.first;
+        uint32_t n = en.second, ld = n;
+        while (ld > 0 && s[ld - 1] != '.') ld--;
+        bool single = ld == 0;
+        uint32_t ll = n - ld;
+        if (ll == 0 || ll > 7) continue;
+        if ((pass == 0) != single) continue;
+        uint64_t key = key_of(s + ld, ll);
+        uint64_t* e = find(key);
+        if (*e != 0) continue;  // pass 1: already an ACCEPT entry (or a SLOW duplicate)
+        if (++used > TLD_SLOTS * 3 / 4) { err = "PSL has too many distinct last labels for the device table"; return false; }
+        *e = single ? key : (key | TLD_SLOW);
+      }
+  }
   return true;
 }
 
@@ -75,8 +103,13 @@ struct PreparedDb {
   std::vector<uint32_t> gram2, gram3;  // bitmaps over the first 2 / 3 bytes of every AC literal
   std::vector<uint64_t> pfx_keys;      // prefix map (see DbView::ac_pfx_*)
   std::vector<uint32_t> pfx_vals;
+  std::vector<uint32_t> hot;           // fast string path: hot (shared-memory) and cold (L2) Bloom filters
+  std::vector<uint64_t> cold;
   uint32_t ac_node_count = 0;
 };
+
+struct FilterKey { uint64_t v0, v1; uint32_t tag, k; };
+inline uint64_t prep_bytes_le(const uint8_t* p, uint32_t k) { uint64_t v = 0; for (uint32_t i = 0; i < k; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
 
 inline uint32_t prep_le32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
@@ -114,6 +147,9 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     db.v4_start_node = node;
     if (L.node_count == 0) db.has_ip = 0;
   }
+  std::vector<FilterKey> lit_tail_keys, glob_keys;
+  std::vector<uint64_t> lit_full_keys;
+  bool fast = L.match_mode == 0;
   // --- literal hash
   if (L.has_literal) {
     const uint8_t* lh = d + L.lit_off;
@@ -149,6 +185,21 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         P.lh_bloom[(size_t)((uint32_t)(h >> 20) & (uint32_t)(words - 1))] |= (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63));
       }
       db.lh_bloom_mask = (uint32_t)(words - 1);
+      // fast string path: (last min(len,8) bytes) -> hot key, (len, first 8, last 8) -> cold key, for every stored string
+      for (uint32_t k = 0; k < table_size; k++) {
+        const uint8_t* e = lh + tstart + (uint64_t)k * 16;
+        uint32_t so = prep_le32(e + 8);
+        if (so == NONE32) continue;
+        uint64_t abs = (uint64_t)strings_offset + so;
+        if (abs + 2 > len) continue;
+        uint32_t sl = (uint32_t)lh[abs] | ((uint32_t)lh[abs + 1] << 8);
+        if (sl == 0 || abs + 2 + sl > len) continue;
+        const uint8_t* sp = lh + abs + 2;
+        uint32_t kk = sl >= 8 ? 8u : sl;
+        uint64_t tailv = prep_bytes_le(sp + sl - kk, kk), headv = prep_bytes_le(sp, kk);
+        lit_tail_keys.push_back(FilterKey{tailv, 0, (uint32_t)TAG_LIT_TAIL, kk});
+        lit_full_keys.push_back(cold_key_full(headv, tailv << (8 * (8 - kk)), sl));
+      }
     }
     db.lh_len = len; db.has_literal = 1;
     db.lh_num_shards = num_shards; db.lh_strings_offset = strings_offset; db.lh_table_start = 32 + (num_shards + 1) * 4;
@@ -301,6 +352,74 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     }
     db.aclh_n = (uint32_t)(P.aclh.size() / 2);
     db.glob_data_n = (uint32_t)L.map_count;
+    // fast string path: classify every pattern some AC literal leads to (string_filters() in device_fns.cuh)
+    if (db.wild_count != 0) fast = false;
+    if (fast) {
+      std::vector<uint8_t> reach(pattern_count, 0);
+      for (size_t lit = 0; lit + 1 < P.aclh.size(); lit += 2)
+        for (uint32_t j = 0; j < P.aclh[lit + 1]; j++) { uint32_t pid = prep_le32(pg + P.aclh[lit] + j * 4); if (pid < pattern_count) reach[pid] = 1; else fast = false; }
+      for (uint32_t pid = 0; pid < pattern_count && fast; pid++) {
+        if (!reach[pid]) continue;
+        uint64_t eo = (uint64_t)db.patterns_offset + (uint64_t)pid * 16;
+        if (eo + 16 > pg_len) continue;                     // find_all skips it
+        uint32_t entry_id = prep_le32(pg + eo);
+        if (pg[eo + 4] == 0) { fast = false; break; }       // literal-type pattern: substring semantics (quirk 12)
+        uint64_t io = (uint64_t)gso + (uint64_t)entry_id * 8;
+        if (io + 8 > pg_len) continue;                      // match_glob_from_buffer fails: never a match
+        uint32_t first = prep_le32(pg + io), cnt = (uint32_t)pg[io + 4] | ((uint32_t)pg[io + 5] << 8);
+        if (cnt == 0) continue;                             // matches the empty text only; tokens are never empty
+        if ((uint64_t)first + (uint64_t)cnt * 12 > pg_len) { fast = false; break; }
+        auto lit_of = [&](uint32_t idx, const uint8_t*& ptr, uint32_t& dl) -> int {  // 1 literal, 0 other, -1 unmatchable literal
+          const uint8_t* sh = pg + first + (uint64_t)idx * 12;
+          if (sh[0] != 0) return 0;
+          dl = prep_le32(sh + 4);
+          uint32_t doff = prep_le32(sh + 8);
+          if ((uint64_t)doff + dl > pg_len) return -1;
+          ptr = pg + doff;
+          return dl > 0 ? 1 : 0;
+        };
+        const uint8_t* ptr = nullptr; uint32_t dl = 0;
+        int r = lit_of(cnt - 1, ptr, dl);
+        if (r < 0) continue;
+        if (r == 1) { uint32_t k = glob_key_len(dl), k0 = k < 8 ? k : 8; const uint8_t* q = ptr + dl - k; glob_keys.push_back(FilterKey{prep_bytes_le(q, k0), prep_bytes_le(q + k0, k - k0), (uint32_t)TAG_GLOB_S, k}); db.glob_s_lens |= 1u << k; continue; }
+        r = lit_of(0, ptr, dl);
+        if (r < 0) continue;
+        if (r == 1) { uint32_t k = glob_key_len(dl), k0 = k < 8 ? k : 8; glob_keys.push_back(FilterKey{prep_bytes_le(ptr, k0), prep_bytes_le(ptr + k0, k - k0), (uint32_t)TAG_GLOB_P, k}); db.glob_p_lens |= 1u << k; continue; }
+        fast = false;                                       // neither end is a literal: any position can match
+      }
+    }
+  }
+  // --- fast string path filters
+  db.fast_ok = fast ? 1u : 0u;
+  if (fast) {
+    P.hot.assign(HOT_WORDS, 0);
+    auto try_tag = [&](const std::vector<FilterKey>& keys, uint32_t tag) {
+      // a tag class joins the hot filter only while the filter stays selective (<= 30 % of its bits set)
+      std::vector<uint32_t> h = P.hot;
+      bool any = false;
+      for (auto& key : keys) {
+        if (key.tag != tag) continue;
+        uint32_t x = hot_hash(key.v0, key.v1, key.tag, key.k);
+        h[x >> 17] |= (1u << (x & 31)) | (1u << ((x >> 5) & 31));
+        any = true;
+      }
+      uint64_t bits = 0;
+      for (uint32_t w : h) bits += (uint64_t)__builtin_popcount(w);
+      if (any && bits * 10 > (uint64_t)HOT_WORDS * 32 * 3) return;
+      P.hot.swap(h);
+      db.hot_tags |= 1u << tag;
+    };
+    try_tag(glob_keys, TAG_GLOB_S);
+    try_tag(glob_keys, TAG_GLOB_P);
+    try_tag(lit_tail_keys, TAG_LIT_TAIL);
+    uint64_t nkeys = glob_keys.size() + lit_full_keys.size();
+    uint64_t words = 1024;
+    while (words * 4 < nkeys) words <<= 1;  // >= 16 bits per key
+    P.cold.assign((size_t)words, 0);
+    auto cold_add = [&](uint64_t h) { P.cold[(size_t)((uint32_t)(h >> 20) & (uint32_t)(words - 1))] |= (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63)); };
+    for (auto& key : glob_keys) cold_add(cold_key(key.v0, key.v1, key.tag, key.k));
+    for (uint64_t h : lit_full_keys) cold_add(h);
+    db.cold_mask = (uint32_t)(words - 1);
   }
   return true;
 }

@@ -70,7 +70,60 @@ struct DbView {
   const uint32_t* psl_vals;       // pool offset << 8 | length
   const uint8_t* psl_pool;
   uint32_t psl_mask, psl_max_len;
+  const uint64_t* psl_tld;        // derived: last-label table (TLD_SLOTS entries), see tld_class()
+  // --- fast string path (derived, result-neutral: necessary conditions for a match, see string_filters()) ---
+  uint32_t fast_ok;               // 1: case-sensitive, no pure-wildcard patterns, every reachable glob is suffix- or prefix-anchored
+  uint32_t glob_s_lens, glob_p_lens;  // bit K (K in 1,2,3,4,8,12,16): some suffix- / prefix-anchored glob has a key of K bytes
+  uint32_t hot_tags;              // bit t: keys of tag class t are in the hot filter (else that class skips the hot test)
+  const uint32_t* hot;            // HOT_WORDS-word blocked Bloom filter; the token kernel keeps a copy in shared memory
+  const uint64_t* cold;           // blocked Bloom filter in L2 (>= 16 bits per key) over the same keys + full literal keys
+  uint32_t cold_mask;
 };
+
+// ---- fast string path: filter geometry and key hashing (shared by db_prepare.h and the kernels) ----
+static const uint32_t TLD_SLOTS = 4096;      // 32 KiB of shared memory
+static const uint32_t HOT_WORDS = 32768;     // 128 KiB of shared memory
+static const uint64_t TLD_SLOW = 1ULL << 63; // entry flag: the label only ends multi-label PSL entries -> general PSL walk
+enum { TAG_GLOB_S = 0, TAG_GLOB_P = 1, TAG_LIT_TAIL = 2, TAG_LIT_FULL = 3 };
+enum { F_LIT = 0x100u, F_GLOB = 0x200u };    // StrTok.type flag bits: which exact lookups the token still needs
+
+MGPU_HD uint32_t tld_slot(uint64_t key) {
+  uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
+  return (h ^ (h >> 15)) & (TLD_SLOTS - 1);
+}
+// Key of an anchored glob / a literal: K bytes of text, K in {1,2,3,4,8,12,16}, held little-endian in (v0, v1), zero-padded.
+// glob_key_len: the key length used for an anchor literal of m bytes (long literals use their first / last 16 bytes).
+MGPU_HD uint32_t glob_key_len(uint32_t m) { return m < 4 ? m : (m >= 16 ? 16u : (m & ~3u)); }
+MGPU_HD uint32_t hot_hash(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
+  uint32_t h = ((uint32_t)v0 ^ (tag * 0x632BE5ABu + k * 0x7F4A7C15u)) * 0x9E3779B1u;
+  h ^= h >> 15;
+  h = (h ^ (uint32_t)(v0 >> 32)) * 0x85EBCA77u;
+  h ^= h >> 13;
+  h = (h ^ (uint32_t)v1) * 0xC2B2AE3Du;
+  h ^= h >> 16;
+  h = (h ^ (uint32_t)(v1 >> 32)) * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  h *= 0x165667B1u;
+  return h ^ (h >> 16);
+}
+MGPU_HD bool hot_test(const uint32_t* hot, uint32_t h) {
+  uint32_t m = (1u << (h & 31)) | (1u << ((h >> 5) & 31));
+  return (hot[h >> 17] & m) == m;
+}
+MGPU_HD uint64_t cold_mix(uint64_t x) {
+  x ^= x >> 31; x *= 0x7FB5D329728EA185ULL; x ^= x >> 27; x *= 0x81DADEF4BC2DD44DULL; x ^= x >> 33;
+  return x;
+}
+MGPU_HD uint64_t cold_key(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
+  return cold_mix(cold_mix(v0 ^ ((uint64_t)(tag * 32 + k) * 0x9E3779B97F4A7C15ULL)) ^ (v1 * 0xD6E8FEB86659FD93ULL));
+}
+MGPU_HD uint64_t cold_key_full(uint64_t head8, uint64_t tail8, uint32_t n) {
+  return cold_mix((head8 * 0xFF51AFD7ED558CCDULL) ^ ((tail8 << 29) | (tail8 >> 35)) ^ ((uint64_t)n * 0xC4CEB9FE1A85EC53ULL) ^ 0x3C6EF372FE94F82BULL);
+}
+MGPU_HD bool cold_test(const uint64_t* cold, uint32_t mask, uint64_t h) {
+  uint64_t need = (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63));
+  return (cold[(uint32_t)(h >> 20) & mask] & need) == need;
+}
 
 MGPU_HD uint32_t ld32(const uint8_t* p) {  // little-endian; 4-byte aligned on the device (layout chosen at upload)
 #ifdef __CUDA_ARCH__
@@ -304,6 +357,118 @@ MGPU_HDN bool domain_word_psl_utf8(const DbView& db, const uint8_t* w, uint32_t 
   if (!hit) return false;
   if ((high & 0x80808080u) && !valid_utf8(w, n)) return false;
   return true;
+}
+
+// ---- fast path of the two functions above and of the string lookups: constant work per token ----
+// The last min(n,8) bytes of w[0..n) with the LAST byte in bits 56..63 (missing leading bytes are zero), and the
+// first min(n,8) bytes with the FIRST byte in bits 0..7 (missing trailing bytes are zero).  n >= 1.
+MGPU_HD uint64_t load_tail8(const uint8_t* w, uint32_t n) { return n >= 8 ? ldu64_fast(w + n - 8) : (ldu64_fast(w) << (8 * (8 - n))); }
+MGPU_HD uint64_t load_head8(const uint8_t* w, uint32_t n) { uint64_t v = ldu64_fast(w); return n >= 8 ? v : (v & ((1ULL << (8 * n)) - 1)); }
+
+enum { TLD_REJECT = 0, TLD_ACCEPT = 1, TLD_GENERAL = 2 };
+// PSL decision from the last label alone.  find_valid_tld_suffix_bytes (lib.rs:1671-1692) accepts iff ANY dot-suffix of
+// the word is a PSL entry, and every dot-suffix ends with the word's last label L.  So: L itself an entry -> accept;
+// L neither an entry nor the last label of any multi-label entry -> no suffix can be an entry -> reject; otherwise
+// (or when L is longer than 7 bytes) the general right-to-left walk decides.  `tld` holds (label bytes | len << 56),
+// flagged TLD_SLOW for the third kind.  tail8 = load_tail8 of a word made of domain characters only ('/' cannot occur,
+// which makes the borrow trick below exact).
+MGPU_HD int tld_class(const uint64_t* tld, uint64_t tail8) {
+  uint64_t x = tail8 ^ 0x2E2E2E2E2E2E2E2EULL;
+  uint64_t z = (x - 0x0101010101010101ULL) & ~x & 0x8080808080808080ULL;  // 0x80 in every byte that is '.'
+  if (z == 0) return TLD_GENERAL;                                          // no dot within the last 8 bytes
+#ifdef __CUDA_ARCH__
+  uint32_t L = (uint32_t)__clzll((long long)z) >> 3;                       // bytes after the last dot
+#else
+  uint32_t L = (uint32_t)__builtin_clzll(z) >> 3;
+#endif
+  if (L == 0) return TLD_GENERAL;
+  uint64_t key = (tail8 >> (8 * (8 - L))) | ((uint64_t)L << 56);
+  uint32_t slot = tld_slot(key);
+  for (;;) {
+    uint64_t k = tld[slot];
+    if (k == 0) return TLD_REJECT;
+    if ((k & ~TLD_SLOW) == key) return (k & TLD_SLOW) ? TLD_GENERAL : TLD_ACCEPT;
+    slot = (slot + 1) & (TLD_SLOTS - 1);
+  }
+}
+// domain_word_psl_utf8 with the constant-time front end.  maybe_high = false promises that w[0..n) is pure ASCII.
+MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint8_t* w, uint32_t n, bool maybe_high) {
+  int c = tld_class(tld, load_tail8(w, n));
+  if (c == TLD_REJECT) return false;
+  if (c == TLD_GENERAL) return domain_word_psl_utf8(db, w, n);
+  if (!maybe_high) return true;
+  uint32_t high = 0;
+  for (uint32_t k = 0; k < n; k += 4) {
+    uint32_t v = ldu32_fast(w + k);
+    if (k + 4 > n) v &= 0xFFFFFFFFu >> (8 * (k + 4 - n));
+    high |= v;
+  }
+  return !(high & 0x80808080u) || valid_utf8(w, n);
+}
+
+// Bytes [n-16, n-8) of w[0..n) the way load_tail8 holds [n-8, n), and bytes [8, 16) the way load_head8 holds [0, 8).
+MGPU_HD uint64_t load_tail16_hi(const uint8_t* w, uint32_t n) { return n >= 16 ? ldu64_fast(w + n - 16) : (n > 8 ? (ldu64_fast(w) << (8 * (16 - n))) : 0ULL); }
+MGPU_HD uint64_t load_head16_hi(const uint8_t* w, uint32_t n) { return n >= 16 ? ldu64_fast(w + 8) : (n > 8 ? (ldu64_fast(w + 8) & ((1ULL << (8 * (n - 8))) - 1)) : 0ULL); }
+// (v0, v1) of the LAST k bytes given t0 = load_tail16_hi, t1 = load_tail8;  of the FIRST k bytes given h0 = load_head8, h1 = load_head16_hi
+MGPU_HD void tail_key(uint64_t t0, uint64_t t1, uint32_t k, uint64_t& v0, uint64_t& v1) {
+  if (k <= 8) { v0 = t1 >> (8 * (8 - k)); v1 = 0; }
+  else if (k == 16) { v0 = t0; v1 = t1; }
+  else { uint32_t s = 8 * (16 - k); v0 = (t0 >> s) | (t1 << (64 - s)); v1 = t1 >> s; }  // 8 < k < 16
+}
+MGPU_HD void head_key(uint64_t h0, uint64_t h1, uint32_t k, uint64_t& v0, uint64_t& v1) {
+  if (k < 8) { v0 = h0 & ((1ULL << (8 * k)) - 1); v1 = 0; }
+  else if (k == 8) { v0 = h0; v1 = 0; }
+  else if (k == 16) { v0 = h0; v1 = h1; }
+  else { v0 = h0; v1 = h1 & ((1ULL << (8 * (k - 8))) - 1); }
+}
+
+// Which exact lookups can a string token still need?  Necessary conditions only (no false negatives):
+//  * literal hash (LiteralHash::lookup is an exact string match): some stored literal has the same last 8 bytes (hot
+//    filter) and the same (length, first 8, last 8 bytes) (cold filter);
+//  * globs, when db.fast_ok: a pattern whose LAST segment is a literal can only match a text that ends with it, one whose
+//    FIRST segment is a literal only a text that starts with it (match_segments_impl anchors segment 0 at position 0 and
+//    requires the whole text to be consumed, paraglob_offset.rs:1402-1639); keys are the last / first glob_key_len(len)
+//    bytes of that literal.  Literal-type patterns (substring semantics), patterns with neither anchor, pure wildcards
+//    and case-insensitive databases clear fast_ok and every token takes the exact path.
+// `hot` may point at a shared-memory copy of db.hot.  Returns F_LIT | F_GLOB bits.
+MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const uint8_t* w, uint32_t n) {
+  uint32_t flags = 0;
+  const uint64_t t1 = load_tail8(w, n), h0 = load_head8(w, n);
+  if (db.has_literal) {
+    const uint32_t k = n >= 8 ? 8u : n;
+    if (!((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, hot_hash(t1 >> (8 * (8 - k)), 0, TAG_LIT_TAIL, k))) {
+      if (cold_test(db.cold, db.cold_mask, cold_key_full(h0, t1, n))) flags |= F_LIT;
+    }
+  }
+  if (db.has_glob && (db.glob_s_lens | db.glob_p_lens)) {
+    const uint64_t t0 = load_tail16_hi(w, n), h1 = load_head16_hi(w, n);
+    bool g = false;
+    uint64_t v0, v1;
+    for (uint32_t lens = db.glob_s_lens; lens && !g; lens &= lens - 1) {
+#ifdef __CUDA_ARCH__
+      uint32_t k = (uint32_t)__ffs((int)lens) - 1u;
+#else
+      uint32_t k = (uint32_t)__builtin_ctz(lens);
+#endif
+      if (k > n) break;
+      tail_key(t0, t1, k, v0, v1);
+      if (((db.hot_tags >> TAG_GLOB_S) & 1u) && !hot_test(hot, hot_hash(v0, v1, TAG_GLOB_S, k))) continue;
+      g = cold_test(db.cold, db.cold_mask, cold_key(v0, v1, TAG_GLOB_S, k));
+    }
+    for (uint32_t lens = db.glob_p_lens; lens && !g; lens &= lens - 1) {
+#ifdef __CUDA_ARCH__
+      uint32_t k = (uint32_t)__ffs((int)lens) - 1u;
+#else
+      uint32_t k = (uint32_t)__builtin_ctz(lens);
+#endif
+      if (k > n) break;
+      head_key(h0, h1, k, v0, v1);
+      if (((db.hot_tags >> TAG_GLOB_P) & 1u) && !hot_test(hot, hot_hash(v0, v1, TAG_GLOB_P, k))) continue;
+      g = cold_test(db.cold, db.cold_mask, cold_key(v0, v1, TAG_GLOB_P, k));
+    }
+    if (g) flags |= F_GLOB;
+  }
+  return flags;
 }
 
 // extract_email_at: buf[lo..n) is the chunk, at = position of '@'.
@@ -758,6 +923,43 @@ MGPU_HDN void find_all_visit(const DbView& db, const uint8_t* text, uint32_t tn,
     if (i < tn) ch = lc(text[i], fold);
   }
 }
+// The anchored formulation of find_all_visit, one START POSITION at a time (db.ac_anchored, no pure wildcards): every
+// pattern reached through a literal occurrence that starts at text[i].  The union over all i is what find_all_visit
+// emits (as a set); positions are independent, which is what the warp-cooperative exact kernel exploits.
+template <typename F>
+MGPU_HD void anchored_visit_at(const DbView& db, const uint8_t* text, uint32_t tn, uint32_t i, const uint32_t* gram2, F&& emit) {
+  if (i + 3 > tn) return;  // every literal has at least 3 bytes
+  const bool fold = db.match_mode == 1;
+  const uint8_t* ac = db.pg + db.ac_start;
+  const uint32_t g2 = ((uint32_t)lc(text[i], fold) << 8) | lc(text[i + 1], fold);
+  if (!((gram2[g2 >> 5] >> (g2 & 31)) & 1u)) return;
+  const uint32_t g3 = (g2 << 8) | lc(text[i + 2], fold);
+  if (!((db.ac_gram3[g3 >> 5] >> (g3 & 31)) & 1u)) return;
+  const uint64_t v = load_prefix8(text, i, fold);
+  const uint32_t avail = tn - i;
+  for (uint32_t lens = db.ac_short_lens; lens; lens &= lens - 1) {
+#ifdef __CUDA_ARCH__
+    uint32_t m = (uint32_t)__ffs((int)lens) - 1u;
+#else
+    uint32_t m = (uint32_t)__builtin_ctz(lens);
+#endif
+    if (m > avail) break;
+    uint32_t off = prefix_node(db, low_bytes(v, m), m);
+    if (off) { AcNode sn = ac_fetch(ac, off); ac_outputs(db, ac, sn, text, tn, emit); }
+  }
+  if (avail < 8) return;
+  uint32_t off = prefix_node(db, v, 8);
+  if (!off) return;
+  AcNode nd = ac_fetch(ac, off);
+  if (nd.w0 >> 24) ac_outputs(db, ac, nd, text, tn, emit);
+  for (uint32_t j = i + 8; j < tn; j++) {
+    uint32_t nx = ac_goto(ac, nd, lc(text[j], fold));
+    if (!nx) return;
+    nd = ac_fetch(ac, nx);
+    if (nd.w0 >> 24) ac_outputs(db, ac, nd, text, tn, emit);
+  }
+}
+
 // the root's dense table, if the root is a Dense state
 MGPU_HD const uint32_t* ac_root_table(const DbView& db) {
   if (!db.has_glob || db.ac_size < 20) return nullptr;

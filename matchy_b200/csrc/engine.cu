@@ -2,7 +2,8 @@
 //
 // Replaces the body of processing::Worker::process_bytes (crates/matchy/src/processing/mod.rs:353-448):
 //   tokenize_kernel  (K1)  candidates: words / '@' / "::" anchors          extractor lib.rs:409-488 (first half)
-//   validate_kernel  (K2)  candidate -> typed token (IPv4/IPv6/domain/e-mail/hash)   (second half)
+//   token_kernel     (K2)  candidate -> typed token (IPv4/IPv6/domain/e-mail/hash)   (second half)
+//                          + constant-time string filters that decide which tokens need the exact lookups at all
 //   iptrie_kernel    (K3)  SearchTree::lookup per IP token + record emission      mmdb/tree.rs:46-125
 //   lithash_kernel   (K4)  LiteralHash::lookup per string token                    matchy-literal-hash lib.rs:467-575
 //   acglob_kernel    (K5)  Paraglob::find_all per string token + record emission   paraglob_offset.rs:1028-1182
@@ -33,24 +34,29 @@ struct StrTok { uint32_t start, len, type; };
 struct IpTok { uint32_t start, len, type, pad; uint32_t w[4]; };  // v4: w[0]; v6: w[k] = seg[2k] << 16 | seg[2k+1]
 
 struct DevCounters {
-  uint32_t q_count[Q_COUNT];  // slots handed out per candidate queue (includes invalidated padding)
   uint32_t n_str, n_ip, n_rec, n_ids;
-  uint32_t overflow;          // bit q: queue q, 8: str tokens, 9: ip tokens, 10: records, 11: ids
+  uint32_t overflow;          // bit q: candidate queue q, 8: str tokens, 9: ip tokens, 10: records, 11: ids
   uint32_t pad[3];
   unsigned long long lines;
   unsigned long long by_type[12];
   unsigned long long matches;
 };
 
+// Candidate queues are SEGMENTED: tokenizer warp w owns slots [w * seg_cap[q], (w+1) * seg_cap[q]) of queue q and
+// writes how many it filled to seg_cnt[q * nseg_max + w].  No atomics, no padding, and every segment is sorted by log
+// position, which is what lets the token kernel read tokens through one shared-memory window per warp.
 struct ScanArgs {
   const uint8_t* buf;  // 16-byte aligned, readable up to round_up(n, 1024); the chunk is buf[lo .. n)
   uint64_t lo;         // 0..15: bytes before the chunk (alignment padding, treated like a chunk edge)
   uint64_t n;          // end of the chunk relative to buf
   uint64_t base;       // absolute log offset of buf[0]
   uint32_t flags;
+  uint32_t fast;       // 1: the token kernel applies string_filters() and only flagged string tokens reach the exact kernel
   DbView db;
   Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2;
-  uint32_t cap_q[Q_COUNT];
+  uint32_t seg_cap[Q_COUNT];
+  uint32_t* seg_cnt;   // [Q_COUNT][nseg_max]
+  uint32_t nseg, nseg_max;
   StrTok* str; uint32_t cap_str;
   IpTok* ip; uint32_t cap_ip;
   uint32_t* lh_res;
@@ -60,7 +66,7 @@ struct ScanArgs {
 };
 
 static const int K1_THREADS = 512;
-static const uint32_t RESERVE = 512;  // queue slots a warp takes per atomic
+static const int K1_WARPS = K1_THREADS / 32;
 
 // ---------------------------------------------------------------------------------------------------------
 // K1 tokenize
@@ -85,42 +91,18 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
   return v;
 }
 
-struct QueueCursor { uint32_t base, left; };
-
-__device__ __forceinline__ void q_invalidate(const ScanArgs& a, int q, uint32_t from, uint32_t count, uint32_t lane) {
-  for (uint32_t i = lane; i < count; i += 32) {
-    uint32_t s = from + i;
-    if (s >= a.cap_q[q]) break;
-    if (q == Q_DOTTED) a.q_dotted[s].start = NONE32;
-    else if (q == Q_HASH) a.q_hash[s].start = NONE32;
-    else if (q == Q_AT) a.q_at[s] = NONE32;
-    else a.q_c2[s] = NONE32;
-  }
-}
-
-// Slots for `total` new entries of queue q (warp-uniform).  NONE32 = dropped, overflow flagged.
-__device__ __forceinline__ uint32_t warp_reserve(const ScanArgs& a, int q, uint32_t total, uint32_t lane, QueueCursor& c) {
-  if (total <= c.left) { uint32_t b = c.base; c.base += total; c.left -= total; return b; }
-  q_invalidate(a, q, c.base, c.left, lane);
-  uint32_t sz = total > RESERVE ? total : RESERVE;
-  uint32_t b = 0;
-  if (lane == 0) b = atomicAdd(&a.ctr->q_count[q], sz);
-  b = __shfl_sync(0xFFFFFFFFu, b, 0);
-  if ((uint64_t)b + sz > a.cap_q[q]) {
-    if (lane == 0) atomicOr(&a.ctr->overflow, 1u << q);
-    if (b < a.cap_q[q]) q_invalidate(a, q, b, a.cap_q[q] - b, lane);
-    c.base = 0; c.left = 0;
-    return NONE32;
-  }
-  c.base = b + total; c.left = sz - total;
-  return b;
+// exclusive prefix over the lanes of a per-lane count < 16, and the warp total, from four ballots (no shuffle chain)
+__device__ __forceinline__ uint32_t warp_excl_count4(uint32_t cnt, uint32_t lt_mask, uint32_t& total) {
+  const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cnt & 1u), b1 = __ballot_sync(0xFFFFFFFFu, cnt & 2u);
+  const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, cnt & 4u), b3 = __ballot_sync(0xFFFFFFFFu, cnt & 8u);
+  total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+  return __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask) + 8 * __popc(b3 & lt_mask);
 }
 
 __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   // class table replicated per lane: entry (b, lane) at b*256 + lane*8 -> every LDS.64 of a warp is conflict-free
   uint2* lut = reinterpret_cast<uint2*>(smem);
-  uint32_t* sB_all = reinterpret_cast<uint32_t*>(smem + 256 * 32 * 8);
   for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
     uint32_t c = class_bits((uint8_t)(i >> 5));
     uint2 e;
@@ -130,170 +112,183 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* sB = sB_all + warp * 32;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint8_t* lut_lane = smem + lane * 8;
-  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-  const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const uint64_t nwarps = (uint64_t)gridDim.x * K1_WARPS;  // == a.nseg
+  const uint64_t w = (uint64_t)blockIdx.x * K1_WARPS + warp;
   const uint64_t tiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
   const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
   const uint64_t t0 = w * tpw;
   uint64_t t1 = t0 + tpw;
   if (t1 > tiles) t1 = tiles;
-  if (t0 >= t1) return;
-
-  TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
-  QueueCursor qc[Q_COUNT];
-#pragma unroll
-  for (int q = 0; q < Q_COUNT; q++) { qc[q].base = 0; qc[q].left = 0; }
+  // this warp's queue segments and fill counts (warp-uniform)
+  Cand* const qd = a.q_dotted + w * a.seg_cap[Q_DOTTED];
+  Cand* const qh = a.q_hash + w * a.seg_cap[Q_HASH];
+  uint32_t* const qa = a.q_at + w * a.seg_cap[Q_AT];
+  uint32_t* const qc = a.q_c2 + w * a.seg_cap[Q_COLON2];
+  uint32_t nd = 0, nh = 0, na = 0, nc = 0, ovf = 0;
   uint32_t lines = 0;
-  const bool want_dot = (a.flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
-  const bool want_hash = (a.flags & MGPU_X_HASHES) != 0;
-  const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
-  const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
-
-  for (uint64_t t = t0; t < t1; t++) {
-    const uint64_t tile_base = t * TILE_BYTES;
-    const uint64_t p = tile_base + (uint64_t)lane * SLICE_BYTES;
-    uint4 v0 = ld_stream(a.buf + p), v1 = ld_stream(a.buf + p + 16);
-    uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
+  if (t0 < t1) {
+    TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
+    const bool want_dot = (a.flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
+    const bool want_hash = (a.flags & MGPU_X_HASHES) != 0;
+    const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
+    const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
+    for (uint64_t t = t0; t < t1; t++) {
+      const uint64_t tile_base = t * TILE_BYTES;
+      const uint64_t p = tile_base + (uint64_t)lane * SLICE_BYTES;
+      uint4 v0 = ld_stream(a.buf + p), v1 = ld_stream(a.buf + p + 16);
+      uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+      for (int j = 0; j < 8; j++) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        uint32_t off = __byte_perm(wds[j], 0, 0x4404u | ((uint32_t)k << 4));  // byte k of the word, times 256
-        uint2 e = *reinterpret_cast<const uint2*>(lut_lane + off);
-        const uint32_t sh = (uint32_t)((j & 1) * 4 + k);
-        accLo[j >> 1] += e.x << sh;
-        accHi[j >> 1] += e.y << sh;
-      }
-    }
-    LaneMasks m;
-    m.B = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 0);
-    m.DOT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 1);
-    m.AT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 2);
-    m.CL = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 3);
-    m.NL = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 0);
-    m.DM = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 1);
-    m.HX = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 2);
-    m.DASH = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 3);
-    if (tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
-      uint64_t valid = a.n > p ? a.n - p : 0;
-      uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
-      if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
-      m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep; m.DASH &= keep;
-    }
-    if (!(cy.prev & PV_T)) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
-    lines += __popc(m.NL);
-    sB[lane] = m.B;
-    __syncwarp();
-
-    const uint32_t T = ~m.B;
-    const uint32_t my_prev = prev_bits_of(m);
-    uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, my_prev, 1);
-    if (lane == 0) pv = cy.prev;  // lane 0 looks into the previous tile
-    const uint32_t pT = pv & PV_T;
-    const uint32_t S = T & ~((T << 1) | pT);
-    uint32_t bad, bad_end;
-    domain_rule_masks(m, S, pv, bad, bad_end);
-
-    uint32_t A_DM, A_DN, A_HX;
-    {
-      uint32_t g, pr, co;
-      uint32_t G = m.DM & ~bad, Sg = S & G;  // well-formed domain bytes
-      gp_bits(G, Sg, g, pr);
-      uint32_t cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cDM, co);
-      A_DM = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B) & ~bad_end;
-      cy.cDM = co;
-      G = m.DM & ~m.DOT; Sg = S & G;
-      gp_bits(G, Sg, g, pr);
-      cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cDN, co);
-      A_DN = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B);
-      cy.cDN = co;
-      G = m.HX; Sg = S & G;
-      gp_bits(G, Sg, g, pr);
-      cv = carry_chain(__ballot_sync(0xFFFFFFFFu, g), __ballot_sync(0xFFFFFFFFu, pr), cy.cHX, co);
-      A_HX = all_class_ends(G, Sg, (cv >> lane) & 1u, m.B);
-      cy.cHX = co;
-    }
-    uint32_t candDot = want_dot ? (A_DM & ~A_DN) : 0u;
-    // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
-    uint32_t candHex = (want_hash && pT) ? (A_HX & (m.B & (0u - m.B))) : 0u;
-    uint32_t candAt = want_at ? m.AT : 0u;
-    // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
-    uint32_t cl1 = (m.CL << 1) | ((pv >> 3) & 1u), cl2 = (m.CL << 2) | (((pv >> 3) & 1u) << 1) | ((pv >> 4) & 1u);
-    uint32_t candC2 = want_c2 ? (m.CL & cl1 & ~cl2) : 0u;
-
-    // ---- emission ----
-    if (__any_sync(0xFFFFFFFFu, candDot != 0)) {
-      uint32_t cnt = __popc(candDot), incl = warp_incl_scan(cnt, lane);
-      uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      uint32_t b = warp_reserve(a, Q_DOTTED, total, lane, qc[Q_DOTTED]);
-      if (b != NONE32) {
-        uint32_t idx = b + incl - cnt, mm = candDot;
-        while (mm) {
-          uint32_t bit = __ffs(mm) - 1; mm &= mm - 1;
-          uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
-          a.q_dotted[idx++] = Cand{(uint32_t)s, (uint32_t)(e - s)};
+        for (int k = 0; k < 4; k++) {
+          uint32_t off = __byte_perm(wds[j], 0, 0x4404u | ((uint32_t)k << 4));  // byte k of the word, times 256
+          uint2 e = *reinterpret_cast<const uint2*>(lut_lane + off);
+          const uint32_t sh = (uint32_t)((j & 1) * 4 + k);
+          accLo[j >> 1] += e.x << sh;
+          accHi[j >> 1] += e.y << sh;
         }
       }
-    }
-    if (__any_sync(0xFFFFFFFFu, candHex != 0)) {
-      bool keep = false; Cand c{0, 0};
-      if (candHex) {
-        uint32_t bit = __ffs(candHex) - 1;
-        uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
-        keep = is_hash_len(e - s);
-        c.start = (uint32_t)s; c.len = (uint32_t)(e - s);
+      LaneMasks m;
+      m.B = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 0);
+      m.DOT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 1);
+      m.AT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 2);
+      m.CL = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 3);
+      m.NL = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 0);
+      m.DM = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 1);
+      m.HX = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 2);
+      m.DASH = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 3);
+      if (tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
+        uint64_t valid = a.n > p ? a.n - p : 0;
+        uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
+        if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
+        m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep; m.DASH &= keep;
       }
-      uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-      if (bal) {
-        uint32_t b = warp_reserve(a, Q_HASH, __popc(bal), lane, qc[Q_HASH]);
-        if (b != NONE32 && keep) a.q_hash[b + __popc(bal & ((1u << lane) - 1u))] = c;
-      }
-    }
-    if (__any_sync(0xFFFFFFFFu, candAt != 0)) {
-      uint32_t cnt = __popc(candAt), incl = warp_incl_scan(cnt, lane);
-      uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      uint32_t b = warp_reserve(a, Q_AT, total, lane, qc[Q_AT]);
-      if (b != NONE32) {
-        uint32_t idx = b + incl - cnt, mm = candAt;
-        while (mm) { uint32_t bit = __ffs(mm) - 1; mm &= mm - 1; a.q_at[idx++] = (uint32_t)(p + bit); }
-      }
-    }
-    if (__any_sync(0xFFFFFFFFu, candC2 != 0)) {
-      uint32_t cnt = __popc(candC2), incl = warp_incl_scan(cnt, lane);
-      uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      uint32_t b = warp_reserve(a, Q_COLON2, total, lane, qc[Q_COLON2]);
-      if (b != NONE32) {
-        uint32_t idx = b + incl - cnt, mm = candC2;
-        while (mm) { uint32_t bit = __ffs(mm) - 1; mm &= mm - 1; a.q_c2[idx++] = (uint32_t)(p + bit - 1); }
-      }
-    }
+      if (!(cy.prev & PV_T)) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
+      lines += __popc(m.NL);
 
-    // ---- carry into the next tile ----
-    uint32_t hasB = __ballot_sync(0xFFFFFFFFu, m.B != 0);
-    if (hasB) {
-      uint32_t ll = 31u - (uint32_t)__clz((int)hasB);
-      uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
-      cy.open_start = tile_base + (uint64_t)ll * 32 + (31u - (uint32_t)__clz((int)Bl)) + 1;
-    }
-    cy.prev = __shfl_sync(0xFFFFFFFFu, my_prev, 31);
-    __syncwarp();
-  }
+      const uint32_t T = ~m.B;
+      const uint32_t my_prev = prev_bits_of(m);
+      uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, my_prev, 1);
+      if (lane == 0) pv = cy.prev;  // lane 0 looks into the previous tile
+      const uint32_t pT = pv & PV_T;
+      const uint32_t S = T & ~((T << 1) | pT);
+      uint32_t bad, bad_end;
+      domain_rule_masks(m, S, pv, bad, bad_end);
+
+      // three "does the word contain ..." chains: a byte that rules out a domain, a '.', a non-hex byte
+      const uint32_t Y1 = T & (~m.DM | bad), Y2 = m.DOT, Y3 = T & ~m.HX;
+      const uint32_t g1 = chain_gen(T, Y1), g2 = chain_gen(T, Y2), g3 = chain_gen(T, Y3);
+      const uint32_t pb = __ballot_sync(0xFFFFFFFFu, T == 0xFFFFFFFFu);
+      const uint32_t G1 = __ballot_sync(0xFFFFFFFFu, g1), G2 = __ballot_sync(0xFFFFFFFFu, g2), G3 = __ballot_sync(0xFFFFFFFFu, g3);
+      uint32_t co1, co2, co3;
+      const uint32_t cv1 = carry_chain(G1, pb & ~G1, cy.cBad, co1), cv2 = carry_chain(G2, pb & ~G2, cy.cDot, co2), cv3 = carry_chain(G3, pb & ~G3, cy.cNhx, co3);
+      cy.cBad = co1; cy.cDot = co2; cy.cNhx = co3;
+      const uint32_t E = m.B & ((T << 1) | pT);  // boundaries that end a word
+      const uint32_t hasBad = chain_ends(T, Y1, (cv1 >> lane) & 1u, m.B), hasDot = chain_ends(T, Y2, (cv2 >> lane) & 1u, m.B);
+      const uint32_t hasNhx = chain_ends(T, Y3, (cv3 >> lane) & 1u, m.B);
+      const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
+      // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
+      const uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
+      const uint32_t candAt = want_at ? m.AT : 0u;
+      // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
+      const uint32_t cl1 = (m.CL << 1) | ((pv >> 3) & 1u), cl2 = (m.CL << 2) | (((pv >> 3) & 1u) << 1) | ((pv >> 4) & 1u);
+      const uint32_t candC2 = want_c2 ? (m.CL & cl1 & ~cl2) : 0u;
+
+      // where the word that is open at the start of my slice begins
+      const uint32_t hasB = __ballot_sync(0xFFFFFFFFu, m.B != 0);
+      const uint32_t src = lane_below_with_boundary(hasB, lane);
+      const uint32_t Bsrc = __shfl_sync(0xFFFFFFFFu, m.B, src & 31u);
+      const uint64_t lane_open = src < 32u ? tile_base + (uint64_t)src * 32 + top_bit(Bsrc) + 1 : cy.open_start;
+
+      // ---- emission ----
+      {
+        uint32_t total;
+        const uint32_t cnt = __popc(candDot), excl = warp_excl_count4(cnt, lt_mask, total);
+        if (total) {
+          if (nd + total <= a.seg_cap[Q_DOTTED]) {
+            Cand* dst = qd + nd + excl;
+            for (uint32_t mm = candDot; mm; mm &= mm - 1) {
+              const uint32_t bit = __ffs(mm) - 1;
+              const uint64_t s = word_start_in_lane(m.B, bit, p, lane_open);
+              *dst++ = Cand{(uint32_t)s, (uint32_t)(p + bit - s)};
+            }
+          } else ovf |= 1u << Q_DOTTED;
+          nd += total;
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2) != 0)) {  // rare in most logs: one vote covers the three
+        {
+          bool keep = false; Cand c{0, 0};
+          if (candHex) {
+            const uint32_t bit = __ffs(candHex) - 1;
+            const uint64_t s = word_start_in_lane(m.B, bit, p, lane_open);
+            keep = is_hash_len(p + bit - s);
+            c.start = (uint32_t)s; c.len = (uint32_t)(p + bit - s);
+          }
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+          if (bal) {
+            const uint32_t total = __popc(bal);
+            if (nh + total <= a.seg_cap[Q_HASH]) { if (keep) qh[nh + __popc(bal & lt_mask)] = c; }
+            else ovf |= 1u << Q_HASH;
+            nh += total;
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, candAt != 0)) {
+          // up to 32 '@' per slice: prefix by shuffle scan
+          uint32_t cnt = __popc(candAt), incl = cnt;
 #pragma unroll
-  for (int q = 0; q < Q_COUNT; q++) q_invalidate(a, q, qc[q].base, qc[q].left, lane);
+          for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+          const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (na + total <= a.seg_cap[Q_AT]) {
+            uint32_t idx = na + incl - cnt;
+            for (uint32_t mm = candAt; mm; mm &= mm - 1) qa[idx++] = (uint32_t)(p + __ffs(mm) - 1);
+          } else ovf |= 1u << Q_AT;
+          na += total;
+        }
+        if (__any_sync(0xFFFFFFFFu, candC2 != 0)) {
+          uint32_t cnt = __popc(candC2), incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+          const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (nc + total <= a.seg_cap[Q_COLON2]) {
+            uint32_t idx = nc + incl - cnt;
+            for (uint32_t mm = candC2; mm; mm &= mm - 1) qc[idx++] = (uint32_t)(p + __ffs(mm) - 2);
+          } else ovf |= 1u << Q_COLON2;
+          nc += total;
+        }
+      }
+
+      // ---- carry into the next tile ----
+      if (hasB) {
+        const uint32_t ll = top_bit(hasB);
+        const uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
+        cy.open_start = tile_base + (uint64_t)ll * 32 + top_bit(Bl) + 1;
+      }
+      cy.prev = __shfl_sync(0xFFFFFFFFu, my_prev, 31);
+    }
+  }
+  if (lane == 0) {
+    uint32_t* sc = a.seg_cnt + w;
+    sc[Q_DOTTED * a.nseg_max] = ovf & (1u << Q_DOTTED) ? 0u : nd;
+    sc[Q_HASH * a.nseg_max] = ovf & (1u << Q_HASH) ? 0u : nh;
+    sc[Q_AT * a.nseg_max] = ovf & (1u << Q_AT) ? 0u : na;
+    sc[Q_COLON2 * a.nseg_max] = ovf & (1u << Q_COLON2) ? 0u : nc;
+    if (ovf) atomicOr(&a.ctr->overflow, ovf);
+  }
   for (int d = 16; d; d >>= 1) lines += __shfl_down_sync(0xFFFFFFFFu, lines, d);
   if (lane == 0 && lines) atomicAdd(&a.ctr->lines, (unsigned long long)lines);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Token bytes: a warp handles 32 consecutive queue entries, which lie close together in the log (queues are filled
-// in log order per tokenizer warp).  The warp copies the covering window into shared memory with coalesced 16-byte
-// loads, and every lane then reads its token from there instead of issuing 32 scattered sector requests per byte.
+// Token bytes (generic lookup kernels): a warp handles 32 consecutive tokens, which lie close together in the log.
+// The warp copies the covering window into shared memory with coalesced 16-byte loads, and every lane then reads
+// its token from there instead of issuing 32 scattered sector requests per byte.
 // ---------------------------------------------------------------------------------------------------------
 static const uint32_t WIN_BYTES = 4096;
-static const int KT_THREADS = 256;  // validate / lithash / acglob block size
+static const int KT_THREADS = 256;  // lithash / acglob block size
 static const int KT_WARPS = KT_THREADS / 32;
 
 // Returns p with p[pos] readable for pos in [lo, hi + 16).  Falls back to the global buffer for wide windows.
@@ -308,25 +303,16 @@ __device__ __forceinline__ const uint8_t* stage_window(const uint8_t* buf, uint8
   return win - alo;
 }
 
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t incl = warp_incl_scan(v, lane);
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  uint32_t off = 0, tot = 0;
-  for (uint32_t k = 0; k < (blockDim.x >> 5); k++) { uint32_t x = s_warp[k]; if (k < warp) off += x; tot += x; }
-  __syncthreads();
-  total = tot;
-  return off + incl - v;
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// K2 validate: candidate -> token.  One thread per candidate.  Every warp owns a contiguous range of the candidate
-// index space, so the tokens it appends stay in log order (the lookup kernels rely on that for their windows);
-// appends go through per-warp reservations of TOK_RESERVE slots, unused slots are marked invalid.
+// K2 = the token kernel: candidate -> typed token (second half of the extractor), then — on the fast string path —
+// the constant-time filters that decide which string tokens need the exact lookups at all.  One thread per candidate;
+// token-kernel warp w reads tokenizer segment w.  Shared memory holds the PSL last-label table, the hot string filter and
+// one 2 KiB log window per warp.  Tokens are appended through per-warp reservations of TOK_RESERVE slots (unused slots
+// are marked invalid), so a warp's tokens stay in log order for the generic lookup kernels.
 // ---------------------------------------------------------------------------------------------------------
 static const uint32_t TOK_RESERVE = 128;
 static const uint32_t TOK_INVALID = 0xFFu;  // StrTok.type / IpTok.type of a padding slot
+struct QueueCursor { uint32_t base, left; };
 
 __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap, uint32_t need, uint32_t lane, QueueCursor& c,
                                                  StrTok* str, IpTok* ip, uint32_t* overflow, uint32_t ovf_bit) {
@@ -346,96 +332,157 @@ __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap,
   return b;
 }
 
-__global__ void __launch_bounds__(KT_THREADS) validate_kernel(ScanArgs a) {
-  __shared__ __align__(16) uint8_t s_win[KT_WARPS][WIN_BYTES + 32];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t nD = min(a.ctr->q_count[Q_DOTTED], a.cap_q[Q_DOTTED]);
-  const uint32_t nH = min(a.ctr->q_count[Q_HASH], a.cap_q[Q_HASH]);
-  const uint32_t nA = min(a.ctr->q_count[Q_AT], a.cap_q[Q_AT]);
-  const uint32_t nC = min(a.ctr->q_count[Q_COLON2], a.cap_q[Q_COLON2]);
-  const uint64_t total = (uint64_t)nD + nH + nA + nC;
-  const uint64_t nwarps = (uint64_t)gridDim.x * KT_WARPS;
-  const uint64_t per = ((total + nwarps - 1) / nwarps + 31) & ~(uint64_t)31;
-  const uint64_t w_begin = ((uint64_t)blockIdx.x * KT_WARPS + warp) * per;
-  uint64_t w_end = w_begin + per;
-  if (w_end > total) w_end = total;
-  QueueCursor cs{0, 0}, ci{0, 0};
-  uint32_t n_dom = 0, n_mail = 0, n_v4 = 0, n_v6 = 0, n_md5 = 0, n_sha1 = 0, n_sha256 = 0, n_sha384 = 0, n_sha512 = 0;
-  for (uint64_t w0 = w_begin; w0 < w_end; w0 += 32) {
-    const uint64_t i = w0 + lane;
+static const int TK_THREADS = 1024;  // one persistent block per SM
+static const int TK_WARPS = TK_THREADS / 32;
+static const uint32_t TK_WIN = 2048;
+static const size_t TOKEN_SMEM = (size_t)TLD_SLOTS * 8 + (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32);
+
+struct TokenWarp {  // per-warp state of the token kernel
+  QueueCursor cs, ci;
+  uint32_t n_dom, n_mail, n_v4, n_v6, n_md5, n_sha1, n_sha256, n_sha384, n_sha512;
+};
+
+__device__ __forceinline__ uint32_t hash_type_of(uint32_t len) {
+  return len == 32 ? MGPU_T_MD5 : len == 40 ? MGPU_T_SHA1 : len == 64 ? MGPU_T_SHA256 : len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
+}
+
+// Append this iteration's tokens (ws: my lane has a string token st, wi: an IP token it).
+__device__ __forceinline__ void append_tokens(const ScanArgs& a, TokenWarp& tw, uint32_t lane, bool ws, const StrTok& st, bool wi, const IpTok& it) {
+  const uint32_t bs = __ballot_sync(0xFFFFFFFFu, ws), bi = __ballot_sync(0xFFFFFFFFu, wi);
+  if (bs && a.fast) {  // fast path: flagged tokens are rare and their order is irrelevant -> one aggregated atomic, no padding
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&a.ctr->n_str, (uint32_t)__popc(bs));
+    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+    if ((uint64_t)b + __popc(bs) > a.cap_str) { if (lane == 0) atomicOr(&a.ctr->overflow, 1u << 8); }
+    else if (ws) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
+  } else if (bs) {
+    uint32_t b = tok_reserve(&a.ctr->n_str, a.cap_str, __popc(bs), lane, tw.cs, a.str, nullptr, &a.ctr->overflow, 1u << 8);
+    if (ws && b != NONE32) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
+  }
+  if (bi) {
+    uint32_t b = tok_reserve(&a.ctr->n_ip, a.cap_ip, __popc(bi), lane, tw.ci, nullptr, a.ip, &a.ctr->overflow, 1u << 9);
+    if (wi && b != NONE32) a.ip[b + __popc(bi & ((1u << lane) - 1u))] = it;
+  }
+}
+
+// A string token passed validation: count it, then (fast path) let the filters decide whether anything can match it.
+__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const uint32_t* s_hot, const uint8_t* text, StrTok& st) {
+  tw.n_dom += st.type == MGPU_T_DOMAIN; tw.n_mail += st.type == MGPU_T_EMAIL; tw.n_md5 += st.type == MGPU_T_MD5; tw.n_sha1 += st.type == MGPU_T_SHA1;
+  tw.n_sha256 += st.type == MGPU_T_SHA256; tw.n_sha384 += st.type == MGPU_T_SHA384; tw.n_sha512 += st.type == MGPU_T_SHA512;
+  if (!fast) return true;
+  const uint32_t f = string_filters(a.db, s_hot, text + st.start, st.len);
+  st.type |= f;
+  return f != 0;
+}
+
+// One segment of a word queue (DOTTED: dotted domain-character words -> IPv4 / domain; else: hash-length hex words).
+// The segment is sorted by position; every iteration takes as many consecutive candidates (at most 32) as fit in the
+// warp's window, stages the window with coalesced 16-byte loads and lets one lane handle one candidate.
+template <bool DOTTED>
+__device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t n, uint8_t* s_win, const uint64_t* s_tld,
+                                            const uint32_t* s_hot, bool fast, uint32_t lane) {
+  const bool want_dom = (a.flags & MGPU_X_DOMAINS) != 0, want_v4 = (a.flags & MGPU_X_IPV4) != 0;
+  for (uint32_t i0 = 0; i0 < n;) {
+    const uint32_t idx = i0 + lane;
+    const bool have = idx < n;
+    Cand c{0xFFFFFFFFu, 0};
+    if (have) c = q[idx];
+    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c.start, 0);
+    const uint32_t alo = lo & ~15u;
+    const bool fits = !have || ((uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN && c.start >= lo);
+    const uint32_t nf = __ballot_sync(0xFFFFFFFFu, !fits);
+    uint32_t g = nf ? (uint32_t)__ffs((int)nf) - 1u : 32u;  // candidates of this iteration: lanes [0, g)
+    const uint8_t* p = a.buf;
+    bool high = true;  // "the token bytes may hold bytes >= 0x80"
+    if (g == 0) g = 1;  // a single word longer than the window: read it from global memory
+    else {
+      const bool mine = have && lane < g;
+      const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, mine ? c.start + c.len : 0u);
+      const uint32_t ahi = (hi + 31u) & ~15u;
+      __syncwarp();
+      uint32_t hb = 0;
+      for (uint32_t o = alo + lane * 16; o < ahi; o += 512) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a.buf + o);
+        *reinterpret_cast<uint4*>(s_win + (o - alo)) = v;
+        hb |= v.x | v.y | v.z | v.w;
+      }
+      high = __any_sync(0xFFFFFFFFu, (hb & 0x80808080u) != 0);  // (also orders the window writes before the reads below)
+      p = s_win - alo;
+    }
+    const bool active = have && lane < g && (uint64_t)c.start + c.len <= a.n;
     bool ws = false, wi = false;
-    StrTok st{0, 0, 0};
-    IpTok it{0, 0, 0, 0, {0, 0, 0, 0}};
-    if (w0 + 32 <= nD) {
-      // a full warp of dotted words: stage their window
-      Cand c = a.q_dotted[i];
-      bool ok = c.start != NONE32 && (uint64_t)c.start + c.len <= a.n;
-      uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, ok ? c.start : 0xFFFFFFFFu);
-      uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, ok ? c.start + c.len : 0u);
-      const uint8_t* p = stage_window(a.buf, s_win[warp], lo, hi, lane);
-      if (ok) {
-        const uint8_t* wp = p + c.start;
-        uint32_t addr;
-        if ((a.flags & MGPU_X_IPV4) && parse_ipv4_word(wp, c.len, addr)) {
-          wi = true; it.start = c.start; it.len = c.len; it.type = MGPU_T_IPV4; it.w[0] = addr;
-        }
-        if ((a.flags & MGPU_X_DOMAINS) && domain_word_psl_utf8(a.db, wp, c.len)) {
-          ws = true; st.start = c.start; st.len = c.len; st.type = MGPU_T_DOMAIN;
-        }
-      }
-    } else if (i < w_end) {
-      if (i < nD) {
-        Cand c = a.q_dotted[i];
-        if (c.start != NONE32 && (uint64_t)c.start + c.len <= a.n) {
-          const uint8_t* wp = a.buf + c.start;
-          uint32_t addr;
-          if ((a.flags & MGPU_X_IPV4) && parse_ipv4_word(wp, c.len, addr)) {
-            wi = true; it.start = c.start; it.len = c.len; it.type = MGPU_T_IPV4; it.w[0] = addr;
-          }
-          if ((a.flags & MGPU_X_DOMAINS) && domain_word_psl_utf8(a.db, wp, c.len)) {
-            ws = true; st.start = c.start; st.len = c.len; st.type = MGPU_T_DOMAIN;
-          }
-        }
-      } else if (i < (uint64_t)nD + nH) {
-        Cand c = a.q_hash[i - nD];
-        if (c.start != NONE32 && (uint64_t)c.start + c.len <= a.n) {
-          ws = true; st.start = c.start; st.len = c.len;
-          st.type = c.len == 32 ? MGPU_T_MD5 : c.len == 40 ? MGPU_T_SHA1 : c.len == 64 ? MGPU_T_SHA256 : c.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
-        }
-      } else if (i < (uint64_t)nD + nH + nA) {
-        uint32_t at = a.q_at[i - nD - nH];
+    StrTok st{c.start, c.len, 0};
+    IpTok it{c.start, c.len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
+    if (DOTTED) {
+      const uint8_t* wp = p + c.start;
+      if (active && want_v4 && c.len >= 7 && c.len <= 15 && is_digit(wp[0])) wi = parse_ipv4_word(wp, c.len, it.w[0]);
+      __syncwarp();
+      if (active && want_dom) { st.type = MGPU_T_DOMAIN; ws = domain_word_fast(a.db, s_tld, wp, c.len, high); }
+      __syncwarp();
+    } else if (active) { st.type = hash_type_of(c.len); ws = true; }
+    if (ws) ws = string_token(a, tw, fast, s_hot, p, st);
+    __syncwarp();
+    if (wi) tw.n_v4++;
+    append_tokens(a, tw, lane, ws, st, wi, it);
+    i0 += g;
+  }
+}
+
+__global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
+  extern __shared__ __align__(16) uint8_t tk_smem[];
+  uint64_t* s_tld = reinterpret_cast<uint64_t*>(tk_smem);
+  uint32_t* s_hot = reinterpret_cast<uint32_t*>(tk_smem + (size_t)TLD_SLOTS * 8);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* s_win = tk_smem + (size_t)TLD_SLOTS * 8 + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
+  const bool fast = a.fast != 0;
+  if (a.flags & (MGPU_X_DOMAINS | MGPU_X_EMAILS)) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.db.psl_tld);
+    for (uint32_t i = threadIdx.x; i < TLD_SLOTS / 2; i += blockDim.x) reinterpret_cast<uint4*>(s_tld)[i] = src[i];
+  }
+  if (fast) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.db.hot);
+    for (uint32_t i = threadIdx.x; i < HOT_WORDS / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_hot)[i] = src[i];
+  }
+  __syncthreads();
+  TokenWarp tw;
+  memset(&tw, 0, sizeof tw);
+  const uint32_t nwarps = gridDim.x * TK_WARPS;
+  for (uint32_t seg = blockIdx.x * TK_WARPS + warp; seg < a.nseg; seg += nwarps) {
+    const uint32_t* sc = a.seg_cnt + seg;
+    token_words<true>(a, tw, a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED], sc[Q_DOTTED * a.nseg_max], s_win, s_tld, s_hot, fast, lane);
+    token_words<false>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], sc[Q_HASH * a.nseg_max], s_win, s_tld, s_hot, fast, lane);
+    // '@' and "::" anchors: rare, straight from the log buffer
+    const uint32_t nA = sc[Q_AT * a.nseg_max], nC = sc[Q_COLON2 * a.nseg_max];
+    const uint32_t* qa = a.q_at + (size_t)seg * a.seg_cap[Q_AT];
+    const uint32_t* qc = a.q_c2 + (size_t)seg * a.seg_cap[Q_COLON2];
+    for (uint32_t i0 = 0; i0 < nA + nC; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      bool ws = false, wi = false;
+      StrTok st{0, 0, 0};
+      IpTok it{0, 0, 0, 0, {0, 0, 0, 0}};
+      if (i < nA) {
+        const uint32_t at = qa[i];
         size_t s, e;
-        if (at != NONE32 && at < a.n && email_at(a.db, a.buf, (size_t)a.lo, (size_t)a.n, at, s, e)) {
-          ws = true; st.start = (uint32_t)s; st.len = (uint32_t)(e - s); st.type = MGPU_T_EMAIL;
-        }
-      } else {
-        uint32_t at = a.q_c2[i - nD - nH - nA];
-        size_t s, e; uint16_t seg[8];
-        if (at != NONE32 && (uint64_t)at + 2 <= a.n && ipv6_at(a.buf, (size_t)a.lo, (size_t)a.n, at, s, e, seg)) {
+        if (at < a.n && email_at(a.db, a.buf, (size_t)a.lo, (size_t)a.n, at, s, e)) { ws = true; st.start = (uint32_t)s; st.len = (uint32_t)(e - s); st.type = MGPU_T_EMAIL; }
+      } else if (i < nA + nC) {
+        const uint32_t at = qc[i - nA];
+        size_t s, e; uint16_t sg[8];
+        if ((uint64_t)at + 2 <= a.n && ipv6_at(a.buf, (size_t)a.lo, (size_t)a.n, at, s, e, sg)) {
           wi = true; it.start = (uint32_t)s; it.len = (uint32_t)(e - s); it.type = MGPU_T_IPV6;
-          for (int k = 0; k < 4; k++) it.w[k] = ((uint32_t)seg[2 * k] << 16) | seg[2 * k + 1];
+          for (int k = 0; k < 4; k++) it.w[k] = ((uint32_t)sg[2 * k] << 16) | sg[2 * k + 1];
+          tw.n_v6++;
         }
       }
-    }
-    const uint32_t bs = __ballot_sync(0xFFFFFFFFu, ws), bi = __ballot_sync(0xFFFFFFFFu, wi);
-    if (bs) {
-      uint32_t b = tok_reserve(&a.ctr->n_str, a.cap_str, __popc(bs), lane, cs, a.str, nullptr, &a.ctr->overflow, 1u << 8);
-      if (ws && b != NONE32) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
-      if (ws) {
-        n_dom += st.type == MGPU_T_DOMAIN; n_mail += st.type == MGPU_T_EMAIL; n_md5 += st.type == MGPU_T_MD5; n_sha1 += st.type == MGPU_T_SHA1;
-        n_sha256 += st.type == MGPU_T_SHA256; n_sha384 += st.type == MGPU_T_SHA384; n_sha512 += st.type == MGPU_T_SHA512;
-      }
-    }
-    if (bi) {
-      uint32_t b = tok_reserve(&a.ctr->n_ip, a.cap_ip, __popc(bi), lane, ci, nullptr, a.ip, &a.ctr->overflow, 1u << 9);
-      if (wi && b != NONE32) a.ip[b + __popc(bi & ((1u << lane) - 1u))] = it;
-      if (wi) { n_v4 += it.type == MGPU_T_IPV4; n_v6 += it.type == MGPU_T_IPV6; }
+      __syncwarp();
+      if (ws) ws = string_token(a, tw, fast, s_hot, a.buf, st);
+      __syncwarp();
+      append_tokens(a, tw, lane, ws, st, wi, it);
     }
   }
-  for (uint32_t i = lane; i < cs.left; i += 32) a.str[cs.base + i].type = TOK_INVALID;
-  for (uint32_t i = lane; i < ci.left; i += 32) a.ip[ci.base + i].type = TOK_INVALID;
+  for (uint32_t i = lane; i < tw.cs.left; i += 32) a.str[tw.cs.base + i].type = TOK_INVALID;
+  for (uint32_t i = lane; i < tw.ci.left; i += 32) a.ip[tw.ci.base + i].type = TOK_INVALID;
   // per-type candidate counters (WorkerStats): warp-reduce, one atomic per warp and type
-  uint32_t cnt[9] = {n_dom, n_mail, n_v4, n_v6, n_md5, n_sha1, n_sha256, n_sha384, n_sha512};
+  uint32_t cnt[9] = {tw.n_dom, tw.n_mail, tw.n_v4, tw.n_v6, tw.n_md5, tw.n_sha1, tw.n_sha256, tw.n_sha384, tw.n_sha512};
 #pragma unroll
   for (int t = 0; t < 9; t++) {
     uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cnt[t]);
@@ -485,6 +532,42 @@ __device__ __forceinline__ const uint8_t* stage_tokens(const ScanArgs& a, uint8_
   uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, valid ? t.start : 0xFFFFFFFFu);
   uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, valid ? t.start + t.len : 0u);
   return stage_window(a.buf, win, lo, hi, lane, win_bytes);
+}
+
+// One string token's result: the literal-hash id first, then every glob id find_all returns, sorted and deduplicated
+// (database.rs:916-965, paraglob_offset.rs:1173-1181); a record is written iff there is at least one id.
+__device__ __forceinline__ void emit_string_match(const ScanArgs& a, const StrTok& t, const uint8_t* text, bool lit_ok, uint32_t lit_pid,
+                                                  uint32_t lit_off, bool exact, const AcAccel& acc) {
+  uint32_t cnt = 0;
+  if (exact) find_all_visit(a.db, text, t.len, acc, [&](uint32_t) { cnt++; });
+  if (!lit_ok && cnt == 0) return;
+  uint32_t total = cnt + (lit_ok ? 1u : 0u);
+  uint32_t b = agg_add(&a.ctr->n_ids, total);
+  if ((uint64_t)b + total > a.cap_ids) { atomicOr(&a.ctr->overflow, 1u << 11); return; }
+  uint32_t k = b;
+  if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
+  const uint32_t g0 = k;
+  if (cnt) {
+    find_all_visit(a.db, text, t.len, acc, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
+    for (uint32_t x = g0 + 1; x < k; x++) {
+      uint32_t v = a.ids[x].pattern_id, y = x;
+      while (y > g0 && a.ids[y - 1].pattern_id > v) { a.ids[y].pattern_id = a.ids[y - 1].pattern_id; y--; }
+      a.ids[y].pattern_id = v;
+    }
+    uint32_t u = g0;
+    for (uint32_t x = g0; x < k; x++) if (x == g0 || a.ids[x].pattern_id != a.ids[u - 1].pattern_id) a.ids[u++].pattern_id = a.ids[x].pattern_id;
+    k = u;
+    for (uint32_t x = g0; x < k; x++) {
+      uint32_t off;
+      a.ids[x].data_offset = glob_data_offset(a.db, a.ids[x].pattern_id, off) ? off : MGPU_NO_DATA;
+    }
+  }
+  uint32_t r_i = agg_add(&a.ctr->n_rec, 1u);
+  if (r_i >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); return; }
+  mgpu_match r;
+  r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_PATTERN; r.prefix_len = 0; r.reserved = 0;
+  r.n_ids = k - b; r.ids_index = b; r.data_offset = MGPU_NO_DATA; r.pad = 0;
+  a.recs[r_i] = r;
 }
 
 // K4: literal hash probe per string token
@@ -677,37 +760,73 @@ __global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
     uint32_t lit_pid = a.db.has_literal ? a.lh_res[i] : NONE32, lit_off = 0;
     bool lit_ok = lit_pid != NONE32 && lh_data_offset(a.db, lit_pid, lit_off);
     if (!lit_ok && !exact) continue;
-    // ---- exact path (rare): every id find_all returns, sorted and deduplicated ----
+    emit_string_match(a, t, text, lit_ok, lit_pid, lit_off, exact, acc);
+  }
+}
+
+// K3 on the fast path: the few string tokens whose filters passed (StrTok.type carries F_LIT / F_GLOB) get the exact
+// LiteralHash::lookup and Paraglob::find_all, straight from the log buffer.  One WARP per token: the lanes share the
+// start positions of the anchored literal search (positions are independent, anchored_visit_at), pattern ids meet in a
+// small shared-memory list, lane 0 sorts, deduplicates and writes the record.
+static const uint32_t EX_IDS = 96;
+__global__ void __launch_bounds__(256) exact_kernel(ScanArgs a) {
+  __shared__ uint32_t s_ids[8][EX_IDS];
+  __shared__ uint32_t s_n[8];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n = min(a.ctr->n_str, a.cap_str);
+  AcAccel acc;
+  acc.root_tab = ac_root_table(a.db);
+  acc.gram2 = a.db.ac_gram2;
+  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp; i < n; i += nwarps) {
+    StrTok t = a.str[i];
+    if ((t.type & 0xFFu) == TOK_INVALID) continue;
+    const uint32_t f = t.type;
+    t.type &= 0xFFu;
+    const uint8_t* text = a.buf + t.start;
+    uint32_t lit_pid = NONE32, lit_off = 0;  // every lane computes the same probe: the loads coalesce into broadcasts
+    const bool lit_ok = (f & F_LIT) && a.db.has_literal && lh_lookup(a.db, text, t.len, lit_pid) && lh_data_offset(a.db, lit_pid, lit_off);
+    const bool exact = (f & F_GLOB) && a.db.has_glob;
+    if (!lit_ok && !exact) continue;
     uint32_t cnt = 0;
-    if (exact) find_all_visit(a.db, text, t.len, acc, [&](uint32_t) { cnt++; });
-    if (!lit_ok && cnt == 0) continue;
-    uint32_t total = cnt + (lit_ok ? 1u : 0u);
-    uint32_t b = agg_add(&a.ctr->n_ids, total);
+    bool serial = exact && !(a.db.ac_anchored && a.db.wild_count == 0 && a.db.ac_size >= 20);
+    if (exact && !serial) {
+      if (lane == 0) s_n[warp] = 0;
+      __syncwarp();
+      for (uint32_t pos = lane; pos + 3 <= t.len; pos += 32)
+        anchored_visit_at(a.db, text, t.len, pos, acc.gram2, [&](uint32_t pid) { uint32_t k = atomicAdd(&s_n[warp], 1u); if (k < EX_IDS) s_ids[warp][k] = pid; });
+      __syncwarp();
+      cnt = s_n[warp];
+      if (cnt > EX_IDS) serial = true;  // more ids than the list holds: let one lane redo it with the two-pass emitter
+    }
+    __syncwarp();
+    if (lane != 0) continue;
+    if (serial) { emit_string_match(a, t, text, lit_ok, lit_pid, lit_off, true, acc); continue; }
+    // sort_unstable + dedup (paraglob_offset.rs:1173-1181)
+    uint32_t* ids = s_ids[warp];
+    for (uint32_t x = 1; x < cnt; x++) {
+      uint32_t v = ids[x], y = x;
+      while (y > 0 && ids[y - 1] > v) { ids[y] = ids[y - 1]; y--; }
+      ids[y] = v;
+    }
+    uint32_t u = 0;
+    for (uint32_t x = 0; x < cnt; x++) if (x == 0 || ids[x] != ids[u - 1]) ids[u++] = ids[x];
+    const uint32_t total = u + (lit_ok ? 1u : 0u);
+    if (total == 0) continue;
+    const uint32_t b = atomicAdd(&a.ctr->n_ids, total);
     if ((uint64_t)b + total > a.cap_ids) { atomicOr(&a.ctr->overflow, 1u << 11); continue; }
     uint32_t k = b;
     if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
-    const uint32_t g0 = k;
-    if (cnt) {
-      find_all_visit(a.db, text, t.len, acc, [&](uint32_t pid) { if (k < b + total) a.ids[k++].pattern_id = pid; });
-      // sort_unstable + dedup (paraglob_offset.rs:1173-1181)
-      for (uint32_t x = g0 + 1; x < k; x++) {
-        uint32_t v = a.ids[x].pattern_id, y = x;
-        while (y > g0 && a.ids[y - 1].pattern_id > v) { a.ids[y].pattern_id = a.ids[y - 1].pattern_id; y--; }
-        a.ids[y].pattern_id = v;
-      }
-      uint32_t u = g0;
-      for (uint32_t x = g0; x < k; x++) if (x == g0 || a.ids[x].pattern_id != a.ids[u - 1].pattern_id) a.ids[u++].pattern_id = a.ids[x].pattern_id;
-      k = u;
-      for (uint32_t x = g0; x < k; x++) {
-        uint32_t off;
-        a.ids[x].data_offset = glob_data_offset(a.db, a.ids[x].pattern_id, off) ? off : MGPU_NO_DATA;
-      }
+    for (uint32_t x = 0; x < u; x++, k++) {
+      uint32_t off;
+      a.ids[k].pattern_id = ids[x];
+      a.ids[k].data_offset = glob_data_offset(a.db, ids[x], off) ? off : MGPU_NO_DATA;
     }
-    uint32_t r_i = agg_add(&a.ctr->n_rec, 1u);
+    const uint32_t r_i = atomicAdd(&a.ctr->n_rec, 1u);
     if (r_i >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); continue; }
     mgpu_match r;
     r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_PATTERN; r.prefix_len = 0; r.reserved = 0;
-    r.n_ids = k - b; r.ids_index = b; r.data_offset = MGPU_NO_DATA; r.pad = 0;
+    r.n_ids = total; r.ids_index = b; r.data_offset = MGPU_NO_DATA; r.pad = 0;
     a.recs[r_i] = r;
   }
 }
@@ -820,7 +939,7 @@ struct mgpu_ctx {
   mgpu_db_info info{};
   // PSL
   std::vector<uint8_t> psl_text;
-  void* d_psl_keys = nullptr; void* d_psl_vals = nullptr; void* d_psl_pool = nullptr;
+  void* d_psl_keys = nullptr; void* d_psl_vals = nullptr; void* d_psl_pool = nullptr; void* d_psl_tld = nullptr;
   // results of the last scan
   std::vector<mgpu_match> recs;
   std::vector<mgpu_id_pair> ids;
@@ -828,6 +947,7 @@ struct mgpu_ctx {
   mgpu_timing timing{};
   bool keep_results = true;
   bool force_ac_walk = false;
+  bool force_generic = false;  // tests: run the generic string path (lithash + acglob kernels) even when the fast path applies
   std::vector<StrTok> x_str; std::vector<IpTok> x_ip;  // extraction-only capture
   bool capture_tokens = false;
 };
@@ -857,8 +977,8 @@ void mgpu_destroy(mgpu_ctx* c) {
   }
   for (auto& e : c->ev_k) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
-  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.str, c->args.ip, c->args.lh_res,
-                  c->args.recs, c->args.ids, c->args.ctr, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool};
+  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
+                  c->args.recs, c->args.ids, c->args.ctr, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   if (c->h_cut) cudaFreeHost(c->h_cut);
@@ -895,18 +1015,23 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   ScanArgs& a = c->args;
   memset(&a, 0, sizeof a);
   auto cap32 = [](size_t v) { return (uint32_t)std::min<size_t>(v, 0x7FFFFFFFu); };
-  a.cap_q[Q_DOTTED] = cap32(chunk_bytes / 8 + 4 * RESERVE);
-  a.cap_q[Q_HASH] = cap32(chunk_bytes / 33 + 64 * RESERVE);
-  a.cap_q[Q_AT] = cap32(chunk_bytes / 16 + 4 * RESERVE);
-  a.cap_q[Q_COLON2] = cap32(chunk_bytes / 16 + 4 * RESERVE);
+  // candidate queue segments: one per tokenizer warp; capacity = its share of the density budget (1 dotted word per 8 log
+  // bytes, ...), but never less than the worst case of a single 1 KiB tile, so that splitting a piece always ends overflows
+  a.nseg_max = (uint32_t)launch_grid(c, 2) * K1_WARPS;
+  const size_t share = chunk_bytes / a.nseg_max;
+  a.seg_cap[Q_DOTTED] = cap32(std::max<size_t>(share / 8 + 32, 256));
+  a.seg_cap[Q_HASH] = cap32(std::max<size_t>(share / 33 + 8, 32));
+  a.seg_cap[Q_AT] = cap32(std::max<size_t>(share / 16 + 32, 1024));
+  a.seg_cap[Q_COLON2] = cap32(std::max<size_t>(share / 16 + 32, 512));
   a.cap_str = cap32(chunk_bytes / 8 + 1024);
   a.cap_ip = cap32(chunk_bytes / 8 + 1024);
   a.cap_rec = cap32(chunk_bytes / 16 + 4096);
   a.cap_ids = cap32(chunk_bytes / 8 + 8192);
-  CK(cudaMalloc(&a.q_dotted, (size_t)a.cap_q[Q_DOTTED] * sizeof(Cand)));
-  CK(cudaMalloc(&a.q_hash, (size_t)a.cap_q[Q_HASH] * sizeof(Cand)));
-  CK(cudaMalloc(&a.q_at, (size_t)a.cap_q[Q_AT] * 4));
-  CK(cudaMalloc(&a.q_c2, (size_t)a.cap_q[Q_COLON2] * 4));
+  CK(cudaMalloc(&a.q_dotted, (size_t)a.seg_cap[Q_DOTTED] * a.nseg_max * sizeof(Cand)));
+  CK(cudaMalloc(&a.q_hash, (size_t)a.seg_cap[Q_HASH] * a.nseg_max * sizeof(Cand)));
+  CK(cudaMalloc(&a.q_at, (size_t)a.seg_cap[Q_AT] * a.nseg_max * 4));
+  CK(cudaMalloc(&a.q_c2, (size_t)a.seg_cap[Q_COLON2] * a.nseg_max * 4));
+  CK(cudaMalloc(&a.seg_cnt, (size_t)Q_COUNT * a.nseg_max * 4));
   CK(cudaMalloc(&a.str, (size_t)a.cap_str * sizeof(StrTok)));
   CK(cudaMalloc(&a.ip, (size_t)a.cap_ip * sizeof(IpTok)));
   CK(cudaMalloc(&a.lh_res, (size_t)a.cap_str * 4));
@@ -919,7 +1044,8 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMalloc(&c->d_small, 65536 + TILE_BYTES));
   CK(cudaMalloc(&c->d_small_out, 64));
   CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
-  CK(cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8 + (K1_THREADS / 32) * 32 * 4));
+  CK(cudaFuncSetAttribute(token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOKEN_SMEM));
+  CK(cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
   return MGPU_OK;
 }
 
@@ -930,7 +1056,7 @@ mgpu_ctx* mgpu_create(int device, size_t chunk_bytes) {
 }
 
 void mgpu_set_keep_results(mgpu_ctx* c, int keep) { c->keep_results = keep != 0; }
-void mgpu_set_ac_mode(mgpu_ctx* c, int mode) { c->force_ac_walk = mode == 1; }
+void mgpu_set_ac_mode(mgpu_ctx* c, int mode) { c->force_ac_walk = mode == 1; c->force_generic = mode == 1 || mode == 2; }
 
 // ---- PSL ------------------------------------------------------------------------------------------------
 int mgpu_set_psl(mgpu_ctx* c, const uint8_t* text, size_t len) {
@@ -938,16 +1064,18 @@ int mgpu_set_psl(mgpu_ctx* c, const uint8_t* text, size_t len) {
   PslTable t;
   std::string err;
   if (!build_psl(text, len, t, err)) { set_err(err); return MGPU_E_FORMAT; }
-  if (c->d_psl_keys) { cudaFree(c->d_psl_keys); cudaFree(c->d_psl_vals); cudaFree(c->d_psl_pool); }
+  if (c->d_psl_keys) { cudaFree(c->d_psl_keys); cudaFree(c->d_psl_vals); cudaFree(c->d_psl_pool); cudaFree(c->d_psl_tld); }
   CK(cudaMalloc(&c->d_psl_keys, t.keys.size() * 8));
   CK(cudaMalloc(&c->d_psl_vals, t.vals.size() * 4));
   CK(cudaMalloc(&c->d_psl_pool, t.pool.size() + 16));
   CK(cudaMemcpy(c->d_psl_keys, t.keys.data(), t.keys.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_psl_vals, t.vals.data(), t.vals.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_psl_pool, t.pool.data(), t.pool.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_psl_tld, t.tld.size() * 8));
+  CK(cudaMemcpy(c->d_psl_tld, t.tld.data(), t.tld.size() * 8, cudaMemcpyHostToDevice));
   DbView& db = c->args.db;
   db.psl_keys = (const uint64_t*)c->d_psl_keys; db.psl_vals = (const uint32_t*)c->d_psl_vals; db.psl_pool = (const uint8_t*)c->d_psl_pool;
-  db.psl_mask = t.mask; db.psl_max_len = t.max_len;
+  db.psl_mask = t.mask; db.psl_max_len = t.max_len; db.psl_tld = (const uint64_t*)c->d_psl_tld;
   return MGPU_OK;
 }
 
@@ -974,7 +1102,7 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
   const mxy::Layout& L = P.L;
   DbView db = P.view;  // scalar fields filled; pointers below
   db.psl_keys = c->args.db.psl_keys; db.psl_vals = c->args.db.psl_vals; db.psl_pool = c->args.db.psl_pool;
-  db.psl_mask = c->args.db.psl_mask; db.psl_max_len = c->args.db.psl_max_len;
+  db.psl_mask = c->args.db.psl_mask; db.psl_max_len = c->args.db.psl_max_len; db.psl_tld = c->args.db.psl_tld;
   void* p;
   int rc = dev_copy(c, d, (size_t)L.tree_size, 0, 256, &p);
   if (rc) return rc;
@@ -1016,6 +1144,14 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
     if (rc) return rc;
     db.glob_data = (const uint32_t*)p;
   }
+  if (db.fast_ok) {
+    rc = dev_copy(c, P.hot.data(), P.hot.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.hot = (const uint32_t*)p;
+    rc = dev_copy(c, P.cold.data(), P.cold.size() * 8, 0, 256, &p);
+    if (rc) return rc;
+    db.cold = (const uint64_t*)p;
+  }
   c->args.db = db;
   c->layout = L;
   c->db_loaded = true;
@@ -1051,22 +1187,25 @@ static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t 
   CK(cudaEventRecord(c->ev_k[0], st));
   {
     uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
-    int warps_per_block = K1_THREADS / 32;
-    uint64_t want_blocks = (tiles + warps_per_block - 1) / warps_per_block;
+    uint64_t want_blocks = (tiles + K1_WARPS - 1) / K1_WARPS;
     int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 2));
     if (grid < 1) grid = 1;
-    size_t smem = 256 * 32 * 8 + (size_t)warps_per_block * 32 * 4;
+    a.nseg = (uint32_t)grid * K1_WARPS;
+    size_t smem = 256 * 32 * 8;
     tokenize_kernel<<<grid, K1_THREADS, smem, st>>>(a);
   }
   CK(cudaEventRecord(c->ev_k[1], st));
-  validate_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
+  const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
+  a.fast = fast ? 1u : 0u;
+  token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
   CK(cudaEventRecord(c->ev_k[2], st));
   if (lookups) {
     iptrie_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
     CK(cudaEventRecord(c->ev_k[3], st));
-    if (a.db.has_literal) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
+    if (a.db.has_literal && !fast) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
     CK(cudaEventRecord(c->ev_k[4], st));
-    if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, st>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
+    if (fast) exact_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
+    else if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, st>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
     CK(cudaEventRecord(c->ev_k[5], st));
   } else {
     for (int k = 3; k <= 5; k++) CK(cudaEventRecord(c->ev_k[k], st));
@@ -1082,7 +1221,7 @@ static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t 
   c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_VALIDATE]++;
   if (lookups) {
     c->timing.launches[MGPU_K_IPTRIE]++;
-    if (a.db.has_literal) c->timing.launches[MGPU_K_LITHASH]++;
+    if (a.db.has_literal && !fast) c->timing.launches[MGPU_K_LITHASH]++;
     if (a.db.has_literal || a.db.has_glob) c->timing.launches[MGPU_K_ACGLOB]++;
   }
   float tot = 0;

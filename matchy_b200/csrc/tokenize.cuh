@@ -42,7 +42,7 @@ struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX, DASH; };
 // State carried into a tile (identical in all lanes of the warp).
 struct TileCarry {
   uint32_t prev;        // facts about the bytes just before the tile: PV_* bits
-  uint32_t cDM, cDN, cHX;  // the open word so far is a well-formed domain prefix / all dot-less domain bytes / all hex
+  uint32_t cBad, cDot, cNhx;  // the open word so far holds a byte that rules out a domain / a '.' / a non-hex byte
   uint64_t open_start;  // chunk offset where the open word starts (valid when prev & PV_T)
 };
 // bits of the "previous bytes" word that travels lane -> lane (one shuffle) and tile -> tile
@@ -59,12 +59,14 @@ MGPU_HD void domain_rule_masks(const LaneMasks& m, uint32_t S, uint32_t pv, uint
   bad_end = prevDOT | prevDASH;
 }
 
-// carry generate/propagate of (G + Sg) for one lane
-MGPU_HD void gp_bits(uint32_t G, uint32_t Sg, uint32_t& g, uint32_t& p) {
-  uint64_t s0 = (uint64_t)G + Sg;
-  g = (uint32_t)(s0 >> 32);
-  p = (uint32_t)(((s0 + 1) >> 32) & 1u) & ~g;
-}
+// "Does the word that ends here contain a byte of Y?" for every word at once.  T = ~B marks word bytes, Y is a subset
+// of T.  In T + Y a carry is born at the lowest Y bit of a word, ripples through the rest of the word (all ones in T)
+// and lands on the boundary bit that follows it; boundaries stop it, so words do not influence each other.  Hence
+// bit e of (T + Y + cin) & B  <=>  e is a boundary and the word ending at e-1 holds a Y byte (cin: the word that was open
+// at the start of the slice already held one).  Across lanes the carries resolve like a 32-bit adder over the
+// per-lane (generate, propagate) pairs: generate = carry out of T + Y, propagate = T is all ones (shared by all chains).
+MGPU_HD uint32_t chain_gen(uint32_t T, uint32_t Y) { return (uint32_t)(((uint64_t)T + Y) >> 32); }
+MGPU_HD uint32_t chain_ends(uint32_t T, uint32_t Y, uint32_t cin, uint32_t B) { return (T + Y + cin) & B; }
 // Given per-lane generate/propagate ballots and the carry into lane 0, the carry into every lane (bit i) and
 // out of lane 31: c[i+1] = g[i] | (p[i] & c[i]) is exactly the carry chain of (g|p) + g + c0.
 MGPU_HD uint32_t carry_chain(uint32_t gen, uint32_t prop, uint32_t c0, uint32_t& cout) {
@@ -74,29 +76,29 @@ MGPU_HD uint32_t carry_chain(uint32_t gen, uint32_t prop, uint32_t c0, uint32_t&
   cout = (uint32_t)(c >> 32) & 1u;
   return (uint32_t)c;
 }
-// Bits where a word made only of class-G bytes ends: bit i set <=> byte i is a boundary, byte i-1 is the last byte of
-// a word, and every byte of that word is in G.  (carry injected at word starts ripples through G and must land on B)
-MGPU_HD uint32_t all_class_ends(uint32_t G, uint32_t Sg, uint32_t cin, uint32_t B) {
-  uint64_t x = (uint64_t)G + Sg + cin;
-  uint32_t carry_into = (uint32_t)x ^ G ^ Sg;
-  return carry_into & ~G & B;
-}
 
-// Start (chunk offset) of the word that ends at boundary bit `bit` of lane `lane`.
-// sB[j] = boundary mask of lane j of this tile.
-MGPU_HD uint64_t word_start(const uint32_t* sB, uint32_t lane, uint32_t bit, uint64_t tile_base, uint64_t open_start) {
-  uint32_t below = bit ? (sB[lane] & (0xFFFFFFFFu >> (32 - bit))) : 0u;
-  int j = (int)lane;
-  while (below == 0) {
-    if (--j < 0) return open_start;
-    below = sB[j];
-  }
+// Chunk offset where the word that is open at the START of lane `lane` begins: just after the last boundary of the
+// lanes below (hasB = ballot of "my slice has a boundary", Bsrc = boundary mask of the highest such lane below, fetched by
+// the caller with one shuffle from lane src_lane), or the tile's own open_start when there is none.
+MGPU_HD uint32_t lane_below_with_boundary(uint32_t hasB, uint32_t lane) {  // 32 = none
+  uint32_t lower = hasB & ((1u << lane) - 1u);
 #ifdef __CUDA_ARCH__
-  uint32_t hi = 31u - (uint32_t)__clz((int)below);
+  return lower ? 31u - (uint32_t)__clz((int)lower) : 32u;
 #else
-  uint32_t hi = 31u - (uint32_t)__builtin_clz(below);
+  return lower ? 31u - (uint32_t)__builtin_clz(lower) : 32u;
 #endif
-  return tile_base + (uint64_t)j * 32 + hi + 1;
+}
+MGPU_HD uint32_t top_bit(uint32_t x) {  // x != 0
+#ifdef __CUDA_ARCH__
+  return 31u - (uint32_t)__clz((int)x);
+#else
+  return 31u - (uint32_t)__builtin_clz(x);
+#endif
+}
+// start of the word that ends at boundary bit `bit` of a lane whose slice starts at chunk offset p
+MGPU_HD uint64_t word_start_in_lane(uint32_t B, uint32_t bit, uint64_t p, uint64_t lane_open_start) {
+  uint32_t below = bit ? (B & (0xFFFFFFFFu >> (32 - bit))) : 0u;
+  return below ? p + top_bit(below) + 1 : lane_open_start;
 }
 
 MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len == 64 || len == 96 || len == 128; }
@@ -105,28 +107,27 @@ MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len ==
 // word that is open there.
 MGPU_HDN TileCarry range_prologue(const uint8_t* buf, uint64_t lo, uint64_t a) {
   TileCarry c;
-  c.prev = 0; c.cDM = 0; c.cDN = 0; c.cHX = 0; c.open_start = a;
+  c.prev = 0; c.cBad = 0; c.cDot = 0; c.cNhx = 0; c.open_start = a;
   if (a <= lo) return c;
   uint8_t prev = buf[a - 1];
   c.prev = (prev == '.' ? (uint32_t)PV_DOT : 0u) | (prev == '-' ? (uint32_t)PV_DASH : 0u) | (prev == ':' ? (uint32_t)PV_CL1 : 0u) |
            ((a >= lo + 2 && buf[a - 2] == ':') ? (uint32_t)PV_CL2 : 0u);
   if (is_boundary(prev)) return c;
   c.prev |= PV_T;
-  uint32_t dm = 1, dn = 1, hx = 1;
+  uint32_t bad = 0, dot = 0, nhx = 0;
   uint64_t s = a;
   uint8_t right = 0;  // the byte to the right of b inside the open word (0 = none yet)
   while (s > lo) {
     uint8_t b = buf[s - 1];
     if (is_boundary(b)) break;
-    bool d = is_domain_fast(b);
-    dm &= d; dn &= (d && b != '.'); hx &= is_hex(b);
-    if (right == '.' && (b == '.' || b == '-')) dm = 0;  // "..", "-."
-    if (right == '-' && b == '.') dm = 0;                // ".-"
+    bad |= !is_domain_fast(b); dot |= b == '.'; nhx |= !is_hex(b);
+    if (right == '.' && (b == '.' || b == '-')) bad = 1;  // "..", "-."
+    if (right == '-' && b == '.') bad = 1;                // ".-"
     right = b;
     s--;
   }
-  if (right == '.' || right == '-') dm = 0;  // the word starts with '.' or '-'
-  c.cDM = dm; c.cDN = dn; c.cHX = hx; c.open_start = s;
+  if (right == '.' || right == '-') bad = 1;  // the word starts with '.' or '-'
+  c.cBad = bad; c.cDot = dot; c.cNhx = nhx; c.open_start = s;
   return c;
 }
 

@@ -39,6 +39,9 @@ def lib():
         L.emu_db_upload.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.emu_set_anchored.argtypes = [C.c_void_p, C.c_int]
         L.emu_is_anchored_exact.argtypes = [C.c_void_p]
+        L.emu_set_generic.argtypes = [C.c_void_p, C.c_int]
+        L.emu_is_fast.argtypes = [C.c_void_p]
+        L.emu_filter_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.emu_default_flags.restype = C.c_uint32
         L.emu_default_flags.argtypes = [C.c_void_p]
         L.emu_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int]
@@ -75,6 +78,20 @@ class Emu:
     def set_anchored(self, on: bool):
         """Choose between the anchored literal search and the Aho-Corasick formulation (both must give the oracle's answer)."""
         self.L.emu_set_anchored(self.h, 1 if on else 0)
+
+    def set_generic(self, on: bool):
+        """True: never use the constant-time string filters (generic lithash + acglob path)."""
+        self.L.emu_set_generic(self.h, 1 if on else 0)
+
+    def is_fast(self):
+        """Does the uploaded database qualify for the fast string path?"""
+        return bool(self.L.emu_is_fast(self.h))
+
+    def filter_stats(self):
+        """(tokens passing the literal filter, tokens passing the glob filter, tokens tested) of the last scan."""
+        out = (C.c_uint64 * 3)()
+        self.L.emu_filter_stats(self.h, out)
+        return tuple(int(x) for x in out)
 
     def anchored_exact(self):
         return bool(self.L.emu_is_anchored_exact(self.h))

@@ -31,12 +31,14 @@ struct emu_ctx {
   DbView db;
   bool loaded = false;
   bool use_anchored = true;  // false: force the Aho-Corasick formulation (both are exercised by the tests)
+  bool force_generic = false;  // true: never take the fast string path (string_filters), like mgpu_set_ac_mode(2)
   std::vector<mgpu_match> recs;
   std::vector<mgpu_id_pair> ids;
   mgpu_counters counters;
   std::vector<StrTok> str;
   std::vector<IpTok> ip;
   std::string err;
+  uint64_t filter_pass[3] = {0, 0, 0};  // fast path: tokens that passed the literal / glob filters, tokens tested
 };
 
 // ---- K1: tokenize_kernel, one "warp" per range of tiles -------------------------------------------------
@@ -54,7 +56,6 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
     for (uint64_t t = t0; t < t1; t++) {
       const uint64_t tile_base = t * TILE_BYTES;
       LaneMasks m[32];
-      uint32_t sB[32];
       for (uint32_t lane = 0; lane < 32; lane++) {
         uint64_t p = tile_base + (uint64_t)lane * 32;
         LaneMasks x{0, 0, 0, 0, 0, 0, 0, 0};
@@ -65,59 +66,61 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
           x.CL |= ((c >> CLS_CL) & 1u) << i; x.NL |= ((c >> CLS_NL) & 1u) << i; x.DM |= ((c >> CLS_DM) & 1u) << i;
           x.HX |= ((c >> CLS_HX) & 1u) << i; x.DASH |= ((c >> CLS_DASH) & 1u) << i;
         }
-        m[lane] = x; sB[lane] = x.B;
+        m[lane] = x;
         lines += (uint64_t)__builtin_popcount(x.NL);
       }
       if (!(cy.prev & PV_T)) cy.open_start = tile_base;
-      uint32_t pT[32], pv[32], S[32], bad[32], bad_end[32];
+      uint32_t pT[32], pv[32], S[32], bad[32], bad_end[32], T[32];
       for (uint32_t lane = 0; lane < 32; lane++) {
         pv[lane] = lane ? prev_bits_of(m[lane - 1]) : cy.prev;
         pT[lane] = pv[lane] & PV_T;
-        uint32_t T = ~m[lane].B;
-        S[lane] = T & ~((T << 1) | pT[lane]);
+        T[lane] = ~m[lane].B;
+        S[lane] = T[lane] & ~((T[lane] << 1) | pT[lane]);
         domain_rule_masks(m[lane], S[lane], pv[lane], bad[lane], bad_end[lane]);
       }
-      uint32_t A[3][32];
+      // the three "word contains ..." chains of tokenize_kernel: ballots are bit loops here
+      uint32_t H[3][32];
+      uint32_t pb = 0;
+      for (uint32_t lane = 0; lane < 32; lane++) pb |= (T[lane] == 0xFFFFFFFFu ? 1u : 0u) << lane;
       for (int cls = 0; cls < 3; cls++) {
-        uint32_t gen = 0, prop = 0, G[32], Sg[32];
+        uint32_t gen = 0, Y[32];
         for (uint32_t lane = 0; lane < 32; lane++) {
-          G[lane] = cls == 0 ? (m[lane].DM & ~bad[lane]) : cls == 1 ? (m[lane].DM & ~m[lane].DOT) : m[lane].HX;
-          Sg[lane] = S[lane] & G[lane];
-          uint32_t g, p;
-          gp_bits(G[lane], Sg[lane], g, p);
-          gen |= g << lane; prop |= p << lane;
+          Y[lane] = cls == 0 ? (T[lane] & (~m[lane].DM | bad[lane])) : cls == 1 ? m[lane].DOT : (T[lane] & ~m[lane].HX);
+          gen |= chain_gen(T[lane], Y[lane]) << lane;
         }
-        uint32_t& c0 = cls == 0 ? cy.cDM : cls == 1 ? cy.cDN : cy.cHX;
-        uint32_t co, cv = carry_chain(gen, prop, c0, co);
-        for (uint32_t lane = 0; lane < 32; lane++)
-          A[cls][lane] = all_class_ends(G[lane], Sg[lane], (cv >> lane) & 1u, m[lane].B) & (cls == 0 ? ~bad_end[lane] : 0xFFFFFFFFu);
+        uint32_t& c0 = cls == 0 ? cy.cBad : cls == 1 ? cy.cDot : cy.cNhx;
+        uint32_t co, cv = carry_chain(gen, pb & ~gen, c0, co);
+        for (uint32_t lane = 0; lane < 32; lane++) H[cls][lane] = chain_ends(T[lane], Y[lane], (cv >> lane) & 1u, m[lane].B);
         c0 = co;
       }
+      uint32_t hasB = 0;
+      for (uint32_t lane = 0; lane < 32; lane++) hasB |= (m[lane].B != 0 ? 1u : 0u) << lane;
       for (uint32_t lane = 0; lane < 32; lane++) {
         uint64_t p = tile_base + (uint64_t)lane * 32;
-        uint32_t candDot = want_dot ? (A[0][lane] & ~A[1][lane]) : 0u;
-        uint32_t candHex = (want_hash && pT[lane]) ? (A[2][lane] & (m[lane].B & (0u - m[lane].B))) : 0u;
+        uint32_t E = m[lane].B & ((T[lane] << 1) | pT[lane]);
+        uint32_t candDot = want_dot ? (H[1][lane] & ~H[0][lane] & ~bad_end[lane]) : 0u;
+        uint32_t candHex = (want_hash && pT[lane]) ? (E & ~H[2][lane] & (m[lane].B & (0u - m[lane].B))) : 0u;
         uint32_t candAt = want_at ? m[lane].AT : 0u;
         uint32_t cl1 = (m[lane].CL << 1) | ((pv[lane] >> 3) & 1u), cl2 = (m[lane].CL << 2) | (((pv[lane] >> 3) & 1u) << 1) | ((pv[lane] >> 4) & 1u);
         uint32_t candC2 = want_c2 ? (m[lane].CL & cl1 & ~cl2) : 0u;
+        uint32_t src = lane_below_with_boundary(hasB, lane);
+        uint64_t lane_open = src < 32u ? tile_base + (uint64_t)src * 32 + top_bit(m[src].B) + 1 : cy.open_start;
         for (uint32_t mm = candDot; mm; mm &= mm - 1) {
           uint32_t bit = (uint32_t)__builtin_ctz(mm);
-          uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
-          qd.push_back(Cand{(uint32_t)s, (uint32_t)(e - s)});
+          uint64_t s = word_start_in_lane(m[lane].B, bit, p, lane_open);
+          qd.push_back(Cand{(uint32_t)s, (uint32_t)(p + bit - s)});
         }
         if (candHex) {
           uint32_t bit = (uint32_t)__builtin_ctz(candHex);
-          uint64_t e = p + bit, s = word_start(sB, lane, bit, tile_base, cy.open_start);
-          if (is_hash_len(e - s)) qh.push_back(Cand{(uint32_t)s, (uint32_t)(e - s)});
+          uint64_t s = word_start_in_lane(m[lane].B, bit, p, lane_open);
+          if (is_hash_len(p + bit - s)) qh.push_back(Cand{(uint32_t)s, (uint32_t)(p + bit - s)});
         }
         for (uint32_t mm = candAt; mm; mm &= mm - 1) qa.push_back((uint32_t)(p + (uint32_t)__builtin_ctz(mm)));
         for (uint32_t mm = candC2; mm; mm &= mm - 1) qc.push_back((uint32_t)(p + (uint32_t)__builtin_ctz(mm) - 1));
       }
-      uint32_t hasB = 0;
-      for (uint32_t lane = 0; lane < 32; lane++) hasB |= (m[lane].B != 0 ? 1u : 0u) << lane;
       if (hasB) {
-        uint32_t ll = 31u - (uint32_t)__builtin_clz(hasB);
-        cy.open_start = tile_base + (uint64_t)ll * 32 + (31u - (uint32_t)__builtin_clz(m[ll].B)) + 1;
+        uint32_t ll = top_bit(hasB);
+        cy.open_start = tile_base + (uint64_t)ll * 32 + top_bit(m[ll].B) + 1;
       }
       cy.prev = prev_bits_of(m[31]);
     }
@@ -136,7 +139,9 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
     const uint8_t* wp = buf + cd.start;
     uint32_t addr;
     if ((flags & MGPU_X_IPV4) && parse_ipv4_word(wp, cd.len, addr)) c->ip.push_back(IpTok{cd.start, cd.len, MGPU_T_IPV4, {addr, 0, 0, 0}});
-    if ((flags & MGPU_X_DOMAINS) && domain_word_psl_utf8(db, wp, cd.len)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
+    bool high = false;  // the kernel passes a per-window flag; the promise "false => pure ASCII" is what matters
+    for (uint32_t k = 0; k < cd.len; k++) high |= wp[k] >= 0x80;
+    if ((flags & MGPU_X_DOMAINS) && domain_word_fast(db, db.psl_tld, wp, cd.len, high)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
   }
   for (auto& cd : qh) {
     uint32_t ty = cd.len == 32 ? MGPU_T_MD5 : cd.len == 40 ? MGPU_T_SHA1 : cd.len == 64 ? MGPU_T_SHA256 : cd.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
@@ -175,17 +180,25 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
       r.data_offset = off;
       c->recs.push_back(r);
     }
-    // K4 + K5
+    // K4 + K5 (generic) or the filters of K2 + the exact kernel (fast path)
+    const bool fast = db.fast_ok && !c->force_generic && (db.has_literal || db.has_glob);
     for (size_t k = s0; k < c->str.size(); k++) {
       const StrTok& t = c->str[k];
       const uint8_t* text = buf + t.start;
+      uint32_t f = fast ? string_filters(db, db.hot, text, t.len) : (uint32_t)(F_LIT | F_GLOB);
+      if (fast) c->filter_pass[0] += (f & F_LIT) != 0, c->filter_pass[1] += (f & F_GLOB) != 0, c->filter_pass[2]++;
+      if (!f) continue;
       uint32_t lit_pid = NONE32, lit_off = 0;
-      if (db.has_literal && !lh_lookup(db, text, t.len, lit_pid)) lit_pid = NONE32;
+      if (!(f & F_LIT) || !db.has_literal || !lh_lookup(db, text, t.len, lit_pid)) lit_pid = NONE32;
       bool lit_ok = lit_pid != NONE32 && lh_data_offset(db, lit_pid, lit_off);
       std::vector<uint32_t> g;
       AcAccel acc;
       acc.root_tab = ac_root_table(db); acc.gram2 = c->use_anchored ? db.ac_gram2 : nullptr;
-      if (db.has_glob) find_all_visit(db, text, t.len, acc, [&](uint32_t pid) { g.push_back(pid); });
+      if (db.has_glob && (f & F_GLOB)) {
+        if (fast && db.ac_anchored && db.wild_count == 0 && db.ac_size >= 20)  // exact_kernel: the lanes share these positions
+          for (uint32_t pos = 0; pos + 3 <= t.len; pos++) anchored_visit_at(db, text, t.len, pos, db.ac_gram2, [&](uint32_t pid) { g.push_back(pid); });
+        else find_all_visit(db, text, t.len, acc, [&](uint32_t pid) { g.push_back(pid); });
+      }
       if (!lit_ok && g.empty()) continue;
       std::sort(g.begin(), g.end());
       g.erase(std::unique(g.begin(), g.end()), g.end());
@@ -228,12 +241,16 @@ int emu_db_upload(emu_ctx* c, const uint8_t* mxy, size_t len) {
     c->db.glob_data = reinterpret_cast<const uint32_t*>(c->file.data() + L.map_off);
   }
   c->db.psl_keys = c->psl.keys.data(); c->db.psl_vals = c->psl.vals.data(); c->db.psl_pool = c->psl.pool.data();
-  c->db.psl_mask = c->psl.mask; c->db.psl_max_len = c->psl.max_len;
+  c->db.psl_mask = c->psl.mask; c->db.psl_max_len = c->psl.max_len; c->db.psl_tld = c->psl.tld.data();
+  if (c->db.fast_ok) { c->db.hot = c->P.hot.data(); c->db.cold = c->P.cold.data(); }
   c->loaded = true;
   return MGPU_OK;
 }
 
 void emu_set_anchored(emu_ctx* c, int on) { c->use_anchored = on != 0; }
+void emu_set_generic(emu_ctx* c, int on) { c->force_generic = on != 0; }
+int emu_is_fast(emu_ctx* c) { return (int)c->db.fast_ok; }
+void emu_filter_stats(emu_ctx* c, uint64_t out[3]) { for (int k = 0; k < 3; k++) out[k] = c->filter_pass[k]; }
 int emu_is_anchored_exact(emu_ctx* c) { return (int)c->db.ac_anchored; }
 
 uint32_t emu_default_flags(emu_ctx* c) {
@@ -249,6 +266,7 @@ int emu_scan(emu_ctx* c, const uint8_t* data, size_t len, uint64_t base, uint32_
              int lookups) {
   c->recs.clear(); c->ids.clear(); c->str.clear(); c->ip.clear();
   memset(&c->counters, 0, sizeof c->counters);
+  c->filter_pass[0] = c->filter_pass[1] = c->filter_pass[2] = 0;
   if (!c->loaded && lookups) return MGPU_E_NODB;
   if (chunk_bytes == 0) chunk_bytes = len ? len : 1;
   size_t pos = 0;

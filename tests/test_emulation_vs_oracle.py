@@ -18,6 +18,12 @@ def test_configs(small_dbs, cfg):
     want = orc.scan(log, chunk_size=128 * 1024)
     for chunk, nwarps, mis in ((0, 1, 0), (70000, 3, 5), (0, 7, 15), (150000, 64, 9)):
         assert emu.scan(log, chunk_bytes=chunk, nwarps=nwarps, misalign=mis) == want, (chunk, nwarps, mis)
+    assert emu.is_fast()  # every BASELINE config qualifies for the constant-time string filters
+    lit, glob, tested = emu.filter_stats()
+    if tested:
+        assert lit + glob <= 0.05 * tested + len(want[0]) + 8, (lit, glob, tested)  # the filters must stay selective
+    emu.set_generic(True)  # the generic lithash + acglob path must give the same answer
+    assert emu.scan(log, chunk_bytes=150000, nwarps=5) == want
     if cfg in (2, 5):
         assert emu.anchored_exact()
         emu.set_anchored(False)  # the Aho-Corasick formulation must give the same answer as the anchored walks
@@ -113,3 +119,67 @@ def test_literal_search_formulations_agree(built):
     assert not emu2.anchored_exact()
     data2 = data + b"q=buzz.example.com zz.example.org\n"
     assert emu2.scan(data2) == orc2.scan(data2)
+
+
+def test_fast_string_path_classification(built):
+    """Suffix- / prefix-anchored globs of every key length, tokens shorter than the keys, literals of every length:
+    the constant-time filters (string_filters) may never lose a match.  Databases with an unanchored glob, a
+    literal-type glob or a case-insensitive mode must fall back to the generic path."""
+    from matchy_b200 import DatabaseBuilder, MatchMode
+    rng = random.Random(5)
+    sfx = ["*m", "*om", "*.io", "*l.io", "*il.io", "*vil.io", "*evil.io", "*.evil.io", "*x.evil.io", "*.very-long-suffix.example.net", "*[0-9].bad.org",
+           "a?c*zz.org", "*.??.uk"]
+    pfx = ["a*", "ab*", "abc.*", "abcd*.z?", "abcde*[a-z]", "abcdef.*", "abcdefg*", "abcdefgh*", "abcdefghi.*", "prefix-longer-than-eight-*", "p.q*r?"]
+    lits = ["a.io", "ab.io", "abc.com", "abcd.com", "abcde.io", "evil.io", "x.evil.io", "abcdefgh.com", "a-much-longer-literal.example.com",
+            "5d41402abc4b2a76b9719d911017c592", "user@evil.io"]
+    b = DatabaseBuilder(build_epoch=1)
+    for g in sfx + pfx:
+        b.add_glob(g, {"g": g})
+    for l in lits:
+        b.add_entry(l, {"l": l})
+    db = b.build()
+    orc, emu = O.Oracle(db), E.Emu(db)
+    assert emu.is_fast()
+    toks = [b"a.io", b"ab.io", b"abc.com", b"abcd.zz", b"abcde.az", b"abcdef.com", b"abcdefg.com", b"abcdefgh.com", b"abcdefghi.com", b"evil.io", b"x.evil.io",
+            b"xx.evil.io", b"l.io", b"il.io", b"vil.io", b"m.com", b"a.om", b"prefix-longer-than-eight-x.com", b"prefix-longer-than-eight.com",
+            b"q.very-long-suffix.example.net", b"very-long-suffix.example.net", b"a7.bad.org", b"ax.bad.org", b"abc.qzz.org", b"a.cc.uk", b"p.qr.rs",
+            b"a-much-longer-literal.example.com", b"x-much-longer-literal.example.com", b"user@evil.io", b"u@x.evil.io", b"5d41402abc4b2a76b9719d911017c592",
+            b"5d41402abc4b2a76b9719d911017c593", b"abc.io", b"b.io", b"a.b.c.d.e.io", b"zz.org", b"ac.zz.org", b"abc.zz.org"]
+    data = b"".join(b"k=" + t + b" \n" for t in toks)
+    for _ in range(300):
+        data += b"h=" + rng.choice(toks)[:rng.randint(1, 40)] + rng.choice([b"", b".io", b".com", b"m", b".evil.io", b".uk"]) + b" "
+    want = orc.scan(data)
+    assert len(want[0]) >= 30
+    assert emu.scan(data) == want
+    emu.set_generic(True)
+    assert emu.scan(data) == want
+    # fall-backs
+    for extra, mode in (("*mid*", None), ("glob:plain.example.com", None), (None, MatchMode.CaseInsensitive)):
+        b2 = DatabaseBuilder(mode, build_epoch=1) if mode is not None else DatabaseBuilder(build_epoch=1)
+        for g in sfx[:6] + pfx[:4]:
+            b2.add_glob(g, {"g": g})
+        for l in lits:
+            b2.add_entry(l, {"l": l})
+        if extra and extra.startswith("glob:"):
+            b2.add_entry(extra, {"g": extra})
+        elif extra:
+            b2.add_glob(extra, {"g": extra})
+        db2 = b2.build()
+        orc2, emu2 = O.Oracle(db2), E.Emu(db2)
+        assert not emu2.is_fast(), (extra, mode)
+        d2 = data + b"q=a.mid.com z=xplain.example.com.evil.io Q=ABC.COM\n"
+        assert emu2.scan(d2) == orc2.scan(d2), (extra, mode)
+
+
+def test_tld_fast_front_end(small_dbs):
+    """Last-label decisions: accepted TLDs, multi-label-only suffixes, labels of 7 / 8 / 9 bytes, non-ASCII TLDs, numeric last labels."""
+    db, _ = small_dbs[1]
+    orc, emu = O.Oracle(db), E.Emu(db)
+    words = [b"a.com", b"a.co.uk", b"a.b.kawasaki.jp", b"city.kawasaki.jp", b"x.ck", b"www.ck", b"a.b.ck", b"a.website", b"a.websitex", b"a.shopping", b"a.shoppin",
+             b"a.photography", b"a.international", b"a.xn--p1ai", "a.\u4e2d\u56fd".encode(), "a.\u0440\u0444".encode(), b"a.\xff\xfe", b"a.b.1", b"1.2.3.4", b"a.html",
+             b"x.y.compute.amazonaws.com", b"a.s3.amazonaws.com", b"a.blogspot.com", b"abcdefg.h", b"a.bcdefgh", b"a.museum", b"a.co", b"co.uk", b"uk",
+             b"a.nom.br", b"a.b.nom.br", b"a.appspot.com", b"a.Com", b"a.COM", b"a.c-m", b"a.travelersinsurance", b"a.x.travelersinsurance"]
+    data = b" ".join(words) + b"\n" + b"".join(b"<" + w + b"> " for w in words)
+    want = sorted((s, t, e) for t, s, e in orc.extract(data, 31))
+    assert len(want) >= 20
+    assert sorted((s, t, e) for t, s, e in emu.tokens(data, 31)) == want

@@ -193,11 +193,12 @@ def test_literal_search_formulations_agree_on_device(engines, small_dbs):
         eng, orc, log = engines[cfg]
         eng.scan(log)
         a = (eng.records_as_tuples(), eng.counters_list())
-        eng.set_ac_mode(1)
-        eng.scan(log)
-        b = (eng.records_as_tuples(), eng.counters_list())
-        eng.set_ac_mode(0)
-        assert a == b
+        for mode in (1, 2):  # generic kernels: Aho-Corasick walk / anchored walks; mode 0 = constant-time filters + exact kernel
+            eng.set_ac_mode(mode)
+            eng.scan(log)
+            b = (eng.records_as_tuples(), eng.counters_list())
+            eng.set_ac_mode(0)
+            assert a == b, mode
     bld = DatabaseBuilder(build_epoch=1)
     for g in ("*abcab*", "*bcabc*", "*cab*", "*.evil.com", "*evil.com*", "*aaa*", "*aaaa*", "*abc*abc*", "abcabc", "zz"):
         bld.add_glob(g, {"g": g})
@@ -209,3 +210,39 @@ def test_literal_search_formulations_agree_on_device(engines, small_dbs):
     e.scan(data)
     want, wcnt = orc.scan(data)
     assert e.records_as_tuples() == want and e.counters_list() == wcnt and len(want) >= 5
+
+
+def test_fast_string_path_on_device(built):
+    """Anchored globs of every key length + literals through the constant-time filters, against the oracle; then the
+    same database with an unanchored glob added (generic kernels)."""
+    from matchy_b200 import DatabaseBuilder, Engine
+    rng = random.Random(5)
+    sfx = ["*m", "*om", "*.io", "*l.io", "*il.io", "*vil.io", "*evil.io", "*.evil.io", "*x.evil.io", "*.very-long-suffix.example.net", "*[0-9].bad.org",
+           "a?c*zz.org", "*.??.uk"]
+    pfx = ["a*", "ab*", "abc.*", "abcd*.z?", "abcde*[a-z]", "abcdef.*", "abcdefg*", "abcdefgh*", "abcdefghi.*", "prefix-longer-than-eight-*", "p.q*r?"]
+    lits = ["a.io", "ab.io", "abc.com", "abcd.com", "abcde.io", "evil.io", "x.evil.io", "abcdefgh.com", "a-much-longer-literal.example.com",
+            "5d41402abc4b2a76b9719d911017c592", "user@evil.io"]
+    toks = [b"a.io", b"ab.io", b"abc.com", b"abcd.zz", b"abcde.az", b"abcdef.com", b"abcdefg.com", b"abcdefgh.com", b"abcdefghi.com", b"evil.io", b"x.evil.io",
+            b"xx.evil.io", b"l.io", b"il.io", b"vil.io", b"m.com", b"a.om", b"prefix-longer-than-eight-x.com", b"prefix-longer-than-eight.com",
+            b"q.very-long-suffix.example.net", b"very-long-suffix.example.net", b"a7.bad.org", b"ax.bad.org", b"abc.qzz.org", b"a.cc.uk", b"p.qr.rs",
+            b"a-much-longer-literal.example.com", b"x-much-longer-literal.example.com", b"user@evil.io", b"u@x.evil.io", b"5d41402abc4b2a76b9719d911017c592",
+            b"5d41402abc4b2a76b9719d911017c593", b"abc.io", b"b.io", b"a.b.c.d.e.io", b"zz.org", b"ac.zz.org", b"abc.zz.org"]
+    data = b"".join(b"k=" + t + b" \n" for t in toks)
+    for _ in range(3000):
+        data += b"h=" + rng.choice(toks)[:rng.randint(1, 40)] + rng.choice([b"", b".io", b".com", b"m", b".evil.io", b".uk"]) + rng.choice([b" ", b"\n"])
+    for extra in (None, "*mid*"):
+        b = DatabaseBuilder(build_epoch=1)
+        for g in sfx + pfx + ([extra] if extra else []):
+            b.add_glob(g, {"g": g})
+        for l in lits:
+            b.add_entry(l, {"l": l})
+        db = b.build()
+        e = Engine(0, chunk_bytes=1 << 20)
+        e.upload(db)
+        orc = O.Oracle(db)
+        want, wcnt = orc.scan(data)
+        assert len(want) >= 30
+        e.scan(data)
+        assert e.counters_list() == wcnt
+        assert e.records_as_tuples() == want
+        e.close()
