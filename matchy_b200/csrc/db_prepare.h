@@ -148,7 +148,7 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     if (L.node_count == 0) db.has_ip = 0;
   }
   std::vector<FilterKey> lit_tail_keys, glob_keys;
-  std::vector<uint64_t> lit_full_keys;
+  std::vector<uint32_t> lit_full_keys;
   bool fast = L.match_mode == 0;
   // --- literal hash
   if (L.has_literal) {
@@ -198,7 +198,8 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         uint32_t kk = sl >= 8 ? 8u : sl;
         uint64_t tailv = prep_bytes_le(sp + sl - kk, kk), headv = prep_bytes_le(sp, kk);
         lit_tail_keys.push_back(FilterKey{tailv, 0, (uint32_t)TAG_LIT_TAIL, kk});
-        lit_full_keys.push_back(cold_key_full(headv, tailv << (8 * (8 - kk)), sl));
+        lit_tail_keys.push_back(FilterKey{headv, 0, (uint32_t)TAG_LIT_HEAD, kk});
+        lit_full_keys.push_back(key_hash(headv, tailv << (8 * (8 - kk)), TAG_LIT_FULL, sl));
       }
     }
     db.lh_len = len; db.has_literal = 1;
@@ -399,8 +400,7 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
       bool any = false;
       for (auto& key : keys) {
         if (key.tag != tag) continue;
-        uint32_t x = hot_hash(key.v0, key.v1, key.tag, key.k);
-        h[x >> 17] |= (1u << (x & 31)) | (1u << ((x >> 5) & 31));
+        hot_set(h.data(), key_hash(key.v0, key.v1, key.tag, key.k));
         any = true;
       }
       uint64_t bits = 0;
@@ -412,13 +412,13 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     try_tag(glob_keys, TAG_GLOB_S);
     try_tag(glob_keys, TAG_GLOB_P);
     try_tag(lit_tail_keys, TAG_LIT_TAIL);
+    try_tag(lit_tail_keys, TAG_LIT_HEAD);
     uint64_t nkeys = glob_keys.size() + lit_full_keys.size();
     uint64_t words = 1024;
     while (words * 4 < nkeys) words <<= 1;  // >= 16 bits per key
     P.cold.assign((size_t)words, 0);
-    auto cold_add = [&](uint64_t h) { P.cold[(size_t)((uint32_t)(h >> 20) & (uint32_t)(words - 1))] |= (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63)); };
-    for (auto& key : glob_keys) cold_add(cold_key(key.v0, key.v1, key.tag, key.k));
-    for (uint64_t h : lit_full_keys) cold_add(h);
+    for (auto& key : glob_keys) cold_set(P.cold.data(), (uint32_t)(words - 1), key_hash(key.v0, key.v1, key.tag, key.k));
+    for (uint32_t h : lit_full_keys) cold_set(P.cold.data(), (uint32_t)(words - 1), h);
     db.cold_mask = (uint32_t)(words - 1);
   }
   return true;

@@ -84,7 +84,7 @@ struct DbView {
 static const uint32_t TLD_SLOTS = 4096;      // 32 KiB of shared memory
 static const uint32_t HOT_WORDS = 32768;     // 128 KiB of shared memory
 static const uint64_t TLD_SLOW = 1ULL << 63; // entry flag: the label only ends multi-label PSL entries -> general PSL walk
-enum { TAG_GLOB_S = 0, TAG_GLOB_P = 1, TAG_LIT_TAIL = 2, TAG_LIT_FULL = 3 };
+enum { TAG_GLOB_S = 0, TAG_GLOB_P = 1, TAG_LIT_TAIL = 2, TAG_LIT_HEAD = 3, TAG_LIT_FULL = 4 };
 enum { F_LIT = 0x100u, F_GLOB = 0x200u };    // StrTok.type flag bits: which exact lookups the token still needs
 
 MGPU_HD uint32_t tld_slot(uint64_t key) {
@@ -94,7 +94,7 @@ MGPU_HD uint32_t tld_slot(uint64_t key) {
 // Key of an anchored glob / a literal: K bytes of text, K in {1,2,3,4,8,12,16}, held little-endian in (v0, v1), zero-padded.
 // glob_key_len: the key length used for an anchor literal of m bytes (long literals use their first / last 16 bytes).
 MGPU_HD uint32_t glob_key_len(uint32_t m) { return m < 4 ? m : (m >= 16 ? 16u : (m & ~3u)); }
-MGPU_HD uint32_t hot_hash(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
+MGPU_HD uint32_t key_hash(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
   uint32_t h = ((uint32_t)v0 ^ (tag * 0x632BE5ABu + k * 0x7F4A7C15u)) * 0x9E3779B1u;
   h ^= h >> 15;
   h = (h ^ (uint32_t)(v0 >> 32)) * 0x85EBCA77u;
@@ -106,24 +106,24 @@ MGPU_HD uint32_t hot_hash(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
   h *= 0x165667B1u;
   return h ^ (h >> 16);
 }
+// hot filter: blocked Bloom, 2 bits in one 32-bit word.  cold filter: blocked Bloom, 3 bits in one 64-bit word; its word
+// index and bit positions come from a second mix of the same key hash, so one hash per key serves both filters.
 MGPU_HD bool hot_test(const uint32_t* hot, uint32_t h) {
   uint32_t m = (1u << (h & 31)) | (1u << ((h >> 5) & 31));
   return (hot[h >> 17] & m) == m;
 }
-MGPU_HD uint64_t cold_mix(uint64_t x) {
-  x ^= x >> 31; x *= 0x7FB5D329728EA185ULL; x ^= x >> 27; x *= 0x81DADEF4BC2DD44DULL; x ^= x >> 33;
-  return x;
+MGPU_HD void hot_set(uint32_t* hot, uint32_t h) { hot[h >> 17] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31)); }
+MGPU_HD uint32_t cold_word(uint32_t h, uint32_t mask) { return ((h * 0x2545F491u) ^ (h >> 11)) & mask; }
+MGPU_HD uint64_t cold_bits(uint32_t h) {
+  uint32_t g = (h ^ 0x5BD1E995u) * 0x846CA68Bu;
+  g ^= g >> 15;
+  return (1ULL << (g & 63)) | (1ULL << ((g >> 6) & 63)) | (1ULL << ((g >> 12) & 63));
 }
-MGPU_HD uint64_t cold_key(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
-  return cold_mix(cold_mix(v0 ^ ((uint64_t)(tag * 32 + k) * 0x9E3779B97F4A7C15ULL)) ^ (v1 * 0xD6E8FEB86659FD93ULL));
+MGPU_HD bool cold_test(const uint64_t* cold, uint32_t mask, uint32_t h) {
+  uint64_t need = cold_bits(h);
+  return (cold[cold_word(h, mask)] & need) == need;
 }
-MGPU_HD uint64_t cold_key_full(uint64_t head8, uint64_t tail8, uint32_t n) {
-  return cold_mix((head8 * 0xFF51AFD7ED558CCDULL) ^ ((tail8 << 29) | (tail8 >> 35)) ^ ((uint64_t)n * 0xC4CEB9FE1A85EC53ULL) ^ 0x3C6EF372FE94F82BULL);
-}
-MGPU_HD bool cold_test(const uint64_t* cold, uint32_t mask, uint64_t h) {
-  uint64_t need = (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63));
-  return (cold[(uint32_t)(h >> 20) & mask] & need) == need;
-}
+MGPU_HD void cold_set(uint64_t* cold, uint32_t mask, uint32_t h) { cold[cold_word(h, mask)] |= cold_bits(h); }
 
 MGPU_HD uint32_t ld32(const uint8_t* p) {  // little-endian; 4-byte aligned on the device (layout chosen at upload)
 #ifdef __CUDA_ARCH__
@@ -310,19 +310,51 @@ MGPU_HDN bool psl_any_suffix(const DbView& db, const uint8_t* d, uint32_t n) {
 // =================================================================================================
 // Token validation (second half of the extractor; candidates come from the tokenizer kernel)
 // =================================================================================================
-// try_parse_ipv4 on a whole boundary-delimited word w[0..n): all of it must be consumed.
+// try_parse_ipv4 (lib.rs:813-869) on a whole boundary-delimited word w[0..n): all of it must be consumed — four groups of
+// 1..3 digits, value <= 255, no leading zero in a multi-digit group, single dots between.  Straight-line SWAR over the
+// (at most 15) bytes held in registers: per-byte digit / dot flags -> 16-bit masks -> dot positions -> group values.
+MGPU_HD uint32_t swar_flags4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }  // 0x80-per-byte flags of 4 bytes -> 4 bits
+MGPU_HD uint32_t swar_flags16(uint64_t lo, uint64_t hi) {
+  return swar_flags4((uint32_t)lo) | (swar_flags4((uint32_t)(lo >> 32)) << 4) | (swar_flags4((uint32_t)hi) << 8) | (swar_flags4((uint32_t)(hi >> 32)) << 12);
+}
+MGPU_HD uint64_t swar_is_digit(uint64_t v) {  // 0x80 in every byte that is '0'..'9'
+  uint64_t x = v ^ 0x3030303030303030ULL;
+  return ~(((x & 0x7F7F7F7F7F7F7F7FULL) + 0x7676767676767676ULL) | x) & 0x8080808080808080ULL;
+}
+MGPU_HD uint64_t swar_is_byte(uint64_t v, uint8_t c) {  // 0x80 in every byte equal to c
+  uint64_t d = v ^ (0x0101010101010101ULL * c);
+  return ~(((d & 0x7F7F7F7F7F7F7F7FULL) + 0x7F7F7F7F7F7F7F7FULL) | d) & 0x8080808080808080ULL;
+}
 MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) {
   if (n < 7 || n > 15) return false;
-  uint32_t pos = 0, addr = 0;
+  uint64_t lo = ldu64_fast(w), hi = ldu64_fast(w + 8);  // (reads stay within the 16 bytes of slack behind every token)
+  hi = n > 8 ? (hi & ((1ULL << (8 * (n - 8))) - 1)) : 0ULL;
+  if (n < 8) lo &= (1ULL << (8 * n)) - 1;
+  const uint32_t D = swar_flags16(swar_is_digit(lo), swar_is_digit(hi)), P = swar_flags16(swar_is_byte(lo, '.'), swar_is_byte(hi, '.'));
+  if ((D | P) != (1u << n) - 1u) return false;  // digits and dots only
+#ifdef __CUDA_ARCH__
+  if (__popc(P) != 3) return false;
+  const uint32_t p1 = (uint32_t)__ffs((int)P) - 1u, P2 = P & (P - 1), p2 = (uint32_t)__ffs((int)P2) - 1u, p3 = (uint32_t)__ffs((int)(P2 & (P2 - 1))) - 1u;
+#else
+  if (__builtin_popcount(P) != 3) return false;
+  const uint32_t p1 = (uint32_t)__builtin_ctz(P), P2 = P & (P - 1), p2 = (uint32_t)__builtin_ctz(P2), p3 = (uint32_t)__builtin_ctz(P2 & (P2 - 1));
+#endif
+  const uint32_t st[4] = {0u, p1 + 1, p2 + 1, p3 + 1}, ln[4] = {p1, p2 - p1 - 1, p3 - p2 - 1, n - p3 - 1};
+  uint32_t addr = 0;
+  bool ok = true;
+#pragma unroll
   for (int k = 0; k < 4; k++) {
-    uint32_t v = 0, digits = 0, st = pos;
-    while (pos < n && is_digit(w[pos]) && digits < 3) { v = v * 10 + (uint32_t)(w[pos] - '0'); pos++; digits++; }
-    if (digits == 0 || v > 255) return false;
-    if (digits > 1 && w[st] == '0') return false;
-    addr = (addr << 8) | v;
-    if (k < 3) { if (pos >= n || w[pos] != '.') return false; pos++; }
+    const uint32_t s = st[k], l = ln[k];
+    ok = ok && l >= 1 && l <= 3;  // (an unsigned wrap-around of an empty group fails l <= 3)
+    // the (up to) 3 digit bytes of the group, first digit in the low byte
+    const uint64_t win = s >= 8 ? (hi >> (8 * (s & 7))) : (s ? ((lo >> (8 * s)) | (hi << (64 - 8 * s))) : lo);
+    const uint32_t dv = ((uint32_t)win ^ 0x30303030u);
+    const uint32_t d0 = dv & 0xFF, d1 = (dv >> 8) & 0xFF, d2 = (dv >> 16) & 0xFF;
+    const uint32_t v = l == 1 ? d0 : (l == 2 ? d0 * 10 + d1 : d0 * 100 + d1 * 10 + d2);
+    ok = ok && v <= 255 && !(l > 1 && d0 == 0);
+    addr = (addr << 8) | (v & 0xFF);
   }
-  if (pos != n) return false;  // the byte after the address must be a boundary == end of the word
+  if (!ok) return false;
   addr_out = addr;
   return true;
 }
@@ -436,9 +468,9 @@ MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const ui
   const uint64_t t1 = load_tail8(w, n), h0 = load_head8(w, n);
   if (db.has_literal) {
     const uint32_t k = n >= 8 ? 8u : n;
-    if (!((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, hot_hash(t1 >> (8 * (8 - k)), 0, TAG_LIT_TAIL, k))) {
-      if (cold_test(db.cold, db.cold_mask, cold_key_full(h0, t1, n))) flags |= F_LIT;
-    }
+    bool pass = !((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, key_hash(t1 >> (8 * (8 - k)), 0, TAG_LIT_TAIL, k));
+    pass = pass && (!((db.hot_tags >> TAG_LIT_HEAD) & 1u) || hot_test(hot, key_hash(h0, 0, TAG_LIT_HEAD, k)));
+    if (pass && cold_test(db.cold, db.cold_mask, key_hash(h0, t1, TAG_LIT_FULL, n))) flags |= F_LIT;
   }
   if (db.has_glob && (db.glob_s_lens | db.glob_p_lens)) {
     const uint64_t t0 = load_tail16_hi(w, n), h1 = load_head16_hi(w, n);
@@ -452,8 +484,9 @@ MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const ui
 #endif
       if (k > n) break;
       tail_key(t0, t1, k, v0, v1);
-      if (((db.hot_tags >> TAG_GLOB_S) & 1u) && !hot_test(hot, hot_hash(v0, v1, TAG_GLOB_S, k))) continue;
-      g = cold_test(db.cold, db.cold_mask, cold_key(v0, v1, TAG_GLOB_S, k));
+      const uint32_t h = key_hash(v0, v1, TAG_GLOB_S, k);
+      if (((db.hot_tags >> TAG_GLOB_S) & 1u) && !hot_test(hot, h)) continue;
+      g = cold_test(db.cold, db.cold_mask, h);
     }
     for (uint32_t lens = db.glob_p_lens; lens && !g; lens &= lens - 1) {
 #ifdef __CUDA_ARCH__
@@ -463,8 +496,9 @@ MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const ui
 #endif
       if (k > n) break;
       head_key(h0, h1, k, v0, v1);
-      if (((db.hot_tags >> TAG_GLOB_P) & 1u) && !hot_test(hot, hot_hash(v0, v1, TAG_GLOB_P, k))) continue;
-      g = cold_test(db.cold, db.cold_mask, cold_key(v0, v1, TAG_GLOB_P, k));
+      const uint32_t h = key_hash(v0, v1, TAG_GLOB_P, k);
+      if (((db.hot_tags >> TAG_GLOB_P) & 1u) && !hot_test(hot, h)) continue;
+      g = cold_test(db.cold, db.cold_mask, h);
     }
     if (g) flags |= F_GLOB;
   }

@@ -33,8 +33,11 @@ struct Cand { uint32_t start, len; };
 struct StrTok { uint32_t start, len, type; };
 struct IpTok { uint32_t start, len, type, pad; uint32_t w[4]; };  // v4: w[0]; v6: w[k] = seg[2k] << 16 | seg[2k+1]
 
-struct DevCounters {
-  uint32_t n_str, n_ip, n_rec, n_ids;
+struct ScanTotals { uint32_t n_rec, n_ids; };  // records / id pairs appended so far to the shared result buffers (all pieces of a batch)
+
+struct DevCounters {  // one per piece
+  uint32_t n_str, n_ip;
+  uint32_t n_rec, n_ids;      // snapshot of ScanTotals when the piece finished (piece_end_kernel)
   uint32_t overflow;          // bit q: candidate queue q, 8: str tokens, 9: ip tokens, 10: records, 11: ids
   uint32_t pad[3];
   unsigned long long lines;
@@ -63,6 +66,7 @@ struct ScanArgs {
   mgpu_match* recs; uint32_t cap_rec;
   mgpu_id_pair* ids; uint32_t cap_ids;
   DevCounters* ctr;
+  ScanTotals* tot;
 };
 
 static const int K1_THREADS = 512;
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint8_t* lut_lane = smem + lane * 8;
+  const uint32_t lane8 = lane * 8;
   const uint64_t nwarps = (uint64_t)gridDim.x * K1_WARPS;  // == a.nseg
   const uint64_t w = (uint64_t)blockIdx.x * K1_WARPS + warp;
   const uint64_t tiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
@@ -135,8 +139,8 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
     const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
     for (uint64_t t = t0; t < t1; t++) {
-      const uint64_t tile_base = t * TILE_BYTES;
-      const uint64_t p = tile_base + (uint64_t)lane * SLICE_BYTES;
+      const uint32_t tile_base = (uint32_t)(t * TILE_BYTES);  // chunks are at most 2 GiB: positions fit 32 bits
+      const uint32_t p = tile_base + lane * SLICE_BYTES;
       uint4 v0 = ld_stream(a.buf + p), v1 = ld_stream(a.buf + p + 16);
       uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
@@ -144,8 +148,8 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       for (int j = 0; j < 8; j++) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          uint32_t off = __byte_perm(wds[j], 0, 0x4404u | ((uint32_t)k << 4));  // byte k of the word, times 256
-          uint2 e = *reinterpret_cast<const uint2*>(lut_lane + off);
+          uint32_t off = __byte_perm(wds[j], lane8, 0x5504u | ((uint32_t)k << 4));  // (byte k of the word) * 256 + lane * 8
+          uint2 e = *reinterpret_cast<const uint2*>(smem + off);
           const uint32_t sh = (uint32_t)((j & 1) * 4 + k);
           accLo[j >> 1] += e.x << sh;
           accHi[j >> 1] += e.y << sh;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       m.DM = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 1);
       m.HX = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 2);
       m.DASH = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 3);
-      if (tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
+      if ((uint64_t)tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
         uint64_t valid = a.n > p ? a.n - p : 0;
         uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
         if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       const uint32_t hasB = __ballot_sync(0xFFFFFFFFu, m.B != 0);
       const uint32_t src = lane_below_with_boundary(hasB, lane);
       const uint32_t Bsrc = __shfl_sync(0xFFFFFFFFu, m.B, src & 31u);
-      const uint64_t lane_open = src < 32u ? tile_base + (uint64_t)src * 32 + top_bit(Bsrc) + 1 : cy.open_start;
+      const uint32_t lane_open = src < 32u ? tile_base + src * 32 + top_bit(Bsrc) + 1 : (uint32_t)cy.open_start;
 
       // ---- emission ----
       {
@@ -212,8 +216,9 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
             Cand* dst = qd + nd + excl;
             for (uint32_t mm = candDot; mm; mm &= mm - 1) {
               const uint32_t bit = __ffs(mm) - 1;
-              const uint64_t s = word_start_in_lane(m.B, bit, p, lane_open);
-              *dst++ = Cand{(uint32_t)s, (uint32_t)(p + bit - s)};
+              const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+              const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+              *dst++ = Cand{s, p + bit - s};
             }
           } else ovf |= 1u << Q_DOTTED;
           nd += total;
@@ -224,9 +229,10 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
           bool keep = false; Cand c{0, 0};
           if (candHex) {
             const uint32_t bit = __ffs(candHex) - 1;
-            const uint64_t s = word_start_in_lane(m.B, bit, p, lane_open);
+            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
             keep = is_hash_len(p + bit - s);
-            c.start = (uint32_t)s; c.len = (uint32_t)(p + bit - s);
+            c.start = s; c.len = p + bit - s;
           }
           const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
           if (bal) {
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       if (hasB) {
         const uint32_t ll = top_bit(hasB);
         const uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
-        cy.open_start = tile_base + (uint64_t)ll * 32 + top_bit(Bl) + 1;
+        cy.open_start = tile_base + ll * 32 + top_bit(Bl) + 1;
       }
       cy.prev = __shfl_sync(0xFFFFFFFFu, my_prev, 31);
     }
@@ -435,6 +441,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* s_win = tk_smem + (size_t)TLD_SLOTS * 8 + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
   const bool fast = a.fast != 0;
+  if (a.ctr->overflow) return;  // an earlier stage of this piece ran out of room: the host redoes the piece in smaller parts
   if (a.flags & (MGPU_X_DOMAINS | MGPU_X_EMAILS)) {
     const uint4* src = reinterpret_cast<const uint4*>(a.db.psl_tld);
     for (uint32_t i = threadIdx.x; i < TLD_SLOTS / 2; i += blockDim.x) reinterpret_cast<uint4*>(s_tld)[i] = src[i];
@@ -505,7 +512,7 @@ __device__ __forceinline__ uint32_t agg_add(uint32_t* ctr, uint32_t v) {
 // K3: IP tokens
 __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
-  if (!a.db.has_ip) return;
+  if (!a.db.has_ip || a.ctr->overflow) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     IpTok t = a.ip[i];
     if (t.type == TOK_INVALID) continue;
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
       hit = trie_lookup_v6(a.db, seg, off, pl);
     }
     if (!hit) continue;
-    uint32_t k = agg_add(&a.ctr->n_rec, 1u);
+    uint32_t k = agg_add(&a.tot->n_rec, 1u);
     if (k >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); continue; }
     mgpu_match r;
     r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_IP; r.prefix_len = pl; r.reserved = 0;
@@ -542,7 +549,7 @@ __device__ __forceinline__ void emit_string_match(const ScanArgs& a, const StrTo
   if (exact) find_all_visit(a.db, text, t.len, acc, [&](uint32_t) { cnt++; });
   if (!lit_ok && cnt == 0) return;
   uint32_t total = cnt + (lit_ok ? 1u : 0u);
-  uint32_t b = agg_add(&a.ctr->n_ids, total);
+  uint32_t b = agg_add(&a.tot->n_ids, total);
   if ((uint64_t)b + total > a.cap_ids) { atomicOr(&a.ctr->overflow, 1u << 11); return; }
   uint32_t k = b;
   if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
@@ -562,7 +569,7 @@ __device__ __forceinline__ void emit_string_match(const ScanArgs& a, const StrTo
       a.ids[x].data_offset = glob_data_offset(a.db, a.ids[x].pattern_id, off) ? off : MGPU_NO_DATA;
     }
   }
-  uint32_t r_i = agg_add(&a.ctr->n_rec, 1u);
+  uint32_t r_i = agg_add(&a.tot->n_rec, 1u);
   if (r_i >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); return; }
   mgpu_match r;
   r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_PATTERN; r.prefix_len = 0; r.reserved = 0;
@@ -576,6 +583,7 @@ __global__ void __launch_bounds__(KT_THREADS) lithash_kernel(ScanArgs a) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
   const uint32_t nround = (n + 31u) & ~31u;
+  if (a.ctr->overflow) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
     bool valid = i < n;
     StrTok t{0, 0, 0};
@@ -694,6 +702,7 @@ __global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
   uint32_t* s_hit = s_cnt + KT_WARPS;
   uint32_t* s_wcnt = s_hit + KT_WARPS;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (a.ctr->overflow) return;
   // hot state in shared memory: the root's dense table (every walk starts there) and the 2-byte prefix bitmap that
   // almost every token position fails
   AcAccel acc;
@@ -774,6 +783,7 @@ __global__ void __launch_bounds__(256) exact_kernel(ScanArgs a) {
   __shared__ uint32_t s_n[8];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
+  if (a.ctr->overflow) return;
   AcAccel acc;
   acc.root_tab = ac_root_table(a.db);
   acc.gram2 = a.db.ac_gram2;
@@ -813,7 +823,7 @@ __global__ void __launch_bounds__(256) exact_kernel(ScanArgs a) {
     for (uint32_t x = 0; x < cnt; x++) if (x == 0 || ids[x] != ids[u - 1]) ids[u++] = ids[x];
     const uint32_t total = u + (lit_ok ? 1u : 0u);
     if (total == 0) continue;
-    const uint32_t b = atomicAdd(&a.ctr->n_ids, total);
+    const uint32_t b = atomicAdd(&a.tot->n_ids, total);
     if ((uint64_t)b + total > a.cap_ids) { atomicOr(&a.ctr->overflow, 1u << 11); continue; }
     uint32_t k = b;
     if (lit_ok) { a.ids[k].pattern_id = lit_pid; a.ids[k].data_offset = lit_off; k++; }
@@ -822,13 +832,39 @@ __global__ void __launch_bounds__(256) exact_kernel(ScanArgs a) {
       a.ids[k].pattern_id = ids[x];
       a.ids[k].data_offset = glob_data_offset(a.db, ids[x], off) ? off : MGPU_NO_DATA;
     }
-    const uint32_t r_i = atomicAdd(&a.ctr->n_rec, 1u);
+    const uint32_t r_i = atomicAdd(&a.tot->n_rec, 1u);
     if (r_i >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); continue; }
     mgpu_match r;
     r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_PATTERN; r.prefix_len = 0; r.reserved = 0;
     r.n_ids = total; r.ids_index = b; r.data_offset = MGPU_NO_DATA; r.pad = 0;
     a.recs[r_i] = r;
   }
+}
+
+// end of a piece: snapshot the running totals into the piece's counter block
+__global__ void piece_end_kernel(DevCounters* ctr, const ScanTotals* tot) { ctr->n_rec = tot->n_rec; ctr->n_ids = tot->n_ids; }
+
+// Cut points of a resident buffer, all at once: out[k] = position just after the last '\n' in [at[k] - span, at[k]), or
+// NONE64 when that window holds none.  One block per cut.
+static const uint64_t NONE64 = ~0ULL;
+__global__ void cuts_back_kernel(const uint8_t* buf, const uint64_t* at, uint64_t span, uint64_t* out) {
+  __shared__ unsigned long long best;
+  const uint64_t hi = at[blockIdx.x], lo = hi > span ? hi - span : 0;
+  uint64_t end = hi;
+  while (end > lo) {
+    uint64_t beg = end - lo > 8192 ? end - 8192 : lo;
+    if (threadIdx.x == 0) best = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (uint64_t i = beg + threadIdx.x; i < end; i += blockDim.x) if (buf[i] == '\n') mine = i + 1;
+    if (mine) atomicMax(&best, mine);
+    __syncthreads();
+    unsigned long long b = best;
+    __syncthreads();
+    if (b) { if (threadIdx.x == 0) out[blockIdx.x] = b; return; }
+    end = beg;
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = NONE64;
 }
 
 // position just after the first '\n' at or after `from` (or n): where a newline-aligned cut may be made
@@ -921,14 +957,16 @@ struct mgpu_ctx {
   size_t chunk_bytes = 0;
   cudaStream_t compute = nullptr, copy = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-  cudaEvent_t ev_k[MGPU_K_COUNT + 1] = {};
+  static const int MAX_BATCH = 32;  // pieces launched back to back before the host looks at their counters
+  cudaEvent_t ev_k[MAX_BATCH][MGPU_K_COUNT + 1] = {};
   cudaEvent_t ev_scan[2] = {nullptr, nullptr};
   // log staging (double buffered) and pinned bounce buffers for pageable callers
   uint8_t* d_log[2] = {nullptr, nullptr};
   uint8_t* h_pin[2] = {nullptr, nullptr};
   // work buffers
   ScanArgs args;  // device pointers + capacities (buf/n/base/flags filled per chunk)
-  DevCounters* h_ctr = nullptr;  // pinned
+  DevCounters* h_ctr = nullptr;  // pinned, MAX_BATCH entries (args.ctr points at the device copy of entry 0)
+  ScanTotals* d_tot = nullptr;
   uint64_t* d_cut = nullptr; uint64_t* h_cut = nullptr;
   uint8_t* d_small = nullptr; uint32_t* d_small_out = nullptr;
   void* d_flush = nullptr;
@@ -975,10 +1013,10 @@ void mgpu_destroy(mgpu_ctx* c) {
     if (c->ev_copied[s]) cudaEventDestroy(c->ev_copied[s]);
     if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
   }
-  for (auto& e : c->ev_k) if (e) cudaEventDestroy(e);
+  for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
   void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
-                  c->args.recs, c->args.ids, c->args.ctr, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
+                  c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   if (c->h_cut) cudaFreeHost(c->h_cut);
@@ -1010,7 +1048,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
     CK(cudaMalloc(&c->d_log[s], chunk_bytes + TILE_BYTES));
     CK(cudaMallocHost(&c->h_pin[s], std::min(chunk_bytes, (size_t)64 << 20)));
   }
-  for (auto& e : c->ev_k) CK(cudaEventCreate(&e));
+  for (auto& row : c->ev_k) for (auto& e : row) CK(cudaEventCreate(&e));
   for (auto& e : c->ev_scan) CK(cudaEventCreate(&e));
   ScanArgs& a = c->args;
   memset(&a, 0, sizeof a);
@@ -1037,10 +1075,12 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMalloc(&a.lh_res, (size_t)a.cap_str * 4));
   CK(cudaMalloc(&a.recs, (size_t)a.cap_rec * sizeof(mgpu_match)));
   CK(cudaMalloc(&a.ids, (size_t)a.cap_ids * sizeof(mgpu_id_pair)));
-  CK(cudaMalloc(&a.ctr, sizeof(DevCounters)));
-  CK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters)));
-  CK(cudaMalloc(&c->d_cut, 64 * sizeof(uint64_t) * 2));
-  CK(cudaMallocHost(&c->h_cut, 64 * sizeof(uint64_t) * 2));
+  CK(cudaMalloc(&a.ctr, sizeof(DevCounters) * mgpu_ctx::MAX_BATCH));
+  CK(cudaMalloc(&c->d_tot, sizeof(ScanTotals)));
+  a.tot = c->d_tot;
+  CK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters) * mgpu_ctx::MAX_BATCH));
+  CK(cudaMalloc(&c->d_cut, 4096 * sizeof(uint64_t) * 2));
+  CK(cudaMallocHost(&c->h_cut, 4096 * sizeof(uint64_t) * 2));
   CK(cudaMalloc(&c->d_small, 65536 + TILE_BYTES));
   CK(cudaMalloc(&c->d_small_out, 64));
   CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
@@ -1178,13 +1218,15 @@ uint32_t mgpu_default_flags(mgpu_ctx* c) {
 }
 
 // ---- scanning -------------------------------------------------------------------------------------------
-static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, bool lookups) {
+// Launch the kernels of one piece into batch slot `slot` (counter block + event row).  No host synchronisation.
+static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, bool lookups) {
   ScanArgs a = c->args;
   a.buf = d_buf; a.lo = lo; a.n = n; a.base = base; a.flags = flags;
+  a.ctr = c->args.ctr + slot;
   if (c->force_ac_walk) a.db.ac_anchored = 0;
   cudaStream_t st = c->compute;
-  CK(cudaMemsetAsync(a.ctr, 0, sizeof(DevCounters), st));
-  CK(cudaEventRecord(c->ev_k[0], st));
+  cudaEvent_t* ev = c->ev_k[slot];
+  CK(cudaEventRecord(ev[0], st));
   {
     uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
     uint64_t want_blocks = (tiles + K1_WARPS - 1) / K1_WARPS;
@@ -1194,41 +1236,76 @@ static int run_kernels(mgpu_ctx* c, const uint8_t* d_buf, uint64_t lo, uint64_t 
     size_t smem = 256 * 32 * 8;
     tokenize_kernel<<<grid, K1_THREADS, smem, st>>>(a);
   }
-  CK(cudaEventRecord(c->ev_k[1], st));
+  CK(cudaEventRecord(ev[1], st));
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
   a.fast = fast ? 1u : 0u;
   token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
-  CK(cudaEventRecord(c->ev_k[2], st));
+  CK(cudaEventRecord(ev[2], st));
   if (lookups) {
     iptrie_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
-    CK(cudaEventRecord(c->ev_k[3], st));
+    CK(cudaEventRecord(ev[3], st));
     if (a.db.has_literal && !fast) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
-    CK(cudaEventRecord(c->ev_k[4], st));
+    CK(cudaEventRecord(ev[4], st));
     if (fast) exact_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
     else if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, st>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
-    CK(cudaEventRecord(c->ev_k[5], st));
+    CK(cudaEventRecord(ev[5], st));
   } else {
-    for (int k = 3; k <= 5; k++) CK(cudaEventRecord(c->ev_k[k], st));
+    for (int k = 3; k <= 5; k++) CK(cudaEventRecord(ev[k], st));
   }
+  piece_end_kernel<<<1, 1, 0, st>>>(a.ctr, a.tot);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(c->h_ctr, a.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  for (int k = 0; k < MGPU_K_COUNT; k++) {
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->ev_k[k], c->ev_k[k + 1]));
-    c->timing.kernel_ms[k] += ms;
-  }
   c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_VALIDATE]++;
   if (lookups) {
     c->timing.launches[MGPU_K_IPTRIE]++;
     if (a.db.has_literal && !fast) c->timing.launches[MGPU_K_LITHASH]++;
     if (a.db.has_literal || a.db.has_glob) c->timing.launches[MGPU_K_ACGLOB]++;
   }
-  float tot = 0;
-  CK(cudaEventElapsedTime(&tot, c->ev_k[0], c->ev_k[MGPU_K_COUNT]));
-  c->timing.total_ms += tot;
+  c->timing.aux_launches++;
   c->timing.chunks++;
   return MGPU_OK;
+}
+
+// Start a batch: zero the counter blocks and the running totals.
+static int begin_batch(mgpu_ctx* c, int pieces) {
+  CK(cudaMemsetAsync(c->args.ctr, 0, sizeof(DevCounters) * pieces, c->compute));
+  CK(cudaMemsetAsync(c->d_tot, 0, sizeof(ScanTotals), c->compute));
+  return MGPU_OK;
+}
+// Finish a batch: counters to the host, one synchronisation, kernel times.
+static int end_batch(mgpu_ctx* c, int pieces) {
+  CK(cudaMemcpyAsync(c->h_ctr, c->args.ctr, sizeof(DevCounters) * pieces, cudaMemcpyDeviceToHost, c->compute));
+  CK(cudaStreamSynchronize(c->compute));
+  for (int p = 0; p < pieces; p++) {
+    for (int k = 0; k < MGPU_K_COUNT; k++) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, c->ev_k[p][k], c->ev_k[p][k + 1]));
+      c->timing.kernel_ms[k] += ms;
+    }
+    float tot = 0;
+    CK(cudaEventElapsedTime(&tot, c->ev_k[p][0], c->ev_k[p][MGPU_K_COUNT]));
+    c->timing.total_ms += tot;
+  }
+  return MGPU_OK;
+}
+// Copy the records [r_lo, r_hi) / id pairs [i_lo, i_hi) of the shared device buffers behind the host vectors.
+static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_lo, uint32_t i_hi) {
+  if (!c->keep_results || r_hi <= r_lo) return MGPU_OK;
+  size_t r0 = c->recs.size(), i0 = c->ids.size();
+  c->recs.resize(r0 + (r_hi - r_lo));
+  CK(cudaMemcpyAsync(c->recs.data() + r0, c->args.recs + r_lo, (size_t)(r_hi - r_lo) * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->compute));
+  if (i_hi > i_lo) {
+    c->ids.resize(i0 + (i_hi - i_lo));
+    CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids + i_lo, (size_t)(i_hi - i_lo) * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
+  }
+  CK(cudaStreamSynchronize(c->compute));
+  for (size_t k = r0; k < c->recs.size(); k++) if (c->recs[k].kind == MGPU_KIND_PATTERN) c->recs[k].ids_index = (uint32_t)(c->recs[k].ids_index - i_lo + i0);
+  return MGPU_OK;
+}
+static void add_counters(mgpu_ctx* c, const DevCounters& h, uint64_t bytes, uint32_t n_rec) {
+  c->counters.lines += h.lines;
+  c->counters.bytes += bytes;
+  for (int k = 0; k < 12; k++) { c->counters.by_type[k] += h.by_type[k]; c->counters.candidates += h.by_type[k]; }
+  c->counters.matches += n_rec;
 }
 
 // first newline-aligned cut point at or after each of `from` inside dev[0..n)
@@ -1250,9 +1327,13 @@ static int find_cuts(mgpu_ctx* c, const uint8_t* dev, uint64_t n, const std::vec
 static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t end, uint64_t base, uint32_t flags, bool lookups, int depth) {
   if (end <= pos) return MGPU_OK;
   const uint64_t al = pos & ~(uint64_t)15;
-  int rc = run_kernels(c, dev + al, pos - al, end - al, base + al, flags, lookups);
+  int rc = begin_batch(c, 1);
   if (rc) return rc;
-  DevCounters& h = *c->h_ctr;
+  rc = launch_piece(c, 0, dev + al, pos - al, end - al, base + al, flags, lookups);
+  if (rc) return rc;
+  rc = end_batch(c, 1);
+  if (rc) return rc;
+  DevCounters& h = c->h_ctr[0];
   if (h.overflow) {
     if (depth >= 6 || end - pos < 4096) { set_err("result buffers exhausted (match density too high for the configured chunk size)"); return MGPU_E_OVERFLOW; }
     std::vector<uint64_t> from, cuts;
@@ -1270,10 +1351,7 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
     return MGPU_OK;
   }
   // collect
-  c->counters.lines += h.lines;
-  c->counters.bytes += end - pos;
-  for (int k = 0; k < 12; k++) { c->counters.by_type[k] += h.by_type[k]; c->counters.candidates += h.by_type[k]; }
-  c->counters.matches += h.n_rec;
+  add_counters(c, h, end - pos, h.n_rec);
   if (c->capture_tokens) {
     size_t s0 = c->x_str.size(), i0 = c->x_ip.size();
     c->x_str.resize(s0 + h.n_str); c->x_ip.resize(i0 + h.n_ip);
@@ -1285,18 +1363,7 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
     for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);
     for (size_t k = i0; k < c->x_ip.size(); k++) c->x_ip[k].start += (uint32_t)(base + al);
   }
-  if (c->keep_results && h.n_rec) {
-    size_t r0 = c->recs.size(), i0 = c->ids.size();
-    c->recs.resize(r0 + h.n_rec);
-    CK(cudaMemcpyAsync(c->recs.data() + r0, c->args.recs, (size_t)h.n_rec * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->compute));
-    if (h.n_ids) {
-      c->ids.resize(i0 + h.n_ids);
-      CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids, (size_t)h.n_ids * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
-    }
-    CK(cudaStreamSynchronize(c->compute));
-    for (size_t k = r0; k < c->recs.size(); k++) if (c->recs[k].kind == MGPU_KIND_PATTERN) c->recs[k].ids_index += (uint32_t)i0;
-  }
-  return MGPU_OK;
+  return fetch_results(c, 0, h.n_rec, 0, h.n_ids);
 }
 
 static void begin_scan(mgpu_ctx* c) {
@@ -1339,25 +1406,83 @@ static int check_ready(mgpu_ctx* c, uint32_t flags) {
   return MGPU_OK;
 }
 
-// dev[0..len) resident in HBM: pieces of at most chunk_bytes, each ending just after a newline
-// (FileReader::next_batch, processing/mod.rs:206-251: cut at the last '\n' of the window; the tail goes last)
+// dev[0..len) resident in HBM: pieces of at most chunk_bytes, each ending just after a newline (any newline-aligned
+// partition gives the same result; FileReader::next_batch, processing/mod.rs:206-251, is one such
+// partition).  All cut points come from one kernel; the pieces of a batch are launched back to back with a counter
+// block each and the host synchronises once per batch.  A piece that ran out of room is redone through scan_piece().
 static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_t base, uint32_t flags, bool lookups) {
   if (((uintptr_t)dev & 15) != 0) { set_err("device buffer must be 16-byte aligned"); return MGPU_E_PARAM; }
-  uint64_t pos = 0;
-  const uint64_t window = c->chunk_bytes - 16;  // run_kernels realigns the start downwards by up to 15 bytes
-  while (pos < len) {
-    uint64_t end = std::min<uint64_t>(len, pos + window);
-    if (end < len) {
-      rfind_nl_kernel<<<1, 256, 0, c->compute>>>(dev, pos, end, c->d_cut);
-      c->timing.aux_launches++;
-      CK(cudaMemcpyAsync(c->h_cut, c->d_cut, 8, cudaMemcpyDeviceToHost, c->compute));
-      CK(cudaStreamSynchronize(c->compute));
-      if (c->h_cut[0] == 0) { set_err("a single line is longer than the scan chunk; raise chunk_bytes"); return MGPU_E_OVERFLOW; }
-      end = c->h_cut[0];
+  if (len == 0) return MGPU_OK;
+  const uint64_t slack = std::min<uint64_t>((uint64_t)1 << 20, c->chunk_bytes / 4);  // longest line the parallel cut search allows
+  const uint64_t stride = c->chunk_bytes - 16 - slack;  // launch_piece realigns a piece's start downwards by up to 15 bytes
+  std::vector<uint64_t> cuts;  // piece k = [cuts[k], cuts[k+1])
+  cuts.push_back(0);
+  const uint64_t ncut = (len - 1) / stride;  // nominal boundaries stride, 2*stride, ... < len
+  bool sequential = c->capture_tokens || ncut > 4096;
+  if (!sequential && ncut > 0) {
+    for (uint64_t k = 0; k < ncut; k++) c->h_cut[k] = (k + 1) * stride;
+    CK(cudaMemcpyAsync(c->d_cut, c->h_cut, ncut * 8, cudaMemcpyHostToDevice, c->compute));
+    cuts_back_kernel<<<(unsigned)ncut, 256, 0, c->compute>>>(dev, c->d_cut, slack, c->d_cut + 4096);
+    c->timing.aux_launches++;
+    CK(cudaMemcpyAsync(c->h_cut + 4096, c->d_cut + 4096, ncut * 8, cudaMemcpyDeviceToHost, c->compute));
+    CK(cudaStreamSynchronize(c->compute));
+    for (uint64_t k = 0; k < ncut && !sequential; k++) {
+      if (c->h_cut[4096 + k] == NONE64) sequential = true;  // a line longer than `slack`: take the sequential search below
+      else if (c->h_cut[4096 + k] > cuts.back()) cuts.push_back(c->h_cut[4096 + k]);
     }
-    int rc = scan_piece(c, dev, pos, end, base, flags, lookups, 0);
+  }
+  if (sequential) {
+    uint64_t pos = 0;
+    const uint64_t window = c->chunk_bytes - 16;
+    while (pos < len) {
+      uint64_t end = std::min<uint64_t>(len, pos + window);
+      if (end < len) {
+        rfind_nl_kernel<<<1, 256, 0, c->compute>>>(dev, pos, end, c->d_cut);
+        c->timing.aux_launches++;
+        CK(cudaMemcpyAsync(c->h_cut, c->d_cut, 8, cudaMemcpyDeviceToHost, c->compute));
+        CK(cudaStreamSynchronize(c->compute));
+        if (c->h_cut[0] == 0) { set_err("a single line is longer than the scan chunk; raise chunk_bytes"); return MGPU_E_OVERFLOW; }
+        end = c->h_cut[0];
+      }
+      int rc = scan_piece(c, dev, pos, end, base, flags, lookups, 0);
+      if (rc) return rc;
+      pos = end;
+    }
+    return MGPU_OK;
+  }
+  cuts.push_back(len);
+  const size_t npieces = cuts.size() - 1;
+  for (size_t p0 = 0; p0 < npieces; p0 += mgpu_ctx::MAX_BATCH) {
+    const int nb = (int)std::min<size_t>(mgpu_ctx::MAX_BATCH, npieces - p0);
+    int rc = begin_batch(c, nb);
     if (rc) return rc;
-    pos = end;
+    for (int k = 0; k < nb; k++) {
+      const uint64_t pos = cuts[p0 + k], end = cuts[p0 + k + 1], al = pos & ~(uint64_t)15;
+      rc = launch_piece(c, k, dev + al, pos - al, end - al, base + al, flags, lookups);
+      if (rc) return rc;
+    }
+    rc = end_batch(c, nb);
+    if (rc) return rc;
+    // gather: runs of pieces without overflow share one copy; overflowed pieces are redone afterwards
+    std::vector<DevCounters> h(c->h_ctr, c->h_ctr + nb);  // (scan_piece below reuses the pinned block)
+    std::vector<int> redo;
+    uint32_t r_prev = 0, i_prev = 0, run_r = 0, run_i = 0;
+    bool in_run = false;
+    for (int k = 0; k <= nb; k++) {
+      const bool ok = k < nb && !h[k].overflow;
+      if (ok) {
+        if (!in_run) { run_r = r_prev; run_i = i_prev; in_run = true; }
+        add_counters(c, h[k], cuts[p0 + k + 1] - cuts[p0 + k], h[k].n_rec - r_prev);
+      } else {
+        if (in_run) { rc = fetch_results(c, run_r, r_prev, run_i, i_prev); if (rc) return rc; in_run = false; }
+        if (k < nb) redo.push_back(k);
+      }
+      if (k < nb) { r_prev = std::min(h[k].n_rec, c->args.cap_rec); i_prev = std::min(h[k].n_ids, c->args.cap_ids); }
+    }
+    for (int k : redo) {
+      rc = scan_piece(c, dev, cuts[p0 + k], cuts[p0 + k + 1], base, flags, lookups, 0);
+      if (rc) return rc;
+    }
   }
   return MGPU_OK;
 }
