@@ -108,8 +108,7 @@ struct PreparedDb {
   uint32_t ac_node_count = 0;
 };
 
-struct FilterKey { uint64_t v0, v1; uint32_t tag, k; };
-inline uint64_t prep_bytes_le(const uint8_t* p, uint32_t k) { uint64_t v = 0; for (uint32_t i = 0; i < k; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
+struct FilterKey { uint32_t h, tag; };  // key hash (device_fns.cuh), tag class
 
 inline uint32_t prep_le32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
@@ -195,11 +194,11 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         uint32_t sl = (uint32_t)lh[abs] | ((uint32_t)lh[abs + 1] << 8);
         if (sl == 0 || abs + 2 + sl > len) continue;
         const uint8_t* sp = lh + abs + 2;
-        uint32_t kk = sl >= 8 ? 8u : sl;
-        uint64_t tailv = prep_bytes_le(sp + sl - kk, kk), headv = prep_bytes_le(sp, kk);
-        lit_tail_keys.push_back(FilterKey{tailv, 0, (uint32_t)TAG_LIT_TAIL, kk});
-        lit_tail_keys.push_back(FilterKey{headv, 0, (uint32_t)TAG_LIT_HEAD, kk});
-        lit_full_keys.push_back(key_hash(headv, tailv << (8 * (8 - kk)), TAG_LIT_FULL, sl));
+        uint32_t th, hh, fh;
+        lit_key_hashes(sp, sl, th, hh, fh);
+        lit_tail_keys.push_back(FilterKey{th, (uint32_t)TAG_LIT_TAIL});
+        lit_tail_keys.push_back(FilterKey{hh, (uint32_t)TAG_LIT_HEAD});
+        lit_full_keys.push_back(fh);
       }
     }
     db.lh_len = len; db.has_literal = 1;
@@ -382,10 +381,10 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         const uint8_t* ptr = nullptr; uint32_t dl = 0;
         int r = lit_of(cnt - 1, ptr, dl);
         if (r < 0) continue;
-        if (r == 1) { uint32_t k = glob_key_len(dl), k0 = k < 8 ? k : 8; const uint8_t* q = ptr + dl - k; glob_keys.push_back(FilterKey{prep_bytes_le(q, k0), prep_bytes_le(q + k0, k - k0), (uint32_t)TAG_GLOB_S, k}); db.glob_s_lens |= 1u << k; continue; }
+        if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_S), (uint32_t)TAG_GLOB_S}); db.glob_s_lens |= 1u << glob_key_len(dl); continue; }
         r = lit_of(0, ptr, dl);
         if (r < 0) continue;
-        if (r == 1) { uint32_t k = glob_key_len(dl), k0 = k < 8 ? k : 8; glob_keys.push_back(FilterKey{prep_bytes_le(ptr, k0), prep_bytes_le(ptr + k0, k - k0), (uint32_t)TAG_GLOB_P, k}); db.glob_p_lens |= 1u << k; continue; }
+        if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_P), (uint32_t)TAG_GLOB_P}); db.glob_p_lens |= 1u << glob_key_len(dl); continue; }
         fast = false;                                       // neither end is a literal: any position can match
       }
     }
@@ -400,7 +399,7 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
       bool any = false;
       for (auto& key : keys) {
         if (key.tag != tag) continue;
-        hot_set(h.data(), key_hash(key.v0, key.v1, key.tag, key.k));
+        hot_set(h.data(), key.h);
         any = true;
       }
       uint64_t bits = 0;
@@ -417,7 +416,7 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     uint64_t words = 1024;
     while (words * 4 < nkeys) words <<= 1;  // >= 16 bits per key
     P.cold.assign((size_t)words, 0);
-    for (auto& key : glob_keys) cold_set(P.cold.data(), (uint32_t)(words - 1), key_hash(key.v0, key.v1, key.tag, key.k));
+    for (auto& key : glob_keys) cold_set(P.cold.data(), (uint32_t)(words - 1), key.h);
     for (uint32_t h : lit_full_keys) cold_set(P.cold.data(), (uint32_t)(words - 1), h);
     db.cold_mask = (uint32_t)(words - 1);
   }

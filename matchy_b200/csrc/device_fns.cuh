@@ -91,20 +91,29 @@ MGPU_HD uint32_t tld_slot(uint64_t key) {
   uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
   return (h ^ (h >> 15)) & (TLD_SLOTS - 1);
 }
-// Key of an anchored glob / a literal: K bytes of text, K in {1,2,3,4,8,12,16}, held little-endian in (v0, v1), zero-padded.
-// glob_key_len: the key length used for an anchor literal of m bytes (long literals use their first / last 16 bytes).
+// Keys of the string filters.  A key is (tag class, K, K bytes of text); the bytes are fed to the hash as little-endian
+// 32-bit WORDS: K in {4, 8, 12, 16} is K/4 whole words, K in {1, 2, 3} one word masked to K bytes.  Head keys feed the words
+// front to back, tail keys back to front, and the hash is incremental (key_mix per word, key_fin per key), so a token's
+// 16-byte key extends its 12-byte key by one step.
+//   glob anchor literal of m bytes -> K = glob_key_len(m) of its first (prefix-anchored) / last (suffix-anchored) bytes
+//   stored literal of n bytes      -> K = lit_key_len(n) of its last bytes (TAG_LIT_TAIL) and of its first bytes (TAG_LIT_HEAD);
+//                                     (n, first K, last K bytes) for the cold filter (TAG_LIT_FULL)
 MGPU_HD uint32_t glob_key_len(uint32_t m) { return m < 4 ? m : (m >= 16 ? 16u : (m & ~3u)); }
-MGPU_HD uint32_t key_hash(uint64_t v0, uint64_t v1, uint32_t tag, uint32_t k) {
-  uint32_t h = ((uint32_t)v0 ^ (tag * 0x632BE5ABu + k * 0x7F4A7C15u)) * 0x9E3779B1u;
-  h ^= h >> 15;
-  h = (h ^ (uint32_t)(v0 >> 32)) * 0x85EBCA77u;
-  h ^= h >> 13;
-  h = (h ^ (uint32_t)v1) * 0xC2B2AE3Du;
-  h ^= h >> 16;
-  h = (h ^ (uint32_t)(v1 >> 32)) * 0x27D4EB2Fu;
-  h ^= h >> 15;
-  h *= 0x165667B1u;
-  return h ^ (h >> 16);
+MGPU_HD uint32_t lit_key_len(uint32_t n) { return n >= 8 ? 8u : (n >= 4 ? 4u : n); }
+MGPU_HD uint32_t key_seed(uint32_t tag) { return 0x811C9DC5u ^ (tag * 0x632BE5ABu); }
+MGPU_HD uint32_t key_mix(uint32_t s, uint32_t w) { s = (s ^ w) * 0x9E3779B1u; return s ^ (s >> 15); }
+MGPU_HD uint32_t key_fin(uint32_t s, uint32_t k) {
+  s = (s ^ (k * 0x7F4A7C15u)) * 0x85EBCA77u;
+  s ^= s >> 13;
+  s *= 0xC2B2AE3Du;
+  return s ^ (s >> 16);
+}
+MGPU_HD uint32_t low_bytes32(uint32_t w, uint32_t k) { return k >= 4 ? w : (w & ((1u << (8 * k)) - 1u)); }
+// hash of a whole key given its words in feeding order (host side: database preparation)
+MGPU_HD uint32_t key_hash_words(const uint32_t* words, uint32_t k, uint32_t tag) {
+  uint32_t s = key_seed(tag);
+  for (uint32_t i = 0; i < (k + 3) / 4; i++) s = key_mix(s, words[i]);
+  return key_fin(s, k);
 }
 // hot filter: blocked Bloom, 2 bits in one 32-bit word.  cold filter: blocked Bloom, 3 bits in one 64-bit word; its word
 // index and bit positions come from a second mix of the same key hash, so one hash per key serves both filters.
@@ -310,45 +319,74 @@ MGPU_HDN bool psl_any_suffix(const DbView& db, const uint8_t* d, uint32_t n) {
 // =================================================================================================
 // Token validation (second half of the extractor; candidates come from the tokenizer kernel)
 // =================================================================================================
-// try_parse_ipv4 (lib.rs:813-869) on a whole boundary-delimited word w[0..n): all of it must be consumed — four groups of
-// 1..3 digits, value <= 255, no leading zero in a multi-digit group, single dots between.  Straight-line SWAR over the
-// (at most 15) bytes held in registers: per-byte digit / dot flags -> 16-bit masks -> dot positions -> group values.
-MGPU_HD uint32_t swar_flags4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }  // 0x80-per-byte flags of 4 bytes -> 4 bits
-MGPU_HD uint32_t swar_flags16(uint64_t lo, uint64_t hi) {
-  return swar_flags4((uint32_t)lo) | (swar_flags4((uint32_t)(lo >> 32)) << 4) | (swar_flags4((uint32_t)hi) << 8) | (swar_flags4((uint32_t)(hi >> 32)) << 12);
-}
-MGPU_HD uint64_t swar_is_digit(uint64_t v) {  // 0x80 in every byte that is '0'..'9'
-  uint64_t x = v ^ 0x3030303030303030ULL;
-  return ~(((x & 0x7F7F7F7F7F7F7F7FULL) + 0x7676767676767676ULL) | x) & 0x8080808080808080ULL;
-}
-MGPU_HD uint64_t swar_is_byte(uint64_t v, uint8_t c) {  // 0x80 in every byte equal to c
-  uint64_t d = v ^ (0x0101010101010101ULL * c);
-  return ~(((d & 0x7F7F7F7F7F7F7F7FULL) + 0x7F7F7F7F7F7F7F7FULL) | d) & 0x8080808080808080ULL;
-}
-MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) {
-  if (n < 7 || n > 15) return false;
-  uint64_t lo = ldu64_fast(w), hi = ldu64_fast(w + 8);  // (reads stay within the 16 bytes of slack behind every token)
-  hi = n > 8 ? (hi & ((1ULL << (8 * (n - 8))) - 1)) : 0ULL;
-  if (n < 8) lo &= (1ULL << (8 * n)) - 1;
-  const uint32_t D = swar_flags16(swar_is_digit(lo), swar_is_digit(hi)), P = swar_flags16(swar_is_byte(lo, '.'), swar_is_byte(hi, '.'));
-  if ((D | P) != (1u << n) - 1u) return false;  // digits and dots only
+// First 16 / last 16 bytes of a token as little-endian words.  h[i] = bytes [4i, 4i+4) (bytes past the token are whatever
+// follows it in the buffer: every buffer has 16 bytes of slack).  t[i] = bytes [n-16+4i, n-12+4i), loaded only when they lie
+// inside the token (n >= 16-4i), else 0 — keys never use bytes outside the token.
+struct KeyWords { uint32_t h[4], t[4]; };
+MGPU_HD void load_head_words(const uint8_t* w, uint32_t h[4]) {
 #ifdef __CUDA_ARCH__
-  if (__popc(P) != 3) return false;
-  const uint32_t p1 = (uint32_t)__ffs((int)P) - 1u, P2 = P & (P - 1), p2 = (uint32_t)__ffs((int)P2) - 1u, p3 = (uint32_t)__ffs((int)(P2 & (P2 - 1))) - 1u;
+  const uintptr_t a = (uintptr_t)w;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3) * 8;
+  const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+  h[0] = __funnelshift_r(w0, w1, sh); h[1] = __funnelshift_r(w1, w2, sh); h[2] = __funnelshift_r(w2, w3, sh); h[3] = __funnelshift_r(w3, w4, sh);
 #else
-  if (__builtin_popcount(P) != 3) return false;
-  const uint32_t p1 = (uint32_t)__builtin_ctz(P), P2 = P & (P - 1), p2 = (uint32_t)__builtin_ctz(P2), p3 = (uint32_t)__builtin_ctz(P2 & (P2 - 1));
+  for (int i = 0; i < 4; i++) h[i] = ld32u(w + 4 * i);
+#endif
+}
+MGPU_HD void load_tail_words(const uint8_t* w, uint32_t n, uint32_t t[4]) {
+  t[3] = n >= 4 ? ldu32_fast(w + n - 4) : 0u;
+  t[2] = n >= 8 ? ldu32_fast(w + n - 8) : 0u;
+  t[1] = n >= 12 ? ldu32_fast(w + n - 12) : 0u;
+  t[0] = n >= 16 ? ldu32_fast(w + n - 16) : 0u;
+}
+
+// try_parse_ipv4 (lib.rs:813-869) on a whole boundary-delimited word of n bytes held in h[0..4) (only the first n bytes count):
+// all of it must be consumed — four groups of 1..3 digits, value <= 255, no leading zero in a multi-digit group, single dots
+// between.  Straight-line SWAR: per-byte digit / dot flags -> 16-bit masks -> dot positions -> group values.
+MGPU_HD uint32_t swar_flags4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }  // 0x80-per-byte flags of 4 bytes -> 4 bits
+MGPU_HD uint32_t swar_is_digit(uint32_t v) {  // 0x80 in every byte that is '0'..'9'
+  uint32_t x = v ^ 0x30303030u;
+  return ~(((x & 0x7F7F7F7Fu) + 0x76767676u) | x) & 0x80808080u;
+}
+MGPU_HD uint32_t swar_is_dot(uint32_t v) {  // 0x80 in every byte that is '.'
+  uint32_t d = v ^ 0x2E2E2E2Eu;
+  return ~(((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+}
+MGPU_HD uint32_t word_at(const uint32_t h[4], uint32_t s) {  // bytes [s, s+4) of the 16 (zero past the end), s < 16
+  const uint32_t i = s >> 2, sh = (s & 3) * 8;
+  const uint32_t a = i == 0 ? h[0] : (i == 1 ? h[1] : (i == 2 ? h[2] : h[3]));
+  const uint32_t b = i == 0 ? h[1] : (i == 1 ? h[2] : (i == 2 ? h[3] : 0u));
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(a, b, sh);
+#else
+  return sh ? ((a >> sh) | (b << (32 - sh))) : a;
+#endif
+}
+MGPU_HDN bool parse_ipv4_words(const uint32_t h[4], uint32_t n, uint32_t& addr_out) {
+  if (n < 7 || n > 15) return false;
+  const uint32_t D = swar_flags4(swar_is_digit(h[0])) | (swar_flags4(swar_is_digit(h[1])) << 4) | (swar_flags4(swar_is_digit(h[2])) << 8) |
+                     (swar_flags4(swar_is_digit(h[3])) << 12);
+  const uint32_t P = swar_flags4(swar_is_dot(h[0])) | (swar_flags4(swar_is_dot(h[1])) << 4) | (swar_flags4(swar_is_dot(h[2])) << 8) |
+                     (swar_flags4(swar_is_dot(h[3])) << 12);
+  const uint32_t all = (1u << n) - 1u;
+  if (((D | P) & all) != all) return false;  // digits and dots only
+  const uint32_t Pn = P & all;
+#ifdef __CUDA_ARCH__
+  if (__popc(Pn) != 3) return false;
+  const uint32_t p1 = (uint32_t)__ffs((int)Pn) - 1u, P2 = Pn & (Pn - 1), p2 = (uint32_t)__ffs((int)P2) - 1u, p3 = (uint32_t)__ffs((int)(P2 & (P2 - 1))) - 1u;
+#else
+  if (__builtin_popcount(Pn) != 3) return false;
+  const uint32_t p1 = (uint32_t)__builtin_ctz(Pn), P2 = Pn & (Pn - 1), p2 = (uint32_t)__builtin_ctz(P2), p3 = (uint32_t)__builtin_ctz(P2 & (P2 - 1));
 #endif
   const uint32_t st[4] = {0u, p1 + 1, p2 + 1, p3 + 1}, ln[4] = {p1, p2 - p1 - 1, p3 - p2 - 1, n - p3 - 1};
   uint32_t addr = 0;
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const uint32_t s = st[k], l = ln[k];
-    ok = ok && l >= 1 && l <= 3;  // (an unsigned wrap-around of an empty group fails l <= 3)
-    // the (up to) 3 digit bytes of the group, first digit in the low byte
-    const uint64_t win = s >= 8 ? (hi >> (8 * (s & 7))) : (s ? ((lo >> (8 * s)) | (hi << (64 - 8 * s))) : lo);
-    const uint32_t dv = ((uint32_t)win ^ 0x30303030u);
+    const uint32_t l = ln[k];
+    ok = ok && l >= 1 && l <= 3;
+    const uint32_t dv = word_at(h, st[k] & 15u) ^ 0x30303030u;  // the group's digits, first digit in the low byte
     const uint32_t d0 = dv & 0xFF, d1 = (dv >> 8) & 0xFF, d2 = (dv >> 16) & 0xFF;
     const uint32_t v = l == 1 ? d0 : (l == 2 ? d0 * 10 + d1 : d0 * 100 + d1 * 10 + d2);
     ok = ok && v <= 255 && !(l > 1 && d0 == 0);
@@ -357,6 +395,12 @@ MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) 
   if (!ok) return false;
   addr_out = addr;
   return true;
+}
+MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) {
+  if (n < 7 || n > 15) return false;
+  uint32_t h[4];
+  load_head_words(w, h);
+  return parse_ipv4_words(h, n, addr_out);
 }
 
 // A boundary-delimited word made only of domain characters (incl. bytes >= 0x80), containing a '.', whose labels are
@@ -392,10 +436,8 @@ MGPU_HDN bool domain_word_psl_utf8(const DbView& db, const uint8_t* w, uint32_t 
 }
 
 // ---- fast path of the two functions above and of the string lookups: constant work per token ----
-// The last min(n,8) bytes of w[0..n) with the LAST byte in bits 56..63 (missing leading bytes are zero), and the
-// first min(n,8) bytes with the FIRST byte in bits 0..7 (missing trailing bytes are zero).  n >= 1.
+// The last min(n,8) bytes of w[0..n) with the LAST byte in bits 56..63 (missing leading bytes are zero).  n >= 1.
 MGPU_HD uint64_t load_tail8(const uint8_t* w, uint32_t n) { return n >= 8 ? ldu64_fast(w + n - 8) : (ldu64_fast(w) << (8 * (8 - n))); }
-MGPU_HD uint64_t load_head8(const uint8_t* w, uint32_t n) { uint64_t v = ldu64_fast(w); return n >= 8 ? v : (v & ((1ULL << (8 * n)) - 1)); }
 
 enum { TLD_REJECT = 0, TLD_ACCEPT = 1, TLD_GENERAL = 2 };
 // PSL decision from the last label alone.  find_valid_tld_suffix_bytes (lib.rs:1671-1692) accepts iff ANY dot-suffix of
@@ -424,8 +466,8 @@ MGPU_HD int tld_class(const uint64_t* tld, uint64_t tail8) {
   }
 }
 // domain_word_psl_utf8 with the constant-time front end.  maybe_high = false promises that w[0..n) is pure ASCII.
-MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint8_t* w, uint32_t n, bool maybe_high) {
-  int c = tld_class(tld, load_tail8(w, n));
+MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint8_t* w, uint32_t n, bool maybe_high, uint64_t tail8) {
+  int c = tld_class(tld, tail8);
   if (c == TLD_REJECT) return false;
   if (c == TLD_GENERAL) return domain_word_psl_utf8(db, w, n);
   if (!maybe_high) return true;
@@ -437,72 +479,111 @@ MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint
   }
   return !(high & 0x80808080u) || valid_utf8(w, n);
 }
-
-// Bytes [n-16, n-8) of w[0..n) the way load_tail8 holds [n-8, n), and bytes [8, 16) the way load_head8 holds [0, 8).
-MGPU_HD uint64_t load_tail16_hi(const uint8_t* w, uint32_t n) { return n >= 16 ? ldu64_fast(w + n - 16) : (n > 8 ? (ldu64_fast(w) << (8 * (16 - n))) : 0ULL); }
-MGPU_HD uint64_t load_head16_hi(const uint8_t* w, uint32_t n) { return n >= 16 ? ldu64_fast(w + 8) : (n > 8 ? (ldu64_fast(w + 8) & ((1ULL << (8 * (n - 8))) - 1)) : 0ULL); }
-// (v0, v1) of the LAST k bytes given t0 = load_tail16_hi, t1 = load_tail8;  of the FIRST k bytes given h0 = load_head8, h1 = load_head16_hi
-MGPU_HD void tail_key(uint64_t t0, uint64_t t1, uint32_t k, uint64_t& v0, uint64_t& v1) {
-  if (k <= 8) { v0 = t1 >> (8 * (8 - k)); v1 = 0; }
-  else if (k == 16) { v0 = t0; v1 = t1; }
-  else { uint32_t s = 8 * (16 - k); v0 = (t0 >> s) | (t1 << (64 - s)); v1 = t1 >> s; }  // 8 < k < 16
-}
-MGPU_HD void head_key(uint64_t h0, uint64_t h1, uint32_t k, uint64_t& v0, uint64_t& v1) {
-  if (k < 8) { v0 = h0 & ((1ULL << (8 * k)) - 1); v1 = 0; }
-  else if (k == 8) { v0 = h0; v1 = 0; }
-  else if (k == 16) { v0 = h0; v1 = h1; }
-  else { v0 = h0; v1 = h1 & ((1ULL << (8 * (k - 8))) - 1); }
+MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint8_t* w, uint32_t n, bool maybe_high) {
+  return domain_word_fast(db, tld, w, n, maybe_high, load_tail8(w, n));
 }
 
 // Which exact lookups can a string token still need?  Necessary conditions only (no false negatives):
-//  * literal hash (LiteralHash::lookup is an exact string match): some stored literal has the same last 8 bytes (hot
-//    filter) and the same (length, first 8, last 8 bytes) (cold filter);
+//  * literal hash (LiteralHash::lookup is an exact string match): some stored literal has the same last K and the same first
+//    K bytes (hot filter; K = lit_key_len(n)) and the same (length, first K, last K bytes) (cold filter);
 //  * globs, when db.fast_ok: a pattern whose LAST segment is a literal can only match a text that ends with it, one whose
 //    FIRST segment is a literal only a text that starts with it (match_segments_impl anchors segment 0 at position 0 and
 //    requires the whole text to be consumed, paraglob_offset.rs:1402-1639); keys are the last / first glob_key_len(len)
 //    bytes of that literal.  Literal-type patterns (substring semantics), patterns with neither anchor, pure wildcards
 //    and case-insensitive databases clear fast_ok and every token takes the exact path.
-// `hot` may point at a shared-memory copy of db.hot.  Returns F_LIT | F_GLOB bits.
-MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const uint8_t* w, uint32_t n) {
+// Hot tests first (shared memory, `hot` may point at a copy of db.hot); at most one cold test (L2) per class afterwards.
+// Returns F_LIT | F_GLOB bits.
+MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const KeyWords& kw, uint32_t n) {
   uint32_t flags = 0;
-  const uint64_t t1 = load_tail8(w, n), h0 = load_head8(w, n);
   if (db.has_literal) {
-    const uint32_t k = n >= 8 ? 8u : n;
-    bool pass = !((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, key_hash(t1 >> (8 * (8 - k)), 0, TAG_LIT_TAIL, k));
-    pass = pass && (!((db.hot_tags >> TAG_LIT_HEAD) & 1u) || hot_test(hot, key_hash(h0, 0, TAG_LIT_HEAD, k)));
-    if (pass && cold_test(db.cold, db.cold_mask, key_hash(h0, t1, TAG_LIT_FULL, n))) flags |= F_LIT;
+    const uint32_t k = lit_key_len(n);
+    uint32_t st, sh;  // tail / head states
+    if (k == 8) { st = key_mix(key_mix(key_seed(TAG_LIT_TAIL), kw.t[3]), kw.t[2]); sh = key_mix(key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]), kw.h[1]); }
+    else if (k == 4) { st = key_mix(key_seed(TAG_LIT_TAIL), kw.t[3]); sh = key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]); }
+    else { const uint32_t x = low_bytes32(kw.h[0], k); st = key_mix(key_seed(TAG_LIT_TAIL), x); sh = key_mix(key_seed(TAG_LIT_HEAD), x); }  // n < 4: head == tail
+    bool pass = !((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, key_fin(st, k));
+    pass = pass && (!((db.hot_tags >> TAG_LIT_HEAD) & 1u) || hot_test(hot, key_fin(sh, k)));
+    if (pass) {
+      // (n, first K, last K bytes): continue the head state with the tail words
+      uint32_t s = sh ^ key_seed(TAG_LIT_FULL);
+      if (k == 8) s = key_mix(key_mix(s, kw.t[3]), kw.t[2]);
+      else if (k == 4) s = key_mix(s, kw.t[3]);
+      if (cold_test(db.cold, db.cold_mask, key_fin(s, n))) flags |= F_LIT;
+    }
   }
   if (db.has_glob && (db.glob_s_lens | db.glob_p_lens)) {
-    const uint64_t t0 = load_tail16_hi(w, n), h1 = load_head16_hi(w, n);
-    bool g = false;
-    uint64_t v0, v1;
-    for (uint32_t lens = db.glob_s_lens; lens && !g; lens &= lens - 1) {
-#ifdef __CUDA_ARCH__
-      uint32_t k = (uint32_t)__ffs((int)lens) - 1u;
-#else
-      uint32_t k = (uint32_t)__builtin_ctz(lens);
-#endif
-      if (k > n) break;
-      tail_key(t0, t1, k, v0, v1);
-      const uint32_t h = key_hash(v0, v1, TAG_GLOB_S, k);
-      if (((db.hot_tags >> TAG_GLOB_S) & 1u) && !hot_test(hot, h)) continue;
-      g = cold_test(db.cold, db.cold_mask, h);
+    // every key length present in the database, shortest first; `cand` = the first key that passed the hot filter
+    uint32_t cand = 0, cand2 = 0, npass = 0;
+    const bool hot_s = (db.hot_tags >> TAG_GLOB_S) & 1u, hot_p = (db.hot_tags >> TAG_GLOB_P) & 1u;
+    {
+      const uint32_t lens = db.glob_s_lens;
+      if (lens & 0xEu) {  // K = 1, 2, 3: the last K bytes sit in the top bytes of t[3] (n >= 4) or are the head word's low bytes
+        for (uint32_t k = 1; k <= 3; k++) {
+          if (!((lens >> k) & 1u) || k > n) continue;
+          const uint32_t x = n >= 4 ? (kw.t[3] >> (8 * (4 - k))) : (low_bytes32(kw.h[0], n) >> (8 * (n - k)));
+          const uint32_t h = key_fin(key_mix(key_seed(TAG_GLOB_S), x), k);
+          if (!hot_s || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; }
+        }
+      }
+      uint32_t s = key_seed(TAG_GLOB_S);
+#pragma unroll
+      for (uint32_t j = 0; j < 4; j++) {
+        const uint32_t k = 4 * (j + 1);
+        if ((lens >> k) == 0 || k > n) break;
+        s = key_mix(s, kw.t[3 - j]);
+        if ((lens >> k) & 1u) { const uint32_t h = key_fin(s, k); if (!hot_s || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; } }
+      }
     }
-    for (uint32_t lens = db.glob_p_lens; lens && !g; lens &= lens - 1) {
-#ifdef __CUDA_ARCH__
-      uint32_t k = (uint32_t)__ffs((int)lens) - 1u;
-#else
-      uint32_t k = (uint32_t)__builtin_ctz(lens);
-#endif
-      if (k > n) break;
-      head_key(h0, h1, k, v0, v1);
-      const uint32_t h = key_hash(v0, v1, TAG_GLOB_P, k);
-      if (((db.hot_tags >> TAG_GLOB_P) & 1u) && !hot_test(hot, h)) continue;
-      g = cold_test(db.cold, db.cold_mask, h);
+    {
+      const uint32_t lens = db.glob_p_lens;
+      if (lens & 0xEu) {
+        for (uint32_t k = 1; k <= 3; k++) {
+          if (!((lens >> k) & 1u) || k > n) continue;
+          const uint32_t h = key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k);
+          if (!hot_p || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; }
+        }
+      }
+      uint32_t s = key_seed(TAG_GLOB_P);
+#pragma unroll
+      for (uint32_t j = 0; j < 4; j++) {
+        const uint32_t k = 4 * (j + 1);
+        if ((lens >> k) == 0 || k > n) break;
+        s = key_mix(s, kw.h[j]);
+        if ((lens >> k) & 1u) { const uint32_t h = key_fin(s, k); if (!hot_p || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; } }
+      }
     }
-    if (g) flags |= F_GLOB;
+    // the cold filter decides for the keys that passed (up to two; more is rare enough to take the exact path unasked)
+    if (npass > 2 || (npass >= 1 && cold_test(db.cold, db.cold_mask, cand)) || (npass == 2 && cold_test(db.cold, db.cold_mask, cand2))) flags |= F_GLOB;
   }
   return flags;
+}
+MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const uint8_t* w, uint32_t n) {
+  KeyWords kw;
+  load_head_words(w, kw.h);
+  load_tail_words(w, n, kw.t);
+  return string_filters(db, hot, kw, n);
+}
+
+// The same key hashes from a literal's bytes (database preparation; must mirror string_filters exactly).
+MGPU_HD uint32_t bytes_le32(const uint8_t* p, uint32_t k) { uint32_t v = 0; for (uint32_t i = 0; i < k && i < 4; i++) v |= (uint32_t)p[i] << (8 * i); return v; }
+MGPU_HD uint32_t glob_key_hash(const uint8_t* lit, uint32_t m, uint32_t tag) {  // tag: TAG_GLOB_S (last bytes) or TAG_GLOB_P (first bytes)
+  const uint32_t k = glob_key_len(m);
+  uint32_t s = key_seed(tag);
+  if (k < 4) return key_fin(key_mix(s, bytes_le32(tag == TAG_GLOB_S ? lit + m - k : lit, k)), k);
+  for (uint32_t j = 0; j < k / 4; j++) s = key_mix(s, tag == TAG_GLOB_S ? bytes_le32(lit + m - 4 * (j + 1), 4) : bytes_le32(lit + 4 * j, 4));
+  return key_fin(s, k);
+}
+MGPU_HD void lit_key_hashes(const uint8_t* str, uint32_t n, uint32_t& tail_h, uint32_t& head_h, uint32_t& full_h) {
+  const uint32_t k = lit_key_len(n);
+  uint32_t st = key_seed(TAG_LIT_TAIL), sh = key_seed(TAG_LIT_HEAD);
+  if (k == 8) { st = key_mix(key_mix(st, bytes_le32(str + n - 4, 4)), bytes_le32(str + n - 8, 4)); sh = key_mix(key_mix(sh, bytes_le32(str, 4)), bytes_le32(str + 4, 4)); }
+  else if (k == 4) { st = key_mix(st, bytes_le32(str + n - 4, 4)); sh = key_mix(sh, bytes_le32(str, 4)); }
+  else { const uint32_t x = bytes_le32(str, k); st = key_mix(st, x); sh = key_mix(sh, x); }
+  tail_h = key_fin(st, k); head_h = key_fin(sh, k);
+  uint32_t s = sh ^ key_seed(TAG_LIT_FULL);
+  if (k == 8) s = key_mix(key_mix(s, bytes_le32(str + n - 4, 4)), bytes_le32(str + n - 8, 4));
+  else if (k == 4) s = key_mix(s, bytes_le32(str + n - 4, 4));
+  full_h = key_fin(s, n);
 }
 
 // extract_email_at: buf[lo..n) is the chunk, at = position of '@'.

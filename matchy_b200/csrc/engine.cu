@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       const uint32_t tile_base = (uint32_t)(t * TILE_BYTES);  // chunks are at most 2 GiB: positions fit 32 bits
       const uint32_t p = tile_base + lane * SLICE_BYTES;
       uint4 v0 = ld_stream(a.buf + p), v1 = ld_stream(a.buf + p + 16);
+      if (t + 4 < t1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.buf + p + 4 * TILE_BYTES));  // my slice of the tile four steps ahead
       uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -195,7 +196,12 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       const uint32_t hasNhx = chain_ends(T, Y3, (cv3 >> lane) & 1u, m.B);
       const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
       // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
-      const uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
+      uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
+      {  // ... and at least 32 bytes long: the previous slice has no boundary at or above the bit position where the word ends here
+        uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1);
+        if (lane == 0) Bprev = cy.prevB;
+        if (candHex && (Bprev >> (__ffs(candHex) - 1)) != 0) candHex = 0;
+      }
       const uint32_t candAt = want_at ? m.AT : 0u;
       // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
       const uint32_t cl1 = (m.CL << 1) | ((pv >> 3) & 1u), cl2 = (m.CL << 2) | (((pv >> 3) & 1u) << 1) | ((pv >> 4) & 1u);
@@ -209,8 +215,8 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
 
       // ---- emission ----
       {
-        uint32_t total;
-        const uint32_t cnt = __popc(candDot), excl = warp_excl_count4(cnt, lt_mask, total);
+        const uint32_t cnt = __popc(candDot), incl = warp_incl_scan(cnt, lane);
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - cnt;
         if (total) {
           if (nd + total <= a.seg_cap[Q_DOTTED]) {
             Cand* dst = qd + nd + excl;
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
         cy.open_start = tile_base + ll * 32 + top_bit(Bl) + 1;
       }
       cy.prev = __shfl_sync(0xFFFFFFFFu, my_prev, 31);
+      cy.prevB = __shfl_sync(0xFFFFFFFFu, m.B, 31);
     }
   }
   if (lane == 0) {
@@ -341,7 +348,8 @@ __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap,
 static const int TK_THREADS = 1024;  // one persistent block per SM
 static const int TK_WARPS = TK_THREADS / 32;
 static const uint32_t TK_WIN = 2048;
-static const size_t TOKEN_SMEM = (size_t)TLD_SLOTS * 8 + (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32);
+static const uint32_t IP_RING = 64;  // per-warp list of deferred IPv4 candidates (start, len)
+static const size_t TOKEN_SMEM = (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32) + (size_t)TK_WARPS * IP_RING * sizeof(Cand);
 
 struct TokenWarp {  // per-warp state of the token kernel
   QueueCursor cs, ci;
@@ -372,30 +380,63 @@ __device__ __forceinline__ void append_tokens(const ScanArgs& a, TokenWarp& tw, 
 }
 
 // A string token passed validation: count it, then (fast path) let the filters decide whether anything can match it.
-__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const uint32_t* s_hot, const uint8_t* text, StrTok& st) {
+__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const uint32_t* s_hot, const KeyWords& kw, StrTok& st) {
   tw.n_dom += st.type == MGPU_T_DOMAIN; tw.n_mail += st.type == MGPU_T_EMAIL; tw.n_md5 += st.type == MGPU_T_MD5; tw.n_sha1 += st.type == MGPU_T_SHA1;
   tw.n_sha256 += st.type == MGPU_T_SHA256; tw.n_sha384 += st.type == MGPU_T_SHA384; tw.n_sha512 += st.type == MGPU_T_SHA512;
   if (!fast) return true;
-  const uint32_t f = string_filters(a.db, s_hot, text + st.start, st.len);
+  const uint32_t f = string_filters(a.db, s_hot, kw, st.len);
   st.type |= f;
   return f != 0;
+}
+
+// streaming 16-byte load that does not allocate in L1 (L1 is left to the PSL last-label table and the filter words)
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ Cand ld_cand(const Cand* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return Cand{r.x, r.y};
+}
+
+// Deferred IPv4 candidates of a warp: words of 7..15 bytes that start and end with a digit.  Parsing them 32 at a time keeps
+// every lane busy (in a log line one dotted word in three or four is an address); their bytes come straight from the
+// log buffer (L2: the window that held them was staged moments ago).
+__device__ __forceinline__ void drain_ipv4(const ScanArgs& a, TokenWarp& tw, const Cand* ring, uint32_t count, uint32_t lane) {
+  bool wi = false;
+  IpTok it{0, 0, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
+  if (lane < count) {
+    const Cand c = ring[lane];
+    uint32_t h[4];
+    load_head_words(a.buf + c.start, h);
+    it.start = c.start; it.len = c.len;
+    wi = parse_ipv4_words(h, c.len, it.w[0]);
+  }
+  __syncwarp();
+  if (wi) tw.n_v4++;
+  append_tokens(a, tw, lane, false, StrTok{0, 0, 0}, wi, it);
 }
 
 // One segment of a word queue (DOTTED: dotted domain-character words -> IPv4 / domain; else: hash-length hex words).
 // The segment is sorted by position; every iteration takes as many consecutive candidates (at most 32) as fit in the
 // warp's window, stages the window with coalesced 16-byte loads and lets one lane handle one candidate.
 template <bool DOTTED>
-__device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t n, uint8_t* s_win, const uint64_t* s_tld,
+__device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t n, uint8_t* s_win, Cand* s_ring,
                                             const uint32_t* s_hot, bool fast, uint32_t lane) {
   const bool want_dom = (a.flags & MGPU_X_DOMAINS) != 0, want_v4 = (a.flags & MGPU_X_IPV4) != 0;
+  uint32_t nring = 0;
+  Cand cn{0xFFFFFFFFu, 0};  // prefetched: candidate i0 + lane of the NEXT iteration (assuming a full group of 32)
+  if (lane < n) cn = ld_cand(q + lane);
   for (uint32_t i0 = 0; i0 < n;) {
     const uint32_t idx = i0 + lane;
     const bool have = idx < n;
-    Cand c{0xFFFFFFFFu, 0};
-    if (have) c = q[idx];
+    const Cand c = cn;
+    if (idx + 32 < n) cn = ld_cand(q + idx + 32); else cn = Cand{0xFFFFFFFFu, 0};
     const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c.start, 0);
     const uint32_t alo = lo & ~15u;
-    const bool fits = !have || ((uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN && c.start >= lo);
+    const bool fits = !have || (uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN;
     const uint32_t nf = __ballot_sync(0xFFFFFFFFu, !fits);
     uint32_t g = nf ? (uint32_t)__ffs((int)nf) - 1u : 32u;  // candidates of this iteration: lanes [0, g)
     const uint8_t* p = a.buf;
@@ -406,46 +447,70 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
       const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, mine ? c.start + c.len : 0u);
       const uint32_t ahi = (hi + 31u) & ~15u;
       __syncwarp();
+      // all (up to four) 16-byte loads of a lane are issued before the first store, so their latencies overlap
+      uint4 v[4];
+      const uint32_t o0 = alo + lane * 16;
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = (o0 + j * 512 < ahi) ? ld_stream16(a.buf + o0 + j * 512) : make_uint4(0, 0, 0, 0);
+      // the next iteration's window starts about where this one ends: pull it towards L2 meanwhile (64-byte line per lane)
+      if ((uint64_t)ahi + lane * 64 < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.buf + ahi + lane * 64));
       uint32_t hb = 0;
-      for (uint32_t o = alo + lane * 16; o < ahi; o += 512) {
-        const uint4 v = *reinterpret_cast<const uint4*>(a.buf + o);
-        *reinterpret_cast<uint4*>(s_win + (o - alo)) = v;
-        hb |= v.x | v.y | v.z | v.w;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (o0 + j * 512 < ahi) *reinterpret_cast<uint4*>(s_win + (o0 - alo) + j * 512) = v[j];
+        hb |= v[j].x | v[j].y | v[j].z | v[j].w;
       }
       high = __any_sync(0xFFFFFFFFu, (hb & 0x80808080u) != 0);  // (also orders the window writes before the reads below)
       p = s_win - alo;
     }
     const bool active = have && lane < g && (uint64_t)c.start + c.len <= a.n;
-    bool ws = false, wi = false;
+    bool ws = false;
     StrTok st{c.start, c.len, 0};
-    IpTok it{c.start, c.len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
+    KeyWords kw;
+    const uint8_t* wp = p + (active ? c.start : lo);
+    load_head_words(wp, kw.h);
+    load_tail_words(wp, active ? c.len : 0u, kw.t);
     if (DOTTED) {
-      const uint8_t* wp = p + c.start;
-      if (active && want_v4 && c.len >= 7 && c.len <= 15 && is_digit(wp[0])) wi = parse_ipv4_word(wp, c.len, it.w[0]);
-      __syncwarp();
-      if (active && want_dom) { st.type = MGPU_T_DOMAIN; ws = domain_word_fast(a.db, s_tld, wp, c.len, high); }
+      // IPv4 candidates are parked in the warp's ring and parsed 32 at a time
+      const bool ip_like = active && want_v4 && c.len >= 7 && c.len <= 15 && (uint8_t)((kw.h[0] & 0xFF) - '0') < 10 && (uint8_t)((kw.t[3] >> 24) - '0') < 10;
+      const uint32_t bi = __ballot_sync(0xFFFFFFFFu, ip_like);
+      if (bi) {
+        if (ip_like) s_ring[nring + __popc(bi & ((1u << lane) - 1u))] = c;
+        nring += __popc(bi);
+        __syncwarp();
+        if (nring >= 32) {
+          drain_ipv4(a, tw, s_ring + (nring - 32), 32, lane);
+          nring -= 32;
+          __syncwarp();
+        }
+      }
+      if (active && want_dom) {
+        st.type = MGPU_T_DOMAIN;
+        const uint64_t tail8 = c.len >= 8 ? (((uint64_t)kw.t[3] << 32) | kw.t[2]) : load_tail8(wp, c.len);
+        ws = domain_word_fast(a.db, a.db.psl_tld, wp, c.len, high, tail8);
+      }
       __syncwarp();
     } else if (active) { st.type = hash_type_of(c.len); ws = true; }
-    if (ws) ws = string_token(a, tw, fast, s_hot, p, st);
+    if (ws) ws = string_token(a, tw, fast, s_hot, kw, st);
     __syncwarp();
-    if (wi) tw.n_v4++;
-    append_tokens(a, tw, lane, ws, st, wi, it);
+    append_tokens(a, tw, lane, ws, st, false, IpTok{0, 0, 0, 0, {0, 0, 0, 0}});
+    if (g != 32) {  // a short group: the prefetch assumed 32; fetch the right candidates again
+      cn = Cand{0xFFFFFFFFu, 0};
+      if (i0 + g + lane < n) cn = ld_cand(q + i0 + g + lane);
+    }
     i0 += g;
   }
+  if (DOTTED && nring) drain_ipv4(a, tw, s_ring, nring, lane);
 }
 
 __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   extern __shared__ __align__(16) uint8_t tk_smem[];
-  uint64_t* s_tld = reinterpret_cast<uint64_t*>(tk_smem);
-  uint32_t* s_hot = reinterpret_cast<uint32_t*>(tk_smem + (size_t)TLD_SLOTS * 8);
+  uint32_t* s_hot = reinterpret_cast<uint32_t*>(tk_smem);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* s_win = tk_smem + (size_t)TLD_SLOTS * 8 + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
+  uint8_t* s_win = tk_smem + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
+  Cand* s_ring = reinterpret_cast<Cand*>(tk_smem + (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32)) + (size_t)warp * IP_RING;
   const bool fast = a.fast != 0;
   if (a.ctr->overflow) return;  // an earlier stage of this piece ran out of room: the host redoes the piece in smaller parts
-  if (a.flags & (MGPU_X_DOMAINS | MGPU_X_EMAILS)) {
-    const uint4* src = reinterpret_cast<const uint4*>(a.db.psl_tld);
-    for (uint32_t i = threadIdx.x; i < TLD_SLOTS / 2; i += blockDim.x) reinterpret_cast<uint4*>(s_tld)[i] = src[i];
-  }
   if (fast) {
     const uint4* src = reinterpret_cast<const uint4*>(a.db.hot);
     for (uint32_t i = threadIdx.x; i < HOT_WORDS / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_hot)[i] = src[i];
@@ -456,8 +521,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   const uint32_t nwarps = gridDim.x * TK_WARPS;
   for (uint32_t seg = blockIdx.x * TK_WARPS + warp; seg < a.nseg; seg += nwarps) {
     const uint32_t* sc = a.seg_cnt + seg;
-    token_words<true>(a, tw, a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED], sc[Q_DOTTED * a.nseg_max], s_win, s_tld, s_hot, fast, lane);
-    token_words<false>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], sc[Q_HASH * a.nseg_max], s_win, s_tld, s_hot, fast, lane);
+    token_words<true>(a, tw, a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED], sc[Q_DOTTED * a.nseg_max], s_win, s_ring, s_hot, fast, lane);
+    token_words<false>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], sc[Q_HASH * a.nseg_max], s_win, s_ring, s_hot, fast, lane);
     // '@' and "::" anchors: rare, straight from the log buffer
     const uint32_t nA = sc[Q_AT * a.nseg_max], nC = sc[Q_COLON2 * a.nseg_max];
     const uint32_t* qa = a.q_at + (size_t)seg * a.seg_cap[Q_AT];
@@ -481,7 +546,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
         }
       }
       __syncwarp();
-      if (ws) ws = string_token(a, tw, fast, s_hot, a.buf, st);
+      if (ws) {
+        KeyWords kw;
+        load_head_words(a.buf + st.start, kw.h);
+        load_tail_words(a.buf + st.start, st.len, kw.t);
+        ws = string_token(a, tw, fast, s_hot, kw, st);
+      }
       __syncwarp();
       append_tokens(a, tw, lane, ws, st, wi, it);
     }
@@ -951,6 +1021,33 @@ static void set_err(const std::string& s) { g_err = s; }
     }                                                                                              \
   } while (0)
 
+// Growable array in pinned host memory (results land here by DMA; pageable std::vector storage would be staged by the
+// driver at a fraction of the PCIe rate).  The storage is kept between scans.
+template <typename T>
+struct PinnedVec {
+  T* p = nullptr; size_t n = 0, cap = 0;
+  ~PinnedVec() { if (p) cudaFreeHost(p); }
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    size_t nc = std::max(want, cap * 2);
+    if (nc < 4096) nc = 4096;
+    T* q = nullptr;
+    if (cudaMallocHost(&q, nc * sizeof(T)) != cudaSuccess) return false;
+    if (n) memcpy(q, p, n * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = q; cap = nc;
+    return true;
+  }
+  bool resize(size_t m) { if (!reserve(m)) return false; n = m; return true; }
+  void clear() { n = 0; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T* data() { return p; }
+  T* begin() { return p; }
+  T* end() { return p + n; }
+  T& operator[](size_t i) { return p[i]; }
+};
+
 struct mgpu_ctx {
   int device = 0;
   int sm_count = 148;
@@ -979,8 +1076,9 @@ struct mgpu_ctx {
   std::vector<uint8_t> psl_text;
   void* d_psl_keys = nullptr; void* d_psl_vals = nullptr; void* d_psl_pool = nullptr; void* d_psl_tld = nullptr;
   // results of the last scan
-  std::vector<mgpu_match> recs;
-  std::vector<mgpu_id_pair> ids;
+  PinnedVec<mgpu_match> recs;
+  PinnedVec<mgpu_id_pair> ids;
+  std::vector<mgpu_id_pair> ids_tmp;
   mgpu_counters counters{};
   mgpu_timing timing{};
   bool keep_results = true;
@@ -1291,10 +1389,10 @@ static int end_batch(mgpu_ctx* c, int pieces) {
 static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_lo, uint32_t i_hi) {
   if (!c->keep_results || r_hi <= r_lo) return MGPU_OK;
   size_t r0 = c->recs.size(), i0 = c->ids.size();
-  c->recs.resize(r0 + (r_hi - r_lo));
+  if (!c->recs.resize(r0 + (r_hi - r_lo))) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
   CK(cudaMemcpyAsync(c->recs.data() + r0, c->args.recs + r_lo, (size_t)(r_hi - r_lo) * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->compute));
   if (i_hi > i_lo) {
-    c->ids.resize(i0 + (i_hi - i_lo));
+    if (!c->ids.resize(i0 + (i_hi - i_lo))) { set_err("out of pinned host memory for match ids"); return MGPU_E_CUDA; }
     CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids + i_lo, (size_t)(i_hi - i_lo) * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
   }
   CK(cudaStreamSynchronize(c->compute));
@@ -1386,7 +1484,8 @@ static void finish_scan(mgpu_ctx* c) {
     return x.len < y.len;
   });
   if (!c->ids.empty()) {
-    std::vector<mgpu_id_pair> packed;
+    std::vector<mgpu_id_pair>& packed = c->ids_tmp;
+    packed.clear();
     packed.reserve(c->ids.size());
     for (auto& r : c->recs) {
       if (r.kind != MGPU_KIND_PATTERN) continue;
@@ -1394,7 +1493,8 @@ static void finish_scan(mgpu_ctx* c) {
       packed.insert(packed.end(), c->ids.begin() + r.ids_index, c->ids.begin() + r.ids_index + r.n_ids);
       r.ids_index = at;
     }
-    c->ids.swap(packed);
+    c->ids.n = packed.size();
+    if (!packed.empty()) memcpy(c->ids.data(), packed.data(), packed.size() * sizeof(mgpu_id_pair));
   }
 }
 

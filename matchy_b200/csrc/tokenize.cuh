@@ -43,6 +43,7 @@ struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX, DASH; };
 struct TileCarry {
   uint32_t prev;        // facts about the bytes just before the tile: PV_* bits
   uint32_t cBad, cDot, cNhx;  // the open word so far holds a byte that rules out a domain / a '.' / a non-hex byte
+  uint32_t prevB;       // boundary mask of the 32 bytes before the tile (bit i = byte i - 32 of the tile)
   uint64_t open_start;  // chunk offset where the open word starts (valid when prev & PV_T)
 };
 // bits of the "previous bytes" word that travels lane -> lane (one shuffle) and tile -> tile
@@ -107,8 +108,10 @@ MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len ==
 // word that is open there.
 MGPU_HDN TileCarry range_prologue(const uint8_t* buf, uint64_t lo, uint64_t a) {
   TileCarry c;
-  c.prev = 0; c.cBad = 0; c.cDot = 0; c.cNhx = 0; c.open_start = a;
+  c.prev = 0; c.cBad = 0; c.cDot = 0; c.cNhx = 0; c.open_start = a; c.prevB = 0xFFFFFFFFu;
   if (a <= lo) return c;
+  c.prevB = 0;
+  for (uint32_t k = 0; k < 32; k++) if (a < lo + 32 - k || is_boundary(buf[a - 32 + k])) c.prevB |= 1u << k;  // bytes before the chunk count as boundaries
   uint8_t prev = buf[a - 1];
   c.prev = (prev == '.' ? (uint32_t)PV_DOT : 0u) | (prev == '-' ? (uint32_t)PV_DASH : 0u) | (prev == ':' ? (uint32_t)PV_CL1 : 0u) |
            ((a >= lo + 2 && buf[a - 2] == ':') ? (uint32_t)PV_CL2 : 0u);

@@ -100,6 +100,8 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         uint32_t E = m[lane].B & ((T[lane] << 1) | pT[lane]);
         uint32_t candDot = want_dot ? (H[1][lane] & ~H[0][lane] & ~bad_end[lane]) : 0u;
         uint32_t candHex = (want_hash && pT[lane]) ? (E & ~H[2][lane] & (m[lane].B & (0u - m[lane].B))) : 0u;
+        uint32_t Bprev = lane ? m[lane - 1].B : cy.prevB;
+        if (candHex && (Bprev >> __builtin_ctz(candHex)) != 0) candHex = 0;  // shorter than 32 bytes
         uint32_t candAt = want_at ? m[lane].AT : 0u;
         uint32_t cl1 = (m[lane].CL << 1) | ((pv[lane] >> 3) & 1u), cl2 = (m[lane].CL << 2) | (((pv[lane] >> 3) & 1u) << 1) | ((pv[lane] >> 4) & 1u);
         uint32_t candC2 = want_c2 ? (m[lane].CL & cl1 & ~cl2) : 0u;
@@ -123,6 +125,7 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         cy.open_start = tile_base + (uint64_t)ll * 32 + top_bit(m[ll].B) + 1;
       }
       cy.prev = prev_bits_of(m[31]);
+      cy.prevB = m[31].B;
     }
   }
 }
