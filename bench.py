@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench.py — `matchy match` log-scan throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
-A "step" is one pass of the whole hot path (tokenize → validate → IP-trie / literal-hash / AC+glob → records)
-over one batch of synthetic log resident in HBM.  At N=1 the workload is BASELINE.json configs[1]
+A "step" is one pass of the whole hot path (tokenize → token validation + string filters → IP-trie / exact string
+lookups → records) over one batch of synthetic log resident in HBM.  At N=1 the workload is BASELINE.json configs[1]
 (100 K globs + 1 M literal domains over 10 GB of DNS/proxy log lines).  With N>1 every rank scans its own
 10 GB shard of the same deterministic stream (byte-range sharding, database replicated per GPU, no data-path
 collective; only the summary counters are all-reduced over NCCL) — weak scaling.
@@ -65,6 +65,15 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per log byte of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return float(json.load(f)["kernels"][kernel]["dram_bytes_per_log_byte"])
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -146,7 +155,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--gb", type=float, default=10.0, help="log bytes per GPU per step, in GB (1e9)")
     ap.add_argument("--scale", type=float, default=1.0, help="database size scale (1.0 = the BASELINE.json counts)")
-    ap.add_argument("--chunk-mb", type=int, default=512)
+    ap.add_argument("--chunk-mb", type=int, default=2040, help="scan piece size (MiB, < 2048); pieces of a resident scan are launched back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -256,7 +265,10 @@ def main():
     dom_ms, dom_launches = kern[dom]
     bytes_per_launch = nbytes * args.steps / max(dom_launches, 1)  # 1 algorithmic byte per log byte scanned
     achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1000.0) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    per_byte = ncu_traffic(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": per_byte * bytes_per_launch if per_byte is not None else None,
+                "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per log byte of this kernel (ncu --set full, cfg2), scaled to this launch size",
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
                 "whole_path_frac": (nbytes * args.steps / dev_s / 1e9) / peak if world == 1 else None}

@@ -77,11 +77,11 @@ typedef struct mgpu_id_pair { uint32_t pattern_id, data_offset; } mgpu_id_pair;
 typedef struct mgpu_counters { uint64_t lines, bytes, candidates, matches, by_type[12]; } mgpu_counters;
 
 /* per-kernel device time of the last scan (CUDA events on the scan stream), milliseconds */
-#define MGPU_K_TOKENIZE 0
-#define MGPU_K_VALIDATE 1
-#define MGPU_K_IPTRIE 2
-#define MGPU_K_LITHASH 3
-#define MGPU_K_ACGLOB 4
+#define MGPU_K_TOKENIZE 0 /* tokenize_kernel: log bytes -> candidate words / anchors */
+#define MGPU_K_TOKEN 1    /* token_kernel: candidates -> typed tokens (+ constant-time string filters on the fast path) */
+#define MGPU_K_IPTRIE 2   /* iptrie_kernel */
+#define MGPU_K_LITHASH 3  /* lithash_kernel (generic string path only) */
+#define MGPU_K_STRINGS 4  /* exact_kernel (fast string path) or acglob_kernel (generic string path) */
 #define MGPU_K_COUNT 5
 typedef struct mgpu_timing {
   float kernel_ms[MGPU_K_COUNT];    /* summed over the chunks of the scan */

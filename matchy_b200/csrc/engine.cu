@@ -1352,11 +1352,11 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   }
   piece_end_kernel<<<1, 1, 0, st>>>(a.ctr, a.tot);
   CK(cudaGetLastError());
-  c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_VALIDATE]++;
+  c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_TOKEN]++;
   if (lookups) {
     c->timing.launches[MGPU_K_IPTRIE]++;
     if (a.db.has_literal && !fast) c->timing.launches[MGPU_K_LITHASH]++;
-    if (a.db.has_literal || a.db.has_glob) c->timing.launches[MGPU_K_ACGLOB]++;
+    if (a.db.has_literal || a.db.has_glob) c->timing.launches[MGPU_K_STRINGS]++;
   }
   c->timing.aux_launches++;
   c->timing.chunks++;

@@ -11,7 +11,7 @@ X_SUPPORTED = 0x1F
 ITEM_TYPE_NAMES = ["Domain", "Email", "IPv4", "IPv6", "MD5", "SHA1", "SHA256", "SHA384", "SHA512", "Bitcoin", "Ethereum", "Monero"]
 KIND_IP, KIND_PATTERN = 1, 2
 NO_DATA = 0xFFFFFFFF
-KERNEL_NAMES = ["tokenize", "validate", "iptrie", "lithash", "acglob"]
+KERNEL_NAMES = ["tokenize", "token", "iptrie", "lithash", "strings"]  # MGPU_K_* order (include/matchy_b200.h)
 
 
 class EngineError(RuntimeError):
