@@ -1049,12 +1049,14 @@ struct PinnedVec {
 };
 
 struct mgpu_ctx {
+  static const int MAX_BATCH = 32;  // pieces launched back to back before the host looks at their counters
   int device = 0;
   int sm_count = 148;
   size_t chunk_bytes = 0;
   cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t lookup = nullptr;  // IP-trie and exact string lookups of piece i run here, beside the tokenizer of piece i+1
+  cudaEvent_t ev_tokens[MAX_BATCH] = {}, ev_looked[MAX_BATCH] = {};  // token lists of the slot's piece written / consumed
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-  static const int MAX_BATCH = 32;  // pieces launched back to back before the host looks at their counters
   cudaEvent_t ev_k[MAX_BATCH][MGPU_K_COUNT + 1] = {};
   cudaEvent_t ev_scan[2] = {nullptr, nullptr};
   // log staging (double buffered) and pinned bounce buffers for pageable callers
@@ -1083,6 +1085,7 @@ struct mgpu_ctx {
   mgpu_timing timing{};
   bool keep_results = true;
   bool force_ac_walk = false;
+  bool looked_pending = false; int looked_slot = 0;  // the lookup stream still owns the token lists (event ev_looked[looked_slot])
   bool force_generic = false;  // tests: run the generic string path (lithash + acglob kernels) even when the fast path applies
   std::vector<StrTok> x_str; std::vector<IpTok> x_ip;  // extraction-only capture
   bool capture_tokens = false;
@@ -1120,6 +1123,9 @@ void mgpu_destroy(mgpu_ctx* c) {
   if (c->h_cut) cudaFreeHost(c->h_cut);
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->copy) cudaStreamDestroy(c->copy);
+  if (c->lookup) cudaStreamDestroy(c->lookup);
+  for (auto& e : c->ev_tokens) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_looked) if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -1140,6 +1146,9 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   c->chunk_bytes = chunk_bytes;
   CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->lookup, cudaStreamNonBlocking));
+  for (auto& e : c->ev_tokens) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : c->ev_looked) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int s = 0; s < 2; s++) {
     CK(cudaEventCreateWithFlags(&c->ev_copied[s], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming));
@@ -1337,20 +1346,28 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   CK(cudaEventRecord(ev[1], st));
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
   a.fast = fast ? 1u : 0u;
+  // The token kernel overwrites the token lists the previous piece's lookups read: wait for them.  The lookups themselves
+  // (latency-bound, a fraction of the SMs busy) run on a second stream, beside the tokenizer of the next piece.
+  if (c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
   token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
   CK(cudaEventRecord(ev[2], st));
+  cudaStream_t ls = c->lookup;
+  CK(cudaEventRecord(c->ev_tokens[slot], st));
+  CK(cudaStreamWaitEvent(ls, c->ev_tokens[slot], 0));
   if (lookups) {
-    iptrie_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
-    CK(cudaEventRecord(ev[3], st));
-    if (a.db.has_literal && !fast) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, st>>>(a);
-    CK(cudaEventRecord(ev[4], st));
-    if (fast) exact_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a);
-    else if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, st>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
-    CK(cudaEventRecord(ev[5], st));
+    iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
+    CK(cudaEventRecord(ev[3], ls));
+    if (a.db.has_literal && !fast) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, ls>>>(a);
+    CK(cudaEventRecord(ev[4], ls));
+    if (fast) exact_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
+    else if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, ls>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
+    CK(cudaEventRecord(ev[5], ls));
   } else {
-    for (int k = 3; k <= 5; k++) CK(cudaEventRecord(ev[k], st));
+    for (int k = 3; k <= 5; k++) CK(cudaEventRecord(ev[k], ls));
   }
-  piece_end_kernel<<<1, 1, 0, st>>>(a.ctr, a.tot);
+  piece_end_kernel<<<1, 1, 0, ls>>>(a.ctr, a.tot);
+  CK(cudaEventRecord(c->ev_looked[slot], ls));
+  c->looked_pending = true; c->looked_slot = slot;
   CK(cudaGetLastError());
   c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_TOKEN]++;
   if (lookups) {
@@ -1371,6 +1388,7 @@ static int begin_batch(mgpu_ctx* c, int pieces) {
 }
 // Finish a batch: counters to the host, one synchronisation, kernel times.
 static int end_batch(mgpu_ctx* c, int pieces) {
+  if (c->looked_pending) { CK(cudaStreamWaitEvent(c->compute, c->ev_looked[c->looked_slot], 0)); c->looked_pending = false; }
   CK(cudaMemcpyAsync(c->h_ctr, c->args.ctr, sizeof(DevCounters) * pieces, cudaMemcpyDeviceToHost, c->compute));
   CK(cudaStreamSynchronize(c->compute));
   for (int p = 0; p < pieces; p++) {
