@@ -56,7 +56,7 @@ struct ScanArgs {
   uint32_t flags;
   uint32_t fast;       // 1: the token kernel applies string_filters() and only flagged string tokens reach the exact kernel
   DbView db;
-  Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2;
+  Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2; Cand* q_numeric;
   uint32_t seg_cap[Q_COUNT];
   uint32_t* seg_cnt;   // [Q_COUNT][nseg_max]
   uint32_t nseg, nseg_max;
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   Cand* const qh = a.q_hash + w * a.seg_cap[Q_HASH];
   uint32_t* const qa = a.q_at + w * a.seg_cap[Q_AT];
   uint32_t* const qc = a.q_c2 + w * a.seg_cap[Q_COLON2];
-  uint32_t nd = 0, nh = 0, na = 0, nc = 0, ovf = 0;
+  Cand* const qn = a.q_numeric + w * a.seg_cap[Q_NUMERIC];
+  uint32_t nd = 0, nh = 0, na = 0, nc = 0, nn = 0, ovf = 0;
   uint32_t lines = 0;
   if (t0 < t1) {
     TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
@@ -183,17 +184,20 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       uint32_t bad, bad_end;
       domain_rule_masks(m, S, pv, bad, bad_end);
 
-      // three "does the word contain ..." chains: a byte that rules out a domain, a '.', a non-hex byte
-      const uint32_t Y1 = T & (~m.DM | bad), Y2 = m.DOT, Y3 = T & ~m.HX;
-      const uint32_t g1 = chain_gen(T, Y1), g2 = chain_gen(T, Y2), g3 = chain_gen(T, Y3);
+      // four "does the word contain ..." chains: a byte that rules out a domain, a '.', a non-hex byte, a byte that is
+      // neither a hex digit nor a '.'
+      const uint32_t Y1 = T & (~m.DM | bad), Y2 = m.DOT, Y3 = T & ~m.HX, Y4 = Y3 & ~m.DOT;
+      const uint32_t g1 = chain_gen(T, Y1), g2 = chain_gen(T, Y2), g3 = chain_gen(T, Y3), g4 = chain_gen(T, Y4);
       const uint32_t pb = __ballot_sync(0xFFFFFFFFu, T == 0xFFFFFFFFu);
       const uint32_t G1 = __ballot_sync(0xFFFFFFFFu, g1), G2 = __ballot_sync(0xFFFFFFFFu, g2), G3 = __ballot_sync(0xFFFFFFFFu, g3);
-      uint32_t co1, co2, co3;
+      const uint32_t G4 = __ballot_sync(0xFFFFFFFFu, g4);
+      uint32_t co1, co2, co3, co4;
       const uint32_t cv1 = carry_chain(G1, pb & ~G1, cy.cBad, co1), cv2 = carry_chain(G2, pb & ~G2, cy.cDot, co2), cv3 = carry_chain(G3, pb & ~G3, cy.cNhx, co3);
-      cy.cBad = co1; cy.cDot = co2; cy.cNhx = co3;
+      const uint32_t cv4 = carry_chain(G4, pb & ~G4, cy.cNhd, co4);
+      cy.cBad = co1; cy.cDot = co2; cy.cNhx = co3; cy.cNhd = co4;
       const uint32_t E = m.B & ((T << 1) | pT);  // boundaries that end a word
       const uint32_t hasBad = chain_ends(T, Y1, (cv1 >> lane) & 1u, m.B), hasDot = chain_ends(T, Y2, (cv2 >> lane) & 1u, m.B);
-      const uint32_t hasNhx = chain_ends(T, Y3, (cv3 >> lane) & 1u, m.B);
+      const uint32_t hasNhx = chain_ends(T, Y3, (cv3 >> lane) & 1u, m.B), hasNhd = chain_ends(T, Y4, (cv4 >> lane) & 1u, m.B);
       const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
       // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
       uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
@@ -215,19 +219,27 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
 
       // ---- emission ----
       {
-        const uint32_t cnt = __popc(candDot), incl = warp_incl_scan(cnt, lane);
+        // dotted words of hex digits and dots only go to the numeric queue (IPv4 candidates), the rest to the dotted queue;
+        // one scan serves both (counts packed in the two halves of a word)
+        const uint32_t candNum = candDot & ~hasNhd;
+        const uint32_t cnt = __popc(candNum) | (__popc(candDot & hasNhd) << 16), incl = warp_incl_scan(cnt, lane);
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - cnt;
         if (total) {
-          if (nd + total <= a.seg_cap[Q_DOTTED]) {
-            Cand* dst = qd + nd + excl;
-            for (uint32_t mm = candDot; mm; mm &= mm - 1) {
-              const uint32_t bit = __ffs(mm) - 1;
-              const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
-              const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
-              *dst++ = Cand{s, p + bit - s};
-            }
-          } else ovf |= 1u << Q_DOTTED;
-          nd += total;
+          const uint32_t tn = total & 0xFFFFu, td = total >> 16;
+          const bool okn = nn + tn <= a.seg_cap[Q_NUMERIC], okd = nd + td <= a.seg_cap[Q_DOTTED];
+          Cand* dn = qn + nn + (excl & 0xFFFFu);
+          Cand* dd = qd + nd + (excl >> 16);
+          for (uint32_t mm = candDot; mm; mm &= mm - 1) {
+            const uint32_t bit = __ffs(mm) - 1;
+            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+            const Cand c{s, p + bit - s};
+            if ((candNum >> bit) & 1u) { if (okn) *dn++ = c; }
+            else if (okd) *dd++ = c;
+          }
+          if (!okn) ovf |= 1u << Q_NUMERIC;
+          if (!okd) ovf |= 1u << Q_DOTTED;
+          nn += tn; nd += td;
         }
       }
       if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2) != 0)) {  // rare in most logs: one vote covers the three
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     sc[Q_HASH * a.nseg_max] = ovf & (1u << Q_HASH) ? 0u : nh;
     sc[Q_AT * a.nseg_max] = ovf & (1u << Q_AT) ? 0u : na;
     sc[Q_COLON2 * a.nseg_max] = ovf & (1u << Q_COLON2) ? 0u : nc;
+    sc[Q_NUMERIC * a.nseg_max] = ovf & (1u << Q_NUMERIC) ? 0u : nn;
     if (ovf) atomicOr(&a.ctr->overflow, ovf);
   }
   for (int d = 16; d; d >>= 1) lines += __shfl_down_sync(0xFFFFFFFFu, lines, d);
@@ -348,8 +361,7 @@ __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap,
 static const int TK_THREADS = 1024;  // one persistent block per SM
 static const int TK_WARPS = TK_THREADS / 32;
 static const uint32_t TK_WIN = 2048;
-static const uint32_t IP_RING = 64;  // per-warp list of deferred IPv4 candidates (start, len)
-static const size_t TOKEN_SMEM = (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32) + (size_t)TK_WARPS * IP_RING * sizeof(Cand);
+static const size_t TOKEN_SMEM = (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32);
 
 struct TokenWarp {  // per-warp state of the token kernel
   QueueCursor cs, ci;
@@ -401,32 +413,17 @@ __device__ __forceinline__ Cand ld_cand(const Cand* p) {
   return Cand{r.x, r.y};
 }
 
-// Deferred IPv4 candidates of a warp: words of 7..15 bytes that start and end with a digit.  Parsing them 32 at a time keeps
-// every lane busy (in a log line one dotted word in three or four is an address); their bytes come straight from the
-// log buffer (L2: the window that held them was staged moments ago).
-__device__ __forceinline__ void drain_ipv4(const ScanArgs& a, TokenWarp& tw, const Cand* ring, uint32_t count, uint32_t lane) {
-  bool wi = false;
-  IpTok it{0, 0, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
-  if (lane < count) {
-    const Cand c = ring[lane];
-    uint32_t h[4];
-    load_head_words(a.buf + c.start, h);
-    it.start = c.start; it.len = c.len;
-    wi = parse_ipv4_words(h, c.len, it.w[0]);
-  }
-  __syncwarp();
-  if (wi) tw.n_v4++;
-  append_tokens(a, tw, lane, false, StrTok{0, 0, 0}, wi, it);
-}
-
-// One segment of a word queue (DOTTED: dotted domain-character words -> IPv4 / domain; else: hash-length hex words).
-// The segment is sorted by position; every iteration takes as many consecutive candidates (at most 32) as fit in the
-// warp's window, stages the window with coalesced 16-byte loads and lets one lane handle one candidate.
-template <bool DOTTED>
-__device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t n, uint8_t* s_win, Cand* s_ring,
+// One segment of a word queue.  W_DOTTED: dotted domain-character words that hold a byte which is neither a hex digit nor a
+// '.' (domains; never an IPv4 address).  W_NUMERIC: dotted words of hex digits and dots only (IPv4 addresses, and the odd
+// domain such as "cafe.de").  W_HASH: hash-length hex words.  The segment is sorted by position; every iteration takes as
+// many consecutive candidates (at most 32) as fit in the warp's window, stages the window with coalesced 16-byte loads and
+// lets one lane handle one candidate.
+enum { W_DOTTED = 0, W_NUMERIC = 1, W_HASH = 2 };
+template <int MODE>
+__device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t n, uint8_t* s_win,
                                             const uint32_t* s_hot, bool fast, uint32_t lane) {
   const bool want_dom = (a.flags & MGPU_X_DOMAINS) != 0, want_v4 = (a.flags & MGPU_X_IPV4) != 0;
-  uint32_t nring = 0;
+  if (MODE == W_DOTTED && !want_dom) return;
   Cand cn{0xFFFFFFFFu, 0};  // prefetched: candidate i0 + lane of the NEXT iteration (assuming a full group of 32)
   if (lane < n) cn = ld_cand(q + lane);
   for (uint32_t i0 = 0; i0 < n;) {
@@ -437,11 +434,14 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
     const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c.start, 0);
     const uint32_t alo = lo & ~15u;
     const bool fits = !have || (uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN;
-    const uint32_t nf = __ballot_sync(0xFFFFFFFFu, !fits);
+    const uint32_t nf = MODE == W_NUMERIC ? 0u : __ballot_sync(0xFFFFFFFFu, !fits);
     uint32_t g = nf ? (uint32_t)__ffs((int)nf) - 1u : 32u;  // candidates of this iteration: lanes [0, g)
     const uint8_t* p = a.buf;
     bool high = true;  // "the token bytes may hold bytes >= 0x80"
-    if (g == 0) g = 1;  // a single word longer than the window: read it from global memory
+    if (MODE == W_NUMERIC) {
+      // IPv4 candidates are sparse in most logs (a 2 KiB window would hold a handful): 32 per iteration straight from the
+      // log buffer; all that is needed of each is its first 16 bytes
+    } else if (g == 0) g = 1;  // a single word longer than the window: read it from global memory
     else {
       const bool mine = have && lane < g;
       const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, mine ? c.start + c.len : 0u);
@@ -470,37 +470,33 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
     const uint8_t* wp = p + (active ? c.start : lo);
     load_head_words(wp, kw.h);
     load_tail_words(wp, active ? c.len : 0u, kw.t);
-    if (DOTTED) {
-      // IPv4 candidates are parked in the warp's ring and parsed 32 at a time
-      const bool ip_like = active && want_v4 && c.len >= 7 && c.len <= 15 && (uint8_t)((kw.h[0] & 0xFF) - '0') < 10 && (uint8_t)((kw.t[3] >> 24) - '0') < 10;
-      const uint32_t bi = __ballot_sync(0xFFFFFFFFu, ip_like);
-      if (bi) {
-        if (ip_like) s_ring[nring + __popc(bi & ((1u << lane) - 1u))] = c;
-        nring += __popc(bi);
-        __syncwarp();
-        if (nring >= 32) {
-          drain_ipv4(a, tw, s_ring + (nring - 32), 32, lane);
-          nring -= 32;
-          __syncwarp();
-        }
-      }
-      if (active && want_dom) {
+    bool wi = false;
+    IpTok it{c.start, c.len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
+    if (MODE == W_NUMERIC) {
+      if (active && want_v4) wi = parse_ipv4_words(kw.h, c.len, it.w[0]);
+      __syncwarp();
+      if (wi) tw.n_v4++;
+    }
+    if (MODE != W_HASH) {
+      // a valid IPv4 address is never a domain: its last label is numeric, and no PSL entry ends in one (checked at upload)
+      if (active && want_dom && !wi) {
         st.type = MGPU_T_DOMAIN;
         const uint64_t tail8 = c.len >= 8 ? (((uint64_t)kw.t[3] << 32) | kw.t[2]) : load_tail8(wp, c.len);
         ws = domain_word_fast(a.db, a.db.psl_tld, wp, c.len, high, tail8);
       }
       __syncwarp();
     } else if (active) { st.type = hash_type_of(c.len); ws = true; }
-    if (ws) ws = string_token(a, tw, fast, s_hot, kw, st);
-    __syncwarp();
-    append_tokens(a, tw, lane, ws, st, false, IpTok{0, 0, 0, 0, {0, 0, 0, 0}});
+    if (__any_sync(0xFFFFFFFFu, ws)) {
+      if (ws) ws = string_token(a, tw, fast, s_hot, kw, st);
+      __syncwarp();
+    }
+    append_tokens(a, tw, lane, ws, st, wi, it);
     if (g != 32) {  // a short group: the prefetch assumed 32; fetch the right candidates again
       cn = Cand{0xFFFFFFFFu, 0};
       if (i0 + g + lane < n) cn = ld_cand(q + i0 + g + lane);
     }
     i0 += g;
   }
-  if (DOTTED && nring) drain_ipv4(a, tw, s_ring, nring, lane);
 }
 
 __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
@@ -508,7 +504,6 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   uint32_t* s_hot = reinterpret_cast<uint32_t*>(tk_smem);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* s_win = tk_smem + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
-  Cand* s_ring = reinterpret_cast<Cand*>(tk_smem + (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32)) + (size_t)warp * IP_RING;
   const bool fast = a.fast != 0;
   if (a.ctr->overflow) return;  // an earlier stage of this piece ran out of room: the host redoes the piece in smaller parts
   if (fast) {
@@ -521,8 +516,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   const uint32_t nwarps = gridDim.x * TK_WARPS;
   for (uint32_t seg = blockIdx.x * TK_WARPS + warp; seg < a.nseg; seg += nwarps) {
     const uint32_t* sc = a.seg_cnt + seg;
-    token_words<true>(a, tw, a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED], sc[Q_DOTTED * a.nseg_max], s_win, s_ring, s_hot, fast, lane);
-    token_words<false>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], sc[Q_HASH * a.nseg_max], s_win, s_ring, s_hot, fast, lane);
+    token_words<W_DOTTED>(a, tw, a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED], sc[Q_DOTTED * a.nseg_max], s_win, s_hot, fast, lane);
+    token_words<W_NUMERIC>(a, tw, a.q_numeric + (size_t)seg * a.seg_cap[Q_NUMERIC], sc[Q_NUMERIC * a.nseg_max], s_win, s_hot, fast, lane);
+    token_words<W_HASH>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], sc[Q_HASH * a.nseg_max], s_win, s_hot, fast, lane);
     // '@' and "::" anchors: rare, straight from the log buffer
     const uint32_t nA = sc[Q_AT * a.nseg_max], nC = sc[Q_COLON2 * a.nseg_max];
     const uint32_t* qa = a.q_at + (size_t)seg * a.seg_cap[Q_AT];
@@ -1116,7 +1112,7 @@ void mgpu_destroy(mgpu_ctx* c) {
   }
   for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
-  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
+  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
                   c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -1168,6 +1164,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   a.seg_cap[Q_HASH] = cap32(std::max<size_t>(share / 33 + 8, 32));
   a.seg_cap[Q_AT] = cap32(std::max<size_t>(share / 16 + 32, 1024));
   a.seg_cap[Q_COLON2] = cap32(std::max<size_t>(share / 16 + 32, 512));
+  a.seg_cap[Q_NUMERIC] = cap32(std::max<size_t>(share / 8 + 32, 256));
   a.cap_str = cap32(chunk_bytes / 8 + 1024);
   a.cap_ip = cap32(chunk_bytes / 8 + 1024);
   a.cap_rec = cap32(chunk_bytes / 16 + 4096);
@@ -1176,6 +1173,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMalloc(&a.q_hash, (size_t)a.seg_cap[Q_HASH] * a.nseg_max * sizeof(Cand)));
   CK(cudaMalloc(&a.q_at, (size_t)a.seg_cap[Q_AT] * a.nseg_max * 4));
   CK(cudaMalloc(&a.q_c2, (size_t)a.seg_cap[Q_COLON2] * a.nseg_max * 4));
+  CK(cudaMalloc(&a.q_numeric, (size_t)a.seg_cap[Q_NUMERIC] * a.nseg_max * sizeof(Cand)));
   CK(cudaMalloc(&a.seg_cnt, (size_t)Q_COUNT * a.nseg_max * 4));
   CK(cudaMalloc(&a.str, (size_t)a.cap_str * sizeof(StrTok)));
   CK(cudaMalloc(&a.ip, (size_t)a.cap_ip * sizeof(IpTok)));

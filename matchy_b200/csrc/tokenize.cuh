@@ -20,7 +20,7 @@
 namespace mgpu {
 
 enum { CLS_B = 0, CLS_DOT = 1, CLS_AT = 2, CLS_CL = 3, CLS_NL = 4, CLS_DM = 5, CLS_HX = 6, CLS_DASH = 7 };
-enum { Q_DOTTED = 0, Q_HASH = 1, Q_AT = 2, Q_COLON2 = 3, Q_COUNT = 4 };
+enum { Q_DOTTED = 0, Q_HASH = 1, Q_AT = 2, Q_COLON2 = 3, Q_NUMERIC = 4, Q_COUNT = 5 };  // Q_NUMERIC: dotted words of hex digits and dots only (IPv4 candidates)
 static const uint32_t TILE_BYTES = 1024;
 static const uint32_t SLICE_BYTES = 32;
 
@@ -43,6 +43,7 @@ struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX, DASH; };
 struct TileCarry {
   uint32_t prev;        // facts about the bytes just before the tile: PV_* bits
   uint32_t cBad, cDot, cNhx;  // the open word so far holds a byte that rules out a domain / a '.' / a non-hex byte
+  uint32_t cNhd;        // ... a byte that is neither a hex digit nor a '.' (such a word cannot be an IPv4 address)
   uint32_t prevB;       // boundary mask of the 32 bytes before the tile (bit i = byte i - 32 of the tile)
   uint64_t open_start;  // chunk offset where the open word starts (valid when prev & PV_T)
 };
@@ -108,7 +109,7 @@ MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len ==
 // word that is open there.
 MGPU_HDN TileCarry range_prologue(const uint8_t* buf, uint64_t lo, uint64_t a) {
   TileCarry c;
-  c.prev = 0; c.cBad = 0; c.cDot = 0; c.cNhx = 0; c.open_start = a; c.prevB = 0xFFFFFFFFu;
+  c.prev = 0; c.cBad = 0; c.cDot = 0; c.cNhx = 0; c.cNhd = 0; c.open_start = a; c.prevB = 0xFFFFFFFFu;
   if (a <= lo) return c;
   c.prevB = 0;
   for (uint32_t k = 0; k < 32; k++) if (a < lo + 32 - k || is_boundary(buf[a - 32 + k])) c.prevB |= 1u << k;  // bytes before the chunk count as boundaries
@@ -117,20 +118,20 @@ MGPU_HDN TileCarry range_prologue(const uint8_t* buf, uint64_t lo, uint64_t a) {
            ((a >= lo + 2 && buf[a - 2] == ':') ? (uint32_t)PV_CL2 : 0u);
   if (is_boundary(prev)) return c;
   c.prev |= PV_T;
-  uint32_t bad = 0, dot = 0, nhx = 0;
+  uint32_t bad = 0, dot = 0, nhx = 0, nhd = 0;
   uint64_t s = a;
   uint8_t right = 0;  // the byte to the right of b inside the open word (0 = none yet)
   while (s > lo) {
     uint8_t b = buf[s - 1];
     if (is_boundary(b)) break;
-    bad |= !is_domain_fast(b); dot |= b == '.'; nhx |= !is_hex(b);
+    bad |= !is_domain_fast(b); dot |= b == '.'; nhx |= !is_hex(b); nhd |= !is_hex(b) && b != '.';
     if (right == '.' && (b == '.' || b == '-')) bad = 1;  // "..", "-."
     if (right == '-' && b == '.') bad = 1;                // ".-"
     right = b;
     s--;
   }
   if (right == '.' || right == '-') bad = 1;  // the word starts with '.' or '-'
-  c.cBad = bad; c.cDot = dot; c.cNhx = nhx; c.open_start = s;
+  c.cBad = bad; c.cDot = dot; c.cNhx = nhx; c.cNhd = nhd; c.open_start = s;
   return c;
 }
 

@@ -44,7 +44,7 @@ struct emu_ctx {
 // ---- K1: tokenize_kernel, one "warp" per range of tiles -------------------------------------------------
 static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t flags, uint64_t nwarps,
                          std::vector<Cand>& qd, std::vector<Cand>& qh, std::vector<uint32_t>& qa, std::vector<uint32_t>& qc,
-                         uint64_t& lines) {
+                         std::vector<Cand>& qn, uint64_t& lines) {
   const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
   const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
   const bool want_dot = (flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0, want_hash = (flags & MGPU_X_HASHES) != 0;
@@ -79,16 +79,16 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         domain_rule_masks(m[lane], S[lane], pv[lane], bad[lane], bad_end[lane]);
       }
       // the three "word contains ..." chains of tokenize_kernel: ballots are bit loops here
-      uint32_t H[3][32];
+      uint32_t H[4][32];
       uint32_t pb = 0;
       for (uint32_t lane = 0; lane < 32; lane++) pb |= (T[lane] == 0xFFFFFFFFu ? 1u : 0u) << lane;
-      for (int cls = 0; cls < 3; cls++) {
+      for (int cls = 0; cls < 4; cls++) {
         uint32_t gen = 0, Y[32];
         for (uint32_t lane = 0; lane < 32; lane++) {
-          Y[lane] = cls == 0 ? (T[lane] & (~m[lane].DM | bad[lane])) : cls == 1 ? m[lane].DOT : (T[lane] & ~m[lane].HX);
+          Y[lane] = cls == 0 ? (T[lane] & (~m[lane].DM | bad[lane])) : cls == 1 ? m[lane].DOT : cls == 2 ? (T[lane] & ~m[lane].HX) : (T[lane] & ~m[lane].HX & ~m[lane].DOT);
           gen |= chain_gen(T[lane], Y[lane]) << lane;
         }
-        uint32_t& c0 = cls == 0 ? cy.cBad : cls == 1 ? cy.cDot : cy.cNhx;
+        uint32_t& c0 = cls == 0 ? cy.cBad : cls == 1 ? cy.cDot : cls == 2 ? cy.cNhx : cy.cNhd;
         uint32_t co, cv = carry_chain(gen, pb & ~gen, c0, co);
         for (uint32_t lane = 0; lane < 32; lane++) H[cls][lane] = chain_ends(T[lane], Y[lane], (cv >> lane) & 1u, m[lane].B);
         c0 = co;
@@ -110,7 +110,7 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
         for (uint32_t mm = candDot; mm; mm &= mm - 1) {
           uint32_t bit = (uint32_t)__builtin_ctz(mm);
           uint64_t s = word_start_in_lane(m[lane].B, bit, p, lane_open);
-          qd.push_back(Cand{(uint32_t)s, (uint32_t)(p + bit - s)});
+          ((H[3][lane] >> bit) & 1u ? qd : qn).push_back(Cand{(uint32_t)s, (uint32_t)(p + bit - s)});
         }
         if (candHex) {
           uint32_t bit = (uint32_t)__builtin_ctz(candHex);
@@ -131,21 +131,22 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
 }
 
 static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, uint64_t nwarps, bool lookups) {
-  std::vector<Cand> qd, qh;
+  std::vector<Cand> qd, qh, qn;
   std::vector<uint32_t> qa, qc;
   uint64_t lines = 0;
-  emu_tokenize(buf, lo, n, flags, nwarps, qd, qh, qa, qc, lines);
+  emu_tokenize(buf, lo, n, flags, nwarps, qd, qh, qa, qc, qn, lines);
   const DbView& db = c->db;
   size_t s0 = c->str.size(), i0 = c->ip.size();
-  // K2 validate
-  for (auto& cd : qd) {
-    const uint8_t* wp = buf + cd.start;
-    uint32_t addr;
-    if ((flags & MGPU_X_IPV4) && parse_ipv4_word(wp, cd.len, addr)) c->ip.push_back(IpTok{cd.start, cd.len, MGPU_T_IPV4, {addr, 0, 0, 0}});
-    bool high = false;  // the kernel passes a per-window flag; the promise "false => pure ASCII" is what matters
-    for (uint32_t k = 0; k < cd.len; k++) high |= wp[k] >= 0x80;
-    if ((flags & MGPU_X_DOMAINS) && domain_word_fast(db, db.psl_tld, wp, cd.len, high)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
-  }
+  // K2 token kernel: dotted queue = domains only; numeric queue = IPv4, else maybe a domain
+  for (int numeric = 0; numeric < 2; numeric++)
+    for (auto& cd : (numeric ? qn : qd)) {
+      const uint8_t* wp = buf + cd.start;
+      uint32_t addr;
+      bool high = false;  // the kernel passes a per-window flag; the promise "false => pure ASCII" is what matters
+      for (uint32_t k = 0; k < cd.len; k++) high |= wp[k] >= 0x80;
+      if (numeric && (flags & MGPU_X_IPV4) && parse_ipv4_word(wp, cd.len, addr)) { c->ip.push_back(IpTok{cd.start, cd.len, MGPU_T_IPV4, {addr, 0, 0, 0}}); continue; }
+      if ((flags & MGPU_X_DOMAINS) && domain_word_fast(db, db.psl_tld, wp, cd.len, high)) c->str.push_back(StrTok{cd.start, cd.len, MGPU_T_DOMAIN});
+    }
   for (auto& cd : qh) {
     uint32_t ty = cd.len == 32 ? MGPU_T_MD5 : cd.len == 40 ? MGPU_T_SHA1 : cd.len == 64 ? MGPU_T_SHA256 : cd.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
     c->str.push_back(StrTok{cd.start, cd.len, ty});
