@@ -117,9 +117,19 @@ MGPU_HD uint32_t key_hash_words(const uint32_t* words, uint32_t k, uint32_t tag)
 }
 // hot filter: blocked Bloom, 2 bits in one 32-bit word.  cold filter: blocked Bloom, 3 bits in one 64-bit word; its word
 // index and bit positions come from a second mix of the same key hash, so one hash per key serves both filters.
-MGPU_HD bool hot_test(const uint32_t* hot, uint32_t h) {
+// Where the hot filter's words come from: a plain pointer (host emulation, database preparation) or the token kernel's
+// shared-memory copy addressed with ld.shared (a generic pointer would cost the generic-address path on every test).
+struct HotPtr { const uint32_t* p; MGPU_HD uint32_t word(uint32_t i) const { return p[i]; } };
+#ifdef __CUDACC__
+struct HotShared {
+  uint32_t base;  // shared-space byte address of word 0
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + i * 4)); return v; }
+};
+#endif
+template <typename H>
+MGPU_HD bool hot_test(const H& hot, uint32_t h) {
   uint32_t m = (1u << (h & 31)) | (1u << ((h >> 5) & 31));
-  return (hot[h >> 17] & m) == m;
+  return (hot.word(h >> 17) & m) == m;
 }
 MGPU_HD void hot_set(uint32_t* hot, uint32_t h) { hot[h >> 17] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31)); }
 MGPU_HD uint32_t cold_word(uint32_t h, uint32_t mask) { return ((h * 0x2545F491u) ^ (h >> 11)) & mask; }
@@ -341,6 +351,30 @@ MGPU_HD void load_tail_words(const uint8_t* w, uint32_t n, uint32_t t[4]) {
   t[0] = n >= 16 ? ldu32_fast(w + n - 16) : 0u;
 }
 
+#ifdef __CUDACC__
+// the same two loaders for a token that lies in a shared-memory window (saddr = shared-space byte address of its first byte)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_unaligned32(uint32_t saddr) {
+  const uint32_t q = saddr & ~3u;
+  return __funnelshift_r(lds_u32(q), lds_u32(q + 4), (saddr & 3u) * 8);
+}
+__device__ __forceinline__ void load_head_words_shared(uint32_t saddr, uint32_t h[4]) {
+  const uint32_t q = saddr & ~3u, sh = (saddr & 3u) * 8;
+  const uint32_t w0 = lds_u32(q), w1 = lds_u32(q + 4), w2 = lds_u32(q + 8), w3 = lds_u32(q + 12), w4 = lds_u32(q + 16);
+  h[0] = __funnelshift_r(w0, w1, sh); h[1] = __funnelshift_r(w1, w2, sh); h[2] = __funnelshift_r(w2, w3, sh); h[3] = __funnelshift_r(w3, w4, sh);
+}
+__device__ __forceinline__ void load_tail_words_shared(uint32_t saddr, uint32_t n, uint32_t t[4]) {
+  // the four words end at saddr + n; all share one alignment: five aligned words, the lower ones only when inside the token
+  const uint32_t e = saddr + n, q = e & ~3u, sh = (e & 3u) * 8;
+  const uint32_t w4 = sh ? lds_u32(q) : 0u;  // (the word that holds the bytes just below an unaligned end)
+  const uint32_t w3 = n >= 1 ? lds_u32(q - 4) : 0u, w2 = n >= 5 ? lds_u32(q - 8) : 0u, w1 = n >= 9 ? lds_u32(q - 12) : 0u, w0 = n >= 13 ? lds_u32(q - 16) : 0u;
+  t[3] = n >= 4 ? __funnelshift_r(w3, w4, sh) : 0u;
+  t[2] = n >= 8 ? __funnelshift_r(w2, w3, sh) : 0u;
+  t[1] = n >= 12 ? __funnelshift_r(w1, w2, sh) : 0u;
+  t[0] = n >= 16 ? __funnelshift_r(w0, w1, sh) : 0u;
+}
+#endif
+
 // try_parse_ipv4 (lib.rs:813-869) on a whole boundary-delimited word of n bytes held in h[0..4) (only the first n bytes count):
 // all of it must be consumed — four groups of 1..3 digits, value <= 255, no leading zero in a multi-digit group, single dots
 // between.  Straight-line SWAR: per-byte digit / dot flags -> 16-bit masks -> dot positions -> group values.
@@ -493,7 +527,8 @@ MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint
 //    and case-insensitive databases clear fast_ok and every token takes the exact path.
 // Hot tests first (shared memory, `hot` may point at a copy of db.hot); at most one cold test (L2) per class afterwards.
 // Returns F_LIT | F_GLOB bits.
-MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const KeyWords& kw, uint32_t n) {
+template <typename H>
+MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords& kw, uint32_t n) {
   uint32_t flags = 0;
   if (db.has_literal) {
     const uint32_t k = lit_key_len(n);
@@ -561,7 +596,7 @@ MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const ui
   KeyWords kw;
   load_head_words(w, kw.h);
   load_tail_words(w, n, kw.t);
-  return string_filters(db, hot, kw, n);
+  return string_filters(db, HotPtr{hot}, kw, n);
 }
 
 // The same key hashes from a literal's bytes (database preparation; must mirror string_filters exactly).

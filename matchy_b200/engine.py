@@ -62,7 +62,8 @@ class Engine:
 
     # -- scanning
     def scan(self, data, flags=None, base=0):
-        """Scan a host buffer (bytes / numpy uint8).  Returns (records, ids) as numpy structured arrays."""
+        """Scan a host buffer (bytes / numpy uint8).  Returns (records, ids) as numpy structured arrays (views of the engine's
+        result buffers, valid until the next scan; see results())."""
         if flags is None:
             flags = self.default_flags()
         p, n, keep = N.as_ptr(data)
@@ -84,8 +85,12 @@ class Engine:
         ids = C.POINTER(N.MgpuIdPair)()
         nr, ni = C.c_size_t(), C.c_size_t()
         _check(self.L.mgpu_results(self.h, C.byref(recs), C.byref(nr), C.byref(ids), C.byref(ni)), "mgpu_results")
-        r = np.frombuffer(C.string_at(recs, nr.value * 32), dtype=self.REC_DTYPE) if nr.value else np.zeros(0, self.REC_DTYPE)
-        i = np.frombuffer(C.string_at(ids, ni.value * 8), dtype=self.ID_DTYPE) if ni.value else np.zeros(0, self.ID_DTYPE)
+        # zero-copy views of the engine's pinned result buffers: like the C ABI's, they stay valid until the next scan on
+        # this engine (take .copy() to keep them longer)
+        r = (np.frombuffer((C.c_uint8 * (nr.value * 32)).from_address(C.addressof(recs.contents)), dtype=self.REC_DTYPE)
+             if nr.value else np.zeros(0, self.REC_DTYPE))
+        i = (np.frombuffer((C.c_uint8 * (ni.value * 8)).from_address(C.addressof(ids.contents)), dtype=self.ID_DTYPE)
+             if ni.value else np.zeros(0, self.ID_DTYPE))
         return r, i
 
     def records_as_tuples(self):

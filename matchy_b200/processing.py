@@ -141,7 +141,7 @@ class Worker:
             c = db.engine.counters()
             if n == 0:
                 self._stats.add_counters(c, db.engine.timing())
-                self.last_raw = (recs, ids)
+                self.last_raw = (recs.copy(), ids.copy())  # (views of the engine's buffers: keep copies)
             else:
                 self._stats.matches_found += c["matches"]
             mv = memoryview(data) if not isinstance(data, memoryview) else data
