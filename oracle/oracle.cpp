@@ -486,6 +486,175 @@ enum ExtractFlags : uint32_t {  // matchy.h:188-228
   X_DOMAINS = 1, X_EMAILS = 2, X_IPV4 = 4, X_IPV6 = 8, X_HASHES = 16, X_BITCOIN = 32, X_ETHEREUM = 64, X_MONERO = 128
 };
 
+
+// ===========================================================================================
+// Crypto-address validators — matchy-extractor/src/lib.rs:1799-1920.  Third-party crates absent from the tree, restated
+// from their published algorithms: sha2 0.10 (FIPS 180-4 SHA-256), tiny-keccak 2.0 (Keccak-256, original 0x01 padding),
+// bs58 0.5.1 (Bitcoin alphabet, decode_into), bech32 0.11.1 (`decode`: BIP-173 / BIP-350 checksum, either constant).
+// Pinned by the reference's own address vectors (lib.rs:3240-3626) and by standard digests (tests/test_oracle_kats.py).
+// ===========================================================================================
+namespace cryptoaddr {
+
+static inline uint32_t rotr32(uint32_t x, int r) { return (x >> r) | (x << (32 - r)); }
+static void sha256(const uint8_t* msg, size_t len, uint8_t out[32]) {
+  static const uint32_t K[64] = {
+      0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74,
+      0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d,
+      0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e,
+      0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5,
+      0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+  uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  std::vector<uint8_t> m(msg, msg + len);
+  m.push_back(0x80);
+  while (m.size() % 64 != 56) m.push_back(0);
+  uint64_t bits = (uint64_t)len * 8;
+  for (int k = 7; k >= 0; k--) m.push_back((uint8_t)(bits >> (8 * k)));
+  for (size_t off = 0; off < m.size(); off += 64) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)m[off + 4 * i] << 24) | ((uint32_t)m[off + 4 * i + 1] << 16) | ((uint32_t)m[off + 4 * i + 2] << 8) | m[off + 4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+      uint32_t s0 = rotr32(w[i - 15], 7) ^ rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = rotr32(w[i - 2], 17) ^ rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+      uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25), ch = (e & f) ^ (~e & g), t1 = hh + S1 + ch + K[i] + w[i];
+      uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22), mj = (a & b) ^ (a & c) ^ (b & c), t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(h[i] >> 24); out[4 * i + 1] = (uint8_t)(h[i] >> 16); out[4 * i + 2] = (uint8_t)(h[i] >> 8); out[4 * i + 3] = (uint8_t)h[i]; }
+}
+
+static inline uint64_t rotl64(uint64_t x, int r) { return r ? (x << r) | (x >> (64 - r)) : x; }
+static void keccak_f1600(uint64_t st[25]) {
+  static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+                                  0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+                                  0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+                                  0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+  static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};  // [x + 5y]
+  for (int round = 0; round < 24; round++) {
+    uint64_t C[5], D[5], B[25];
+    for (int x = 0; x < 5; x++) C[x] = st[x] ^ st[x + 5] ^ st[x + 10] ^ st[x + 15] ^ st[x + 20];
+    for (int x = 0; x < 5; x++) D[x] = C[(x + 4) % 5] ^ rotl64(C[(x + 1) % 5], 1);
+    for (int i = 0; i < 25; i++) st[i] ^= D[i % 5];
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) B[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(st[x + 5 * y], ROT[x + 5 * y]);
+    for (int y = 0; y < 5; y++)
+      for (int x = 0; x < 5; x++) st[x + 5 * y] = B[x + 5 * y] ^ (~B[(x + 1) % 5 + 5 * y] & B[(x + 2) % 5 + 5 * y]);
+    st[0] ^= RC[round];
+  }
+}
+// Keccak-256 as tiny-keccak's Keccak::v256: rate 136 bytes, domain byte 0x01 (NOT SHA3's 0x06)
+static void keccak256(const uint8_t* msg, size_t len, uint8_t out[32]) {
+  uint64_t st[25] = {0};
+  const size_t rate = 136;
+  std::vector<uint8_t> m(msg, msg + len);
+  m.push_back(0x01);
+  while (m.size() % rate != 0) m.push_back(0);
+  m.back() |= 0x80;
+  for (size_t off = 0; off < m.size(); off += rate) {
+    for (size_t i = 0; i < rate / 8; i++) {
+      uint64_t v = 0;
+      for (int k = 7; k >= 0; k--) v = (v << 8) | m[off + 8 * i + k];
+      st[i] ^= v;
+    }
+    keccak_f1600(st);
+  }
+  for (int i = 0; i < 32; i++) out[i] = (uint8_t)(st[i / 8] >> (8 * (i % 8)));
+}
+
+// bs58 0.5.1 decode (Bitcoin alphabet): false on a character outside the alphabet
+static bool bs58_decode(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
+  static const char* A = "123456789ABCDEFGHJKLMNPQRSTUVWXYZabcdefghijkmnopqrstuvwxyz";
+  int8_t map[128];
+  for (int i = 0; i < 128; i++) map[i] = -1;
+  for (int i = 0; i < 58; i++) map[(int)A[i]] = (int8_t)i;
+  std::vector<uint8_t> le;  // little-endian number
+  for (size_t i = 0; i < n; i++) {
+    if (s[i] > 127 || map[s[i]] < 0) return false;
+    size_t val = (size_t)map[s[i]];
+    for (auto& b : le) { val += (size_t)b * 58; b = (uint8_t)(val & 0xFF); val >>= 8; }
+    while (val > 0) { le.push_back((uint8_t)(val & 0xFF)); val >>= 8; }
+  }
+  for (size_t i = 0; i < n && s[i] == '1'; i++) le.push_back(0);
+  out.assign(le.rbegin(), le.rend());
+  return true;
+}
+static bool bitcoin_base58(const uint8_t* s, size_t n) {  // validate_bitcoin_base58 :1799-1822
+  std::vector<uint8_t> d;
+  if (!bs58_decode(s, n, d) || d.size() < 5) return false;
+  uint8_t h1[32], h2[32];
+  sha256(d.data(), d.size() - 4, h1);
+  sha256(h1, 32, h2);
+  return memcmp(h2, d.data() + d.size() - 4, 4) == 0;
+}
+static bool monero(const uint8_t* s, size_t n) {  // validate_monero_address :1895-1920
+  std::vector<uint8_t> d;
+  if (!bs58_decode(s, n, d) || d.size() < 5) return false;
+  uint8_t h[32];
+  keccak256(d.data(), d.size() - 4, h);
+  return memcmp(h, d.data() + d.size() - 4, 4) == 0;
+}
+// validate_bitcoin_bech32 :1825-1836 — bech32::decode(addr) succeeds and the human-readable part is "bc"
+static bool bitcoin_bech32(const uint8_t* s, size_t n) {
+  static const char* CH = "qpzry9x8gf2tvdw0s3jn54khce6mua7l";
+  // check_characters: scanning from the end, everything after the LAST '1' must be a bech32 character (either case);
+  // no mixed case anywhere; a separator must exist
+  bool upper = false, lower = false;
+  long sep = -1;
+  for (long i = (long)n - 1; i >= 0; i--) {
+    uint8_t ch = s[i];
+    if (ch > 127) return false;  // (a non-ASCII char after the separator is invalid; before it, Hrp::parse rejects it)
+    if (ch == '1' && sep < 0) sep = i;
+    else if (sep < 0) {
+      uint8_t lc = (ch >= 'A' && ch <= 'Z') ? (uint8_t)(ch + 32) : ch;
+      if (!strchr(CH, lc) || lc == 0) return false;
+    }
+    if (ch >= 'A' && ch <= 'Z') upper = true; else if (ch >= 'a' && ch <= 'z') lower = true;
+  }
+  if (upper && lower) return false;
+  if (sep < 0) return false;
+  // Hrp::parse: 1..83 chars of ASCII 33..126; equality with "bc" is case-insensitive
+  if (sep != 2) return false;
+  if (!((s[0] == 'b' || s[0] == 'B') && (s[1] == 'c' || s[1] == 'C'))) return false;
+  size_t dn = n - 3;
+  if (dn < 6) return false;  // shorter than a checksum
+  static const uint32_t GEN[5] = {0x3b6a57b2, 0x26508e6d, 0x1ea119fa, 0x3d4233dd, 0x2a1462b3};
+  uint32_t chk = 1;
+  auto step = [&](uint32_t v) {
+    uint32_t b = chk >> 25;
+    chk = ((chk & 0x1ffffff) << 5) ^ v;
+    for (int i = 0; i < 5; i++) if ((b >> i) & 1) chk ^= GEN[i];
+  };
+  step('b' >> 5); step('c' >> 5); step(0); step('b' & 31); step('c' & 31);
+  for (size_t i = 3; i < n; i++) {
+    uint8_t lc = (s[i] >= 'A' && s[i] <= 'Z') ? (uint8_t)(s[i] + 32) : s[i];
+    step((uint32_t)(strchr(CH, lc) - CH));
+  }
+  return chk == 1 || chk == 0x2bc830a3;  // Bech32 or Bech32m
+}
+// validate_ethereum_checksum :1841-1892 for "0x" + 40 hex digits
+static bool ethereum(const uint8_t* s) {
+  bool lower = false, upper = false;
+  for (int i = 2; i < 42; i++) { if (s[i] >= 'a' && s[i] <= 'f') lower = true; if (s[i] >= 'A' && s[i] <= 'F') upper = true; }
+  if (!(lower && upper)) return true;  // all one case (or digits only): nothing to verify
+  uint8_t lc[40], h[32];
+  for (int i = 0; i < 40; i++) lc[i] = (s[2 + i] >= 'A' && s[2 + i] <= 'F') ? (uint8_t)(s[2 + i] + 32) : s[2 + i];
+  keccak256(lc, 40, h);
+  for (int i = 0; i < 40; i++) {
+    uint8_t c = s[2 + i];
+    bool alpha = (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F');
+    if (!alpha) continue;
+    uint8_t nib = (i % 2 == 0) ? (h[i / 2] >> 4) : (h[i / 2] & 15);
+    if ((c <= 'F') != (nib >= 8)) return false;
+  }
+  return true;
+}
+
+}  // namespace cryptoaddr
+
 struct Item {
   uint8_t type;
   size_t start, end;
@@ -749,8 +918,43 @@ struct Extractor {
     }
   }
 
-  // lib.rs:409-488 — order: IPv6, IPv4, email, domain, hash (crypto extractors: SURVEY §8(f) "next",
-  // not restated; the oracle refuses those flags rather than silently skipping them)
+  // lib.rs:1269-1319 — words of 26..62 bytes: "bc1…" -> bech32, '1…' / '3…' -> Base58Check
+  void extract_bitcoin_chunk(const uint8_t* c, const std::vector<size_t>& bounds, std::vector<Item>& out) const {
+    for (size_t k = 0; k + 1 < bounds.size(); k += 2) {
+      size_t s = bounds[k], e = bounds[k + 1], len = e - s;
+      if (len < 26 || len > 62) continue;
+      bool ok = false;
+      if (c[s] == 'b' && c[s + 1] == 'c' && c[s + 2] == '1') ok = valid_utf8(c + s, len) && cryptoaddr::bitcoin_bech32(c + s, len);
+      else if (c[s] == '1' || c[s] == '3') ok = valid_utf8(c + s, len) && cryptoaddr::bitcoin_base58(c + s, len);
+      if (ok) { Item it; it.type = T_BITCOIN; it.start = s; it.end = e; out.push_back(it); }
+    }
+  }
+  // lib.rs:1328-1361 — every "0x" followed by 40 hex digits, boundary (or chunk edge) on both sides
+  void extract_ethereum_chunk(const uint8_t* c, size_t n, std::vector<Item>& out) const {
+    for (size_t s = 0; s + 1 < n;) {
+      if (!(c[s] == '0' && c[s + 1] == 'x')) { s++; continue; }
+      size_t at = s;
+      s += 2;  // memmem find_iter: non-overlapping occurrences
+      if (at + 42 > n) continue;
+      if (require_word_boundaries && at > 0 && !is_boundary(c[at - 1])) continue;
+      if (require_word_boundaries && at + 42 < n && !is_boundary(c[at + 42])) continue;
+      bool hex = true;
+      for (size_t j = at + 2; j < at + 42; j++) if (!is_hex(c[j])) { hex = false; break; }
+      if (!hex) continue;
+      if (cryptoaddr::ethereum(c + at)) { Item it; it.type = T_ETHEREUM; it.start = at; it.end = at + 42; out.push_back(it); }
+    }
+  }
+  // lib.rs:1367-1409 — words of 90..110 bytes that start with '4' or '8'
+  void extract_monero_chunk(const uint8_t* c, const std::vector<size_t>& bounds, std::vector<Item>& out) const {
+    for (size_t k = 0; k + 1 < bounds.size(); k += 2) {
+      size_t s = bounds[k], e = bounds[k + 1], len = e - s;
+      if (len < 90 || len > 110) continue;
+      if (c[s] != '4' && c[s] != '8') continue;
+      if (valid_utf8(c + s, len) && cryptoaddr::monero(c + s, len)) { Item it; it.type = T_MONERO; it.start = s; it.end = e; out.push_back(it); }
+    }
+  }
+
+  // lib.rs:409-488 — order: IPv6, IPv4, email, domain, hash, bitcoin, ethereum, monero
   void extract_from_chunk(const uint8_t* c, size_t n, std::vector<Item>& out) const {
     std::vector<size_t> bounds, dots;
     if (flags & (X_HASHES | X_BITCOIN | X_MONERO)) find_word_boundaries(c, n, bounds);
@@ -763,6 +967,9 @@ struct Extractor {
     if (flags & X_EMAILS) extract_emails_chunk(c, n, out);
     if (flags & X_DOMAINS) extract_domains_chunk(c, n, dots, out);
     if (flags & X_HASHES) extract_hashes_chunk(c, bounds, out);
+    if (flags & X_BITCOIN) extract_bitcoin_chunk(c, bounds, out);
+    if (flags & X_ETHEREUM) extract_ethereum_chunk(c, n, out);
+    if (flags & X_MONERO) extract_monero_chunk(c, bounds, out);
   }
 };
 
@@ -1439,6 +1646,12 @@ orc_handle* orc_open(const uint8_t* mxy, size_t len, const char* psl_path, int c
   return h;
 }
 const char* orc_error(orc_handle* h) { return h->db.error.c_str(); }
+// digests of the crypto-address validators, for known-answer tests (what: 0 SHA-256, 1 Keccak-256)
+void orc_digest(int what, const uint8_t* msg, size_t len, uint8_t out[32]) { if (what == 0) cryptoaddr::sha256(msg, len, out); else cryptoaddr::keccak256(msg, len, out); }
+// 1 valid / 0 invalid (what: 0 bitcoin Base58Check, 1 bitcoin bech32, 2 ethereum "0x"+40 hex, 3 monero)
+int orc_cryptoaddr(int what, const uint8_t* s, size_t n) {
+  switch (what) { case 0: return cryptoaddr::bitcoin_base58(s, n); case 1: return cryptoaddr::bitcoin_bech32(s, n); case 2: return n == 42 && cryptoaddr::ethereum(s); default: return cryptoaddr::monero(s, n); }
+}
 void orc_close(orc_handle* h) { delete h; }
 
 // default extractor flags as `matchy match` derives them from DB capabilities (match_cmd.rs:277-303),
@@ -1453,7 +1666,6 @@ int orc_has(orc_handle* h, int what) { return what == 0 ? h->db.has_ip_header : 
 
 // scan a buffer the way `matchy match` would scan a file with these bytes (chunk_size = reader block size)
 int orc_scan(orc_handle* h, const uint8_t* data, size_t len, uint64_t base, uint32_t flags, size_t chunk_size) {
-  if (flags & (X_BITCOIN | X_ETHEREUM | X_MONERO)) return -2;  // not restated
   h->scan = Scan();
   h->ex.flags = flags;
   if (chunk_size == 0) process_bytes(h->db, h->ex, data, len, base, h->scan);
@@ -1474,7 +1686,6 @@ void orc_counters(orc_handle* h, uint64_t* out16) {
 // `matchy match -j N` works over N files: one worker per file, processing/parallel.rs:355-372, 416-433),
 // each shard streamed through FileReader::next_batch in 128 KiB reads.  Only the summed counters are kept.
 int orc_scan_mt(orc_handle* h, const uint8_t* data, size_t len, uint32_t flags, int threads, uint64_t* out16) {
-  if (flags & (X_BITCOIN | X_ETHEREUM | X_MONERO)) return -2;
   if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
   if (threads <= 0) threads = 1;
   std::vector<size_t> cuts{0};

@@ -55,6 +55,8 @@ def lib():
         L.orc_ids.restype = C.POINTER(C.c_uint32)
         L.orc_ids.argtypes = [C.c_void_p]
         L.orc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.orc_digest.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p]
+        L.orc_cryptoaddr.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
         L.orc_extract.restype = C.c_size_t
         L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint64), C.c_size_t]
         L.orc_ndjson.restype = C.c_void_p
@@ -200,3 +202,14 @@ def ipv6_display(segs):
 
 def xxh64(b: bytes):
     return lib().orc_xxh64(b, len(b))
+
+
+def digest(what: str, msg: bytes) -> bytes:
+    """SHA-256 / Keccak-256 as the oracle's crypto-address validators compute them (known-answer tests)."""
+    out = C.create_string_buffer(32)
+    lib().orc_digest({"sha256": 0, "keccak256": 1}[what], msg, len(msg), out)
+    return out.raw
+
+
+def cryptoaddr_valid(kind: str, text: bytes) -> bool:
+    return bool(lib().orc_cryptoaddr({"bitcoin_base58": 0, "bitcoin_bech32": 1, "ethereum": 2, "monero": 3}[kind], text, len(text)))

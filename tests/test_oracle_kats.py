@@ -295,3 +295,118 @@ def test_next_batch_chunking_is_result_neutral(small_dbs):
     whole = o.scan(log[:300000] + b"tail without newline 1.2.3.4")
     for cs in (1000, 4096, 128 * 1024):
         assert o.scan(log[:300000] + b"tail without newline 1.2.3.4", chunk_size=cs) == whole
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Crypto-address extractors (matchy-extractor/src/lib.rs:1269-1409, 1799-1920; KATs :3240-3626)
+# ---------------------------------------------------------------------------------------------------------
+X_ALL = 0xFF  # every extractor, like Extractor::new()
+
+
+def _crypto(o, data):
+    return [(t, s) for t, s in o.extract_strings(data, X_ALL) if t in ("Bitcoin", "Ethereum", "Monero")]
+
+
+def test_crypto_digests_known_answers():
+    import hashlib
+    for msg in (b"", b"abc", b"a" * 55, b"a" * 56, b"a" * 64, b"The quick brown fox jumps over the lazy dog", bytes(range(200))):
+        assert O.digest("sha256", msg) == hashlib.sha256(msg).digest(), msg
+    # Keccak-256 (the pre-standard padding tiny-keccak's Keccak::v256 uses — not hashlib's sha3_256)
+    assert O.digest("keccak256", b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert O.digest("keccak256", b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    assert O.digest("keccak256", b"a" * 135) != O.digest("keccak256", b"a" * 136)  # one block vs two
+    assert O.digest("keccak256", b"a" * 200) != hashlib.sha3_256(b"a" * 200).digest()
+
+
+def test_bitcoin_kats(small_dbs):
+    o = O.Oracle(small_dbs[1][0])
+    # lib.rs:3240-3298: legacy, P2SH, bech32
+    assert _crypto(o, b"Send to 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa for payment") == [("Bitcoin", b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa")]
+    assert _crypto(o, b"Payment to 3Cbq7aT1tY8kMxWLbitaG7yT6bPbKChq64 confirmed") == [("Bitcoin", b"3Cbq7aT1tY8kMxWLbitaG7yT6bPbKChq64")]
+    assert _crypto(o, b"Withdraw to bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdq") == [("Bitcoin", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdq")]
+    # :3300-3341: bad checksum, too short
+    assert _crypto(o, b"Fake address 1A1zP1eP5QGefi2DMPTfTL5SLmv7Divf00 is invalid") == []
+    assert _crypto(o, b"Short address 1A1zP1eP is invalid") == []
+    # :3608-3626: chunk mode, one per line
+    chunk = b"Line1: 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa\nLine2: 3Cbq7aT1tY8kMxWLbitaG7yT6bPbKChq64\n"
+    assert [s for _, s in _crypto(o, chunk)] == [b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa", b"3Cbq7aT1tY8kMxWLbitaG7yT6bPbKChq64"]
+    # bech32 details of bech32 0.11 `decode`: Bech32m (BIP-350 taproot vector) accepted too; mixed case, wrong hrp, bad checksum rejected
+    assert O.cryptoaddr_valid("bitcoin_bech32", b"bc1p0xlxvlhemja6c4dqv22uapctqupfhlxm9h8z3k2e72q4k9hcz7vqzk5jj0")
+    assert not O.cryptoaddr_valid("bitcoin_bech32", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdQ")
+    assert not O.cryptoaddr_valid("bitcoin_bech32", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdx")
+    assert not O.cryptoaddr_valid("bitcoin_bech32", b"tb1qw508d6qejxtdg4y5r3zarvary0c5xw7kxpjzsx")
+    assert _crypto(o, b"x bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdq.") == []  # '.' is not a boundary: the word is longer
+    # Base58Check: leading '1's are zero bytes; '0', 'O', 'I', 'l' are not in the alphabet
+    assert O.cryptoaddr_valid("bitcoin_base58", b"1111111111111111111114oLvT2")
+    assert not O.cryptoaddr_valid("bitcoin_base58", b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNO")
+
+
+def test_ethereum_kats(small_dbs):
+    o = O.Oracle(small_dbs[1][0])
+    # lib.rs:3343-3447
+    assert _crypto(o, b"Send to 0x5aeda56215b167893e80b4fe645ba6d5bab767de") == [("Ethereum", b"0x5aeda56215b167893e80b4fe645ba6d5bab767de")]
+    assert _crypto(o, b"Send to 0x5aAeb6053F3E94C9b9A09f33669435E7Ef1BeAed") == [("Ethereum", b"0x5aAeb6053F3E94C9b9A09f33669435E7Ef1BeAed")]
+    assert _crypto(o, b"Bad address 0x5aAeb6053f3e94c9b9a09f33669435e7ef1beaed") == []       # mixed case, wrong checksum
+    assert _crypto(o, b"Short address 0x5aeda56215b167893e80b4fe645ba6d5bab7") == []
+    assert _crypto(o, b"Invalid 0x5aeda56215b167893e80b4fe645ba6d5bab767dg") == []
+    # :3588-3606 in a log line; all upper case needs no checksum; boundaries on both sides are required
+    line = b"2025-01-15 10:32:45 Transaction to=0x5aeda56215b167893e80b4fe645ba6d5bab767de value=1000000000000000000"
+    assert _crypto(o, line) == [("Ethereum", b"0x5aeda56215b167893e80b4fe645ba6d5bab767de")]
+    assert _crypto(o, b"a 0x5AEDA56215B167893E80B4FE645BA6D5BAB767DE b") == [("Ethereum", b"0x5AEDA56215B167893E80B4FE645BA6D5BAB767DE")]
+    assert _crypto(o, b"a x0x5aeda56215b167893e80b4fe645ba6d5bab767de b") == []
+    assert _crypto(o, b"a 0x5aeda56215b167893e80b4fe645ba6d5bab767de0 b") == []
+    # other EIP-55 test vectors (EIP-55 text)
+    for a in (b"0xfB6916095ca1df60bB79Ce92cE3Ea74c37c5d359", b"0xdbF03B407c01E7cD3CBea99509d93f8DDDC8C6FB", b"0xD1220A0cf47c7B9Be7A2E6BA89F429762e7b9aDb"):
+        assert O.cryptoaddr_valid("ethereum", a)
+        assert not O.cryptoaddr_valid("ethereum", a[:-1] + (b"B" if a[-1:] == b"b" else b"b"))
+
+
+def test_monero_kats(small_dbs):
+    o = O.Oracle(small_dbs[1][0])
+    # lib.rs:3449-3518.  The reference decodes the WHOLE string with bs58 (not Monero's block-wise base58), so the real
+    # address of :3455 does not pass its Keccak check — the reference's own test tolerates that outcome; restated as is.
+    addr = b"44AFFq5kSiGBoZ4NMDwYtN18obc8AemS33DBLWs3H7otXft3XjrpDtQGv7SqSsaBYBb98uNbr2VBBEt7f2wfn3RVGQBEP3A"
+    assert _crypto(o, b"Donate to " + addr) == []
+    assert _crypto(o, b"Fake 1AdUndXHHZ6cfufTMvppY6JwXNouMBzSkbLYfpAV5Usx3skxNgYeYTRj5UzqtReoS44qo9mtmXCqY45DJ852K5Jv2684Rge") == []
+    assert _crypto(o, b"Short 4AdUndXHHZ6cfufTMvppY6JwXNouMBzSkbLYfpAV5Usx") == []
+    # a string built to satisfy the reference's rule (payload ‖ Keccak256(payload)[..4], plain base58) IS extracted
+    good = _monero_like(b"\x12" + bytes(range(64)))
+    assert 90 <= len(good) <= 110 and good[:1] in (b"4", b"8")
+    assert _crypto(o, b"to " + good + b" ok") == [("Monero", good)]
+    assert _crypto(o, b"to " + good[:-1] + (b"2" if good[-1:] != b"2" else b"3") + b" ok") == []
+
+
+ALPHABET58 = b"123456789ABCDEFGHJKLMNPQRSTUVWXYZabcdefghijkmnopqrstuvwxyz"
+
+
+def _b58(raw: bytes) -> bytes:
+    n = int.from_bytes(raw, "big")
+    out = bytearray()
+    while n:
+        n, r = divmod(n, 58)
+        out.append(ALPHABET58[r])
+    out.extend(ALPHABET58[0:1] * (len(raw) - len(raw.lstrip(b"\0"))))
+    return bytes(reversed(out))
+
+
+def _monero_like(payload: bytes) -> bytes:
+    """Search the payload's last byte until plain base58 of payload ‖ keccak[..4] starts with '4' or '8' and is 90..110 long."""
+    for tail in range(256):
+        for first in range(1, 256):
+            p = bytes([first]) + payload[1:-1] + bytes([tail])
+            s = _b58(p + O.digest("keccak256", p)[:4])
+            if 90 <= len(s) <= 110 and s[:1] in (b"4", b"8"):
+                return s
+    raise AssertionError("no monero-like string found")
+
+
+def test_crypto_mixed_and_disabled(small_dbs):
+    o = O.Oracle(small_dbs[1][0])
+    # lib.rs:3520-3557
+    line = b"Transaction from 192.168.1.1 to bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdq via example.com"
+    got = o.extract_strings(line, X_ALL)
+    assert ("IPv4", b"192.168.1.1") in got and ("Bitcoin", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdq") in got and ("Domain", b"example.com") in got
+    # :3559-3586 disabled extractors find nothing
+    line = b"BTC: 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa ETH: 0x5aeda56215b167893e80b4fe645ba6d5bab767de"
+    assert _crypto(o, line) == [("Bitcoin", b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa"), ("Ethereum", b"0x5aeda56215b167893e80b4fe645ba6d5bab767de")]
+    assert [x for x in o.extract_strings(line, O.X_DEFAULT) if x[0] in ("Bitcoin", "Ethereum", "Monero")] == []
