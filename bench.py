@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--chunk-mb", type=int, default=2040, help="scan piece size (MiB, < 2048); pieces of a resident scan are launched back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--crypto", action="store_true", help="also run the Bitcoin/Ethereum/Monero extractors (matchy match without --extractors=-crypto)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -184,7 +185,7 @@ def main():
     eng = Engine(local_rank, chunk_bytes=args.chunk_mb << 20)
     eng.upload(db)
     info = eng.db_info()
-    flags = eng.default_flags()
+    flags = eng.default_flags() | (0xE0 if args.crypto else 0)  # configs run with --extractors=-crypto semantics unless --crypto
 
     # this rank's shard of the stream: blocks [rank*nblocks, (rank+1)*nblocks); generated on the host into pinned memory
     import ctypes as C
@@ -284,7 +285,7 @@ def main():
             "metric": "log_scan_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "log_bytes_per_gpu": nbytes, "chunk_bytes": args.chunk_mb << 20,
+            "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "log_bytes_per_gpu": nbytes, "chunk_bytes": args.chunk_mb << 20, "extractor_flags": flags,
                        "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (nbytes / 1e9),
                        "db": {k: info[k] for k in ("node_count", "literal_count", "glob_count", "ac_node_count", "file_bytes")},
                        "parallelism": "byte-range shards x%d, database replicated" % world},

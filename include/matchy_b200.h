@@ -40,7 +40,11 @@ extern "C" {
 #define MGPU_X_IPV4 (1u << 2)
 #define MGPU_X_IPV6 (1u << 3)
 #define MGPU_X_HASHES (1u << 4)
-#define MGPU_X_SUPPORTED 0x1Fu /* bitcoin/ethereum/monero extractors are not on the device path yet */
+#define MGPU_X_BITCOIN (1u << 5)  /* Base58Check ('1…', '3…') and bech32/bech32m ("bc1…") words, lib.rs:1269-1319 */
+#define MGPU_X_ETHEREUM (1u << 6) /* "0x" + 40 hex digits with the EIP-55 rule, lib.rs:1328-1361 */
+#define MGPU_X_MONERO (1u << 7)   /* lib.rs:1367-1409 */
+#define MGPU_X_CRYPTO (MGPU_X_BITCOIN | MGPU_X_ETHEREUM | MGPU_X_MONERO)
+#define MGPU_X_SUPPORTED 0xFFu
 
 /* item types == MATCHY_ITEM_TYPE_* (matchy.h:233-288) */
 #define MGPU_T_DOMAIN 0
@@ -52,6 +56,9 @@ extern "C" {
 #define MGPU_T_SHA256 6
 #define MGPU_T_SHA384 7
 #define MGPU_T_SHA512 8
+#define MGPU_T_BITCOIN 9
+#define MGPU_T_ETHEREUM 10
+#define MGPU_T_MONERO 11
 
 #define MGPU_KIND_IP 1      /* QueryResult::Ip      */
 #define MGPU_KIND_PATTERN 2 /* QueryResult::Pattern */

@@ -26,6 +26,7 @@
 #include "db_prepare.h"
 #include "mxy_reader.h"
 #include "tokenize.cuh"
+#include "crypto_addr.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -40,7 +41,7 @@ struct ScanTotals { uint32_t n_rec, n_ids; };  // records / id pairs appended so
 struct DevCounters {  // one per piece
   uint32_t n_str, n_ip;
   uint32_t n_rec, n_ids;      // snapshot of ScanTotals when the piece finished (piece_end_kernel)
-  uint32_t overflow;          // bit q: candidate queue q, 8: str tokens, 9: ip tokens, 10: records, 11: ids
+  uint32_t overflow;          // bit q (0..5): candidate queue q, 8: str tokens, 9: ip tokens, 10: records, 11: ids
   uint32_t pad[3];
   unsigned long long lines;
   unsigned long long by_type[12];
@@ -58,7 +59,7 @@ struct ScanArgs {
   uint32_t flags;
   uint32_t fast;       // 1: the token kernel applies string_filters() and only flagged string tokens reach the exact kernel
   DbView db;
-  Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2; Cand* q_numeric;
+  Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2; Cand* q_numeric; Cand* q_long;
   uint32_t seg_cap[Q_COUNT];
   uint32_t* seg_cnt;   // [Q_COUNT][nseg_max]
   uint32_t nseg, nseg_max;
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   uint32_t* const qa = a.q_at + w * a.seg_cap[Q_AT];
   uint32_t* const qc = a.q_c2 + w * a.seg_cap[Q_COLON2];
   Cand* const qn = a.q_numeric + w * a.seg_cap[Q_NUMERIC];
-  uint32_t nd = 0, nh = 0, na = 0, nc = 0, nn = 0, ovf = 0;
+  Cand* const ql = a.q_long + w * a.seg_cap[Q_LONG];
+  uint32_t nd = 0, nh = 0, na = 0, nc = 0, nn = 0, nl = 0, ovf = 0;
   uint32_t lines = 0;
   if (t0 < t1) {
     TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     const bool want_hash = (a.flags & MGPU_X_HASHES) != 0;
     const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
     const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
+    const bool want_long = (a.flags & MGPU_X_CRYPTO) != 0;
     for (uint64_t t = t0; t < t1; t++) {
       const uint32_t tile_base = (uint32_t)(t * TILE_BYTES);  // chunks are at most 2 GiB: positions fit 32 bits
       const uint32_t p = tile_base + lane * SLICE_BYTES;
@@ -203,11 +206,11 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
       // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
       uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
-      {  // ... and at least 32 bytes long: the previous slice has no boundary at or above the bit position where the word ends here
-        uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1);
-        if (lane == 0) Bprev = cy.prevB;
-        if (candHex && (Bprev >> (__ffs(candHex) - 1)) != 0) candHex = 0;
-      }
+      uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1);
+      if (lane == 0) Bprev = cy.prevB;
+      // ... and at least 32 bytes long: the previous slice has no boundary at or above the bit position where the word ends here
+      if (candHex && (Bprev >> (__ffs(candHex) - 1)) != 0) candHex = 0;
+      const uint32_t candLong = want_long ? long_word_ends(T, ~Bprev, E) : 0u;  // words of >= 26 bytes (crypto-address candidates)
       const uint32_t candAt = want_at ? m.AT : 0u;
       // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
       const uint32_t cl1 = (m.CL << 1) | ((pv >> 3) & 1u), cl2 = (m.CL << 2) | (((pv >> 3) & 1u) << 1) | ((pv >> 4) & 1u);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
           nn += tn; nd += td;
         }
       }
-      if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2) != 0)) {  // rare in most logs: one vote covers the three
+      if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2 | candLong) != 0)) {  // rare in most logs: one vote covers the four
         {
           bool keep = false; Cand c{0, 0};
           if (candHex) {
@@ -273,6 +276,22 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
             for (uint32_t mm = candAt; mm; mm &= mm - 1) qa[idx++] = (uint32_t)(p + __ffs(mm) - 1);
           } else ovf |= 1u << Q_AT;
           na += total;
+        }
+        if (__any_sync(0xFFFFFFFFu, candLong != 0)) {
+          // at most two per slice; keep those whose exact length is in one of the address ranges
+          Cand c2[2]; uint32_t k = 0;
+          for (uint32_t mm = candLong; mm; mm &= mm - 1) {
+            const uint32_t bit = __ffs(mm) - 1;
+            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+            if (is_crypto_len(p + bit - s) && k < 2) c2[k++] = Cand{s, p + bit - s};
+          }
+          const uint32_t incl = warp_incl_scan(k, lane), total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (total) {
+            if (nl + total <= a.seg_cap[Q_LONG]) { for (uint32_t j = 0; j < k; j++) ql[nl + incl - k + j] = c2[j]; }
+            else ovf |= 1u << Q_LONG;
+            nl += total;
+          }
         }
         if (__any_sync(0xFFFFFFFFu, candC2 != 0)) {
           uint32_t cnt = __popc(candC2), incl = cnt;
@@ -304,6 +323,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     sc[Q_AT * a.nseg_max] = ovf & (1u << Q_AT) ? 0u : na;
     sc[Q_COLON2 * a.nseg_max] = ovf & (1u << Q_COLON2) ? 0u : nc;
     sc[Q_NUMERIC * a.nseg_max] = ovf & (1u << Q_NUMERIC) ? 0u : nn;
+    sc[Q_LONG * a.nseg_max] = ovf & (1u << Q_LONG) ? 0u : nl;
     if (ovf) atomicOr(&a.ctr->overflow, ovf);
   }
   for (int d = 16; d; d >>= 1) lines += __shfl_down_sync(0xFFFFFFFFu, lines, d);
@@ -569,6 +589,32 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   for (int t = 0; t < 9; t++) {
     uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cnt[t]);
     if (lane == 0 && v) atomicAdd(&a.ctr->by_type[t], (unsigned long long)v);
+  }
+}
+
+// K2b crypto kernel: the long-word queue -> Bitcoin / Ethereum / Monero address tokens (lib.rs:1269-1409).  One thread per
+// candidate; candidates are rare and the validators (base58 big-number decode, SHA-256, Keccak-f) are long, so this is a
+// kernel of its own with its own register budget.  Valid tokens are counted and go through the same string filters /
+// token list as every other string token.
+__global__ void __launch_bounds__(128) crypto_kernel(ScanArgs a) {
+  if (a.ctr->overflow) return;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t seg = blockIdx.x * (blockDim.x >> 5) + warp; seg < a.nseg; seg += nwarps) {
+    const uint32_t n = a.seg_cnt[Q_LONG * a.nseg_max + seg];
+    const Cand* q = a.q_long + (size_t)seg * a.seg_cap[Q_LONG];
+    for (uint32_t i = lane; i < n; i += 32) {
+      const Cand c = q[i];
+      if ((uint64_t)c.start + c.len > a.n) continue;
+      const uint8_t* w = a.buf + c.start;
+      const uint32_t type = crypto_word_type(w, c.len, a.flags);
+      if (type == NONE32) continue;
+      atomicAdd(&a.ctr->by_type[type], 1ULL);
+      uint32_t f = 0;
+      if (a.fast) { f = string_filters(a.db, a.db.hot, w, c.len); if (!f) continue; }
+      const uint32_t k = atomicAdd(&a.ctr->n_str, 1u);
+      if (k >= a.cap_str) { atomicOr(&a.ctr->overflow, 1u << 8); continue; }
+      a.str[k] = StrTok{c.start, c.len, type | f};
+    }
   }
 }
 
@@ -1121,7 +1167,7 @@ void mgpu_destroy(mgpu_ctx* c) {
   }
   for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
-  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
+  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.q_long, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
                   c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -1174,6 +1220,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   a.seg_cap[Q_AT] = cap32(std::max<size_t>(share / 16 + 32, 1024));
   a.seg_cap[Q_COLON2] = cap32(std::max<size_t>(share / 16 + 32, 512));
   a.seg_cap[Q_NUMERIC] = cap32(std::max<size_t>(share / 8 + 32, 256));
+  a.seg_cap[Q_LONG] = cap32(std::max<size_t>(share / 27 + 8, 40));
   a.cap_str = cap32(chunk_bytes / 8 + 1024);
   a.cap_ip = cap32(chunk_bytes / 8 + 1024);
   a.cap_rec = cap32(chunk_bytes / 16 + 4096);
@@ -1183,6 +1230,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMalloc(&a.q_at, (size_t)a.seg_cap[Q_AT] * a.nseg_max * 4));
   CK(cudaMalloc(&a.q_c2, (size_t)a.seg_cap[Q_COLON2] * a.nseg_max * 4));
   CK(cudaMalloc(&a.q_numeric, (size_t)a.seg_cap[Q_NUMERIC] * a.nseg_max * sizeof(Cand)));
+  CK(cudaMalloc(&a.q_long, (size_t)a.seg_cap[Q_LONG] * a.nseg_max * sizeof(Cand)));
   CK(cudaMalloc(&a.seg_cnt, (size_t)Q_COUNT * a.nseg_max * 4));
   CK(cudaMalloc(&a.str, (size_t)a.cap_str * sizeof(StrTok)));
   CK(cudaMalloc(&a.ip, (size_t)a.cap_ip * sizeof(IpTok)));
@@ -1357,6 +1405,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   // (latency-bound, a fraction of the SMs busy) run on a second stream, beside the tokenizer of the next piece.
   if (c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
   token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
+  if (flags & MGPU_X_CRYPTO) crypto_kernel<<<launch_grid(c, 8), 128, 0, st>>>(a);
   CK(cudaEventRecord(ev[2], st));
   cudaStream_t ls = c->lookup;
   CK(cudaEventRecord(c->ev_tokens[slot], st));
@@ -1543,7 +1592,7 @@ static void finish_scan(mgpu_ctx* c) {
 static int check_ready(mgpu_ctx* c, uint32_t flags) {
   if (!c) { set_err("null context"); return MGPU_E_PARAM; }
   if (!c->db_loaded) { set_err("no database uploaded"); return MGPU_E_NODB; }
-  if (flags & ~MGPU_X_SUPPORTED) { set_err("bitcoin/ethereum/monero extractors are not available on the device path"); return MGPU_E_PARAM; }
+  if (flags & ~MGPU_X_SUPPORTED) { set_err("unknown extractor flags"); return MGPU_E_PARAM; }
   if ((flags & (MGPU_X_DOMAINS | MGPU_X_EMAILS)) && !c->args.db.psl_keys) { set_err("Public Suffix List not set (mgpu_set_psl)"); return MGPU_E_PARAM; }
   return MGPU_OK;
 }

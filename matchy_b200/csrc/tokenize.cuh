@@ -20,7 +20,7 @@
 namespace mgpu {
 
 enum { CLS_B = 0, CLS_DOT = 1, CLS_AT = 2, CLS_CL = 3, CLS_NL = 4, CLS_DM = 5, CLS_HX = 6, CLS_DASH = 7 };
-enum { Q_DOTTED = 0, Q_HASH = 1, Q_AT = 2, Q_COLON2 = 3, Q_NUMERIC = 4, Q_COUNT = 5 };  // Q_NUMERIC: dotted words of hex digits and dots only (IPv4 candidates)
+enum { Q_DOTTED = 0, Q_HASH = 1, Q_AT = 2, Q_COLON2 = 3, Q_NUMERIC = 4, Q_LONG = 5, Q_COUNT = 6 };  // Q_NUMERIC: dotted words of hex digits and dots only (IPv4 candidates)
 static const uint32_t TILE_BYTES = 1024;
 static const uint32_t SLICE_BYTES = 32;
 
@@ -103,6 +103,16 @@ MGPU_HD uint64_t word_start_in_lane(uint32_t B, uint32_t bit, uint64_t p, uint64
   return below ? p + top_bit(below) + 1 : lane_open_start;
 }
 
+// Q_LONG: words of 26..62 or 90..110 bytes (crypto-address candidates, lib.rs:1269-1409).
+MGPU_HD bool is_crypto_len(uint64_t len) { return (len >= 26 && len <= 62) || (len >= 90 && len <= 110); }
+// Boundaries of a 32-byte slice that end a word of AT LEAST 26 bytes.  T = word bytes of the slice, Tprev = of the 32 bytes
+// before it, E = boundaries of the slice that end a word.  Runs of ones are grown by doubling: r_k has bit j set when bits
+// j-k+1..j are all set.
+MGPU_HD uint32_t long_word_ends(uint32_t T, uint32_t Tprev, uint32_t E) {
+  const uint64_t X = ((uint64_t)T << 32) | Tprev;
+  const uint64_t r2 = X & (X << 1), r4 = r2 & (r2 << 2), r8 = r4 & (r4 << 4), r16 = r8 & (r8 << 8), r24 = r16 & (r8 << 16), r26 = r24 & (r2 << 24);
+  return E & (uint32_t)(r26 >> 31);  // boundary bit i needs the run to reach bit 32 + i - 1
+}
 MGPU_HD bool is_hash_len(uint64_t len) { return len == 32 || len == 40 || len == 64 || len == 96 || len == 128; }
 
 // Carry state for a range that starts at offset `a` of a chunk whose first byte is at `lo`: look back over the

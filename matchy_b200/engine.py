@@ -7,7 +7,8 @@ from . import _native as N
 
 X_DOMAINS, X_EMAILS, X_IPV4, X_IPV6, X_HASHES = 1, 2, 4, 8, 16
 X_BITCOIN, X_ETHEREUM, X_MONERO = 32, 64, 128
-X_SUPPORTED = 0x1F
+X_CRYPTO = X_BITCOIN | X_ETHEREUM | X_MONERO
+X_SUPPORTED = 0xFF
 ITEM_TYPE_NAMES = ["Domain", "Email", "IPv4", "IPv6", "MD5", "SHA1", "SHA256", "SHA384", "SHA512", "Bitcoin", "Ethereum", "Monero"]
 KIND_IP, KIND_PATTERN = 1, 2
 NO_DATA = 0xFFFFFFFF

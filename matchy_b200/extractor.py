@@ -69,9 +69,8 @@ class ExtractorBuilder:
 
 
 class Extractor:
-    """`Extractor::new()` enables everything.  The crypto-address extractors (bitcoin/ethereum/monero) have no device
-    implementation yet; asking `extract_from_chunk` for them raises instead of silently skipping them — build with
-    `.extract_bitcoin(False).extract_ethereum(False).extract_monero(False)` (== `--extractors=-crypto`)."""
+    """`Extractor::new()` enables everything, crypto-address extractors (bitcoin/ethereum/monero) included — like the
+    reference.  `.extract_bitcoin(False).extract_ethereum(False).extract_monero(False)` == `--extractors=-crypto`."""
 
     def __init__(self, enabled=None, engine=None, device=0):
         self._f = enabled or {"domains": True, "emails": True, "ipv4": True, "ipv6": True, "hashes": True,
@@ -106,7 +105,7 @@ class Extractor:
     def device_flags(self):
         fl = self.flags()
         if fl & ~E.X_SUPPORTED:
-            raise ExtractorError("bitcoin/ethereum/monero extraction is not implemented on the device path; disable them")
+            raise ExtractorError("unknown extractor flags")
         return fl
 
     def bind(self, engine):
@@ -118,16 +117,16 @@ class Extractor:
             self._engine = E.Engine(self._device)
         return self._engine
 
-    # reference order of extract_from_chunk: IPv6, IPv4, e-mail, domain, hashes; ascending offset inside a type
-    _ORDER = {3: 0, 2: 1, 1: 2, 0: 3, 4: 4, 5: 4, 6: 4, 7: 4, 8: 4}
+    # reference order of extract_from_chunk: IPv6, IPv4, e-mail, domain, hashes, bitcoin, ethereum, monero; ascending offset inside a type
+    _ORDER = {3: 0, 2: 1, 1: 2, 0: 3, 4: 4, 5: 4, 6: 4, 7: 4, 8: 4, 9: 5, 10: 6, 11: 7}
 
     def extract_from_chunk(self, chunk):
         items = self._eng().extract(chunk, self.device_flags())
         items.sort(key=lambda t: (self._ORDER[t[0]], t[1]))
         return [Match(E.ITEM_TYPE_NAMES[t], (s, e), chunk) for t, s, e in items]
 
-    # extract_from_line order (lib.rs:1472-1521): domains, IPv4, e-mails, IPv6, hashes
-    _LINE_ORDER = {0: 0, 2: 1, 1: 2, 3: 3, 4: 4, 5: 4, 6: 4, 7: 4, 8: 4}
+    # extract_from_line order (lib.rs:1472-1521): domains, IPv4, e-mails, IPv6, hashes, bitcoin, ethereum, monero
+    _LINE_ORDER = {0: 0, 2: 1, 1: 2, 3: 3, 4: 4, 5: 4, 6: 4, 7: 4, 8: 4, 9: 5, 10: 6, 11: 7}
 
     def extract_from_line(self, line):
         items = self._eng().extract(line, self.device_flags())

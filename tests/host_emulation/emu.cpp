@@ -17,6 +17,7 @@
 #include "../../include/matchy_b200.h"
 #include "../../matchy_b200/csrc/db_prepare.h"
 #include "../../matchy_b200/csrc/tokenize.cuh"
+#include "../../matchy_b200/csrc/crypto_addr.cuh"
 
 using namespace mgpu;
 
@@ -44,11 +45,11 @@ struct emu_ctx {
 // ---- K1: tokenize_kernel, one "warp" per range of tiles -------------------------------------------------
 static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t flags, uint64_t nwarps,
                          std::vector<Cand>& qd, std::vector<Cand>& qh, std::vector<uint32_t>& qa, std::vector<uint32_t>& qc,
-                         std::vector<Cand>& qn, uint64_t& lines) {
+                         std::vector<Cand>& qn, std::vector<Cand>& ql, uint64_t& lines) {
   const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
   const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
   const bool want_dot = (flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0, want_hash = (flags & MGPU_X_HASHES) != 0;
-  const bool want_at = (flags & MGPU_X_EMAILS) != 0, want_c2 = (flags & MGPU_X_IPV6) != 0;
+  const bool want_at = (flags & MGPU_X_EMAILS) != 0, want_c2 = (flags & MGPU_X_IPV6) != 0, want_long = (flags & MGPU_X_CRYPTO) != 0;
   for (uint64_t w = 0; w < nwarps; w++) {
     uint64_t t0 = w * tpw, t1 = std::min(t0 + tpw, tiles);
     if (t0 >= t1) continue;
@@ -117,6 +118,12 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
           uint64_t s = word_start_in_lane(m[lane].B, bit, p, lane_open);
           if (is_hash_len(p + bit - s)) qh.push_back(Cand{(uint32_t)s, (uint32_t)(p + bit - s)});
         }
+        uint32_t candLong = want_long ? long_word_ends(T[lane], ~Bprev, E) : 0u;
+        for (uint32_t mm = candLong; mm; mm &= mm - 1) {
+          uint32_t bit = (uint32_t)__builtin_ctz(mm);
+          uint64_t s = word_start_in_lane(m[lane].B, bit, p, lane_open);
+          if (is_crypto_len(p + bit - s)) ql.push_back(Cand{(uint32_t)s, (uint32_t)(p + bit - s)});
+        }
         for (uint32_t mm = candAt; mm; mm &= mm - 1) qa.push_back((uint32_t)(p + (uint32_t)__builtin_ctz(mm)));
         for (uint32_t mm = candC2; mm; mm &= mm - 1) qc.push_back((uint32_t)(p + (uint32_t)__builtin_ctz(mm) - 1));
       }
@@ -131,10 +138,10 @@ static void emu_tokenize(const uint8_t* buf, uint64_t lo, uint64_t n, uint32_t f
 }
 
 static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, uint64_t nwarps, bool lookups) {
-  std::vector<Cand> qd, qh, qn;
+  std::vector<Cand> qd, qh, qn, ql;
   std::vector<uint32_t> qa, qc;
   uint64_t lines = 0;
-  emu_tokenize(buf, lo, n, flags, nwarps, qd, qh, qa, qc, qn, lines);
+  emu_tokenize(buf, lo, n, flags, nwarps, qd, qh, qa, qc, qn, ql, lines);
   const DbView& db = c->db;
   size_t s0 = c->str.size(), i0 = c->ip.size();
   // K2 token kernel: dotted queue = domains only; numeric queue = IPv4, else maybe a domain
@@ -150,6 +157,10 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
   for (auto& cd : qh) {
     uint32_t ty = cd.len == 32 ? MGPU_T_MD5 : cd.len == 40 ? MGPU_T_SHA1 : cd.len == 64 ? MGPU_T_SHA256 : cd.len == 96 ? MGPU_T_SHA384 : MGPU_T_SHA512;
     c->str.push_back(StrTok{cd.start, cd.len, ty});
+  }
+  for (auto& cd : ql) {  // crypto_kernel
+    uint32_t ty = crypto_word_type(buf + cd.start, cd.len, flags);
+    if (ty != NONE32) c->str.push_back(StrTok{cd.start, cd.len, ty});
   }
   for (uint32_t at : qa) {
     size_t s, e;

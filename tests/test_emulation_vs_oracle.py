@@ -7,7 +7,7 @@ import pytest
 
 import emu_lib as E
 import oracle_lib as O
-from test_gpu_parity import FRAGS, _fuzz_text
+from test_gpu_parity import CRYPTO_FRAGS, FRAGS, _fuzz_text, _monero_like_word
 
 
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
@@ -183,3 +183,27 @@ def test_tld_fast_front_end(small_dbs):
     want = sorted((s, t, e) for t, s, e in orc.extract(data, 31))
     assert len(want) >= 20
     assert sorted((s, t, e) for t, s, e in emu.tokens(data, 31)) == want
+
+
+def test_crypto_address_extraction(small_dbs):
+    """Host emulation of the crypto-address path (long-word queue of the tokenizer + crypto_addr.cuh) against the oracle."""
+    db, log = small_dbs[1]
+    orc, emu = O.Oracle(db), E.Emu(db)
+    rng = random.Random(17)
+    monero_ok = _monero_like_word()
+    seen = set()
+    for it in range(150):
+        parts = []
+        for _ in range(rng.randint(1, 50)):
+            f = rng.choice(CRYPTO_FRAGS + [monero_ok]) if rng.random() < 0.6 else rng.choice(FRAGS)
+            parts.append(f)
+            parts.append(rng.choice([b" ", b" ", b"\n", b"/", b"=", b":", b"", b".", b",", b"\"", b"-"]))
+        data = b"".join(parts)
+        want = sorted((s, t, e) for t, s, e in orc.extract(data, 0xFF))
+        got = sorted((s, t, e) for t, s, e in emu.tokens(data, 0xFF, nwarps=rng.choice([1, 2, 3]), misalign=rng.choice([0, 7])))
+        assert got == want, (it, data[:200])
+        seen |= {t for _, t, _ in want}
+    assert {9, 10, 11} <= seen
+    data = log[:300000] + b"pay 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa or 0x5aeda56215b167893e80b4fe645ba6d5bab767de now\n"
+    flags = orc.default_flags() | 0xE0
+    assert emu.scan(data, flags=flags, nwarps=3) == orc.scan(data, flags=flags)

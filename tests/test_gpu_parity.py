@@ -85,6 +85,17 @@ FRAGS = [b"1.2.3.4", b"10.0.0.1", b"256.1.1.1", b"1.2.3", b"1.2.3.4.5", b"01.2.3
          b"caf\xc3\xa9.fr", b"\xe2\x82\xac.org", b"\xc3.com", b" ", b"\t", b"\n", b"\r\n", b"/", b",", b";", b":", b"(", b")", b"[", b"]",
          b"{", b"}", b"<", b">", b"\"", b"'", b"=", b"&", b"?", b"-", b"_", b".", b"%", b"#", b"|", b"\\", b"*", b"!", b"~", b"http://",
          b"key=", b"a" * 70 + b".com", b"x" * 1500 + b".org", b"b." * 600 + b"com", b"9" * 40, b"1." * 20, b"deadbeef"]
+# crypto-address material (matchy-extractor/src/lib.rs:3240-3626 and near misses of every rule)
+CRYPTO_FRAGS = [b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa", b"3Cbq7aT1tY8kMxWLbitaG7yT6bPbKChq64", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdq",
+                b"bc1p0xlxvlhemja6c4dqv22uapctqupfhlxm9h8z3k2e72q4k9hcz7vqzk5jj0", b"1A1zP1eP5QGefi2DMPTfTL5SLmv7Divf00", b"1A1zP1eP",
+                b"1111111111111111111114oLvT2", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdQ", b"bc1qar0srrr7xfkvy5l643lydnw9re59gtzzwf5mdx",
+                b"tb1qw508d6qejxtdg4y5r3zarvary0c5xw7kxpjzsx", b"BC1QAR0SRRR7XFKVY5L643LYDNW9RE59GTZZWF5MDQ", b"bc1" + b"q" * 30,
+                b"0x5aeda56215b167893e80b4fe645ba6d5bab767de", b"0x5aAeb6053F3E94C9b9A09f33669435E7Ef1BeAed", b"0x5aAeb6053f3e94c9b9a09f33669435e7ef1beaed",
+                b"0x5AEDA56215B167893E80B4FE645BA6D5BAB767DE", b"0x5aeda56215b167893e80b4fe645ba6d5bab7", b"0x5aeda56215b167893e80b4fe645ba6d5bab767dg",
+                b"0xfB6916095ca1df60bB79Ce92cE3Ea74c37c5d359", b"0xfB6916095ca1df60bB79Ce92cE3Ea74c37c5d35B", b"0X5aeda56215b167893e80b4fe645ba6d5bab767de",
+                b"44AFFq5kSiGBoZ4NMDwYtN18obc8AemS33DBLWs3H7otXft3XjrpDtQGv7SqSsaBYBb98uNbr2VBBEt7f2wfn3RVGQBEP3A",
+                b"4" + b"A" * 94, b"8" + b"z" * 100, b"3" * 30, b"1" * 40, b"3" + b"1" * 25, b"1" + b"2" * 61, b"1" + b"2" * 62, b"13" * 13,
+                b"0123456789abcdef0123456789abcdef", b"3f" * 16, b"1a" * 20, b"x" * 26, b"y" * 25, b"4" * 89, b"4" * 90, b"8" * 110, b"8" * 111]
 
 
 def _fuzz_text(rng, n):
@@ -246,3 +257,48 @@ def test_fast_string_path_on_device(built):
         assert e.counters_list() == wcnt
         assert e.records_as_tuples() == want
         e.close()
+
+
+def test_crypto_address_extraction_on_device(engines):
+    """All extractors on (Extractor::new()): Bitcoin / Ethereum / Monero tokens agree with the oracle on the reference's own
+    vectors, near misses of every rule and random token soup; and a scan with the crypto extractors on keeps the match set."""
+    eng, orc, log = engines[1]
+    rng = random.Random(17)
+    monero_ok = _monero_like_word()
+    seen = set()
+    for it in range(120):
+        parts = []
+        for _ in range(rng.randint(1, 50)):
+            f = rng.choice(CRYPTO_FRAGS + [monero_ok]) if rng.random() < 0.6 else rng.choice(FRAGS)
+            parts.append(f)
+            parts.append(rng.choice([b" ", b" ", b"\n", b"/", b"=", b":", b"", b".", b",", b"\"", b"-"]))
+        data = b"".join(parts)
+        want = sorted((s, t, e) for t, s, e in orc.extract(data, 0xFF))
+        got = sorted((s, t, e) for t, s, e in eng.extract(data, 0xFF))
+        assert got == want, (it, data[:200])
+        seen |= {t for _, t, _ in want}
+    assert {9, 10, 11} <= seen  # every crypto type was exercised
+    data = log[:2_000_000] + b"pay 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa or 0x5aeda56215b167893e80b4fe645ba6d5bab767de now\n"
+    eng.scan(data, flags=eng.default_flags() | 0xE0)
+    got, cnt = eng.records_as_tuples(), eng.counters_list()
+    want, wcnt = orc.scan(data, flags=orc.default_flags() | 0xE0, chunk_size=128 * 1024)
+    assert cnt == wcnt and got == want
+    assert cnt[4 + 9] >= 1 and cnt[4 + 10] >= 1
+
+
+def _monero_like_word():
+    """A word that satisfies the reference's Monero rule (plain base58 of payload + Keccak-256[..4], '4'/'8' first, 90..110 chars)."""
+    A = b"123456789ABCDEFGHJKLMNPQRSTUVWXYZabcdefghijkmnopqrstuvwxyz"
+
+    def b58(raw):
+        n, out = int.from_bytes(raw, "big"), bytearray()
+        while n:
+            n, r = divmod(n, 58)
+            out.append(A[r])
+        return bytes(reversed(out))
+    for first in range(1, 256):
+        p = bytes([first]) + bytes(range(1, 65))
+        s = b58(p + O.digest("keccak256", p)[:4])
+        if 90 <= len(s) <= 110 and s[:1] in (b"4", b"8"):
+            return s
+    raise AssertionError
