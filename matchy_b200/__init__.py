@@ -11,7 +11,7 @@ Importing the package does not touch the GPU; creating a Database / Engine does,
 from . import processing  # noqa: F401
 from .builder import DatabaseBuilder, MatchMode  # noqa: F401
 from .database import Database, DatabaseError, QueryResult  # noqa: F401
-from .engine import Engine, EngineError, RecordFormatter  # noqa: F401
+from .engine import ITEM_TYPE_NAMES, Engine, EngineError, RecordFormatter  # noqa: F401
 from .extractor import Extractor, ExtractorError  # noqa: F401
 
 __version__ = "0.1.0"
