@@ -102,12 +102,8 @@ MGPU_HD uint32_t glob_key_len(uint32_t m) { return m < 4 ? m : (m >= 16 ? 16u : 
 MGPU_HD uint32_t lit_key_len(uint32_t n) { return n >= 8 ? 8u : (n >= 4 ? 4u : n); }
 MGPU_HD uint32_t key_seed(uint32_t tag) { return 0x811C9DC5u ^ (tag * 0x632BE5ABu); }
 MGPU_HD uint32_t key_mix(uint32_t s, uint32_t w) { s = (s ^ w) * 0x9E3779B1u; return s ^ (s >> 15); }
-MGPU_HD uint32_t key_fin(uint32_t s, uint32_t k) {
-  s = (s ^ (k * 0x7F4A7C15u)) * 0x85EBCA77u;
-  s ^= s >> 13;
-  s *= 0xC2B2AE3Du;
-  return s ^ (s >> 16);
-}
+// one more multiply-xorshift round per key; k separates keys of different lengths that feed identical words
+MGPU_HD uint32_t key_fin(uint32_t s, uint32_t k) { s = (s ^ (k * 0x7F4A7C15u)) * 0x85EBCA77u; return s ^ (s >> 15); }
 MGPU_HD uint32_t low_bytes32(uint32_t w, uint32_t k) { return k >= 4 ? w : (w & ((1u << (8 * k)) - 1u)); }
 // hash of a whole key given its words in feeding order (host side: database preparation)
 MGPU_HD uint32_t key_hash_words(const uint32_t* words, uint32_t k, uint32_t tag) {
@@ -126,12 +122,20 @@ struct HotShared {
   __device__ __forceinline__ uint32_t word(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + i * 4)); return v; }
 };
 #endif
+// two independent bits per key inside one 32-bit word: bits (h & 31) and ((h >> 5) & 31)
+MGPU_HD uint32_t hot_mask(uint32_t h) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(1u, 1u, h) | __funnelshift_l(1u, 1u, h >> 5);  // (a rotate takes the shift modulo 32)
+#else
+  return (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
+#endif
+}
 template <typename H>
 MGPU_HD bool hot_test(const H& hot, uint32_t h) {
-  uint32_t m = (1u << (h & 31)) | (1u << ((h >> 5) & 31));
+  const uint32_t m = hot_mask(h);
   return (hot.word(h >> 17) & m) == m;
 }
-MGPU_HD void hot_set(uint32_t* hot, uint32_t h) { hot[h >> 17] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31)); }
+MGPU_HD void hot_set(uint32_t* hot, uint32_t h) { hot[h >> 17] |= hot_mask(h); }
 MGPU_HD uint32_t cold_word(uint32_t h, uint32_t mask) { return ((h * 0x2545F491u) ^ (h >> 11)) & mask; }
 MGPU_HD uint64_t cold_bits(uint32_t h) {
   uint32_t g = (h ^ 0x5BD1E995u) * 0x846CA68Bu;
