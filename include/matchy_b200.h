@@ -120,7 +120,9 @@ uint32_t mgpu_default_flags(mgpu_ctx*);                            /* match_cmd.
 /* Scan one newline-aligned buffer in HOST memory (pinned or pageable): H2D on double-buffered streams,
  * kernels, D2H of records.  == Worker::process_bytes over every chunk FileReader::next_batch would cut. */
 int mgpu_scan(mgpu_ctx*, const uint8_t* host, size_t len, uint64_t base, uint32_t flags);
-/* Same, for a buffer already resident in this device's HBM (16-byte aligned). */
+/* Same, for a buffer already resident in this device's HBM.  `dev` must be 16-byte aligned and readable up to
+ * len rounded up to a multiple of 1024, plus 1024 (the tokenizer reads whole 1 KiB tiles, token readers up to 20 bytes past a
+ * token); mgpu_dev_alloc() allocates with that slack. */
 int mgpu_scan_device(mgpu_ctx*, const uint8_t* dev, size_t len, uint64_t base, uint32_t flags);
 /* Results of the last scan, sorted by (offset, item_type, len); valid until the next scan. */
 int mgpu_results(mgpu_ctx*, const mgpu_match** recs, size_t* n_recs, const mgpu_id_pair** ids, size_t* n_ids);
