@@ -302,3 +302,25 @@ def _monero_like_word():
         if 90 <= len(s) <= 110 and s[:1] in (b"4", b"8"):
             return s
     raise AssertionError
+
+
+def test_match_cli_output_contract(small_dbs, tmp_path):
+    """`python -m matchy_b200 match` prints exactly the oracle's sorted `matchy match` NDJSON for the same files."""
+    import subprocess
+    import sys
+    db, log = small_dbs[5]
+    dbp, l1, l2 = tmp_path / "t.mxy", tmp_path / "a.log", tmp_path / "b.log"
+    dbp.write_bytes(db)
+    cut = log.rfind(b"\n", 0, len(log) // 2) + 1
+    l1.write_bytes(log[:cut])
+    l2.write_bytes(log[cut:])
+    r = subprocess.run([sys.executable, "-m", "matchy_b200", "match", str(dbp), str(l1), str(l2), "--extractors=-crypto", "--stats"],
+                       capture_output=True, cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    assert r.returncode == 0, r.stderr[-500:]
+    orc = O.Oracle(db)
+    want = []
+    for path, part in ((l1, log[:cut]), (l2, log[cut:])):
+        orc.scan(part, chunk_size=128 * 1024)
+        want += orc.ndjson(part, str(path)).splitlines()
+    assert sorted(r.stdout.splitlines()) == sorted(want) and len(want) > 0
+    assert b'"matches"' in r.stderr
