@@ -103,6 +103,7 @@ struct PreparedDb {
   std::vector<uint32_t> gram2, gram3;  // bitmaps over the first 2 / 3 bytes of every AC literal
   std::vector<uint64_t> pfx_keys;      // prefix map (see DbView::ac_pfx_*)
   std::vector<uint32_t> pfx_vals;
+  std::vector<uint32_t> gen2, gen3;    // first 2 / 3 bytes of every AC literal that leads to an UNANCHORED pattern (see string_filters)
   std::vector<uint32_t> hot;           // fast string path: hot (shared-memory) and cold (L2) Bloom filters
   std::vector<uint64_t> cold;
   uint32_t ac_node_count = 0;
@@ -355,7 +356,8 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     // fast string path: classify every pattern some AC literal leads to (string_filters() in device_fns.cuh)
     if (db.wild_count != 0) fast = false;
     if (fast) {
-      std::vector<uint8_t> reach(pattern_count, 0);
+      std::vector<uint8_t> reach(pattern_count, 0), generic(pattern_count, 0);
+      bool any_generic = false;
       for (size_t lit = 0; lit + 1 < P.aclh.size(); lit += 2)
         for (uint32_t j = 0; j < P.aclh[lit + 1]; j++) { uint32_t pid = prep_le32(pg + P.aclh[lit] + j * 4); if (pid < pattern_count) reach[pid] = 1; else fast = false; }
       for (uint32_t pid = 0; pid < pattern_count && fast; pid++) {
@@ -363,7 +365,7 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         uint64_t eo = (uint64_t)db.patterns_offset + (uint64_t)pid * 16;
         if (eo + 16 > pg_len) continue;                     // find_all skips it
         uint32_t entry_id = prep_le32(pg + eo);
-        if (pg[eo + 4] == 0) { fast = false; break; }       // literal-type pattern: substring semantics (quirk 12)
+        if (pg[eo + 4] == 0) { generic[pid] = 1; any_generic = true; continue; }  // literal-type pattern: substring semantics (quirk 12)
         uint64_t io = (uint64_t)gso + (uint64_t)entry_id * 8;
         if (io + 8 > pg_len) continue;                      // match_glob_from_buffer fails: never a match
         uint32_t first = prep_le32(pg + io), cnt = (uint32_t)pg[io + 4] | ((uint32_t)pg[io + 5] << 8);
@@ -385,7 +387,48 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         r = lit_of(0, ptr, dl);
         if (r < 0) continue;
         if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_P), (uint32_t)TAG_GLOB_P}); db.glob_p_lens |= 1u << glob_key_len(dl); continue; }
-        fast = false;                                       // neither end is a literal: any position can match
+        generic[pid] = 1; any_generic = true;               // neither end is a literal: any position can match
+      }
+      // Unanchored patterns: a pattern is only ever a candidate through one of its AC literals (find_all), so a token can
+      // match one only if some literal that leads to an unanchored pattern OCCURS in it.  Collect the first 2 / 3 bytes of
+      // those literals: in the (breadth-first) trie walk the first node that lists a literal id is the node whose path IS
+      // the literal (deeper nodes list it as a merged suffix output).  Needs complete output lists (db.ac_anchored).
+      if (fast && any_generic) {
+        if (!db.ac_anchored) fast = false;
+        else {
+          std::vector<uint8_t> lit_generic(P.aclh.size() / 2, 0);
+          for (size_t lit = 0; lit + 1 < P.aclh.size(); lit += 2)
+            for (uint32_t j = 0; j < P.aclh[lit + 1]; j++) { uint32_t pid = prep_le32(pg + P.aclh[lit] + j * 4); if (pid < pattern_count && generic[pid]) lit_generic[lit / 2] = 1; }
+          P.gen2.assign(65536 / 32, 0);
+          P.gen3.assign((1u << 24) / 32, 0);
+          const uint8_t* ac = pg + db.ac_start;
+          struct Fr { uint32_t off, depth, first3; };
+          std::vector<Fr> cur{{0, 0, 0}}, nxt;
+          std::vector<uint8_t> seen(lit_generic.size(), 0);
+          while (!cur.empty()) {
+            nxt.clear();
+            for (const Fr& f : cur) {
+              const uint8_t* nd = ac + f.off;
+              uint32_t pc = nd[3], po = prep_le32(nd + 16);
+              for (uint32_t k = 0; k < pc; k++) {
+                uint32_t lit = prep_le32(ac + po + k * 4);
+                if (lit >= seen.size() || seen[lit]) continue;
+                seen[lit] = 1;
+                if (!lit_generic[lit]) continue;
+                uint32_t g3 = f.first3 & 0xFFFFFFu, g2 = g3 >> 8;  // (depth >= 3: every literal has at least 3 bytes)
+                P.gen2[g2 >> 5] |= 1u << (g2 & 31);
+                P.gen3[g3 >> 5] |= 1u << (g3 & 31);
+              }
+              uint32_t kind = nd[0], cnt = nd[2], eo = prep_le32(nd + 12);
+              auto push = [&](uint8_t ch, uint32_t t) { nxt.push_back(Fr{t, f.depth + 1, f.depth < 3 ? ((f.first3 << 8) | ch) : f.first3}); };
+              if (kind == 1) push(nd[1], eo);
+              else if (kind == 2) for (uint32_t k = 0; k < cnt; k++) push(ac[eo + k * 8], prep_le32(ac + eo + k * 8 + 4));
+              else if (kind == 3) for (uint32_t k = 0; k < 256; k++) { uint32_t t = prep_le32(ac + eo + k * 4); if (t) push((uint8_t)k, t); }
+            }
+            cur.swap(nxt);
+          }
+          db.has_generic = 1;
+        }
       }
     }
   }

@@ -72,7 +72,10 @@ struct DbView {
   uint32_t psl_mask, psl_max_len;
   const uint64_t* psl_tld;        // derived: last-label table (TLD_SLOTS entries), see tld_class()
   // --- fast string path (derived, result-neutral: necessary conditions for a match, see string_filters()) ---
-  uint32_t fast_ok;               // 1: case-sensitive, no pure-wildcard patterns, every reachable glob is suffix- or prefix-anchored
+  uint32_t fast_ok;               // 1: case-sensitive, no pure-wildcard patterns (unanchored globs are handled through gen_gram2/3)
+  uint32_t has_generic;           // 1: some reachable glob is unanchored (or literal-typed): its literals' first bytes are in gen_gram2/3
+  const uint32_t* gen_gram2;      // bitmaps (2^16 / 2^24 bits) over the first 2 / 3 bytes of the AC literals that lead to such a glob;
+  const uint32_t* gen_gram3;
   uint32_t glob_s_lens, glob_p_lens;  // bit K (K in 1,2,3,4,8,12,16): some suffix- / prefix-anchored glob has a key of K bytes
   uint32_t hot_tags;              // bit t: keys of tag class t are in the hot filter (else that class skips the hot test)
   const uint32_t* hot;            // HOT_WORDS-word blocked Bloom filter; the token kernel keeps a copy in shared memory
@@ -115,11 +118,22 @@ MGPU_HD uint32_t key_hash_words(const uint32_t* words, uint32_t k, uint32_t tag)
 // index and bit positions come from a second mix of the same key hash, so one hash per key serves both filters.
 // Where the hot filter's words come from: a plain pointer (host emulation, database preparation) or the token kernel's
 // shared-memory copy addressed with ld.shared (a generic pointer would cost the generic-address path on every test).
-struct HotPtr { const uint32_t* p; MGPU_HD uint32_t word(uint32_t i) const { return p[i]; } };
+struct HotPtr {
+  const uint32_t* p; const uint32_t* g2;  // hot filter words; gen_gram2 words (or nullptr)
+  MGPU_HD uint32_t word(uint32_t i) const { return p[i]; }
+  MGPU_HD uint32_t gen2(uint32_t i) const { return g2[i]; }
+};
+struct BytesPtr { const uint8_t* p; MGPU_HD uint32_t at(uint32_t i) const { return p[i]; } };  // a token's bytes
 #ifdef __CUDACC__
 struct HotShared {
-  uint32_t base;  // shared-space byte address of word 0
+  uint32_t base;        // shared-space byte address of word 0 of the hot filter
+  const uint32_t* g2;   // gen_gram2 in global memory (8 KiB, L1-resident)
   __device__ __forceinline__ uint32_t word(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + i * 4)); return v; }
+  __device__ __forceinline__ uint32_t gen2(uint32_t i) const { return __ldg(g2 + i); }
+};
+struct BytesShared {  // a token in a shared-memory window
+  uint32_t saddr;
+  __device__ __forceinline__ uint32_t at(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr + i) : "memory"); return v; }
 };
 #endif
 // two independent bits per key inside one 32-bit word: bits (h & 31) and ((h >> 5) & 31)
@@ -527,12 +541,35 @@ MGPU_HDN bool domain_word_fast(const DbView& db, const uint64_t* tld, const uint
 //  * globs, when db.fast_ok: a pattern whose LAST segment is a literal can only match a text that ends with it, one whose
 //    FIRST segment is a literal only a text that starts with it (match_segments_impl anchors segment 0 at position 0 and
 //    requires the whole text to be consumed, paraglob_offset.rs:1402-1639); keys are the last / first glob_key_len(len)
-//    bytes of that literal.  Literal-type patterns (substring semantics), patterns with neither anchor, pure wildcards
-//    and case-insensitive databases clear fast_ok and every token takes the exact path.
+//    bytes of that literal.  Patterns with neither anchor and literal-type patterns (substring semantics) are covered by
+//    generic_literal_scan (one of THEIR literals must occur somewhere in the text); pure wildcards and case-insensitive
+//    databases clear fast_ok and every token takes the exact path.
 // Hot tests first (shared memory, `hot` may point at a copy of db.hot); at most one cold test (L2) per class afterwards.
 // Returns F_LIT | F_GLOB bits.
-template <typename H>
-MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords& kw, uint32_t n) {
+// Unanchored (or literal-typed) globs: does any AC literal that leads to one of them START somewhere in the token?  Exact
+// 2-byte bitmap (shared memory) then exact 3-byte bitmap (L2) per position; literals have at least 3 bytes.
+#ifdef __CUDACC__
+#define MGPU_NOINLINE_HD __host__ __device__ __noinline__
+#else
+#define MGPU_NOINLINE_HD inline
+#endif
+template <typename H, typename B>
+MGPU_NOINLINE_HD bool generic_literal_scan(const DbView& db, const H& hot, const B& bytes, uint32_t n) {
+  if (n < 3) return false;
+  uint32_t g = (bytes.at(0) << 8) | bytes.at(1);
+  for (uint32_t i = 2; i < n; i++) {
+    const uint32_t c = bytes.at(i);
+    if ((hot.gen2(g >> 5) >> (g & 31)) & 1u) {
+      const uint32_t g3 = (g << 8) | c;
+      if ((db.gen_gram3[g3 >> 5] >> (g3 & 31)) & 1u) return true;
+    }
+    g = ((g << 8) | c) & 0xFFFFu;
+  }
+  return false;
+}
+
+template <typename H, typename B>
+MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords& kw, const B& bytes, uint32_t n) {
   uint32_t flags = 0;
   if (db.has_literal) {
     const uint32_t k = lit_key_len(n);
@@ -594,13 +631,14 @@ MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords&
     // the cold filter decides for the keys that passed (up to two; more is rare enough to take the exact path unasked)
     if (npass > 2 || (npass >= 1 && cold_test(db.cold, db.cold_mask, cand)) || (npass == 2 && cold_test(db.cold, db.cold_mask, cand2))) flags |= F_GLOB;
   }
+  if (db.has_glob && db.has_generic && !(flags & F_GLOB) && generic_literal_scan(db, hot, bytes, n)) flags |= F_GLOB;
   return flags;
 }
 MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const uint8_t* w, uint32_t n) {
   KeyWords kw;
   load_head_words(w, kw.h);
   load_tail_words(w, n, kw.t);
-  return string_filters(db, HotPtr{hot}, kw, n);
+  return string_filters(db, HotPtr{hot, db.gen_gram2}, kw, BytesPtr{w}, n);
 }
 
 // The same key hashes from a literal's bytes (database preparation; must mirror string_filters exactly).

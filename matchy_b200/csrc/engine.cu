@@ -383,6 +383,8 @@ __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap,
 static const int TK_THREADS = 1024;  // one persistent block per SM
 static const int TK_WARPS = TK_THREADS / 32;
 static const uint32_t TK_WIN = 2048;
+// hot filter + windows = 193 KiB: stays inside the 196 KiB shared-memory carve-out, which leaves 60 KiB of L1 for the PSL
+// last-label table, the cold filter and gen_gram2 (the next carve-out step, 228 KiB, would leave 28 KiB and thrash them)
 static const size_t TOKEN_SMEM = (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32);
 
 struct TokenWarp {  // per-warp state of the token kernel
@@ -414,11 +416,12 @@ __device__ __forceinline__ void append_tokens(const ScanArgs& a, TokenWarp& tw, 
 }
 
 // A string token passed validation: count it, then (fast path) let the filters decide whether anything can match it.
-__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const HotShared& s_hot, const KeyWords& kw, StrTok& st) {
+template <typename B>
+__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const HotShared& s_hot, const KeyWords& kw, const B& bytes, StrTok& st) {
   tw.n_dom += st.type == MGPU_T_DOMAIN; tw.n_mail += st.type == MGPU_T_EMAIL; tw.n_md5 += st.type == MGPU_T_MD5; tw.n_sha1 += st.type == MGPU_T_SHA1;
   tw.n_sha256 += st.type == MGPU_T_SHA256; tw.n_sha384 += st.type == MGPU_T_SHA384; tw.n_sha512 += st.type == MGPU_T_SHA512;
   if (!fast) return true;
-  const uint32_t f = string_filters(a.db, s_hot, kw, st.len);
+  const uint32_t f = string_filters(a.db, s_hot, kw, bytes, st.len);
   st.type |= f;
   return f != 0;
 }
@@ -515,7 +518,7 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
       __syncwarp();
     } else if (active) { st.type = hash_type_of(c.len); ws = true; }
     if (__any_sync(0xFFFFFFFFu, ws)) {
-      if (ws) ws = string_token(a, tw, fast, s_hot, kw, st);
+      if (ws) ws = string_token(a, tw, fast, s_hot, kw, BytesPtr{wp}, st);  // (one call site: the filters are the bulk of the kernel's code)
       __syncwarp();
     }
     append_tokens(a, tw, lane, ws, st, wi, it);
@@ -530,7 +533,7 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
 __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   extern __shared__ __align__(16) uint8_t tk_smem[];
   uint32_t* s_hot_words = reinterpret_cast<uint32_t*>(tk_smem);
-  const HotShared s_hot{(uint32_t)__cvta_generic_to_shared(tk_smem)};
+  const HotShared s_hot{(uint32_t)__cvta_generic_to_shared(tk_smem), a.db.gen_gram2};
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* s_win = tk_smem + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
   const bool fast = a.fast != 0;
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   if (fast) {
     const uint4* src = reinterpret_cast<const uint4*>(a.db.hot);
     for (uint32_t i = threadIdx.x; i < HOT_WORDS / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_hot_words)[i] = src[i];
+
   }
   __syncthreads();
   TokenWarp tw;
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
         KeyWords kw;
         load_head_words(a.buf + st.start, kw.h);
         load_tail_words(a.buf + st.start, st.len, kw.t);
-        ws = string_token(a, tw, fast, s_hot, kw, st);
+        ws = string_token(a, tw, fast, s_hot, kw, BytesPtr{a.buf + st.start}, st);
       }
       __syncwarp();
       append_tokens(a, tw, lane, ws, st, wi, it);
@@ -1345,6 +1349,14 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
     rc = dev_copy(c, d + L.map_off, (size_t)L.map_count * 4, 0, 256, &p);
     if (rc) return rc;
     db.glob_data = (const uint32_t*)p;
+  }
+  if (db.fast_ok && db.has_generic) {
+    rc = dev_copy(c, P.gen2.data(), P.gen2.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.gen_gram2 = (const uint32_t*)p;
+    rc = dev_copy(c, P.gen3.data(), P.gen3.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.gen_gram3 = (const uint32_t*)p;
   }
   if (db.fast_ok) {
     rc = dev_copy(c, P.hot.data(), P.hot.size() * 4, 0, 256, &p);

@@ -258,6 +258,7 @@ int emu_db_upload(emu_ctx* c, const uint8_t* mxy, size_t len) {
   c->db.psl_keys = c->psl.keys.data(); c->db.psl_vals = c->psl.vals.data(); c->db.psl_pool = c->psl.pool.data();
   c->db.psl_mask = c->psl.mask; c->db.psl_max_len = c->psl.max_len; c->db.psl_tld = c->psl.tld.data();
   if (c->db.fast_ok) { c->db.hot = c->P.hot.data(); c->db.cold = c->P.cold.data(); }
+  if (c->db.fast_ok && c->db.has_generic) { c->db.gen_gram2 = c->P.gen2.data(); c->db.gen_gram3 = c->P.gen3.data(); }
   c->loaded = true;
   return MGPU_OK;
 }

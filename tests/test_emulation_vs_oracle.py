@@ -123,8 +123,8 @@ def test_literal_search_formulations_agree(built):
 
 def test_fast_string_path_classification(built):
     """Suffix- / prefix-anchored globs of every key length, tokens shorter than the keys, literals of every length:
-    the constant-time filters (string_filters) may never lose a match.  Databases with an unanchored glob, a
-    literal-type glob or a case-insensitive mode must fall back to the generic path."""
+    the constant-time filters (string_filters) may never lose a match.  Unanchored and literal-type globs are covered by the
+    per-position literal prefilter; a case-insensitive database must fall back to the generic path."""
     from matchy_b200 import DatabaseBuilder, MatchMode
     rng = random.Random(5)
     sfx = ["*m", "*om", "*.io", "*l.io", "*il.io", "*vil.io", "*evil.io", "*.evil.io", "*x.evil.io", "*.very-long-suffix.example.net", "*[0-9].bad.org",
@@ -166,9 +166,16 @@ def test_fast_string_path_classification(built):
             b2.add_glob(extra, {"g": extra})
         db2 = b2.build()
         orc2, emu2 = O.Oracle(db2), E.Emu(db2)
-        assert not emu2.is_fast(), (extra, mode)
-        d2 = data + b"q=a.mid.com z=xplain.example.com.evil.io Q=ABC.COM\n"
-        assert emu2.scan(d2) == orc2.scan(d2), (extra, mode)
+        # unanchored / literal-typed globs stay on the fast path (generic_literal_scan); case-insensitive databases do not
+        assert emu2.is_fast() == (mode is None), (extra, mode)
+        d2 = data + b"q=a.mid.com z=xplain.example.com.evil.io Q=ABC.COM mid.org amid.st.org xmi.d.com plain.example.co\n"
+        want2 = orc2.scan(d2)
+        assert emu2.scan(d2) == want2, (extra, mode)
+        if mode is None:
+            lit, glob, tested = emu2.filter_stats()
+            assert glob < tested  # the scan must not flag everything
+            emu2.set_generic(True)
+            assert emu2.scan(d2) == want2
 
 
 def test_tld_fast_front_end(small_dbs):
