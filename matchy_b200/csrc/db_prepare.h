@@ -103,6 +103,8 @@ struct PreparedDb {
   std::vector<uint32_t> gram2, gram3;  // bitmaps over the first 2 / 3 bytes of every AC literal
   std::vector<uint64_t> pfx_keys;      // prefix map (see DbView::ac_pfx_*)
   std::vector<uint32_t> pfx_vals;
+  std::vector<uint32_t> top16;         // IPv4 walk state after 16 bits (DbView::v4_top16)
+  std::vector<uint8_t> top16_depth;
   std::vector<uint32_t> gen2, gen3;    // first 2 / 3 bytes of every AC literal that leads to an UNANCHORED pattern (see string_filters)
   std::vector<uint32_t> hot;           // fast string path: hot (shared-memory) and cold (L2) Bloom filters
   std::vector<uint64_t> cold;
@@ -146,6 +148,26 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     }
     db.v4_start_node = node;
     if (L.node_count == 0) db.has_ip = 0;
+    // IPv4 walk state after the first 16 address bits, by depth-first expansion from the start node (2^16 leaves)
+    if (L.node_count > 0 && L.node_count < (1u << 28) && (uint64_t)L.node_count + 16 + data_len < (1ull << 28)) {
+      P.top16.assign(65536, 0);
+      P.top16_depth.assign(65536, 0);
+      struct Fr { uint32_t node, depth, prefix; };
+      std::vector<Fr> st{{node, 0, 0}};
+      while (!st.empty()) {
+        Fr f = st.back(); st.pop_back();
+        if (f.depth == 16) { P.top16[f.prefix] = f.node; continue; }
+        for (int side = 0; side < 2; side++) {
+          const uint32_t r = rec(f.node, side), pfx = f.prefix | ((uint32_t)side << (15 - f.depth));
+          if (r < L.node_count) { st.push_back(Fr{r, f.depth + 1, pfx}); continue; }
+          const uint32_t span = 1u << (15 - f.depth);  // every 16-bit prefix below this branch shares the outcome
+          for (uint32_t k = 0; k < span; k++) {
+            P.top16[pfx + k] = r == L.node_count ? (1u << 28) : ((2u << 28) | r);
+            P.top16_depth[pfx + k] = (uint8_t)(f.depth + 1);
+          }
+        }
+      }
+    }
   }
   std::vector<FilterKey> lit_tail_keys, glob_keys;
   std::vector<uint32_t> lit_full_keys;

@@ -449,6 +449,9 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
                                             const HotShared& s_hot, bool fast, uint32_t lane) {
   const bool want_dom = (a.flags & MGPU_X_DOMAINS) != 0, want_v4 = (a.flags & MGPU_X_IPV4) != 0;
   if (MODE == W_DOTTED && !want_dom) return;
+  // IPv4 candidates are sparse in most logs (a 2 KiB window would hold a handful): 32 per iteration straight from the log
+  // buffer — all that is needed of each is its first 16 bytes.  (Choosing per segment at run time cost 4 % on every config.)
+  constexpr bool direct = MODE == W_NUMERIC;
   Cand cn{0xFFFFFFFFu, 0};  // prefetched: candidate i0 + lane of the NEXT iteration (assuming a full group of 32)
   if (lane < n) cn = ld_cand(q + lane);
   for (uint32_t i0 = 0; i0 < n;) {
@@ -459,13 +462,11 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
     const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c.start, 0);
     const uint32_t alo = lo & ~15u;
     const bool fits = !have || (uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN;
-    const uint32_t nf = MODE == W_NUMERIC ? 0u : __ballot_sync(0xFFFFFFFFu, !fits);
+    const uint32_t nf = direct ? 0u : __ballot_sync(0xFFFFFFFFu, !fits);
     uint32_t g = nf ? (uint32_t)__ffs((int)nf) - 1u : 32u;  // candidates of this iteration: lanes [0, g)
     const uint8_t* p = a.buf;
     bool high = true;  // "the token bytes may hold bytes >= 0x80"
-    if (MODE == W_NUMERIC) {
-      // IPv4 candidates are sparse in most logs (a 2 KiB window would hold a handful): 32 per iteration straight from the
-      // log buffer; all that is needed of each is its first 16 bytes
+    if (direct) {
     } else if (g == 0) g = 1;  // a single word longer than the window: read it from global memory
     else {
       const bool mine = have && lane < g;
@@ -840,8 +841,6 @@ __global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
   }
   __syncthreads();
   const bool use_filter = a.db.has_glob && a.db.ac_anchored && acc.gram2 && a.db.wild_count == 0 && a.db.ac_size >= 20 && a.db.match_mode == 0;
-  AcNode root{0, 0, 0, 0};
-  if (a.db.has_glob && a.db.ac_size >= 20) root = ac_fetch(a.db.pg + a.db.ac_start, 0);
   const uint32_t n = min(a.ctr->n_str, a.cap_str);
   const uint32_t nround = (n + 31u) & ~31u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
@@ -1313,6 +1312,14 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
   int rc = dev_copy(c, d, (size_t)L.tree_size, 0, 256, &p);
   if (rc) return rc;
   db.tree = (const uint8_t*)p;
+  if (!P.top16.empty()) {
+    rc = dev_copy(c, P.top16.data(), P.top16.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.v4_top16 = (const uint32_t*)p;
+    rc = dev_copy(c, P.top16_depth.data(), P.top16_depth.size(), 0, 256, &p);
+    if (rc) return rc;
+    db.v4_top16_depth = (const uint8_t*)p;
+  }
   if (L.has_literal) {
     // the slot table starts at 4 (mod 16) inside the section: base = 12 (mod 16) makes every 16-byte entry aligned
     rc = dev_copy(c, d + L.lit_off, (size_t)L.lit_len, 12, 256, &p);
@@ -1707,7 +1714,6 @@ static int scan_host_impl(mgpu_ctx* c, const uint8_t* host, size_t len, uint64_t
   bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   size_t pos = 0;
-  int slot = 0;
   struct Piece { size_t pos, len; int slot; };
   auto stage = [&](size_t p, size_t l, int s) -> int {
     // H2D of piece [p, p+l) into d_log[s] on the copy stream; waits until the kernels that last read d_log[s] are done
@@ -1759,7 +1765,6 @@ static int scan_host_impl(mgpu_ctx* c, const uint8_t* host, size_t len, uint64_t
     if (!have_next) break;
     cur = nxt;
   }
-  (void)slot;
   return MGPU_OK;
 }
 
