@@ -32,6 +32,7 @@ bool ValueReader::at(size_t& cur, Value& out, int depth) const {
   uint8_t ctrl = p_[cur++];
   unsigned type = ctrl >> 5;
   uint8_t low5 = ctrl & 31;
+  out.mmdb_type = (uint8_t)(type ? type : (cur < n_ ? 7u + p_[cur] : 0u));
   auto be = [&](size_t len, uint64_t& v) {
     v = 0;
     for (size_t k = 0; k < len; k++) v = (v << 8) | p_[cur + k];
@@ -292,6 +293,16 @@ static const Value* field(const Value& m, const char* k) {
   const Value* r = nullptr;
   for (auto& f : m.fields) if (f.first == k) r = &f.second;
   return r;
+}
+
+bool read_metadata(const uint8_t* d, size_t n, Value& out) {
+  static const uint8_t M[14] = {0xAB, 0xCD, 0xEF, 'M', 'a', 'x', 'M', 'i', 'n', 'd', '.', 'c', 'o', 'm'};
+  if (n < 14) return false;
+  size_t from = n > 128 * 1024 ? n - 128 * 1024 : 0, mk = (size_t)-1;
+  for (size_t i = from; i + 14 <= n; i++) if (d[i] == 0xAB && memcmp(d + i, M, 14) == 0) mk = i;
+  if (mk == (size_t)-1) return false;
+  ValueReader mr(d + mk + 14, n - mk - 14);
+  return mr.read(0, out) && out.kind == Value::MAP;
 }
 
 bool locate_sections(const uint8_t* d, size_t n, Layout& L, std::string& err) {

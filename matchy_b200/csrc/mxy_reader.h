@@ -24,10 +24,14 @@ struct Layout {
 };
 
 bool locate_sections(const uint8_t* d, size_t n, Layout& out, std::string& err);
+// the MMDB metadata map at the end of the file (mmdb/format.rs:41-48); false when there is no metadata marker
+struct Value;
+bool read_metadata(const uint8_t* d, size_t n, Value& out);
 
 // decoded MMDB value
 struct Value {
   enum Kind { NUL, STR, F64, F32, BYTES, UINT, INT, U128, MAP, ARR, BOOL, PTR } kind = NUL;
+  uint8_t mmdb_type = 0;  // the MMDB type code the value was stored with (5/6/9 tell the UINT widths apart)
   std::string s;
   double f = 0;
   uint64_t u = 0;
