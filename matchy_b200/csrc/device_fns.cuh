@@ -374,6 +374,25 @@ MGPU_HD void load_tail_words(const uint8_t* w, uint32_t n, uint32_t t[4]) {
   t[0] = n >= 16 ? ldu32_fast(w + n - 16) : 0u;
 }
 
+// The tail words of a token of n <= 16 bytes from its head words (same contract as load_tail_words: t[i] = bytes
+// [n-16+4i, n-12+4i) when they lie inside the token, else 0).
+MGPU_HD uint32_t head_word_at(const uint32_t h[4], uint32_t s) {  // bytes [s, s+4) of the 16 head bytes, s <= 12
+  const uint32_t i = s >> 2, sh = (s & 3) * 8;
+  const uint32_t a = i == 0 ? h[0] : (i == 1 ? h[1] : (i == 2 ? h[2] : h[3]));
+  const uint32_t b = i == 0 ? h[1] : (i == 1 ? h[2] : (i == 2 ? h[3] : 0u));
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(a, b, sh);
+#else
+  return sh ? ((a >> sh) | (b << (32 - sh))) : a;
+#endif
+}
+MGPU_HD void tail_words_from_head(const uint32_t h[4], uint32_t n, uint32_t t[4]) {
+  t[3] = n >= 4 ? head_word_at(h, n - 4) : 0u;
+  t[2] = n >= 8 ? head_word_at(h, n - 8) : 0u;
+  t[1] = n >= 12 ? head_word_at(h, n - 12) : 0u;
+  t[0] = n >= 16 ? h[0] : 0u;
+}
+
 #ifdef __CUDACC__
 // the same two loaders for a token that lies in a shared-memory window (saddr = shared-space byte address of its first byte)
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }

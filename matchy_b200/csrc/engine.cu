@@ -494,7 +494,25 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
     StrTok st{c.start, c.len, 0};
     KeyWords kw;
     const uint8_t* wp = p + (active ? c.start : lo);
-    if (p != a.buf) {  // (warp-uniform) the token lies in the shared-memory window: ld.shared instead of generic loads
+    bool wi = false;
+    IpTok it{c.start, c.len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
+    if (MODE == W_NUMERIC) {
+      // straight from the log buffer: the first 16 bytes decide IPv4; the last 16 are only needed by the few words that
+      // are not an address (domain rules), and for words of at most 16 bytes they are a shift of the first 16
+      load_head_words(wp, kw.h);
+      if (active && want_v4) wi = parse_ipv4_words(kw.h, c.len, it.w[0]);
+      __syncwarp();
+      if (wi) tw.n_v4++;
+      kw.t[0] = kw.t[1] = kw.t[2] = kw.t[3] = 0u;
+      const bool need_tail = active && want_dom && !wi;
+      if (__any_sync(0xFFFFFFFFu, need_tail)) {
+        if (need_tail) {
+          if (c.len <= 16) tail_words_from_head(kw.h, c.len, kw.t);
+          else load_tail_words(wp, c.len, kw.t);
+        }
+        __syncwarp();
+      }
+    } else if (p != a.buf) {  // (warp-uniform) the token lies in the shared-memory window: ld.shared instead of generic loads
       const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s_win) + ((active ? c.start : lo) - alo);
       load_head_words_shared(saddr, kw.h);
       load_tail_words_shared(saddr, active ? c.len : 0u, kw.t);
@@ -502,18 +520,11 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
       load_head_words(wp, kw.h);
       load_tail_words(wp, active ? c.len : 0u, kw.t);
     }
-    bool wi = false;
-    IpTok it{c.start, c.len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
-    if (MODE == W_NUMERIC) {
-      if (active && want_v4) wi = parse_ipv4_words(kw.h, c.len, it.w[0]);
-      __syncwarp();
-      if (wi) tw.n_v4++;
-    }
     if (MODE != W_HASH) {
       // a valid IPv4 address is never a domain: its last label is numeric, and no PSL entry ends in one (checked at upload)
       if (active && want_dom && !wi) {
         st.type = MGPU_T_DOMAIN;
-        const uint64_t tail8 = c.len >= 8 ? (((uint64_t)kw.t[3] << 32) | kw.t[2]) : load_tail8(wp, c.len);
+        const uint64_t tail8 = c.len >= 8 ? (((uint64_t)kw.t[3] << 32) | kw.t[2]) : ((((uint64_t)kw.h[1] << 32) | kw.h[0]) << (8 * (8 - c.len)));  // == load_tail8(wp, len), from registers
         ws = domain_word_fast(a.db, a.db.psl_tld, wp, c.len, high, tail8);
       }
       __syncwarp();
@@ -1489,7 +1500,8 @@ static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_l
     CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids + i_lo, (size_t)(i_hi - i_lo) * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
   }
   CK(cudaStreamSynchronize(c->compute));
-  for (size_t k = r0; k < c->recs.size(); k++) if (c->recs[k].kind == MGPU_KIND_PATTERN) c->recs[k].ids_index = (uint32_t)(c->recs[k].ids_index - i_lo + i0);
+  if ((size_t)i_lo != i0)  // (the first run of a scan lands at the same indices: nothing to rebase — 8 M records per step on config 3)
+    for (size_t k = r0; k < c->recs.size(); k++) if (c->recs[k].kind == MGPU_KIND_PATTERN) c->recs[k].ids_index = (uint32_t)(c->recs[k].ids_index - i_lo + i0);
   return MGPU_OK;
 }
 static void add_counters(mgpu_ctx* c, const DevCounters& h, uint64_t bytes, uint32_t n_rec) {
