@@ -33,38 +33,68 @@ WORKLOADS = {
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line): NVML every 10 ms
+    (a 10 GB step is ~14 ms, so nvidia-smi's ~100 ms per query would see one sample), nvidia-smi as the fallback."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.reasons, self._stop_evt = index, [], 0.0, set(), threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip()]
+        try:
+            return int(ids[index]) if ids else index
+        except (ValueError, IndexError):
+            return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in self.REASONS:
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [x.strip() for x in out.split(",")]
+            self.sm.append(float(r[0])); self.mx = max(self.mx, float(r[1]))
+            for (name, _), v in zip(self.REASONS, r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self.nvml else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def ncu_traffic(kernel):
@@ -142,11 +172,29 @@ def run_reference(args):
         "lines_per_s": cnt[0] * len(times) / total, "matches_per_s": cnt[3] * len(times) / total,
         "note": "CPU restatement (oracle/oracle.cpp) of matchy v1.2.2's matcher; the Rust reference cannot be built here (no cargo/rustc)",
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, build chatter) goes to stderr; the JSON line alone reaches stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -294,7 +342,7 @@ def main():
             "wall_s_timed_region": wall_s,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         }
-        print(json.dumps(line))
+        _emit(line)
     eng.dev_free(dev)
     N.lib().mgpu_host_free_pinned(C.c_void_p(pinned))
     eng.close()

@@ -144,10 +144,14 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
     const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
     const bool want_long = (a.flags & MGPU_X_CRYPTO) != 0;
+    // the next tile's slice is loaded into registers while the current one is processed (the buffer is readable one tile
+    // past the chunk, see mgpu_scan_device), so the loads' latency never sits in front of the classification
+    uint4 nx0 = ld_stream(a.buf + (uint32_t)(t0 * TILE_BYTES) + lane * SLICE_BYTES), nx1 = ld_stream(a.buf + (uint32_t)(t0 * TILE_BYTES) + lane * SLICE_BYTES + 16);
     for (uint64_t t = t0; t < t1; t++) {
       const uint32_t tile_base = (uint32_t)(t * TILE_BYTES);  // chunks are at most 2 GiB: positions fit 32 bits
       const uint32_t p = tile_base + lane * SLICE_BYTES;
-      uint4 v0 = ld_stream(a.buf + p), v1 = ld_stream(a.buf + p + 16);
+      const uint4 v0 = nx0, v1 = nx1;
+      if (t + 1 < t1) { nx0 = ld_stream(a.buf + p + TILE_BYTES); nx1 = ld_stream(a.buf + p + TILE_BYTES + 16); }
       if (t + 4 < t1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.buf + p + 4 * TILE_BYTES));  // my slice of the tile four steps ahead
       uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
