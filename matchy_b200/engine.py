@@ -130,8 +130,8 @@ class Engine:
         """0: automatic; 1: force the reference's Aho-Corasick walk instead of anchored walks (same results)."""
         self.L.mgpu_set_ac_mode(self.h, int(mode))
 
-    def extract(self, data, flags=X_SUPPORTED):
-        """[(item_type, start, end), ...] sorted by (start, item_type)."""
+    def extract_array(self, data, flags=X_SUPPORTED):
+        """uint64 array [n, 3] of (item_type, start, end) rows sorted by (start, item_type)."""
         p, n, keep = N.as_ptr(data)
         cap = 1 << 16
         while True:
@@ -140,9 +140,12 @@ class Engine:
             if cnt < 0:
                 _check(int(cnt), "mgpu_extract")
             if cnt <= cap:
-                a = np.frombuffer(out, dtype=np.uint64, count=3 * cnt).reshape(-1, 3)
-                return [(int(t), int(s), int(e)) for t, s, e in a]
+                return np.frombuffer(out, dtype=np.uint64, count=3 * cnt).reshape(-1, 3).copy()
             cap = int(cnt)
+
+    def extract(self, data, flags=X_SUPPORTED):
+        """[(item_type, start, end), ...] sorted by (start, item_type)."""
+        return [(int(t), int(s), int(e)) for t, s, e in self.extract_array(data, flags)]
 
     def lookup_string(self, q: bytes):
         out = (N.MgpuIdPair * 4096)()

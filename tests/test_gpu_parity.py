@@ -324,3 +324,64 @@ def test_match_cli_output_contract(small_dbs, tmp_path):
         want += orc.ndjson(part, str(path)).splitlines()
     assert sorted(r.stdout.splitlines()) == sorted(want) and len(want) > 0
     assert b'"matches"' in r.stderr
+
+
+def _expected_extract_output(orc, data: bytes, flags, fmt="json", unique=False):
+    """`matchy extract` restated around the ORACLE's extractor, one line at a time (bin/commands/extract_cmd.rs:200-289,
+    LineScanner bin/cli_utils.rs:9-95): trim ASCII whitespace, skip empty lines, extract_from_line order."""
+    ws = b" \t\n\x0c\r"
+    names = ["domain", "email", "ipv4", "ipv6", "md5", "sha1", "sha256", "sha384", "sha512", "bitcoin", "ethereum", "monero"]
+    group = {0: 0, 2: 1, 1: 2, 3: 3, 4: 4, 5: 4, 6: 4, 7: 4, 8: 4, 9: 5, 10: 6, 11: 7}
+    out, seen, lines = [], set(), 0
+    if fmt == "csv":
+        out.append(b"type,value\n")
+    for raw in data.split(b"\n"):
+        line = raw.strip(ws)
+        if not line:
+            continue
+        lines += 1
+        items = sorted(orc.extract(line, flags), key=lambda t: (group[t[0]], t[1]))
+        for t, s, e in items:
+            text = line[s:e]
+            if unique:
+                if text in seen:
+                    continue
+                seen.add(text)
+            if fmt == "json":
+                out.append(b'{"type":"%s","value":"%s"}\n' % (names[t].encode(), text.replace(b"\\", b"\\\\").replace(b'"', b'\\"')))
+            elif fmt == "csv":
+                out.append(b'%s,"%s"\n' % (names[t].encode(), text.replace(b'"', b'""')))
+            else:
+                out.append(text + b"\n")
+    return b"".join(out), lines
+
+
+@pytest.mark.gpu
+def test_extract_subcommand_matches_per_line_oracle(built, small_dbs, tmp_path, capfdbinary):
+    """`python -m matchy_b200 extract` == the reference's `matchy extract` contract, checked against the oracle run line by line."""
+    from matchy_b200.__main__ import main
+    db, log = small_dbs[5]
+    orc = O.Oracle(db)
+    tricky = (b"\x0cevil.com after a form feed\n"            # FF is trimmed by LineScanner but is no token boundary
+              b"  \t padded.example.org \r\n"
+              b"\n   \n\x0c\n"                                # empty after trimming: not lines at all
+              b"mid\x0cdle.com x\x0c\n"                       # FF inside the line stays; trailing FF is trimmed
+              b"dup.example.com dup.example.com 10.1.2.3 10.1.2.3\n"
+              b'quote "a\\b.example.net" user@mail.example.com 2001:db8::7 5d41402abc4b2a76b9719d911017c592\n'
+              b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa 0x5aAeb6053F3E94C9b9A09f33669435E7Ef1BeAed\n"
+              b"last line without newline evil.org")
+    data = tricky[: tricky.rfind(b"\n") + 1] + log[: 96 * 1024][: log[: 96 * 1024].rfind(b"\n") + 1] + tricky[tricky.rfind(b"\n") + 1:]
+    path = tmp_path / "in.log"
+    path.write_bytes(data)
+    for args, flags, fmt, uniq in ((["--format", "json"], 0xFF, "json", False), (["--format", "csv", "-u"], 0xFF, "csv", True),
+                                   (["--format", "text", "--types", "ip"], 0xF0 | 0x0C, "text", False),
+                                   (["--types", "domain,email"], 0xF0 | 0x03, "json", False)):
+        capfdbinary.readouterr()
+        assert main(["extract", str(path)] + args + ["--stats"]) == 0
+        got = capfdbinary.readouterr()
+        want, lines = _expected_extract_output(orc, data, flags, fmt, uniq)
+        assert got.out == want, args
+        assert want.count(b"\n") > 100
+        assert ("Lines processed: %s" % format(lines, ",")).encode() in got.err
+    assert main(["extract", str(path), "--format", "xml"]) == 1
+    assert main(["extract", str(path), "--types", "bogus"]) == 1
