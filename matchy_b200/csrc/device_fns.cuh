@@ -748,6 +748,65 @@ MGPU_HDN bool parse_ipv6_run(const uint8_t* s, uint32_t n, uint16_t out[8]) {
   for (int k = 0; k < 8; k++) out[k] = head[k];
   return true;
 }
+// The same parser as straight-line mask arithmetic (one code path for every lane of a warp; the loop version above costs a
+// three-way divergent branch per character).  For a run of 8..39 bytes made of hex digits and ':' only, the rules of
+// parse_ipv6_run collapse to: the text holds "::" (the caller anchors on one), so the eight-group form cannot consume it all;
+// it is valid iff no single ':' stands at either end, exactly one position starts a "::" (":::" counts twice), no hex
+// field is longer than 4 digits, and there are at most 7 fields; the fields before the "::" fill groups 0.., those after it
+// fill the groups up to 7.  C = colon mask (bit i = byte i).  Output as IpTok words: w[k] = seg[2k] << 16 | seg[2k+1].
+MGPU_HD uint32_t swar_is_colon(uint32_t v) {  // 0x80 in every byte that is ':'
+  uint32_t d = v ^ 0x3A3A3A3Au;
+  return ~(((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+}
+MGPU_HD uint32_t bit_count64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__popcll(x);
+#else
+  return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+MGPU_HD uint32_t low_bit64(uint64_t x) {  // x != 0
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__ffsll((long long)x) - 1u;
+#else
+  return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+MGPU_HDN bool parse_ipv6_run_masks(const uint8_t* s, uint32_t n, uint32_t w[4]) {
+  if (n < 2 || n > 39) return false;
+  uint64_t C = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 10; j++) {
+    const uint32_t v = 4 * j < n ? ldu32_fast(s + 4 * j) : 0u;
+    C |= (uint64_t)swar_flags4(swar_is_colon(v)) << (4 * j);
+  }
+  const uint64_t all = (1ULL << n) - 1;
+  C &= all;
+  const uint64_t H = ~C & all;
+  const uint64_t dc = C & (C >> 1);
+  if (bit_count64(dc) != 1) return false;
+  if (((C & 3) == 1) || ((C >> (n - 2)) & 3) == 2) return false;  // a single ':' at either end (a "::" there is fine)
+  if (H & (H >> 1) & (H >> 2) & (H >> 3) & (H >> 4)) return false;  // a field of five or more digits
+  uint64_t starts = H & ~(H << 1);
+  const uint32_t fields = bit_count64(starts);
+  if (fields > 7) return false;
+  const uint32_t gap_at = low_bit64(dc);  // fields that start beyond the "::" are right-aligned in the eight groups
+  w[0] = w[1] = w[2] = w[3] = 0u;
+#pragma unroll 1
+  for (uint32_t k = 0; k < fields; k++) {
+    const uint32_t at = low_bit64(starts);
+    starts &= starts - 1;
+    const uint32_t len = low_bit64(~(H >> at));  // 1..4
+    const uint32_t v = ldu32_fast(s + at);       // up to four digits, first one in the low byte (the buffer has 16 bytes of slack)
+    const uint32_t nib = (v & 0x0F0F0F0Fu) + 9u * ((v >> 6) & 0x01010101u);  // '0'-'9' -> 0-9, 'a'-'f' / 'A'-'F' -> 10-15
+    const uint32_t val = (((nib & 0xFu) << 12) | (((nib >> 8) & 0xFu) << 8) | (((nib >> 16) & 0xFu) << 4) | ((nib >> 24) & 0xFu)) >> (4 * (4 - len));
+    const uint32_t g = at > gap_at ? 8 - fields + k : k;
+    const uint32_t word = val << ((g & 1u) ? 0 : 16);
+    w[0] |= (g >> 1) == 0 ? word : 0u; w[1] |= (g >> 1) == 1 ? word : 0u; w[2] |= (g >> 1) == 2 ? word : 0u; w[3] |= (g >> 1) == 3 ? word : 0u;
+  }
+  return true;
+}
+
 // extract_ipv6_chunk for the "::" whose first colon is at `at`.  Returns true with the run span and address.
 MGPU_HDN bool ipv6_at(const uint8_t* buf, size_t lo, size_t n, size_t at, size_t& s_out, size_t& e_out, uint16_t segs[8]) {
   // maximal [0-9A-Fa-f:] run around the anchor; a valid address is at most 39 bytes, longer runs cannot parse
@@ -765,6 +824,25 @@ MGPU_HDN bool ipv6_at(const uint8_t* buf, size_t lo, size_t n, size_t at, size_t
     if (c[2] == '8' || c[2] == '9' || t == 'a' || t == 'b') return false;
   }
   if (!parse_ipv6_run(c, len, segs)) return false;
+  s_out = start; e_out = end;
+  return true;
+}
+// The same, for the kernels: run bounds by the same byte loops, address through parse_ipv6_run_masks, as IpTok words.
+MGPU_HDN bool ipv6_at_words(const uint8_t* buf, size_t lo, size_t n, size_t at, size_t& s_out, size_t& e_out, uint32_t w[4]) {
+  size_t start = at;
+  while (start > lo && at - start <= 40) { uint8_t c = buf[start - 1]; if (!is_hex(c) && c != ':') break; start--; }
+  if (at - start > 40) return false;
+  size_t end = at + 2;
+  while (end < n && end - at <= 42) { uint8_t c = buf[end]; if (!is_hex(c) && c != ':') break; end++; }
+  uint32_t len = (uint32_t)(end - start);
+  if (len > 39 || len < 8) return false;
+  const uint8_t* c = buf + start;
+  if ((c[0] == ':' && c[1] == ':') || (c[len - 2] == ':' && c[len - 1] == ':')) return false;
+  if ((c[0] | 32) == 'f' && (c[1] | 32) == 'e') {
+    uint8_t t = c[2] | 32;
+    if (c[2] == '8' || c[2] == '9' || t == 'a' || t == 'b') return false;
+  }
+  if (!parse_ipv6_run_masks(c, len, w)) return false;
   s_out = start; e_out = end;
   return true;
 }

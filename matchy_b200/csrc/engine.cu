@@ -583,10 +583,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
         if (at < a.n && email_at(a.db, a.buf, (size_t)a.lo, (size_t)a.n, at, s, e)) { ws = true; st.start = (uint32_t)s; st.len = (uint32_t)(e - s); st.type = MGPU_T_EMAIL; }
       } else if (i < nA + nC) {
         const uint32_t at = qc[i - nA];
-        size_t s, e; uint16_t sg[8];
-        if ((uint64_t)at + 2 <= a.n && ipv6_at(a.buf, (size_t)a.lo, (size_t)a.n, at, s, e, sg)) {
+        size_t s, e;
+        if ((uint64_t)at + 2 <= a.n && ipv6_at_words(a.buf, (size_t)a.lo, (size_t)a.n, at, s, e, it.w)) {
           wi = true; it.start = (uint32_t)s; it.len = (uint32_t)(e - s); it.type = MGPU_T_IPV6;
-          for (int k = 0; k < 4; k++) it.w[k] = ((uint32_t)sg[2 * k] << 16) | sg[2 * k + 1];
           tw.n_v6++;
         }
       }

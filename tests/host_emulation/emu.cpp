@@ -167,10 +167,10 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
     if (email_at(db, buf, (size_t)lo, (size_t)n, at, s, e)) c->str.push_back(StrTok{(uint32_t)s, (uint32_t)(e - s), MGPU_T_EMAIL});
   }
   for (uint32_t at : qc) {
-    size_t s, e; uint16_t seg[8];
-    if ((uint64_t)at + 2 <= n && ipv6_at(buf, (size_t)lo, (size_t)n, at, s, e, seg)) {
-      IpTok t{(uint32_t)s, (uint32_t)(e - s), MGPU_T_IPV6, {0, 0, 0, 0}};
-      for (int k = 0; k < 4; k++) t.w[k] = ((uint32_t)seg[2 * k] << 16) | seg[2 * k + 1];
+    size_t s, e;
+    IpTok t{0, 0, MGPU_T_IPV6, {0, 0, 0, 0}};
+    if ((uint64_t)at + 2 <= n && ipv6_at_words(buf, (size_t)lo, (size_t)n, at, s, e, t.w)) {  // (the kernel's call)
+      t.start = (uint32_t)s; t.len = (uint32_t)(e - s);
       c->ip.push_back(t);
     }
   }
@@ -314,6 +314,9 @@ int emu_results(emu_ctx* c, const mgpu_match** recs, size_t* n_recs, const mgpu_
   return 0;
 }
 int emu_counters_get(emu_ctx* c, mgpu_counters* out) { *out = c->counters; return 0; }
+
+// the kernels' mask-arithmetic IPv6 parser on a bare run (s must be readable 8 bytes past n); 1 = parsed
+int emu_parse_ipv6_masks(const uint8_t* s, uint32_t n, uint32_t w[4]) { return parse_ipv6_run_masks(s, n, w) ? 1 : 0; }
 
 int64_t emu_tokens(emu_ctx* c, uint64_t* out, size_t cap) {
   std::vector<std::array<uint64_t, 3>> items;

@@ -214,3 +214,41 @@ def test_crypto_address_extraction(small_dbs):
     data = log[:300000] + b"pay 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa or 0x5aeda56215b167893e80b4fe645ba6d5bab767de now\n"
     flags = orc.default_flags() | 0xE0
     assert emu.scan(data, flags=flags, nwarps=3) == orc.scan(data, flags=flags)
+
+
+def test_ipv6_mask_parser_equals_reference_parser():
+    """parse_ipv6_run_masks (device_fns.cuh, straight-line mask arithmetic) == the oracle's restatement of Rust's
+    Ipv6Addr::from_str on every hex/colon run that holds a "::" (the only runs the extractor ever parses, lib.rs:1044-1116)."""
+    import ctypes as C
+    import random
+    L = E.lib()
+    L.emu_parse_ipv6_masks.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    rng = random.Random(20261018)
+    fixed = [b"2001:db8::1", b"1::2", b"1:2:3:4:5:6::7", b"1:2:3:4:5:6:7::8", b"1::2::3", b"1:::2", b":1::2", b"1::2:", b"12345::1", b"1::12345",
+             b"a:b:c:d:e:f::1", b"FFFF::ffff", b"0::0", b"1:2::3:4:5:6:7", b"1:2::3:4:5:6:7:8", b"::1:2:3", b"1:2:3::", b"abcd:ef01::2345:6789",
+             b"1::", b"::", b"1:2:3:4:5:6:7:8::9", b"0000::0000:0000", b"1::2:3:4:5:6:7"]
+    cases = list(fixed)
+    alphabet = b"0123456789abcdefABCDEF"
+    for _ in range(20000):
+        # fields of 0..5 digits joined by ':' (empty fields make "::" / ":::"), plus some fully random strings
+        if rng.random() < 0.85:
+            k = rng.randint(1, 10)
+            fields = [bytes(rng.choice(alphabet) for _ in range(rng.choice((0, 1, 1, 2, 3, 4, 4, 4, 5)))) for _ in range(k)]
+            s = b":".join(fields)
+        else:
+            s = bytes(rng.choice(alphabet + b"::::") for _ in range(rng.randint(2, 44)))
+        cases.append(s)
+    checked = 0
+    for s in cases:
+        if b"::" not in s or len(s) < 2:
+            continue
+        want = O.parse_ipv6(s) if len(s) <= 39 else None
+        w = (C.c_uint32 * 4)()
+        got = L.emu_parse_ipv6_masks(s + b"\0" * 16, len(s), w)
+        if want is None:
+            assert got == 0, s
+        else:
+            assert got == 1, s
+            assert [(w[k // 2] >> (0 if k & 1 else 16)) & 0xFFFF for k in range(8)] == want, s
+        checked += 1
+    assert checked > 5000
