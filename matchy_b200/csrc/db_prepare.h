@@ -103,8 +103,10 @@ struct PreparedDb {
   std::vector<uint32_t> gram2, gram3;  // bitmaps over the first 2 / 3 bytes of every AC literal
   std::vector<uint64_t> pfx_keys;      // prefix map (see DbView::ac_pfx_*)
   std::vector<uint32_t> pfx_vals;
-  std::vector<uint32_t> top16;         // IPv4 walk state after 16 bits (DbView::v4_top16)
+  std::vector<uint32_t> top16;         // IPv4 walk state after v4_top_bits bits (DbView::v4_top16)
   std::vector<uint8_t> top16_depth;
+  std::vector<uint32_t> v6_top16;      // IPv6 walk state after 16 bits, IPv6 trees only (DbView::v6_top16)
+  std::vector<uint8_t> v6_top16_depth;
   std::vector<uint32_t> gen2, gen3;    // first 2 / 3 bytes of every AC literal that leads to an UNANCHORED pattern (see string_filters)
   std::vector<uint32_t> hot;           // fast string path: hot (shared-memory) and cold (L2) Bloom filters
   std::vector<uint64_t> cold;
@@ -148,25 +150,32 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     }
     db.v4_start_node = node;
     if (L.node_count == 0) db.has_ip = 0;
-    // IPv4 walk state after the first 16 address bits, by depth-first expansion from the start node (2^16 leaves)
+    // Walk state after the first TB address bits, by depth-first expansion from the start node (2^TB leaves): IPv4 queries
+    // (TB = 16, or 20 for trees with more than 2^16 nodes, where a /16 bucket still holds a subtree) and, in IPv6 trees, IPv6
+    // queries (16 bits from the root).
     if (L.node_count > 0 && L.node_count < (1u << 28) && (uint64_t)L.node_count + 16 + data_len < (1ull << 28)) {
-      P.top16.assign(65536, 0);
-      P.top16_depth.assign(65536, 0);
-      struct Fr { uint32_t node, depth, prefix; };
-      std::vector<Fr> st{{node, 0, 0}};
-      while (!st.empty()) {
-        Fr f = st.back(); st.pop_back();
-        if (f.depth == 16) { P.top16[f.prefix] = f.node; continue; }
-        for (int side = 0; side < 2; side++) {
-          const uint32_t r = rec(f.node, side), pfx = f.prefix | ((uint32_t)side << (15 - f.depth));
-          if (r < L.node_count) { st.push_back(Fr{r, f.depth + 1, pfx}); continue; }
-          const uint32_t span = 1u << (15 - f.depth);  // every 16-bit prefix below this branch shares the outcome
-          for (uint32_t k = 0; k < span; k++) {
-            P.top16[pfx + k] = r == L.node_count ? (1u << 28) : ((2u << 28) | r);
-            P.top16_depth[pfx + k] = (uint8_t)(f.depth + 1);
+      auto expand = [&](uint32_t root, uint32_t tb, std::vector<uint32_t>& tab, std::vector<uint8_t>& dep) {
+        tab.assign((size_t)1 << tb, 0);
+        dep.assign((size_t)1 << tb, 0);
+        struct Fr { uint32_t node, depth, prefix; };
+        std::vector<Fr> st{{root, 0, 0}};
+        while (!st.empty()) {
+          Fr f = st.back(); st.pop_back();
+          if (f.depth == tb) { tab[f.prefix] = f.node; continue; }
+          for (int side = 0; side < 2; side++) {
+            const uint32_t r = rec(f.node, side), pfx = f.prefix | ((uint32_t)side << (tb - 1 - f.depth));
+            if (r < L.node_count) { st.push_back(Fr{r, f.depth + 1, pfx}); continue; }
+            const uint32_t span = 1u << (tb - 1 - f.depth);  // every TB-bit prefix below this branch shares the outcome
+            for (uint32_t k = 0; k < span; k++) {
+              tab[pfx + k] = r == L.node_count ? (1u << 28) : ((2u << 28) | r);
+              dep[pfx + k] = (uint8_t)(f.depth + 1);
+            }
           }
         }
-      }
+      };
+      db.v4_top_bits = L.node_count > (1u << 16) ? 20u : 16u;
+      expand(node, db.v4_top_bits, P.top16, P.top16_depth);
+      if (L.ip_version == 6) expand(0, 16, P.v6_top16, P.v6_top16_depth);
     }
   }
   std::vector<FilterKey> lit_tail_keys, glob_keys;

@@ -37,11 +37,15 @@ struct DbView {
   const uint8_t* tree;
   uint32_t node_count, record_bits, ip_version, has_ip;
   uint32_t v4_start_node;  // derived: result of find_ipv4_start_node (tree.rs:258-277), identical for every query
-  // derived: the state of the IPv4 walk after its first 16 address bits, for every 16-bit prefix (2^16 entries):
+  // derived: the state of the IPv4 walk after its first v4_top_bits (16 or 20) address bits, for every such prefix:
   // bits 0..27 value, bits 28..31 kind — 0: continue at node `value`; 1: not found; 2: data record `value` found at depth
-  // v4_top16_depth[prefix] (1..16).  Exact: the entry is what the bit-by-bit walk of tree.rs:46-90 reaches.
+  // v4_top16_depth[prefix] (1..v4_top_bits).  Exact: the entry is what the bit-by-bit walk of tree.rs:46-90 reaches.
   const uint32_t* v4_top16;
   const uint8_t* v4_top16_depth;
+  uint32_t v4_top_bits;
+  // the same for IPv6 queries in an IPv6 tree: state after the first 16 address bits, from the root (tree.rs:92-125)
+  const uint32_t* v6_top16;
+  const uint8_t* v6_top16_depth;
   // --- literal hash section ("LHSH") ---
   const uint8_t* lh;
   uint64_t lh_len;
@@ -867,12 +871,13 @@ MGPU_HD uint32_t tree_record(const DbView& db, uint32_t node, uint32_t side) {
 MGPU_HDN bool trie_lookup_v4(const DbView& db, uint32_t bits, uint32_t& data_off, uint8_t& prefix) {
   uint32_t node = db.ip_version == 6 ? db.v4_start_node : 0;
   uint32_t bi = 0;
-  if (db.v4_top16) {  // sixteen dependent node reads in one table read
-    const uint32_t e = db.v4_top16[bits >> 16], kind = e >> 28;
+  if (db.v4_top16) {  // sixteen / twenty dependent node reads in one table read
+    const uint32_t tb = db.v4_top_bits, idx = bits >> (32 - tb);
+    const uint32_t e = db.v4_top16[idx], kind = e >> 28;
     if (kind == 1) return false;
-    if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v4_top16_depth[bits >> 16]; return true; }
+    if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v4_top16_depth[idx]; return true; }
     node = e & 0x0FFFFFFFu;
-    bi = 16;
+    bi = tb;
   }
   for (; bi < 32; bi++) {
     uint32_t rec = tree_record(db, node, (bits >> (31 - bi)) & 1);
@@ -885,8 +890,15 @@ MGPU_HDN bool trie_lookup_v4(const DbView& db, uint32_t bits, uint32_t& data_off
   return false;
 }
 MGPU_HDN bool trie_lookup_v6(const DbView& db, const uint16_t seg[8], uint32_t& data_off, uint8_t& prefix) {
-  uint32_t node = 0;
-  for (uint32_t bi = 0; bi < 128; bi++) {
+  uint32_t node = 0, bi = 0;
+  if (db.v6_top16) {
+    const uint32_t e = db.v6_top16[seg[0]], kind = e >> 28;
+    if (kind == 1) return false;
+    if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v6_top16_depth[seg[0]]; return true; }
+    node = e & 0x0FFFFFFFu;
+    bi = 16;
+  }
+  for (; bi < 128; bi++) {
     uint32_t rec = tree_record(db, node, (seg[bi >> 4] >> (15 - (bi & 15))) & 1);
     if (rec == db.node_count) return false;
     if (rec < db.node_count) { node = rec; continue; }

@@ -32,6 +32,7 @@ namespace cg = cooperative_groups;
 
 namespace mgpu {
 
+static_assert(sizeof(mgpu_match) == 32, "mgpu_match is copied as two 16-byte words");
 struct Cand { uint32_t start, len; };
 struct StrTok { uint32_t start, len, type; };
 struct IpTok { uint32_t start, len, type, pad; uint32_t w[4]; };  // v4: w[0]; v6: w[k] = seg[2k] << 16 | seg[2k+1]
@@ -649,27 +650,58 @@ __device__ __forceinline__ uint32_t agg_add(uint32_t* ctr, uint32_t v) {
   return base + incl - v;
 }
 
-// K3: IP tokens
+// K3: IP tokens.  A hit rate of a few per cent over 10^8 tokens means millions of records: appended one (or one warp's worth)
+// at a time they serialise on the single record counter (same-address atomics retire about one per nanosecond — that, not the
+// tree walk, was this kernel's time on config 3).  So a block stages the records of its 256 tokens in shared memory, takes
+// ONE slot range from the global counter and writes the records out as coalesced 16-byte stores.
 __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
+  __shared__ __align__(16) mgpu_match s_rec[256];
+  __shared__ uint32_t s_cnt, s_base;
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
   if (!a.db.has_ip || a.ctr->overflow) return;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    IpTok t = a.ip[i];
-    if (t.type == TOK_INVALID) continue;
-    uint32_t off = 0; uint8_t pl = 0; bool hit;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {  // (block-uniform trip count)
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t i = base + threadIdx.x;
+    bool hit = false;
+    uint32_t off = 0; uint8_t pl = 0;
+    IpTok t;
+    t.type = TOK_INVALID;
+    if (i < n) t = a.ip[i];
     if (t.type == MGPU_T_IPV4) hit = trie_lookup_v4(a.db, t.w[0], off, pl);
-    else {
+    else if (t.type != TOK_INVALID) {
       uint16_t seg[8];
       for (int k = 0; k < 4; k++) { seg[2 * k] = (uint16_t)(t.w[k] >> 16); seg[2 * k + 1] = (uint16_t)t.w[k]; }
       hit = trie_lookup_v6(a.db, seg, off, pl);
     }
-    if (!hit) continue;
-    uint32_t k = agg_add(&a.tot->n_rec, 1u);
-    if (k >= a.cap_rec) { atomicOr(&a.ctr->overflow, 1u << 10); continue; }
-    mgpu_match r;
-    r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_IP; r.prefix_len = pl; r.reserved = 0;
-    r.n_ids = 0; r.ids_index = 0; r.data_offset = off; r.pad = 0;
-    a.recs[k] = r;
+    __syncwarp();
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
+    if (bal) {
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(&s_cnt, (uint32_t)__popc(bal));
+      b = __shfl_sync(0xFFFFFFFFu, b, 0);
+      if (hit) {
+        mgpu_match r;
+        r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_IP; r.prefix_len = pl; r.reserved = 0;
+        r.n_ids = 0; r.ids_index = 0; r.data_offset = off; r.pad = 0;
+        s_rec[b + __popc(bal & ((1u << lane) - 1u))] = r;
+      }
+    }
+    __syncthreads();
+    const uint32_t cnt = s_cnt;  // block-uniform
+    if (cnt) {
+      if (threadIdx.x == 0) {
+        s_base = atomicAdd(&a.tot->n_rec, cnt);
+        if ((uint64_t)s_base + cnt > a.cap_rec) atomicOr(&a.ctr->overflow, 1u << 10);
+      }
+      __syncthreads();
+      const uint32_t b = s_base;
+      const uint4* src = reinterpret_cast<const uint4*>(s_rec);
+      uint4* dst = reinterpret_cast<uint4*>(a.recs);
+      for (uint32_t j = threadIdx.x; j < 2 * cnt; j += 256) if ((uint64_t)b + (j >> 1) < a.cap_rec) dst[2 * (size_t)b + j] = src[j];
+    }
+    __syncthreads();
   }
 }
 
@@ -1333,6 +1365,14 @@ int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
     rc = dev_copy(c, P.top16_depth.data(), P.top16_depth.size(), 0, 256, &p);
     if (rc) return rc;
     db.v4_top16_depth = (const uint8_t*)p;
+  }
+  if (!P.v6_top16.empty()) {
+    rc = dev_copy(c, P.v6_top16.data(), P.v6_top16.size() * 4, 0, 256, &p);
+    if (rc) return rc;
+    db.v6_top16 = (const uint32_t*)p;
+    rc = dev_copy(c, P.v6_top16_depth.data(), P.v6_top16_depth.size(), 0, 256, &p);
+    if (rc) return rc;
+    db.v6_top16_depth = (const uint8_t*)p;
   }
   if (L.has_literal) {
     // the slot table starts at 4 (mod 16) inside the section: base = 12 (mod 16) makes every 16-byte entry aligned

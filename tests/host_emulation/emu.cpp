@@ -248,6 +248,7 @@ int emu_db_upload(emu_ctx* c, const uint8_t* mxy, size_t len) {
   const mxy::Layout& L = c->P.L;
   c->db.tree = c->file.data();
   if (!c->P.top16.empty()) { c->db.v4_top16 = c->P.top16.data(); c->db.v4_top16_depth = c->P.top16_depth.data(); }
+  if (!c->P.v6_top16.empty()) { c->db.v6_top16 = c->P.v6_top16.data(); c->db.v6_top16_depth = c->P.v6_top16_depth.data(); }
   if (L.has_literal) { c->db.lh = c->file.data() + L.lit_off; c->db.lh_data_index = c->P.lh_index.data(); c->db.lh_bloom = c->P.lh_bloom.data(); }
   if (L.has_glob) {
     c->db.pg = c->file.data() + L.pg_off; c->db.aclh_index = c->P.aclh.data();
