@@ -130,6 +130,48 @@ def cmd_extract(a):
     return 0
 
 
+def cmd_build(a):
+    """`matchy build` (bin/commands/build_cmd.rs): text / csv / json inputs -> one .mxy file, written read-only (0444) like the
+    reference does.  MISP import and schema validation (the `-t <known schema>` case) are off the scan path and not provided."""
+    import os
+    from . import builder as B
+    if a.format not in ("text", "csv", "json"):
+        print("Error: %s" % ("MISP import is not provided by this build" if a.format == "misp" else
+                             "Unknown format: %s. Use 'text', 'csv', 'json', or 'misp'" % a.format), file=sys.stderr)
+        return 1
+    b = B.DatabaseBuilder(B.MatchMode.CaseInsensitive if a.case_insensitive else B.MatchMode.CaseSensitive)
+    if a.database_type:
+        if a.database_type in ("threatdb", "ThreatDB-v1"):  # schemas/mod.rs:137-141: the one built-in schema
+            print("Error: schema validation for '%s' is not provided; use a custom --database-type name" % a.database_type, file=sys.stderr)
+            return 1
+        b.set_database_type(a.database_type)
+    if a.description:
+        b.set_description(a.desc_lang, a.description)
+    add = {"text": B.add_text_file, "csv": B.add_csv_file, "json": B.add_json_file}[a.format]
+    total = 0
+    try:
+        for path in a.inputs:
+            total += add(b, path)
+        st = b.stats()
+        if a.verbose or a.debug:
+            print("\nBuilding database:\n  Total entries:   %d\n  IP entries:      %d\n  Literal entries: %d\n  Glob entries:    %d"
+                  % (total, st["ip_entries"], st["literal_entries"], st["glob_entries"]))
+        data = b.build()
+    except (OSError, ValueError) as e:
+        print("Error: %s" % e, file=sys.stderr)
+        return 1
+    if os.path.exists(a.output):
+        os.chmod(a.output, 0o644)  # (fs::write on a file the previous build left read-only)
+    with open(a.output, "wb") as f:
+        f.write(data)
+    os.chmod(a.output, 0o444)
+    if a.verbose or a.debug:
+        print("\n\u2713 Database built successfully!\n  Output:        %s\n  Database size: %.2f MB (%d bytes)" % (a.output, len(data) / (1024.0 * 1024.0), len(data)))
+    else:
+        print("\u2713 Database built: %s" % a.output)
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m matchy_b200")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -150,9 +192,21 @@ def main(argv=None):
     x.add_argument("-s", "--stats", action="store_true")
     x.add_argument("--show-candidates", action="store_true")
     x.add_argument("--device", type=int, default=0)
+    bl = sub.add_parser("build", help="write a .mxy database from text / csv / json indicator files (host only: no GPU needed)")
+    bl.add_argument("inputs", nargs="+")
+    bl.add_argument("-o", "--output", required=True)
+    bl.add_argument("-f", "--format", default="text")
+    bl.add_argument("-t", "--database-type", default=None)
+    bl.add_argument("-d", "--description", default=None)
+    bl.add_argument("--desc-lang", default="en")
+    bl.add_argument("-v", "--verbose", action="store_true")
+    bl.add_argument("--debug", action="store_true")
+    bl.add_argument("-i", "--case-insensitive", action="store_true")
     a = ap.parse_args(argv)
     if a.cmd == "extract":
         return cmd_extract(a)
+    if a.cmd == "build":
+        return cmd_build(a)
     from . import Engine, RecordFormatter
     db = open(a.database, "rb").read()
     eng = Engine(a.device, chunk_bytes=a.chunk_mb << 20)

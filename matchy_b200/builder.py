@@ -139,8 +139,10 @@ def _csv_value(value):
     return value
 
 
-def build_from_csv(path, build_epoch=None) -> bytes:
-    b = DatabaseBuilder(MatchMode.CaseSensitive, build_epoch)
+def add_csv_file(b, path):
+    """One CSV input of `matchy build -f csv` / `matchy match DB.csv` (build_cmd.rs:168-229): the `entry` / `key` column
+    is the indicator, every other non-empty cell a metadata value typed by _csv_value.  Returns the number of entries."""
+    n = 0
     with open(path, newline="") as f:
         rd = csv.reader(f)
         headers = next(rd)
@@ -156,26 +158,51 @@ def build_from_csv(path, build_epoch=None) -> bytes:
                 if i != col and i < len(row) and row[i] != "":
                     data[name] = _csv_value(row[i])
             b.add_entry(row[col], data)
-    return b.build()
+            n += 1
+    return n
 
 
-def build_from_json(path, build_epoch=None) -> bytes:
-    b = DatabaseBuilder(MatchMode.CaseSensitive, build_epoch)
+def add_json_file(b, path):
+    """`[{"key": ..., "data": {...}}, ...]` (build_cmd.rs:231-278)."""
+    n = 0
     with open(path) as f:
-        for item in json.load(f):
+        for k, item in enumerate(json.load(f)):
+            if not isinstance(item, dict) or not isinstance(item.get("key"), str):
+                raise ValueError("Missing 'key' field at index %d" % k)
             data = item.get("data") or {}
-            flat = {k: v for k, v in data.items() if not isinstance(v, (dict, list))}
+            flat = {k2: v for k2, v in data.items() if not isinstance(v, (dict, list))}
             if len(flat) != len(data):
                 raise ValueError("nested metadata values are not supported by this writer yet")
             b.add_entry(item["key"], flat)
-    return b.build()
+            n += 1
+    return n
 
 
-def build_from_text(path, build_epoch=None) -> bytes:
-    b = DatabaseBuilder(MatchMode.CaseSensitive, build_epoch)
+def add_text_file(b, path):
+    """One indicator per line, blank lines and `#` comments skipped (build_cmd.rs:98-166)."""
+    n = 0
     with open(path) as f:
         for line in f:
             e = line.strip()
             if e and not e.startswith("#"):
                 b.add_entry(e, {})
+                n += 1
+    return n
+
+
+def build_from_csv(path, build_epoch=None) -> bytes:
+    b = DatabaseBuilder(MatchMode.CaseSensitive, build_epoch)
+    add_csv_file(b, path)
+    return b.build()
+
+
+def build_from_json(path, build_epoch=None) -> bytes:
+    b = DatabaseBuilder(MatchMode.CaseSensitive, build_epoch)
+    add_json_file(b, path)
+    return b.build()
+
+
+def build_from_text(path, build_epoch=None) -> bytes:
+    b = DatabaseBuilder(MatchMode.CaseSensitive, build_epoch)
+    add_text_file(b, path)
     return b.build()

@@ -152,3 +152,50 @@ def test_oracle_multithreaded_counters_equal_single_thread(small_dbs):
     o = O.Oracle(db)
     _, cnt = o.scan(log, chunk_size=128 * 1024)
     assert o.scan_mt(log, threads=4) == cnt
+
+
+def test_build_subcommand(built, tmp_path, capsys):
+    """`python -m matchy_b200 build` == the `matchy build` contract (bin/commands/build_cmd.rs): text / csv / json inputs, several
+    files, metadata options, read-only output; the file is read back through the oracle."""
+    import stat
+    from matchy_b200.__main__ import main
+    txt = tmp_path / "a.txt"
+    txt.write_text("# comment\n\n10.0.0.0/8\n  evil.com  \n*.bad.org\nliteral:*.star.com\n")
+    txt2 = tmp_path / "b.txt"
+    txt2.write_text("2001:db8::/32\nother.net\n")
+    out = tmp_path / "t.mxy"
+    assert main(["build", str(txt), str(txt2), "-o", str(out), "-t", "MyCompany-Intel", "-d", "test db", "--desc-lang", "de", "-v"]) == 0
+    msg = capsys.readouterr().out
+    assert "Total entries:   6" in msg and "IP entries:      2" in msg and "Literal entries: 3" in msg and "Glob entries:    1" in msg
+    assert stat.S_IMODE(os.stat(out).st_mode) == 0o444
+    db = out.read_bytes()
+    assert b"MyCompany-Intel" in db[-600:] and b"test db" in db[-600:] and b"de" in db[-600:]
+    o = O.Oracle(db)
+    assert o.lookup_ip4(10 << 24 | 5)[0] and o.lookup_ip6([0x2001, 0xdb8, 1, 0, 0, 0, 0, 1])[0]
+    assert o.lookup_string(b"evil.com") and o.lookup_string(b"x.bad.org") and o.lookup_string(b"*.star.com") and not o.lookup_string(b"a.star.com")
+    # rebuilding over the read-only file works (fs::write would fail on 0444 only for non-owners; root owns it here)
+    assert main(["build", str(txt), "-o", str(out)]) == 0
+    assert "Database built: " in capsys.readouterr().out
+    csvf = tmp_path / "c.csv"
+    csvf.write_text("entry,threat_level,score,ratio,flag,note\n1.2.3.4,high,7,0.5,true,\nEvil.COM,low,-3,,false,\"a,b\"\n")
+    assert main(["build", str(csvf), "-o", str(out), "-f", "csv", "-i"]) == 0
+    o = O.Oracle(out.read_bytes())
+    f, off, pl = o.lookup_ip4(0x01020304)
+    assert f and pl == 32 and json.loads(o.data_json(off)) == {"threat_level": "high", "score": 7, "ratio": 0.5, "flag": True}
+    hit = o.lookup_string(b"evil.com")  # case-insensitive database
+    assert hit and json.loads(o.data_json(hit[0][1])) == {"threat_level": "low", "score": -3, "flag": False, "note": "a,b"}
+    js = tmp_path / "d.json"
+    js.write_text(json.dumps([{"key": "9.9.9.9", "data": {"k": "v", "n": 5}}, {"key": "*.x.io"}]))
+    assert main(["build", str(js), "-o", str(out), "-f", "json"]) == 0
+    o = O.Oracle(out.read_bytes())
+    f, off, pl = o.lookup_ip4(0x09090909)
+    assert f and json.loads(o.data_json(off)) == {"k": "v", "n": 5}
+    assert o.lookup_string(b"a.x.io")
+    capsys.readouterr()
+    assert main(["build", str(js), "-o", str(out), "-f", "xml"]) == 1
+    assert main(["build", str(js), "-o", str(out), "-f", "misp"]) == 1
+    assert main(["build", str(txt), "-o", str(out), "-t", "threatdb"]) == 1
+    bad = tmp_path / "bad.csv"
+    bad.write_text("a,b\n1,2\n")
+    assert main(["build", str(bad), "-o", str(out), "-f", "csv"]) == 1
+    assert "must have an 'entry' or 'key' column" in capsys.readouterr().err
