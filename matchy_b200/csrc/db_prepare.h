@@ -178,6 +178,8 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
       if (L.ip_version == 6) expand(0, 16, P.v6_top16, P.v6_top16_depth);
     }
   }
+  struct Anchor { const uint8_t* p; uint32_t m, tag; };  // anchor literal of a suffix- / prefix-anchored glob
+  std::vector<Anchor> anchors;
   std::vector<FilterKey> lit_tail_keys, glob_keys;
   std::vector<uint32_t> lit_full_keys;
   bool fast = L.match_mode == 0;
@@ -414,10 +416,10 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
         const uint8_t* ptr = nullptr; uint32_t dl = 0;
         int r = lit_of(cnt - 1, ptr, dl);
         if (r < 0) continue;
-        if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_S), (uint32_t)TAG_GLOB_S}); db.glob_s_lens |= 1u << glob_key_len(dl); continue; }
+        if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_S), (uint32_t)TAG_GLOB_S}); anchors.push_back(Anchor{ptr, dl, (uint32_t)TAG_GLOB_S}); db.glob_s_lens |= 1u << glob_key_len(dl); continue; }
         r = lit_of(0, ptr, dl);
         if (r < 0) continue;
-        if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_P), (uint32_t)TAG_GLOB_P}); db.glob_p_lens |= 1u << glob_key_len(dl); continue; }
+        if (r == 1) { glob_keys.push_back(FilterKey{glob_key_hash(ptr, dl, TAG_GLOB_P), (uint32_t)TAG_GLOB_P}); anchors.push_back(Anchor{ptr, dl, (uint32_t)TAG_GLOB_P}); db.glob_p_lens |= 1u << glob_key_len(dl); continue; }
         generic[pid] = 1; any_generic = true;               // neither end is a literal: any position can match
       }
       // Unanchored patterns: a pattern is only ever a candidate through one of its AC literals (find_all), so a token can
@@ -482,10 +484,25 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
       P.hot.swap(h);
       db.hot_tags |= 1u << tag;
     };
-    try_tag(glob_keys, TAG_GLOB_S);
-    try_tag(glob_keys, TAG_GLOB_P);
+    // hot keys of the glob classes (string_gate): keys of 1..3 bytes as they are; for the longer ones the gate key = the
+    // last / first G bytes of the anchor literal, G = the shortest key length >= 4 of the class
+    auto lowest_len = [](uint32_t lens) { lens &= ~0xFu; return lens ? (uint32_t)__builtin_ctz(lens) : 0u; };
+    db.glob_s_gate = lowest_len(db.glob_s_lens);
+    db.glob_p_gate = lowest_len(db.glob_p_lens);
+    std::vector<FilterKey> glob_hot_keys;
+    for (const Anchor& an : anchors) {
+      const uint32_t k = glob_key_len(an.m);
+      const uint32_t h = k < 4 ? glob_key_hash(an.p, an.m, an.tag) : glob_gate_hash(an.p, an.m, an.tag == TAG_GLOB_S ? db.glob_s_gate : db.glob_p_gate, an.tag);
+      glob_hot_keys.push_back(FilterKey{h, an.tag});
+    }
+    try_tag(glob_hot_keys, TAG_GLOB_S);
+    try_tag(glob_hot_keys, TAG_GLOB_P);
     try_tag(lit_tail_keys, TAG_LIT_TAIL);
     try_tag(lit_tail_keys, TAG_LIT_HEAD);
+    if (db.has_literal && !((db.hot_tags >> TAG_LIT_TAIL) & 1u) && !((db.hot_tags >> TAG_LIT_HEAD) & 1u)) db.gate_inline |= G_LIT;
+    if (db.glob_s_lens && !((db.hot_tags >> TAG_GLOB_S) & 1u)) db.gate_inline |= G_S;
+    if (db.glob_p_lens && !((db.hot_tags >> TAG_GLOB_P) & 1u)) db.gate_inline |= G_P;
+    if (db.has_generic) db.gate_inline |= G_GEN;
     uint64_t nkeys = glob_keys.size() + lit_full_keys.size();
     uint64_t words = 1024;
     while (words * 4 < nkeys) words <<= 1;  // >= 16 bits per key

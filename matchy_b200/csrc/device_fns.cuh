@@ -85,6 +85,8 @@ struct DbView {
   uint32_t has_generic;           // 1: some reachable glob is unanchored (or literal-typed): its literals' first bytes are in gen_gram2/3
   const uint32_t* gen_gram2;      // bitmaps (2^16 / 2^24 bits) over the first 2 / 3 bytes of the AC literals that lead to such a glob;
   const uint32_t* gen_gram3;
+  uint32_t glob_s_gate, glob_p_gate;  // shortest key length >= 4 of the suffix / prefix class (0: none): the hot filter's gate keys
+  uint32_t gate_inline;               // G_* bits of the classes whose gate cannot reject (class not in the hot filter, unanchored globs)
   uint32_t glob_s_lens, glob_p_lens;  // bit K (K in 1,2,3,4,8,12,16): some suffix- / prefix-anchored glob has a key of K bytes
   uint32_t hot_tags;              // bit t: keys of tag class t are in the hot filter (else that class skips the hot test)
   const uint32_t* hot;            // HOT_WORDS-word blocked Bloom filter; the token kernel keeps a copy in shared memory
@@ -596,10 +598,22 @@ MGPU_NOINLINE_HD bool generic_literal_scan(const DbView& db, const H& hot, const
   return false;
 }
 
-template <typename H, typename B>
-MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords& kw, const B& bytes, uint32_t n) {
-  uint32_t flags = 0;
-  if (db.has_literal) {
+// The filters run in two stages so that the per-token cost is the cheap one.
+//  Stage 1, string_gate: ONE hot-filter test per key class, in shared memory.  For the glob classes the hot filter holds,
+//    for every anchored glob whose key has K >= 4 bytes, the last (suffix class) / first (prefix class) G bytes of the anchor
+//    literal, G = the shortest such K in the database (db.glob_s_gate / glob_p_gate): a text that ends with the K-byte key ends
+//    with its last G bytes, so "the G-byte key is in the hot filter" is necessary for ANY of those globs; keys of 1..3 bytes are
+//    tested as they are.  For literals the gate is the tail key AND the head key.  Returns G_* bits: the classes that still owe
+//    their exact tests.
+//  Stage 2, string_filters_full: only for tokens with gate bits (a few per cent; the token kernel collects them and runs this
+//    stage with full warps): the cold filter (L2, >= 16 bits per key) on the literal class's full key and on every glob key
+//    length present.  Returns F_LIT | F_GLOB.
+// string_filters() = stage 2 of stage 1: the decision function the tests pin against the oracle.
+enum { G_LIT = 1u, G_S = 2u, G_P = 4u, G_GEN = 8u };
+template <typename H>
+MGPU_HDN uint32_t string_gate(const DbView& db, const H& hot, const KeyWords& kw, uint32_t n) {
+  uint32_t g = 0;
+  if (db.has_literal) {  // some stored literal has the same last K and the same first K bytes (K = lit_key_len(n))
     const uint32_t k = lit_key_len(n);
     uint32_t st, sh;  // tail / head states
     if (k == 8) { st = key_mix(key_mix(key_seed(TAG_LIT_TAIL), kw.t[3]), kw.t[2]); sh = key_mix(key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]), kw.h[1]); }
@@ -607,60 +621,111 @@ MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords&
     else { const uint32_t x = low_bytes32(kw.h[0], k); st = key_mix(key_seed(TAG_LIT_TAIL), x); sh = key_mix(key_seed(TAG_LIT_HEAD), x); }  // n < 4: head == tail
     bool pass = !((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, key_fin(st, k));
     pass = pass && (!((db.hot_tags >> TAG_LIT_HEAD) & 1u) || hot_test(hot, key_fin(sh, k)));
-    if (pass) {
-      // (n, first K, last K bytes): continue the head state with the tail words
-      uint32_t s = sh ^ key_seed(TAG_LIT_FULL);
-      if (k == 8) s = key_mix(key_mix(s, kw.t[3]), kw.t[2]);
-      else if (k == 4) s = key_mix(s, kw.t[3]);
-      if (cold_test(db.cold, db.cold_mask, key_fin(s, n))) flags |= F_LIT;
-    }
+    if (pass) g |= G_LIT;
   }
-  if (db.has_glob && (db.glob_s_lens | db.glob_p_lens)) {
-    // every key length present in the database, shortest first; `cand` = the first key that passed the hot filter
-    uint32_t cand = 0, cand2 = 0, npass = 0;
-    const bool hot_s = (db.hot_tags >> TAG_GLOB_S) & 1u, hot_p = (db.hot_tags >> TAG_GLOB_P) & 1u;
-    {
-      const uint32_t lens = db.glob_s_lens;
-      if (lens & 0xEu) {  // K = 1, 2, 3: the last K bytes sit in the top bytes of t[3] (n >= 4) or are the head word's low bytes
-        for (uint32_t k = 1; k <= 3; k++) {
-          if (!((lens >> k) & 1u) || k > n) continue;
-          const uint32_t x = n >= 4 ? (kw.t[3] >> (8 * (4 - k))) : (low_bytes32(kw.h[0], n) >> (8 * (n - k)));
-          const uint32_t h = key_fin(key_mix(key_seed(TAG_GLOB_S), x), k);
-          if (!hot_s || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; }
+  if (db.has_glob) {
+    if (db.glob_s_lens) {
+      if (!((db.hot_tags >> TAG_GLOB_S) & 1u)) g |= G_S;
+      else {
+        const uint32_t lens = db.glob_s_lens;
+        if (lens & 0xEu) {  // K = 1, 2, 3: the last K bytes sit in the top bytes of t[3] (n >= 4) or are the head word's low bytes
+          for (uint32_t k = 1; k <= 3; k++) {
+            if (!((lens >> k) & 1u) || k > n) continue;
+            const uint32_t x = n >= 4 ? (kw.t[3] >> (8 * (4 - k))) : (low_bytes32(kw.h[0], n) >> (8 * (n - k)));
+            if (hot_test(hot, key_fin(key_mix(key_seed(TAG_GLOB_S), x), k))) g |= G_S;
+          }
+        }
+        const uint32_t gs = db.glob_s_gate;
+        if (gs && n >= gs) {
+          uint32_t s = key_seed(TAG_GLOB_S);
+#pragma unroll
+          for (uint32_t j = 0; j < 4; j++) if (4 * j < gs) s = key_mix(s, kw.t[3 - j]);
+          if (hot_test(hot, key_fin(s, gs))) g |= G_S;
         }
       }
-      uint32_t s = key_seed(TAG_GLOB_S);
-#pragma unroll
-      for (uint32_t j = 0; j < 4; j++) {
-        const uint32_t k = 4 * (j + 1);
-        if ((lens >> k) == 0 || k > n) break;
-        s = key_mix(s, kw.t[3 - j]);
-        if ((lens >> k) & 1u) { const uint32_t h = key_fin(s, k); if (!hot_s || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; } }
-      }
     }
-    {
-      const uint32_t lens = db.glob_p_lens;
-      if (lens & 0xEu) {
-        for (uint32_t k = 1; k <= 3; k++) {
-          if (!((lens >> k) & 1u) || k > n) continue;
-          const uint32_t h = key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k);
-          if (!hot_p || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; }
+    if (db.glob_p_lens) {
+      if (!((db.hot_tags >> TAG_GLOB_P) & 1u)) g |= G_P;
+      else {
+        const uint32_t lens = db.glob_p_lens;
+        if (lens & 0xEu) {
+          for (uint32_t k = 1; k <= 3; k++) {
+            if (!((lens >> k) & 1u) || k > n) continue;
+            if (hot_test(hot, key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k))) g |= G_P;
+          }
+        }
+        const uint32_t gp = db.glob_p_gate;
+        if (gp && n >= gp) {
+          uint32_t s = key_seed(TAG_GLOB_P);
+#pragma unroll
+          for (uint32_t j = 0; j < 4; j++) if (4 * j < gp) s = key_mix(s, kw.h[j]);
+          if (hot_test(hot, key_fin(s, gp))) g |= G_P;
         }
       }
-      uint32_t s = key_seed(TAG_GLOB_P);
-#pragma unroll
-      for (uint32_t j = 0; j < 4; j++) {
-        const uint32_t k = 4 * (j + 1);
-        if ((lens >> k) == 0 || k > n) break;
-        s = key_mix(s, kw.h[j]);
-        if ((lens >> k) & 1u) { const uint32_t h = key_fin(s, k); if (!hot_p || hot_test(hot, h)) { if (!npass) cand = h; else cand2 = h; npass++; } }
+    }
+    if (db.has_generic) g |= G_GEN;
+  }
+  return g;
+}
+
+template <typename H, typename B>
+MGPU_HDN uint32_t string_filters_full(const DbView& db, const H& hot, const KeyWords& kw, const B& bytes, uint32_t n, uint32_t g) {
+  uint32_t flags = 0;
+  if (g & G_LIT) {
+    const uint32_t k = lit_key_len(n);
+    uint32_t sh;  // head state
+    if (k == 8) sh = key_mix(key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]), kw.h[1]);
+    else if (k == 4) sh = key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]);
+    else sh = key_mix(key_seed(TAG_LIT_HEAD), low_bytes32(kw.h[0], k));
+    // (n, first K, last K bytes): continue the head state with the tail words
+    uint32_t s = sh ^ key_seed(TAG_LIT_FULL);
+    if (k == 8) s = key_mix(key_mix(s, kw.t[3]), kw.t[2]);
+    else if (k == 4) s = key_mix(s, kw.t[3]);
+    if (cold_test(db.cold, db.cold_mask, key_fin(s, n))) flags |= F_LIT;
+  }
+  if (g & G_S) {  // every key length present in the database, shortest first, straight to the cold filter
+    const uint32_t lens = db.glob_s_lens;
+    if (lens & 0xEu) {
+      for (uint32_t k = 1; k <= 3; k++) {
+        if (!((lens >> k) & 1u) || k > n) continue;
+        const uint32_t x = n >= 4 ? (kw.t[3] >> (8 * (4 - k))) : (low_bytes32(kw.h[0], n) >> (8 * (n - k)));
+        if (cold_test(db.cold, db.cold_mask, key_fin(key_mix(key_seed(TAG_GLOB_S), x), k))) flags |= F_GLOB;
       }
     }
-    // the cold filter decides for the keys that passed (up to two; more is rare enough to take the exact path unasked)
-    if (npass > 2 || (npass >= 1 && cold_test(db.cold, db.cold_mask, cand)) || (npass == 2 && cold_test(db.cold, db.cold_mask, cand2))) flags |= F_GLOB;
+    uint32_t s = key_seed(TAG_GLOB_S);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t k = 4 * (j + 1);
+      if ((lens >> k) == 0 || k > n || (flags & F_GLOB)) break;
+      s = key_mix(s, kw.t[3 - j]);
+      if (((lens >> k) & 1u) && cold_test(db.cold, db.cold_mask, key_fin(s, k))) flags |= F_GLOB;
+    }
   }
-  if (db.has_glob && db.has_generic && !(flags & F_GLOB) && generic_literal_scan(db, hot, bytes, n)) flags |= F_GLOB;
+  if ((g & G_P) && !(flags & F_GLOB)) {
+    const uint32_t lens = db.glob_p_lens;
+    if (lens & 0xEu) {
+      for (uint32_t k = 1; k <= 3; k++) {
+        if (!((lens >> k) & 1u) || k > n) continue;
+        if (cold_test(db.cold, db.cold_mask, key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k))) flags |= F_GLOB;
+      }
+    }
+    uint32_t s = key_seed(TAG_GLOB_P);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t k = 4 * (j + 1);
+      if ((lens >> k) == 0 || k > n || (flags & F_GLOB)) break;
+      s = key_mix(s, kw.h[j]);
+      if (((lens >> k) & 1u) && cold_test(db.cold, db.cold_mask, key_fin(s, k))) flags |= F_GLOB;
+    }
+  }
+  if ((g & G_GEN) && !(flags & F_GLOB) && generic_literal_scan(db, hot, bytes, n)) flags |= F_GLOB;
   return flags;
+}
+
+template <typename H, typename B>
+MGPU_HDN uint32_t string_filters(const DbView& db, const H& hot, const KeyWords& kw, const B& bytes, uint32_t n) {
+  const uint32_t g = string_gate(db, hot, kw, n);
+  return g ? string_filters_full(db, hot, kw, bytes, n, g) : 0u;
 }
 MGPU_HDN uint32_t string_filters(const DbView& db, const uint32_t* hot, const uint8_t* w, uint32_t n) {
   KeyWords kw;
@@ -677,6 +742,12 @@ MGPU_HD uint32_t glob_key_hash(const uint8_t* lit, uint32_t m, uint32_t tag) {  
   if (k < 4) return key_fin(key_mix(s, bytes_le32(tag == TAG_GLOB_S ? lit + m - k : lit, k)), k);
   for (uint32_t j = 0; j < k / 4; j++) s = key_mix(s, tag == TAG_GLOB_S ? bytes_le32(lit + m - 4 * (j + 1), 4) : bytes_le32(lit + 4 * j, 4));
   return key_fin(s, k);
+}
+// the gate key of a glob anchor literal whose own key has K >= 4 bytes: its last / first g bytes (g in {4, 8, 12, 16}, g <= K)
+MGPU_HD uint32_t glob_gate_hash(const uint8_t* lit, uint32_t m, uint32_t g, uint32_t tag) {
+  uint32_t s = key_seed(tag);
+  for (uint32_t j = 0; j < g / 4; j++) s = key_mix(s, tag == TAG_GLOB_S ? bytes_le32(lit + m - 4 * (j + 1), 4) : bytes_le32(lit + 4 * j, 4));
+  return key_fin(s, g);
 }
 MGPU_HD void lit_key_hashes(const uint8_t* str, uint32_t n, uint32_t& tail_h, uint32_t& head_h, uint32_t& full_h) {
   const uint32_t k = lit_key_len(n);

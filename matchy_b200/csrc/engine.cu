@@ -65,6 +65,7 @@ struct ScanArgs {
   uint32_t* seg_cnt;   // [Q_COUNT][nseg_max]
   uint32_t nseg, nseg_max;
   StrTok* str; uint32_t cap_str;
+  StrTok* defer;       // token kernel: per-warp queues (DEFER_CAP slots each) of tokens that passed string_gate and owe stage 2
   IpTok* ip; uint32_t cap_ip;
   uint32_t* lh_res;
   mgpu_match* recs; uint32_t cap_rec;
@@ -392,8 +393,10 @@ static const uint32_t TK_WIN = 2048;
 // last-label table, the cold filter and gen_gram2 (the next carve-out step, 228 KiB, would leave 28 KiB and thrash them)
 static const size_t TOKEN_SMEM = (size_t)HOT_WORDS * 4 + (size_t)TK_WARPS * (TK_WIN + 32);
 
+static const uint32_t DEFER_CAP = 64;  // a warp drains its queue as soon as it holds 32 tokens, so 63 is the most it ever holds
 struct TokenWarp {  // per-warp state of the token kernel
   QueueCursor cs, ci;
+  StrTok* defer; uint32_t n_def;
   uint32_t n_dom, n_mail, n_v4, n_v6, n_md5, n_sha1, n_sha256, n_sha384, n_sha512;
 };
 
@@ -421,14 +424,59 @@ __device__ __forceinline__ void append_tokens(const ScanArgs& a, TokenWarp& tw, 
 }
 
 // A string token passed validation: count it, then (fast path) let the filters decide whether anything can match it.
+// Returns "append it now"; `gate` != 0 means the token passed stage 1 of the filters and owes stage 2 (defer_push).
 template <typename B>
-__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const HotShared& s_hot, const KeyWords& kw, const B& bytes, StrTok& st) {
+__device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, bool fast, const HotShared& s_hot, const KeyWords& kw, const B& bytes, StrTok& st,
+                                             uint32_t& gate) {
   tw.n_dom += st.type == MGPU_T_DOMAIN; tw.n_mail += st.type == MGPU_T_EMAIL; tw.n_md5 += st.type == MGPU_T_MD5; tw.n_sha1 += st.type == MGPU_T_SHA1;
   tw.n_sha256 += st.type == MGPU_T_SHA256; tw.n_sha384 += st.type == MGPU_T_SHA384; tw.n_sha512 += st.type == MGPU_T_SHA512;
+  gate = 0;
   if (!fast) return true;
-  const uint32_t f = string_filters(a.db, s_hot, kw, bytes, st.len);
-  st.type |= f;
-  return f != 0;
+  const uint32_t g = string_gate(a.db, s_hot, kw, st.len);
+  if (g & a.db.gate_inline) {  // a class whose gate rejects nothing (not in the hot filter / unanchored globs): decide here, as one stage
+    const uint32_t f = string_filters_full(a.db, s_hot, kw, bytes, st.len, g);
+    st.type |= f;
+    return f != 0;
+  }
+  gate = g;
+  return false;
+}
+
+// Stage 2 of the string filters for `count` (<= 32) queued tokens, one per lane, read back from the log buffer.
+__device__ __forceinline__ void defer_drain(const ScanArgs& a, TokenWarp& tw, uint32_t lane, const StrTok* src, uint32_t count, const HotShared& s_hot) {
+  const bool have = lane < count;
+  StrTok t{0, 0, 0};
+  if (have) { t.start = __ldcg(&src[lane].start); t.len = __ldcg(&src[lane].len); t.type = __ldcg(&src[lane].type); }
+  const uint32_t g = t.type >> 16;
+  t.type &= 0xFFFFu;
+  bool ws = false;
+  if (have) {
+    KeyWords kw;
+    const uint8_t* w = a.buf + t.start;
+    load_head_words(w, kw.h);
+    load_tail_words(w, t.len, kw.t);
+    const uint32_t f = string_filters_full(a.db, s_hot, kw, BytesPtr{w}, t.len, g);
+    t.type |= f;
+    ws = f != 0;
+  }
+  __syncwarp();
+  append_tokens(a, tw, lane, ws, t, false, IpTok{0, 0, 0, 0, {0, 0, 0, 0}});
+}
+
+// Queue the lanes' gate-passing tokens; run stage 2 with a full warp once 32 are waiting.
+__device__ __forceinline__ void defer_push(const ScanArgs& a, TokenWarp& tw, uint32_t lane, uint32_t gate, const StrTok& st, const HotShared& s_hot) {
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, gate != 0);
+  if (!bal) return;
+  if (gate) {
+    StrTok* d = tw.defer + tw.n_def + __popc(bal & ((1u << lane) - 1u));
+    __stcg(&d->start, st.start); __stcg(&d->len, st.len); __stcg(&d->type, (st.type & 0xFFFFu) | (gate << 16));
+  }
+  tw.n_def += __popc(bal);
+  __syncwarp();
+  if (tw.n_def >= 32) {
+    tw.n_def -= 32;
+    defer_drain(a, tw, lane, tw.defer + tw.n_def, 32, s_hot);
+  }
 }
 
 // streaming 16-byte load that does not allocate in L1 (L1 is left to the PSL last-label table and the filter words)
@@ -534,11 +582,13 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
       }
       __syncwarp();
     } else if (active) { st.type = hash_type_of(c.len); ws = true; }
+    uint32_t gate = 0;
     if (__any_sync(0xFFFFFFFFu, ws)) {
-      if (ws) ws = string_token(a, tw, fast, s_hot, kw, BytesPtr{wp}, st);  // (one call site: the filters are the bulk of the kernel's code)
+      if (ws) ws = string_token(a, tw, fast, s_hot, kw, BytesPtr{wp}, st, gate);  // (one call site: the filters are the bulk of the kernel's code)
       __syncwarp();
     }
     append_tokens(a, tw, lane, ws, st, wi, it);
+    defer_push(a, tw, lane, gate, st, s_hot);
     if (g != 32) {  // a short group: the prefetch assumed 32; fetch the right candidates again
       cn = Cand{0xFFFFFFFFu, 0};
       if (i0 + g + lane < n) cn = ld_cand(q + i0 + g + lane);
@@ -563,6 +613,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   __syncthreads();
   TokenWarp tw;
   memset(&tw, 0, sizeof tw);
+  tw.defer = a.defer + (size_t)(blockIdx.x * TK_WARPS + warp) * DEFER_CAP;
   const uint32_t nwarps = gridDim.x * TK_WARPS;
   for (uint32_t seg = blockIdx.x * TK_WARPS + warp; seg < a.nseg; seg += nwarps) {
     const uint32_t* sc = a.seg_cnt + seg;
@@ -591,16 +642,19 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
         }
       }
       __syncwarp();
+      uint32_t gate = 0;
       if (ws) {
         KeyWords kw;
         load_head_words(a.buf + st.start, kw.h);
         load_tail_words(a.buf + st.start, st.len, kw.t);
-        ws = string_token(a, tw, fast, s_hot, kw, BytesPtr{a.buf + st.start}, st);
+        ws = string_token(a, tw, fast, s_hot, kw, BytesPtr{a.buf + st.start}, st, gate);
       }
       __syncwarp();
       append_tokens(a, tw, lane, ws, st, wi, it);
+      defer_push(a, tw, lane, gate, st, s_hot);
     }
   }
+  if (tw.n_def) { defer_drain(a, tw, lane, tw.defer, tw.n_def, s_hot); tw.n_def = 0; }  // (n_def is warp-uniform)
   for (uint32_t i = lane; i < tw.cs.left; i += 32) a.str[tw.cs.base + i].type = TOK_INVALID;
   for (uint32_t i = lane; i < tw.ci.left; i += 32) a.ip[tw.ci.base + i].type = TOK_INVALID;
   // per-type candidate counters (WorkerStats): warp-reduce, one atomic per warp and type
@@ -1216,7 +1270,7 @@ void mgpu_destroy(mgpu_ctx* c) {
   }
   for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
-  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.q_long, c->args.seg_cnt, c->args.str, c->args.ip, c->args.lh_res,
+  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.q_long, c->args.seg_cnt, c->args.str, c->args.defer, c->args.ip, c->args.lh_res,
                   c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -1282,6 +1336,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMalloc(&a.q_long, (size_t)a.seg_cap[Q_LONG] * a.nseg_max * sizeof(Cand)));
   CK(cudaMalloc(&a.seg_cnt, (size_t)Q_COUNT * a.nseg_max * 4));
   CK(cudaMalloc(&a.str, (size_t)a.cap_str * sizeof(StrTok)));
+  CK(cudaMalloc(&a.defer, (size_t)launch_grid(c, 1) * TK_WARPS * DEFER_CAP * sizeof(StrTok)));
   CK(cudaMalloc(&a.ip, (size_t)a.cap_ip * sizeof(IpTok)));
   CK(cudaMalloc(&a.lh_res, (size_t)a.cap_str * 4));
   CK(cudaMalloc(&a.recs, (size_t)a.cap_rec * sizeof(mgpu_match)));

@@ -40,6 +40,7 @@ struct emu_ctx {
   std::vector<IpTok> ip;
   std::string err;
   uint64_t filter_pass[3] = {0, 0, 0};  // fast path: tokens that passed the literal / glob filters, tokens tested
+  uint64_t gate_pass[4] = {0, 0, 0, 0};  // stage 1: tokens owing stage 2 for the literal / suffix / prefix class, any class
 };
 
 // ---- K1: tokenize_kernel, one "warp" per range of tiles -------------------------------------------------
@@ -202,6 +203,11 @@ static void emu_piece(emu_ctx* c, const uint8_t* buf, uint64_t lo, uint64_t n, u
       const uint8_t* text = buf + t.start;
       uint32_t f = fast ? string_filters(db, db.hot, text, t.len) : (uint32_t)(F_LIT | F_GLOB);
       if (fast) c->filter_pass[0] += (f & F_LIT) != 0, c->filter_pass[1] += (f & F_GLOB) != 0, c->filter_pass[2]++;
+      if (fast) {  // stage-1 statistics: how many tokens owe stage 2, per class
+        KeyWords kw; load_head_words(text, kw.h); load_tail_words(text, t.len, kw.t);
+        const uint32_t g = string_gate(db, HotPtr{db.hot, db.gen_gram2}, kw, t.len);
+        c->gate_pass[0] += (g & G_LIT) != 0; c->gate_pass[1] += (g & G_S) != 0; c->gate_pass[2] += (g & G_P) != 0; c->gate_pass[3] += g != 0;
+      }
       if (!f) continue;
       uint32_t lit_pid = NONE32, lit_off = 0;
       if (!(f & F_LIT) || !db.has_literal || !lh_lookup(db, text, t.len, lit_pid)) lit_pid = NONE32;
@@ -269,6 +275,7 @@ void emu_set_anchored(emu_ctx* c, int on) { c->use_anchored = on != 0; }
 void emu_set_generic(emu_ctx* c, int on) { c->force_generic = on != 0; }
 int emu_is_fast(emu_ctx* c) { return (int)c->db.fast_ok; }
 void emu_filter_stats(emu_ctx* c, uint64_t out[3]) { for (int k = 0; k < 3; k++) out[k] = c->filter_pass[k]; }
+void emu_gate_stats(emu_ctx* c, uint64_t out[4]) { for (int k = 0; k < 4; k++) out[k] = c->gate_pass[k]; }
 int emu_is_anchored_exact(emu_ctx* c) { return (int)c->db.ac_anchored; }
 
 uint32_t emu_default_flags(emu_ctx* c) {
@@ -285,6 +292,7 @@ int emu_scan(emu_ctx* c, const uint8_t* data, size_t len, uint64_t base, uint32_
   c->recs.clear(); c->ids.clear(); c->str.clear(); c->ip.clear();
   memset(&c->counters, 0, sizeof c->counters);
   c->filter_pass[0] = c->filter_pass[1] = c->filter_pass[2] = 0;
+  c->gate_pass[0] = c->gate_pass[1] = c->gate_pass[2] = c->gate_pass[3] = 0;
   if (!c->loaded && lookups) return MGPU_E_NODB;
   if (chunk_bytes == 0) chunk_bytes = len ? len : 1;
   size_t pos = 0;
