@@ -3,13 +3,26 @@
 
 Prints one JSON object per match, in the reference's parallel-mode format (bin/match_processor/parallel.rs:297-369: keys
 sorted, `timestamp` "0.000", `source` = the file path), and with `--stats` the WorkerStats counters on stderr.  Only what the
-scan path needs: no follow mode, no gzip, no `--format`; the CLI proper is out of scope."""
+scan path needs: `.gz` inputs are inflated on the host, "-" is stdin; no follow mode, no `--format`; the CLI proper is out of scope
+(DESIGN.md)."""
 import argparse
 import json
 import sys
 import time
 
 import numpy as np
+
+
+def read_input(path):
+    """file_reader::open (crates/matchy/src/file_reader.rs:44-110): "-" is stdin, a name ending in .gz (any case) is inflated —
+    on the host, one gzip member like flate2's GzDecoder — everything else is read as it is.  Returns a uint8 array."""
+    if path == "-":
+        return np.frombuffer(sys.stdin.buffer.read(), dtype=np.uint8)
+    if path.lower().endswith(".gz"):
+        import zlib
+        with open(path, "rb") as f:
+            return np.frombuffer(zlib.decompressobj(31).decompress(f.read()), dtype=np.uint8)
+    return np.fromfile(path, dtype=np.uint8)
 
 
 def extract_lines(eng, data, flags):
@@ -221,7 +234,7 @@ def main(argv=None):
     nbytes = 0
     out = sys.stdout.buffer
     for path in a.inputs:
-        data = np.fromfile(path, dtype=np.uint8)
+        data = read_input(path)
         nbytes += data.size
         recs, ids = eng.scan(data, flags)
         out.write(fmt.ndjson(recs, ids, data, 0, path))

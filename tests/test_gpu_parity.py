@@ -309,11 +309,12 @@ def test_match_cli_output_contract(small_dbs, tmp_path):
     import subprocess
     import sys
     db, log = small_dbs[5]
-    dbp, l1, l2 = tmp_path / "t.mxy", tmp_path / "a.log", tmp_path / "b.log"
+    import gzip
+    dbp, l1, l2 = tmp_path / "t.mxy", tmp_path / "a.log", tmp_path / "b.log.GZ"  # .gz in any case is inflated (file_reader.rs:60-75)
     dbp.write_bytes(db)
     cut = log.rfind(b"\n", 0, len(log) // 2) + 1
     l1.write_bytes(log[:cut])
-    l2.write_bytes(log[cut:])
+    l2.write_bytes(gzip.compress(log[cut:]) + gzip.compress(b"second member: 45.0.0.1 is ignored like flate2's GzDecoder does\n"))
     r = subprocess.run([sys.executable, "-m", "matchy_b200", "match", str(dbp), str(l1), str(l2), "--extractors=-crypto", "--stats"],
                        capture_output=True, cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
     assert r.returncode == 0, r.stderr[-500:]
