@@ -140,6 +140,47 @@ def test_scan_fuzz_with_hits(engines, small_dbs):
         assert eng.records_as_tuples() == want, it
 
 
+def test_dense_hits_drain_the_deferred_filter_queue(engines, small_dbs):
+    """48 MiB in which a third of the tokens are indicators of config 2's database or near misses that share their key bytes:
+    every warp's stage-2 queue (token kernel, defer_push) fills and drains many times, the record staging of the exact and
+    IP kernels sees dense output.  Records and counters must equal the oracle's."""
+    import numpy as np
+    eng, orc, log = engines[2]
+    want0, _ = orc.scan(log, chunk_size=128 * 1024)
+    hits = sorted({log[r[0]:r[0] + r[1]] for r in want0})
+    assert len(hits) > 20
+    rng = random.Random(4242)
+    plain = [w for w in log.replace(b"=", b" ").replace(b"\"", b" ").split() if b"." in w][:4000]
+    pool = []
+    for h in hits:
+        pool.append(h)
+        pool.append(bytes([h[0] ^ 1]) + h[1:])                  # same tail, different head
+        pool.append(h[:-1] + bytes([h[-1] ^ 1]))                # same head, different tail
+        pool.append(b"x" + h)                                   # suffix-anchored globs still match, literals do not
+        pool.append(h[: len(h) // 2] + b"0" + h[len(h) // 2:])  # same 8-byte head and tail, different middle
+    lines = []
+    for _ in range(3000):
+        toks = [rng.choice(pool) if rng.random() < 0.35 else rng.choice(plain) for _ in range(rng.randint(3, 9))]
+        lines.append(b" ".join(toks) + b"\n")
+    block = b"".join(lines)
+    data = (block * (48 * 1024 * 1024 // len(block) + 1))[: 48 * 1024 * 1024]
+    data = data[: data.rfind(b"\n") + 1]
+    big = Engine_for(eng)
+    big.scan(np.frombuffer(data, dtype=np.uint8))
+    want, wcnt = orc.scan(data, chunk_size=4 << 20)
+    assert big.counters_list() == wcnt
+    assert big.records_as_tuples() == want
+    assert len(want) > 200000
+
+
+def Engine_for(eng):
+    """An engine with 64 MiB pieces holding the same database as `eng` (the module's engines use 8 MiB pieces: too little per warp)."""
+    from matchy_b200 import Engine
+    e = Engine(0, chunk_bytes=64 << 20)
+    e.upload(eng._db_bytes)
+    return e
+
+
 @pytest.mark.parametrize("data", [b"", b"\n", b"x", b"1.2.3.4", b"evil.com", b"no newline at the end 8.8.8.8", b"\n\n\n", b" " * 5000,
                                   b"a" * 5000, b"a." * 5000 + b"com\n", b"@" * 3000, b":" * 3000, b"." * 3000])
 def test_edge_inputs(engines, data):
