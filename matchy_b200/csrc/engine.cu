@@ -604,7 +604,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* s_win = tk_smem + (size_t)HOT_WORDS * 4 + (size_t)warp * (TK_WIN + 32);
   const bool fast = a.fast != 0;
-  if (a.ctr->overflow) return;  // an earlier stage of this piece ran out of room: the host redoes the piece in smaller parts
+  // an earlier stage of this piece ran out of room: the host redoes the piece in smaller parts.  (One thread reads the flag for
+  // the block: other blocks may set it while this one starts, and the exit has to be uniform in front of the barrier below.)
+  __shared__ uint32_t s_ovf;
+  if (threadIdx.x == 0) s_ovf = a.ctr->overflow;
+  __syncthreads();
+  if (s_ovf) return;
   if (fast) {
     const uint4* src = reinterpret_cast<const uint4*>(a.db.hot);
     for (uint32_t i = threadIdx.x; i < HOT_WORDS / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_hot_words)[i] = src[i];
@@ -712,7 +717,10 @@ __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
   __shared__ __align__(16) mgpu_match s_rec[256];
   __shared__ uint32_t s_cnt, s_base;
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
-  if (!a.db.has_ip || a.ctr->overflow) return;
+  if (threadIdx.x == 0) s_cnt = a.ctr->overflow;  // (read once per block: the exit must be uniform, other blocks may set the flag)
+  __syncthreads();
+  if (!a.db.has_ip || s_cnt) return;
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {  // (block-uniform trip count)
     if (threadIdx.x == 0) s_cnt = 0;
