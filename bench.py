@@ -106,6 +106,41 @@ def ncu_traffic(kernel):
         return None
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: keep this rank's threads — and so the pages of the pinned log buffer it is about to allocate and fill —
+    on the NUMA node its GPU hangs off (sysfs local_cpulist of the GPU's PCI function).  With 8 ranks streaming 53 GB/s each from
+    host memory, buffers that sit on the other socket make the inter-socket link the bottleneck of the e2e figure.  Best effort:
+    returns a description, or None when the topology cannot be read (single node, container without sysfs, ...)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        with open(base + "/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if len(use) < 2 or use == allowed:
+            return None
+        os.sched_setaffinity(0, use)
+        node = None
+        try:
+            with open(base + "/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        return {"pci": bus, "numa_node": node, "cpus": len(use)}
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -229,6 +264,7 @@ def main():
 
     cfg, scale = args.config, args.scale
     nbytes = int(args.gb * 1e9) // 65536 * 65536
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     db = synth.build_db(cfg, scale)
     eng = Engine(local_rank, chunk_bytes=args.chunk_mb << 20)
     eng.upload(db)
@@ -336,7 +372,7 @@ def main():
             "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "log_bytes_per_gpu": nbytes, "chunk_bytes": args.chunk_mb << 20, "extractor_flags": flags,
                        "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (nbytes / 1e9),
                        "db": {k: info[k] for k in ("node_count", "literal_count", "glob_count", "ac_node_count", "file_bytes")},
-                       "parallelism": "byte-range shards x%d, database replicated" % world},
+                       "parallelism": "byte-range shards x%d, database replicated" % world, "rank0_numa_binding": numa},
             "lines_per_s": tot[0] * args.steps / dev_s, "matches_per_s": tot[3] * args.steps / dev_s,
             "counters": {"lines": tot[0], "bytes": tot[1], "candidates": tot[2], "matches": tot[3]},
             "wall_s_timed_region": wall_s,
