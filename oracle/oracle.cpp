@@ -1743,6 +1743,13 @@ const char* orc_ndjson(orc_handle* h, const uint8_t* data, uint64_t base, const 
 int orc_lookup_ip4(orc_handle* h, uint32_t addr, uint32_t* data_off, uint8_t* prefix) { return h->db.lookup_v4(addr, *data_off, *prefix); }
 int orc_lookup_ip6(orc_handle* h, const uint16_t* seg, uint32_t* data_off, uint8_t* prefix) { return h->db.lookup_v6(seg, *data_off, *prefix); }
 int orc_parse_ipv6(const uint8_t* s, size_t n, uint16_t* seg) { return parse_ipv6(s, n, seg) ? 1 : 0; }
+// the record reader on bare tree bytes (pinned by the reference's vectors, mmdb/tree.rs:323-398); -1 = out of range
+int64_t orc_tree_record(const uint8_t* tree, size_t tree_size, uint32_t node_count, int record_bits, uint32_t node, int side) {
+  Db d;
+  d.data = tree; d.tree_size = tree_size; d.node_count = node_count; d.record_bits = record_bits;
+  uint32_t rec = 0;
+  return d.read_record(node, side, rec) ? (int64_t)rec : -1;
+}
 size_t orc_lookup_string(orc_handle* h, const uint8_t* q, size_t n, uint32_t* out_pairs, size_t cap_pairs) {
   std::vector<IdPair> ids;
   h->db.lookup_string(q, n, ids);

@@ -324,6 +324,13 @@ int emu_results(emu_ctx* c, const mgpu_match** recs, size_t* n_recs, const mgpu_
 }
 int emu_counters_get(emu_ctx* c, mgpu_counters* out) { *out = c->counters; return 0; }
 
+// the kernels' tree record reader on bare tree bytes
+uint32_t emu_tree_record(const uint8_t* tree, uint32_t node_count, uint32_t record_bits, uint32_t node, uint32_t side) {
+  DbView db;
+  memset(&db, 0, sizeof db);
+  db.tree = tree; db.node_count = node_count; db.record_bits = record_bits;
+  return tree_record(db, node, side);
+}
 // the kernels' mask-arithmetic IPv6 parser on a bare run (s must be readable 8 bytes past n); 1 = parsed
 int emu_parse_ipv6_masks(const uint8_t* s, uint32_t n, uint32_t w[4]) { return parse_ipv6_run_masks(s, n, w) ? 1 : 0; }
 

@@ -207,3 +207,44 @@ def test_query_and_extract_agree_with_oracle(built, small_dbs):
             L.matchy_free_string(p)
         L.matchy_free_result(C.byref(r))
     L.matchy_close(h)
+
+
+def test_data_codec_round_trips_of_the_reference(built):
+    """The reference's data-format tests (matchy-data-format/src/lib.rs:1054-1290: map, array, complex nested structure, string
+    size classes, deduplication) as writer -> reader round trips: our encoder (behind matchy_builder_add) against the oracle's
+    decoder, which follows DataDecoder (lib.rs:635-1044)."""
+    import json
+    L = _lib()
+    nested = {"threat_level": "high", "category": "malware", "confidence": 0.98, "first_seen": 1704067200,
+              "indicators": {"ip_count": 42, "domain_count": 15}, "tags": ["botnet", "c2"], "active": True}
+    sizes = {"short": "x" * 28, "medium": "x" * 100, "long": "x" * 1000, "huge": "y" * 70000}  # size classes <29, <285, <65821, beyond
+    arr = {"value": ["tag1", "tag2", 123, False]}
+    entries = [
+        (b"10.0.0.1", json.dumps(nested).encode(), 0),
+        (b"10.0.0.2", json.dumps({"country": "US", "asn": 13335, "score": 0.95}).encode(), 0),
+        (b"10.0.0.3", json.dumps(arr["value"]).encode(), 0),          # bare array -> {"value": [...]}
+        (b"10.0.0.4", json.dumps(sizes).encode(), 0),
+        (b"10.0.0.5", json.dumps(nested).encode(), 0),                # same value again: deduplicated
+        (b"same.example.com", json.dumps(nested).encode(), 0),
+        (b"10.0.0.6", json.dumps({"a": {"b": {"c": {"d": [1, [2, [3, {"e": "deep"}]]]}}}}).encode(), 0),
+        (b"10.0.0.7", b'{"u16max":65535,"u32min":65536,"u32max":4294967295,"u64min":4294967296,"u64max":18446744073709551615,"i32min":-2147483648,"m1":-1}', 0),
+    ]
+    db = _build(L, entries)
+    o = O.Oracle(db)
+
+    def data_of(last_octet):
+        f, off, pl = o.lookup_ip4((10 << 24) | last_octet)
+        assert f and pl == 32
+        return off, json.loads(o.data_json(off))
+
+    off1, v1 = data_of(1)
+    assert v1 == nested
+    assert data_of(2)[1] == {"country": "US", "asn": 13335, "score": 0.95}
+    assert data_of(3)[1] == arr
+    assert data_of(4)[1] == sizes
+    off5, v5 = data_of(5)
+    assert off5 == off1 and v5 == nested
+    assert o.lookup_string(b"same.example.com")[0][1] == off1
+    assert data_of(6)[1] == {"a": {"b": {"c": {"d": [1, [2, [3, {"e": "deep"}]]]}}}}
+    assert data_of(7)[1] == {"u16max": 65535, "u32min": 65536, "u32max": 4294967295, "u64min": 4294967296, "u64max": 18446744073709551615,
+                             "i32min": -2147483648, "m1": -1}

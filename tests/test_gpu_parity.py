@@ -427,3 +427,28 @@ def test_extract_subcommand_matches_per_line_oracle(built, small_dbs, tmp_path, 
         assert ("Lines processed: %s" % format(lines, ",")).encode() in got.err
     assert main(["extract", str(path), "--format", "xml"]) == 1
     assert main(["extract", str(path), "--types", "bogus"]) == 1
+
+
+def test_paraglob_integration_vectors_on_device(built):
+    """The reference's paraglob integration pattern sets (matchy-paraglob/tests/integration_tests.rs:11-258, ported in
+    test_oracle_kats.py): the device's single-string lookup returns the oracle's (pattern id, data offset) pairs for every text."""
+    from matchy_b200 import Engine
+    from test_oracle_kats import _globs
+    sets = [(["*.txt", "test*", "*file*"], 0, ["document.txt", "test_case", "myfile.dat", "nomatch"]),
+            (["hello", "world", "test"], 0, ["hello", "world", "hello world", "nomatch"]),
+            (["*test*", "*test*", "hello", "hello"], 0, ["test123", "hello"]),
+            (["*.txt", "*file*", "test*"], 0, ["testfile.txt"]),
+            (["Test*", "HELLO"], 0, ["Test123", "test123", "HELLO", "hello"]),
+            (["Test*", "HELLO"], 1, ["Test123", "test123", "HELLO", "hello"]),
+            (["*test*", "test*", "*test"], 0, ["test", "testing", "mytest", "mytesting"]),
+            (["*.rs", "*.toml", "Cargo.*", "src/*", "*.md"], 0, ["main.rs", "Cargo.toml", "src/lib.rs", "README.md", "test.py"]),
+            (["pattern_%d_*" % i for i in range(1000)], 0, ["pattern_500_test", "pattern_999_data", "nomatch"]),
+            (["hello", "*.txt", "test_*"], 0, ["hello.txt", "test_file.txt"]),
+            (["*", "?", "**"], 0, ["test", "a"])]
+    eng = Engine(0, chunk_bytes=1 << 20)
+    for patterns, mode, texts in sets:
+        orc = _globs(patterns, mode)
+        eng.upload(orc._db)
+        for t in texts:
+            assert eng.lookup_string(t.encode()) == orc.lookup_string(t.encode()), (patterns[:3], t)
+    eng.close()

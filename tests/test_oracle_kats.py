@@ -410,3 +410,77 @@ def test_crypto_mixed_and_disabled(small_dbs):
     line = b"BTC: 1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa ETH: 0x5aeda56215b167893e80b4fe645ba6d5bab767de"
     assert _crypto(o, line) == [("Bitcoin", b"1A1zP1eP5QGefi2DMPTfTL5SLmv7DivfNa"), ("Ethereum", b"0x5aeda56215b167893e80b4fe645ba6d5bab767de")]
     assert [x for x in o.extract_strings(line, O.X_DEFAULT) if x[0] in ("Bitcoin", "Ethereum", "Monero")] == []
+
+
+def test_tree_record_readers():
+    """SearchTree::read_24bit_record / read_28bit_record with the reference's own vectors (matchy-format/src/mmdb/tree.rs:323-376),
+    a 32-bit one of the same shape, and calculate_data_offset (:378-398: record - node_count - 16); the oracle's reader and
+    the device code's reader (tree_record in device_fns.cuh, through the host emulation) both have to return them."""
+    import ctypes as C
+    import emu_lib as E
+    L, M = O.lib(), E.lib()
+    L.orc_tree_record.restype = C.c_int64
+    L.orc_tree_record.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_int, C.c_uint32, C.c_int]
+    M.emu_tree_record.restype = C.c_uint32
+    M.emu_tree_record.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    d24 = bytes([0, 0, 1, 0, 0, 2]) + bytes(994)
+    d28 = bytes([0, 0, 1, 0x12, 0, 0, 2]) + bytes(993)
+    d32 = bytes([0x01, 0x02, 0x03, 0x04, 0xA0, 0xB0, 0xC0, 0xD0]) + bytes(992)
+    cases = [(d24, 24, 60, 0, 0, 1), (d24, 24, 60, 0, 1, 2), (d28, 28, 70, 0, 0, 0x1000001), (d28, 28, 70, 0, 1, 0x2000002),
+             (d32, 32, 80, 0, 0, 0x01020304), (d32, 32, 80, 0, 1, 0xA0B0C0D0), (d24, 24, 60, 1, 0, 0)]
+    for data, bits, tree_size, node, side, want in cases:
+        assert L.orc_tree_record(data, tree_size, 10, bits, node, side) == want
+        assert M.emu_tree_record(data, 10, bits, node, side) == want
+    assert L.orc_tree_record(d24, 60, 10, 24, 10, 0) == -1  # node index out of range is an error in the reference (tree.rs:133-138)
+    # calculate_data_offset: a record above node_count + 16 points (record - node_count - 16) bytes into the data section
+    from matchy_b200 import DatabaseBuilder
+    b = DatabaseBuilder(build_epoch=1)
+    b.add_entry("1.2.3.4", {"a": "first"})
+    b.add_entry("5.6.7.8", {"a": "second value"})
+    o = O.Oracle(b.build())
+    f1, off1, _ = o.lookup_ip4(0x01020304)
+    f2, off2, _ = o.lookup_ip4(0x05060708)
+    assert f1 and f2 and off1 == 0 and off2 > off1
+    import json
+    assert json.loads(o.data_json(off1)) == {"a": "first"} and json.loads(o.data_json(off2)) == {"a": "second value"}
+
+
+def _globs(patterns, mode=0):
+    from matchy_b200 import DatabaseBuilder, MatchMode
+    b = DatabaseBuilder(MatchMode.CaseInsensitive if mode else MatchMode.CaseSensitive, build_epoch=1)
+    for p in patterns:
+        b.add_glob(p, {"p": p})
+    return O.Oracle(b.build())
+
+
+def test_paraglob_integration_vectors():
+    """matchy-paraglob/tests/integration_tests.rs:11-258, pattern sets and expectations as written there (find_all over a
+    paraglob; entries without wildcards are literal-typed patterns = substring matches, quirk 12)."""
+    n = lambda o, text: len(o.lookup_string(text.encode()))
+    ids = lambda o, text: {p for p, _ in o.lookup_string(text.encode())}
+    o = _globs(["*.txt", "test*", "*file*"])                                  # test_basic_wildcards
+    assert n(o, "document.txt") and n(o, "test_case") and n(o, "myfile.dat") and not n(o, "nomatch")
+    o = _globs(["hello", "world", "test"])                                    # test_exact_string_matching
+    assert n(o, "hello") == 1 and n(o, "world") == 1 and n(o, "hello world") == 2 and n(o, "nomatch") == 0
+    o = _globs(["*test*", "*test*", "hello", "hello"])                        # test_duplicate_pattern_deduplication
+    assert n(o, "test123") == 1 and n(o, "hello") == 1
+    o = _globs(["*.txt", "*file*", "test*"])                                  # test_multiple_patterns_matching_same_text
+    assert ids(o, "testfile.txt") == {0, 1, 2}
+    o = _globs(["Test*", "HELLO"])                                            # test_case_sensitivity
+    assert n(o, "Test123") and not n(o, "test123") and n(o, "HELLO") and not n(o, "hello")
+    o = _globs(["Test*", "HELLO"], mode=1)                                    # test_case_insensitivity
+    assert n(o, "Test123") and n(o, "test123") and n(o, "HELLO") and n(o, "hello")
+    o = _globs(["test"])                                                      # test_empty_string_queries
+    assert n(o, "") == 0 and n(o, "test") == 1
+    o = _globs(["exact_match", "another_literal", "third"])                   # test_pure_literal_patterns
+    assert n(o, "exact_match") == 1 and n(o, "another_literal") == 1 and n(o, "nomatch") == 0
+    o = _globs(["*test*", "test*", "*test"])                                  # test_overlapping_literal_patterns
+    assert (n(o, "test"), n(o, "testing"), n(o, "mytest"), n(o, "mytesting")) == (3, 2, 2, 1)
+    o = _globs(["*.rs", "*.toml", "Cargo.*", "src/*", "*.md"])                # test_real_world_file_patterns
+    assert n(o, "main.rs") and n(o, "Cargo.toml") >= 2 and n(o, "src/lib.rs") >= 2 and n(o, "README.md") and not n(o, "test.py")
+    o = _globs(["pattern_%d_*" % i for i in range(1000)])                     # test_large_pattern_set
+    assert 500 in ids(o, "pattern_500_test") and 999 in ids(o, "pattern_999_data") and not n(o, "nomatch")
+    o = _globs(["hello", "*.txt", "test_*"])                                  # test_combined_literal_and_glob_patterns
+    assert ids(o, "hello.txt") == {0, 1} and ids(o, "test_file.txt") == {1, 2}
+    o = _globs(["*", "?", "**"])                                              # test_pure_wildcard_patterns
+    assert n(o, "test") >= 2 and n(o, "a") >= 3
