@@ -1010,7 +1010,7 @@ __global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
 // start positions of the anchored literal search (positions are independent, anchored_visit_at), pattern ids meet in a
 // small shared-memory list, lane 0 sorts, deduplicates and writes the record.
 static const uint32_t EX_IDS = 96;
-__global__ void __launch_bounds__(256) exact_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(256, 5) exact_kernel(ScanArgs a) {
   __shared__ uint32_t s_ids[8][EX_IDS];
   __shared__ uint32_t s_n[8];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
