@@ -86,11 +86,6 @@ __device__ __forceinline__ uint4 ld_stream(const uint8_t* p) {
   return r;
 }
 
-__device__ __forceinline__ uint32_t gather_mask(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t k) {
-  uint32_t s = k | ((4u + k) << 4);
-  return __byte_perm(__byte_perm(a0, a1, s), __byte_perm(a2, a3, s), 0x5410);
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -168,15 +163,20 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
           accHi[j >> 1] += e.y << sh;
         }
       }
+      // byte c of acc[q] = class c of bytes 8q..8q+7: a 4x4 byte transpose (two PRMT stages) turns them into one mask per class
       LaneMasks m;
-      m.B = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 0);
-      m.DOT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 1);
-      m.AT = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 2);
-      m.CL = gather_mask(accLo[0], accLo[1], accLo[2], accLo[3], 3);
-      m.NL = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 0);
-      m.DM = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 1);
-      m.HX = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 2);
-      m.DASH = gather_mask(accHi[0], accHi[1], accHi[2], accHi[3], 3);
+      {
+        const uint32_t t0 = __byte_perm(accLo[0], accLo[1], 0x5140), t1 = __byte_perm(accLo[0], accLo[1], 0x7362);
+        const uint32_t t2 = __byte_perm(accLo[2], accLo[3], 0x5140), t3 = __byte_perm(accLo[2], accLo[3], 0x7362);
+        m.B = __byte_perm(t0, t2, 0x5410); m.DOT = __byte_perm(t0, t2, 0x7632);
+        m.AT = __byte_perm(t1, t3, 0x5410); m.CL = __byte_perm(t1, t3, 0x7632);
+      }
+      {
+        const uint32_t t0 = __byte_perm(accHi[0], accHi[1], 0x5140), t1 = __byte_perm(accHi[0], accHi[1], 0x7362);
+        const uint32_t t2 = __byte_perm(accHi[2], accHi[3], 0x5140), t3 = __byte_perm(accHi[2], accHi[3], 0x7362);
+        m.NL = __byte_perm(t0, t2, 0x5410); m.DM = __byte_perm(t0, t2, 0x7632);
+        m.HX = __byte_perm(t1, t3, 0x5410); m.DASH = __byte_perm(t1, t3, 0x7632);
+      }
       if ((uint64_t)tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
         uint64_t valid = a.n > p ? a.n - p : 0;
         uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
