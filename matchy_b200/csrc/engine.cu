@@ -144,12 +144,13 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
     // the next tile's slice is loaded into registers while the current one is processed (the buffer is readable one tile
     // past the chunk, see mgpu_scan_device), so the loads' latency never sits in front of the classification
     uint4 nx0 = ld_stream(a.buf + (uint32_t)(t0 * TILE_BYTES) + lane * SLICE_BYTES), nx1 = ld_stream(a.buf + (uint32_t)(t0 * TILE_BYTES) + lane * SLICE_BYTES + 16);
-    for (uint64_t t = t0; t < t1; t++) {
-      const uint32_t tile_base = (uint32_t)(t * TILE_BYTES);  // chunks are at most 2 GiB: positions fit 32 bits
+    const uint32_t t_end = (uint32_t)t1, t_last = (uint32_t)(tiles - 1);  // (tile indices fit 32 bits: a chunk has at most 2^21 tiles)
+    for (uint32_t t = (uint32_t)t0; t < t_end; t++) {
+      const uint32_t tile_base = t * TILE_BYTES;  // chunks are at most 2 GiB: positions fit 32 bits
       const uint32_t p = tile_base + lane * SLICE_BYTES;
       const uint4 v0 = nx0, v1 = nx1;
-      if (t + 1 < t1) { nx0 = ld_stream(a.buf + p + TILE_BYTES); nx1 = ld_stream(a.buf + p + TILE_BYTES + 16); }
-      if (t + 4 < t1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.buf + p + 4 * TILE_BYTES));  // my slice of the tile four steps ahead
+      if (t + 1 < t_end) { nx0 = ld_stream(a.buf + p + TILE_BYTES); nx1 = ld_stream(a.buf + p + TILE_BYTES + 16); }
+      if (t + 4 < t_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.buf + p + 4 * TILE_BYTES));  // my slice of the tile four steps ahead
       uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       uint32_t accLo[4] = {0, 0, 0, 0}, accHi[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -166,18 +167,18 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       // byte c of acc[q] = class c of bytes 8q..8q+7: a 4x4 byte transpose (two PRMT stages) turns them into one mask per class
       LaneMasks m;
       {
-        const uint32_t t0 = __byte_perm(accLo[0], accLo[1], 0x5140), t1 = __byte_perm(accLo[0], accLo[1], 0x7362);
-        const uint32_t t2 = __byte_perm(accLo[2], accLo[3], 0x5140), t3 = __byte_perm(accLo[2], accLo[3], 0x7362);
-        m.B = __byte_perm(t0, t2, 0x5410); m.DOT = __byte_perm(t0, t2, 0x7632);
-        m.AT = __byte_perm(t1, t3, 0x5410); m.CL = __byte_perm(t1, t3, 0x7632);
+        const uint32_t r0 = __byte_perm(accLo[0], accLo[1], 0x5140), r1 = __byte_perm(accLo[0], accLo[1], 0x7362);
+        const uint32_t r2 = __byte_perm(accLo[2], accLo[3], 0x5140), r3 = __byte_perm(accLo[2], accLo[3], 0x7362);
+        m.B = __byte_perm(r0, r2, 0x5410); m.DOT = __byte_perm(r0, r2, 0x7632);
+        m.AT = __byte_perm(r1, r3, 0x5410); m.CL = __byte_perm(r1, r3, 0x7632);
       }
       {
-        const uint32_t t0 = __byte_perm(accHi[0], accHi[1], 0x5140), t1 = __byte_perm(accHi[0], accHi[1], 0x7362);
-        const uint32_t t2 = __byte_perm(accHi[2], accHi[3], 0x5140), t3 = __byte_perm(accHi[2], accHi[3], 0x7362);
-        m.NL = __byte_perm(t0, t2, 0x5410); m.DM = __byte_perm(t0, t2, 0x7632);
-        m.HX = __byte_perm(t1, t3, 0x5410); m.DASH = __byte_perm(t1, t3, 0x7632);
+        const uint32_t r0 = __byte_perm(accHi[0], accHi[1], 0x5140), r1 = __byte_perm(accHi[0], accHi[1], 0x7362);
+        const uint32_t r2 = __byte_perm(accHi[2], accHi[3], 0x5140), r3 = __byte_perm(accHi[2], accHi[3], 0x7362);
+        m.NL = __byte_perm(r0, r2, 0x5410); m.DM = __byte_perm(r0, r2, 0x7632);
+        m.HX = __byte_perm(r1, r3, 0x5410); m.DASH = __byte_perm(r1, r3, 0x7632);
       }
-      if ((uint64_t)tile_base + TILE_BYTES > a.n || tile_base < a.lo) {  // bytes outside [lo, n) behave like a boundary (chunk edge)
+      if (t == 0 || t == t_last) {  // only the chunk's first (lo < 16) and last tile can hold bytes outside [lo, n): they behave like a boundary (chunk edge)
         uint64_t valid = a.n > p ? a.n - p : 0;
         uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
         if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
