@@ -103,6 +103,10 @@ __device__ __forceinline__ uint32_t warp_excl_count4(uint32_t cnt, uint32_t lt_m
   return __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask) + 8 * __popc(b3 & lt_mask);
 }
 
+// FIXED = 0: the extractor flags come from a.flags; FIXED != 0: they are that compile-time constant (the `matchy match` default,
+// everything but the crypto-address words), which turns the per-tile flag tests and the branches behind them into nothing.
+static const uint32_t K1_DEFAULT_FLAGS = MGPU_X_DOMAINS | MGPU_X_EMAILS | MGPU_X_IPV4 | MGPU_X_IPV6 | MGPU_X_HASHES;
+template <uint32_t FIXED>
 __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   // class table replicated per lane: entry (b, lane) at b*256 + lane*8 -> every LDS.64 of a warp is conflict-free
@@ -136,11 +140,12 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   uint32_t lines = 0;
   if (t0 < t1) {
     TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
-    const bool want_dot = (a.flags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
-    const bool want_hash = (a.flags & MGPU_X_HASHES) != 0;
-    const bool want_at = (a.flags & MGPU_X_EMAILS) != 0;
-    const bool want_c2 = (a.flags & MGPU_X_IPV6) != 0;
-    const bool want_long = (a.flags & MGPU_X_CRYPTO) != 0;
+    const uint32_t xflags = FIXED ? FIXED : a.flags;
+    const bool want_dot = (xflags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
+    const bool want_hash = (xflags & MGPU_X_HASHES) != 0;
+    const bool want_at = (xflags & MGPU_X_EMAILS) != 0;
+    const bool want_c2 = (xflags & MGPU_X_IPV6) != 0;
+    const bool want_long = (xflags & MGPU_X_CRYPTO) != 0;
     // the next tile's slice is loaded into registers while the current one is processed (the buffer is readable one tile
     // past the chunk, see mgpu_scan_device), so the loads' latency never sits in front of the classification
     uint4 nx0 = ld_stream(a.buf + (uint32_t)(t0 * TILE_BYTES) + lane * SLICE_BYTES), nx1 = ld_stream(a.buf + (uint32_t)(t0 * TILE_BYTES) + lane * SLICE_BYTES + 16);
@@ -1360,7 +1365,8 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMalloc(&c->d_small_out, 64));
   CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
   CK(cudaFuncSetAttribute(token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOKEN_SMEM));
-  CK(cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
+  CK(cudaFuncSetAttribute(tokenize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
+  CK(cudaFuncSetAttribute(tokenize_kernel<K1_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
   return MGPU_OK;
 }
 
@@ -1533,7 +1539,8 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     if (grid < 1) grid = 1;
     a.nseg = (uint32_t)grid * K1_WARPS;
     size_t smem = 256 * 32 * 8;
-    tokenize_kernel<<<grid, K1_THREADS, smem, st>>>(a);
+    if (flags == K1_DEFAULT_FLAGS) tokenize_kernel<K1_DEFAULT_FLAGS><<<grid, K1_THREADS, smem, st>>>(a);
+    else tokenize_kernel<0><<<grid, K1_THREADS, smem, st>>>(a);
   }
   CK(cudaEventRecord(ev[1], st));
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
