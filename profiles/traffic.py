@@ -19,7 +19,7 @@ def val(r, k):
 
 out = {"source": sys.argv[3], "kernels": {}}
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0]
+    name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].strip()  # "void tokenize_kernel<31>(...)" -> tokenize_kernel
     key = NAMES.get(name)
     if key is None or key in out["kernels"]:
         continue
