@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
   uint32_t lines = 0;
   if (t0 < t1) {
     TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
+    // masks of the 32 bytes before the tile, as far as the tile's first bytes can see them (bit 31 = byte -1, bit 30 = byte -2)
+    uint32_t pDOT = (cy.prev & PV_DOT) ? 0x80000000u : 0u, pDASH = (cy.prev & PV_DASH) ? 0x80000000u : 0u;
+    uint32_t pCL = ((cy.prev & PV_CL1) ? 0x80000000u : 0u) | ((cy.prev & PV_CL2) ? 0x40000000u : 0u);
     const uint32_t xflags = FIXED ? FIXED : a.flags;
     const bool want_dot = (xflags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
     const bool want_hash = (xflags & MGPU_X_HASHES) != 0;
@@ -189,17 +192,20 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
         if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
         m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep; m.DASH &= keep;
       }
-      if (!(cy.prev & PV_T)) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
+      if ((int32_t)cy.prevB < 0) cy.open_start = tile_base;  // no word is open (the byte before the tile is a boundary): a word that fills the tile from its first byte starts here
       lines += __popc(m.NL);
 
       const uint32_t T = ~m.B;
-      const uint32_t my_prev = prev_bits_of(m);
-      uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, my_prev, 1);
-      if (lane == 0) pv = cy.prev;  // lane 0 looks into the previous tile
-      const uint32_t pT = pv & PV_T;
-      const uint32_t S = T & ~((T << 1) | pT);
+      // "the byte before byte i is ..." masks: the previous lane's mask funnel-shifted into mine (lane 0 looks into the
+      // previous tile) — one SHF per mask instead of packing five facts into a word on one side and unpacking them on the other
+      uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1), DOTp = __shfl_up_sync(0xFFFFFFFFu, m.DOT, 1);
+      uint32_t DASHp = __shfl_up_sync(0xFFFFFFFFu, m.DASH, 1), CLp = __shfl_up_sync(0xFFFFFFFFu, m.CL, 1);
+      if (lane == 0) { Bprev = cy.prevB; DOTp = pDOT; DASHp = pDASH; CLp = pCL; }
+      const uint32_t prevT = ~__funnelshift_l(Bprev, m.B, 1);  // bit i: byte i-1 is a word byte
+      const bool pT = (int32_t)Bprev >= 0;                      // the byte before my slice is a word byte
+      const uint32_t S = T & ~prevT;
       uint32_t bad, bad_end;
-      domain_rule_masks(m, S, pv, bad, bad_end);
+      domain_rule_masks_prev(m, S, __funnelshift_l(DOTp, m.DOT, 1), __funnelshift_l(DASHp, m.DASH, 1), bad, bad_end);
 
       // four "does the word contain ..." chains: a byte that rules out a domain, a '.', a non-hex byte, a byte that is
       // neither a hex digit nor a '.'
@@ -212,20 +218,18 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
       const uint32_t cv1 = carry_chain(G1, pb & ~G1, cy.cBad, co1), cv2 = carry_chain(G2, pb & ~G2, cy.cDot, co2), cv3 = carry_chain(G3, pb & ~G3, cy.cNhx, co3);
       const uint32_t cv4 = carry_chain(G4, pb & ~G4, cy.cNhd, co4);
       cy.cBad = co1; cy.cDot = co2; cy.cNhx = co3; cy.cNhd = co4;
-      const uint32_t E = m.B & ((T << 1) | pT);  // boundaries that end a word
+      const uint32_t E = m.B & prevT;  // boundaries that end a word
       const uint32_t hasBad = chain_ends(T, Y1, (cv1 >> lane) & 1u, m.B), hasDot = chain_ends(T, Y2, (cv2 >> lane) & 1u, m.B);
       const uint32_t hasNhx = chain_ends(T, Y3, (cv3 >> lane) & 1u, m.B), hasNhd = chain_ends(T, Y4, (cv4 >> lane) & 1u, m.B);
       const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
       // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
       uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
-      uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1);
-      if (lane == 0) Bprev = cy.prevB;
       // ... and at least 32 bytes long: the previous slice has no boundary at or above the bit position where the word ends here
       if (candHex && (Bprev >> (__ffs(candHex) - 1)) != 0) candHex = 0;
       const uint32_t candLong = want_long ? long_word_ends(T, ~Bprev, E) : 0u;  // words of >= 26 bytes (crypto-address candidates)
       const uint32_t candAt = want_at ? m.AT : 0u;
       // second colon of the FIRST "::" of a colon run: ':' at i and i-1, not at i-2
-      const uint32_t cl1 = (m.CL << 1) | ((pv >> 3) & 1u), cl2 = (m.CL << 2) | (((pv >> 3) & 1u) << 1) | ((pv >> 4) & 1u);
+      const uint32_t cl1 = __funnelshift_l(CLp, m.CL, 1), cl2 = __funnelshift_l(CLp, m.CL, 2);
       const uint32_t candC2 = want_c2 ? (m.CL & cl1 & ~cl2) : 0u;
 
       // where the word that is open at the start of my slice begins
@@ -324,8 +328,8 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
         const uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
         cy.open_start = tile_base + ll * 32 + top_bit(Bl) + 1;
       }
-      cy.prev = __shfl_sync(0xFFFFFFFFu, my_prev, 31);
       cy.prevB = __shfl_sync(0xFFFFFFFFu, m.B, 31);
+      pDOT = __shfl_sync(0xFFFFFFFFu, m.DOT, 31); pDASH = __shfl_sync(0xFFFFFFFFu, m.DASH, 31); pCL = __shfl_sync(0xFFFFFFFFu, m.CL, 31);
     }
   }
   if (lane == 0) {

@@ -55,10 +55,13 @@ MGPU_HD uint32_t prev_bits_of(const LaneMasks& m) {  // the same facts about a s
 // Domain label rules as byte-adjacency facts (is_valid_domain / is_valid_label, lib.rs:637-689): no empty label ("..",
 // leading or trailing '.'), no label starting or ending with '-'.  `bad` marks bytes that break a rule when looking back;
 // `bad_end` marks boundary positions whose preceding byte may not end a domain.
-MGPU_HD void domain_rule_masks(const LaneMasks& m, uint32_t S, uint32_t pv, uint32_t& bad, uint32_t& bad_end) {
-  uint32_t prevDOT = (m.DOT << 1) | ((pv >> 1) & 1u), prevDASH = (m.DASH << 1) | ((pv >> 2) & 1u);
+// (prevDOT / prevDASH: bit i = byte i-1 is '.' / '-')
+MGPU_HD void domain_rule_masks_prev(const LaneMasks& m, uint32_t S, uint32_t prevDOT, uint32_t prevDASH, uint32_t& bad, uint32_t& bad_end) {
   bad = (m.DOT & (prevDOT | prevDASH)) | (m.DASH & prevDOT) | (S & (m.DOT | m.DASH));
   bad_end = prevDOT | prevDASH;
+}
+MGPU_HD void domain_rule_masks(const LaneMasks& m, uint32_t S, uint32_t pv, uint32_t& bad, uint32_t& bad_end) {
+  domain_rule_masks_prev(m, S, (m.DOT << 1) | ((pv >> 1) & 1u), (m.DASH << 1) | ((pv >> 2) & 1u), bad, bad_end);
 }
 
 // "Does the word that ends here contain a byte of Y?" for every word at once.  T = ~B marks word bytes, Y is a subset
