@@ -86,11 +86,11 @@ __device__ __forceinline__ uint4 ld_stream(const uint8_t* p) {
   return r;
 }
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+// inclusive prefix sum over the lanes; the shuffle's own "source lane in range" predicate guards the add (no compare per step)
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t /*lane*/) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
-    if (lane >= (uint32_t)d) v += t;
+    asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(v) : "r"(d));
   }
   return v;
 }
@@ -243,23 +243,33 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
         // dotted words of hex digits and dots only go to the numeric queue (IPv4 candidates), the rest to the dotted queue;
         // one scan serves both (counts packed in the two halves of a word)
         const uint32_t candNum = candDot & ~hasNhd;
-        const uint32_t cnt = __popc(candNum) | (__popc(candDot & hasNhd) << 16), incl = warp_incl_scan(cnt, lane);
+        const uint32_t cnt_n = __popc(candNum), cnt = cnt_n | ((__popc(candDot) - cnt_n) << 16), incl = warp_incl_scan(cnt, lane);
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - cnt;
         if (total) {
           const uint32_t tn = total & 0xFFFFu, td = total >> 16;
           const bool okn = nn + tn <= a.seg_cap[Q_NUMERIC], okd = nd + td <= a.seg_cap[Q_DOTTED];
           Cand* dn = qn + nn + (excl & 0xFFFFu);
           Cand* dd = qd + nd + (excl >> 16);
-          for (uint32_t mm = candDot; mm; mm &= mm - 1) {
-            const uint32_t bit = __ffs(mm) - 1;
-            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
-            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
-            const Cand c{s, p + bit - s};
-            if ((candNum >> bit) & 1u) { if (okn) *dn++ = c; }
-            else if (okd) *dd++ = c;
+          if (okn && okd) {  // (the usual case: no capacity test per store)
+            for (uint32_t mm = candDot; mm; mm &= mm - 1) {
+              const uint32_t low = mm & (0u - mm), bit = __ffs(mm) - 1;
+              const uint32_t below = m.B & (low - 1u);
+              const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+              const Cand c{s, p + bit - s};
+              if (candNum & low) *dn++ = c; else *dd++ = c;
+            }
+          } else {
+            for (uint32_t mm = candDot; mm; mm &= mm - 1) {
+              const uint32_t bit = __ffs(mm) - 1;
+              const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+              const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+              const Cand c{s, p + bit - s};
+              if ((candNum >> bit) & 1u) { if (okn) *dn++ = c; }
+              else if (okd) *dd++ = c;
+            }
+            if (!okn) ovf |= 1u << Q_NUMERIC;
+            if (!okd) ovf |= 1u << Q_DOTTED;
           }
-          if (!okn) ovf |= 1u << Q_NUMERIC;
-          if (!okd) ovf |= 1u << Q_DOTTED;
           nn += tn; nd += td;
         }
       }
@@ -283,9 +293,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
         }
         if (__any_sync(0xFFFFFFFFu, candAt != 0)) {
           // up to 32 '@' per slice: prefix by shuffle scan
-          uint32_t cnt = __popc(candAt), incl = cnt;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+          const uint32_t cnt = __popc(candAt), incl = warp_incl_scan(cnt, lane);
           const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
           if (na + total <= a.seg_cap[Q_AT]) {
             uint32_t idx = na + incl - cnt;
@@ -310,9 +318,7 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
           }
         }
         if (__any_sync(0xFFFFFFFFu, candC2 != 0)) {
-          uint32_t cnt = __popc(candC2), incl = cnt;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+          const uint32_t cnt = __popc(candC2), incl = warp_incl_scan(cnt, lane);
           const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
           if (nc + total <= a.seg_cap[Q_COLON2]) {
             uint32_t idx = nc + incl - cnt;
