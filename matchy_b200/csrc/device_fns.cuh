@@ -114,16 +114,21 @@ MGPU_HD uint32_t tld_slot(uint64_t key) {
 //                                     (n, first K, last K bytes) for the cold filter (TAG_LIT_FULL)
 MGPU_HD uint32_t glob_key_len(uint32_t m) { return m < 4 ? m : (m >= 16 ? 16u : (m & ~3u)); }
 MGPU_HD uint32_t lit_key_len(uint32_t n) { return n >= 8 ? 8u : (n >= 4 ? 4u : n); }
-MGPU_HD uint32_t key_seed(uint32_t tag) { return 0x811C9DC5u ^ (tag * 0x632BE5ABu); }
+// The running state depends only on the DIRECTION the words are fed in (tail keys: TAG_GLOB_S, TAG_LIT_TAIL; head keys:
+// TAG_GLOB_P, TAG_LIT_HEAD), the tag class enters in key_fin: a token's suffix-gate key and its literal tail key share their
+// key_mix steps, and so do the prefix-gate key and the literal head key.
+MGPU_HD uint32_t key_seed(uint32_t tag) {
+  return tag == TAG_LIT_FULL ? 0x811C9DC5u ^ (4u * 0x632BE5ABu) : ((tag == TAG_GLOB_S || tag == TAG_LIT_TAIL) ? 0x811C9DC5u : 0x811C9DC5u ^ 0x632BE5ABu);
+}
 MGPU_HD uint32_t key_mix(uint32_t s, uint32_t w) { s = (s ^ w) * 0x9E3779B1u; return s ^ (s >> 15); }
 // one more multiply-xorshift round per key; k separates keys of different lengths that feed identical words
-MGPU_HD uint32_t key_fin(uint32_t s, uint32_t k) { s = (s ^ (k * 0x7F4A7C15u)) * 0x85EBCA77u; return s ^ (s >> 15); }
+MGPU_HD uint32_t key_fin(uint32_t s, uint32_t k, uint32_t tag) { s = (s ^ (k * 0x7F4A7C15u + tag * 0x2C1B3C6Du)) * 0x85EBCA77u; return s ^ (s >> 15); }
 MGPU_HD uint32_t low_bytes32(uint32_t w, uint32_t k) { return k >= 4 ? w : (w & ((1u << (8 * k)) - 1u)); }
 // hash of a whole key given its words in feeding order (host side: database preparation)
 MGPU_HD uint32_t key_hash_words(const uint32_t* words, uint32_t k, uint32_t tag) {
   uint32_t s = key_seed(tag);
   for (uint32_t i = 0; i < (k + 3) / 4; i++) s = key_mix(s, words[i]);
-  return key_fin(s, k);
+  return key_fin(s, k, tag);
 }
 // hot filter: blocked Bloom, 2 bits in one 32-bit word.  cold filter: blocked Bloom, 3 bits in one 64-bit word; its word
 // index and bit positions come from a second mix of the same key hash, so one hash per key serves both filters.
@@ -613,14 +618,17 @@ enum { G_LIT = 1u, G_S = 2u, G_P = 4u, G_GEN = 8u };
 template <typename H>
 MGPU_HDN uint32_t string_gate(const DbView& db, const H& hot, const KeyWords& kw, uint32_t n) {
   uint32_t g = 0;
+  // the two running states every key of this stage is cut from: last words back to front, first words front to back
+  const uint32_t c1 = key_mix(key_seed(TAG_GLOB_S), kw.t[3]), c2 = key_mix(c1, kw.t[2]);
+  const uint32_t d1 = key_mix(key_seed(TAG_GLOB_P), kw.h[0]), d2 = key_mix(d1, kw.h[1]);
   if (db.has_literal) {  // some stored literal has the same last K and the same first K bytes (K = lit_key_len(n))
     const uint32_t k = lit_key_len(n);
     uint32_t st, sh;  // tail / head states
-    if (k == 8) { st = key_mix(key_mix(key_seed(TAG_LIT_TAIL), kw.t[3]), kw.t[2]); sh = key_mix(key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]), kw.h[1]); }
-    else if (k == 4) { st = key_mix(key_seed(TAG_LIT_TAIL), kw.t[3]); sh = key_mix(key_seed(TAG_LIT_HEAD), kw.h[0]); }
+    if (k == 8) { st = c2; sh = d2; }
+    else if (k == 4) { st = c1; sh = d1; }
     else { const uint32_t x = low_bytes32(kw.h[0], k); st = key_mix(key_seed(TAG_LIT_TAIL), x); sh = key_mix(key_seed(TAG_LIT_HEAD), x); }  // n < 4: head == tail
-    bool pass = !((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, key_fin(st, k));
-    pass = pass && (!((db.hot_tags >> TAG_LIT_HEAD) & 1u) || hot_test(hot, key_fin(sh, k)));
+    bool pass = !((db.hot_tags >> TAG_LIT_TAIL) & 1u) || hot_test(hot, key_fin(st, k, TAG_LIT_TAIL));
+    pass = pass && (!((db.hot_tags >> TAG_LIT_HEAD) & 1u) || hot_test(hot, key_fin(sh, k, TAG_LIT_HEAD)));
     if (pass) g |= G_LIT;
   }
   if (db.has_glob) {
@@ -632,15 +640,15 @@ MGPU_HDN uint32_t string_gate(const DbView& db, const H& hot, const KeyWords& kw
           for (uint32_t k = 1; k <= 3; k++) {
             if (!((lens >> k) & 1u) || k > n) continue;
             const uint32_t x = n >= 4 ? (kw.t[3] >> (8 * (4 - k))) : (low_bytes32(kw.h[0], n) >> (8 * (n - k)));
-            if (hot_test(hot, key_fin(key_mix(key_seed(TAG_GLOB_S), x), k))) g |= G_S;
+            if (hot_test(hot, key_fin(key_mix(key_seed(TAG_GLOB_S), x), k, TAG_GLOB_S))) g |= G_S;
           }
         }
         const uint32_t gs = db.glob_s_gate;
         if (gs && n >= gs) {
-          uint32_t s = key_seed(TAG_GLOB_S);
-#pragma unroll
-          for (uint32_t j = 0; j < 4; j++) if (4 * j < gs) s = key_mix(s, kw.t[3 - j]);
-          if (hot_test(hot, key_fin(s, gs))) g |= G_S;
+          uint32_t s = gs == 4 ? c1 : c2;
+          if (gs >= 12) s = key_mix(s, kw.t[1]);
+          if (gs >= 16) s = key_mix(s, kw.t[0]);
+          if (hot_test(hot, key_fin(s, gs, TAG_GLOB_S))) g |= G_S;
         }
       }
     }
@@ -651,15 +659,15 @@ MGPU_HDN uint32_t string_gate(const DbView& db, const H& hot, const KeyWords& kw
         if (lens & 0xEu) {
           for (uint32_t k = 1; k <= 3; k++) {
             if (!((lens >> k) & 1u) || k > n) continue;
-            if (hot_test(hot, key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k))) g |= G_P;
+            if (hot_test(hot, key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k, TAG_GLOB_P))) g |= G_P;
           }
         }
         const uint32_t gp = db.glob_p_gate;
         if (gp && n >= gp) {
-          uint32_t s = key_seed(TAG_GLOB_P);
-#pragma unroll
-          for (uint32_t j = 0; j < 4; j++) if (4 * j < gp) s = key_mix(s, kw.h[j]);
-          if (hot_test(hot, key_fin(s, gp))) g |= G_P;
+          uint32_t s = gp == 4 ? d1 : d2;
+          if (gp >= 12) s = key_mix(s, kw.h[2]);
+          if (gp >= 16) s = key_mix(s, kw.h[3]);
+          if (hot_test(hot, key_fin(s, gp, TAG_GLOB_P))) g |= G_P;
         }
       }
     }
@@ -681,7 +689,7 @@ MGPU_HDN uint32_t string_filters_full(const DbView& db, const H& hot, const KeyW
     uint32_t s = sh ^ key_seed(TAG_LIT_FULL);
     if (k == 8) s = key_mix(key_mix(s, kw.t[3]), kw.t[2]);
     else if (k == 4) s = key_mix(s, kw.t[3]);
-    if (cold_test(db.cold, db.cold_mask, key_fin(s, n))) flags |= F_LIT;
+    if (cold_test(db.cold, db.cold_mask, key_fin(s, n, TAG_LIT_FULL))) flags |= F_LIT;
   }
   if (g & G_S) {  // every key length present in the database, shortest first, straight to the cold filter
     const uint32_t lens = db.glob_s_lens;
@@ -689,7 +697,7 @@ MGPU_HDN uint32_t string_filters_full(const DbView& db, const H& hot, const KeyW
       for (uint32_t k = 1; k <= 3; k++) {
         if (!((lens >> k) & 1u) || k > n) continue;
         const uint32_t x = n >= 4 ? (kw.t[3] >> (8 * (4 - k))) : (low_bytes32(kw.h[0], n) >> (8 * (n - k)));
-        if (cold_test(db.cold, db.cold_mask, key_fin(key_mix(key_seed(TAG_GLOB_S), x), k))) flags |= F_GLOB;
+        if (cold_test(db.cold, db.cold_mask, key_fin(key_mix(key_seed(TAG_GLOB_S), x), k, TAG_GLOB_S))) flags |= F_GLOB;
       }
     }
     uint32_t s = key_seed(TAG_GLOB_S);
@@ -698,7 +706,7 @@ MGPU_HDN uint32_t string_filters_full(const DbView& db, const H& hot, const KeyW
       const uint32_t k = 4 * (j + 1);
       if ((lens >> k) == 0 || k > n || (flags & F_GLOB)) break;
       s = key_mix(s, kw.t[3 - j]);
-      if (((lens >> k) & 1u) && cold_test(db.cold, db.cold_mask, key_fin(s, k))) flags |= F_GLOB;
+      if (((lens >> k) & 1u) && cold_test(db.cold, db.cold_mask, key_fin(s, k, TAG_GLOB_S))) flags |= F_GLOB;
     }
   }
   if ((g & G_P) && !(flags & F_GLOB)) {
@@ -706,7 +714,7 @@ MGPU_HDN uint32_t string_filters_full(const DbView& db, const H& hot, const KeyW
     if (lens & 0xEu) {
       for (uint32_t k = 1; k <= 3; k++) {
         if (!((lens >> k) & 1u) || k > n) continue;
-        if (cold_test(db.cold, db.cold_mask, key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k))) flags |= F_GLOB;
+        if (cold_test(db.cold, db.cold_mask, key_fin(key_mix(key_seed(TAG_GLOB_P), low_bytes32(kw.h[0], k)), k, TAG_GLOB_P))) flags |= F_GLOB;
       }
     }
     uint32_t s = key_seed(TAG_GLOB_P);
@@ -715,7 +723,7 @@ MGPU_HDN uint32_t string_filters_full(const DbView& db, const H& hot, const KeyW
       const uint32_t k = 4 * (j + 1);
       if ((lens >> k) == 0 || k > n || (flags & F_GLOB)) break;
       s = key_mix(s, kw.h[j]);
-      if (((lens >> k) & 1u) && cold_test(db.cold, db.cold_mask, key_fin(s, k))) flags |= F_GLOB;
+      if (((lens >> k) & 1u) && cold_test(db.cold, db.cold_mask, key_fin(s, k, TAG_GLOB_P))) flags |= F_GLOB;
     }
   }
   if ((g & G_GEN) && !(flags & F_GLOB) && generic_literal_scan(db, hot, bytes, n)) flags |= F_GLOB;
@@ -739,15 +747,15 @@ MGPU_HD uint32_t bytes_le32(const uint8_t* p, uint32_t k) { uint32_t v = 0; for 
 MGPU_HD uint32_t glob_key_hash(const uint8_t* lit, uint32_t m, uint32_t tag) {  // tag: TAG_GLOB_S (last bytes) or TAG_GLOB_P (first bytes)
   const uint32_t k = glob_key_len(m);
   uint32_t s = key_seed(tag);
-  if (k < 4) return key_fin(key_mix(s, bytes_le32(tag == TAG_GLOB_S ? lit + m - k : lit, k)), k);
+  if (k < 4) return key_fin(key_mix(s, bytes_le32(tag == TAG_GLOB_S ? lit + m - k : lit, k)), k, tag);
   for (uint32_t j = 0; j < k / 4; j++) s = key_mix(s, tag == TAG_GLOB_S ? bytes_le32(lit + m - 4 * (j + 1), 4) : bytes_le32(lit + 4 * j, 4));
-  return key_fin(s, k);
+  return key_fin(s, k, tag);
 }
 // the gate key of a glob anchor literal whose own key has K >= 4 bytes: its last / first g bytes (g in {4, 8, 12, 16}, g <= K)
 MGPU_HD uint32_t glob_gate_hash(const uint8_t* lit, uint32_t m, uint32_t g, uint32_t tag) {
   uint32_t s = key_seed(tag);
   for (uint32_t j = 0; j < g / 4; j++) s = key_mix(s, tag == TAG_GLOB_S ? bytes_le32(lit + m - 4 * (j + 1), 4) : bytes_le32(lit + 4 * j, 4));
-  return key_fin(s, g);
+  return key_fin(s, g, tag);
 }
 MGPU_HD void lit_key_hashes(const uint8_t* str, uint32_t n, uint32_t& tail_h, uint32_t& head_h, uint32_t& full_h) {
   const uint32_t k = lit_key_len(n);
@@ -755,11 +763,11 @@ MGPU_HD void lit_key_hashes(const uint8_t* str, uint32_t n, uint32_t& tail_h, ui
   if (k == 8) { st = key_mix(key_mix(st, bytes_le32(str + n - 4, 4)), bytes_le32(str + n - 8, 4)); sh = key_mix(key_mix(sh, bytes_le32(str, 4)), bytes_le32(str + 4, 4)); }
   else if (k == 4) { st = key_mix(st, bytes_le32(str + n - 4, 4)); sh = key_mix(sh, bytes_le32(str, 4)); }
   else { const uint32_t x = bytes_le32(str, k); st = key_mix(st, x); sh = key_mix(sh, x); }
-  tail_h = key_fin(st, k); head_h = key_fin(sh, k);
+  tail_h = key_fin(st, k, TAG_LIT_TAIL); head_h = key_fin(sh, k, TAG_LIT_HEAD);
   uint32_t s = sh ^ key_seed(TAG_LIT_FULL);
   if (k == 8) s = key_mix(key_mix(s, bytes_le32(str + n - 4, 4)), bytes_le32(str + n - 8, 4));
   else if (k == 4) s = key_mix(s, bytes_le32(str + n - 4, 4));
-  full_h = key_fin(s, n);
+  full_h = key_fin(s, n, TAG_LIT_FULL);
 }
 
 // extract_email_at: buf[lo..n) is the chunk, at = position of '@'.
