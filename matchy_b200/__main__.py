@@ -116,8 +116,11 @@ def cmd_extract(a):
         buf = []
         for t, s, e in items.tolist():
             text = raw[s:e]
-            if a.show_candidates:
-                print("[CANDIDATE] %s at ...: %s" % (ITEM_TYPE_NAMES[t], text.decode("utf-8", "replace")), file=sys.stderr)
+            if a.show_candidates:  # spans are relative to the trimmed line, like the reference's (extract_cmd.rs:229-237)
+                ls = raw.rfind(b"\n", 0, s) + 1
+                while ls < s and raw[ls] in b" \t\x0c\r":
+                    ls += 1
+                print("[CANDIDATE] %s at %d-%d: %s" % (ITEM_TYPE_NAMES[t], s - ls, e - ls, text.decode("utf-8", "replace")), file=sys.stderr)
             if seen is not None:
                 if text in seen:
                     continue
