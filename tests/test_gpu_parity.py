@@ -425,6 +425,13 @@ def test_extract_subcommand_matches_per_line_oracle(built, small_dbs, tmp_path, 
         assert got.out == want, args
         assert want.count(b"\n") > 100
         assert ("Lines processed: %s" % format(lines, ",")).encode() in got.err
+    small = tmp_path / "small.log"
+    small.write_bytes(b"\x0cevil.com after a form feed\n  \t padded.example.org 10.1.2.3\n")
+    capfdbinary.readouterr()
+    assert main(["extract", str(small), "--format", "text", "--show-candidates"]) == 0
+    got = capfdbinary.readouterr()
+    assert got.out == b"evil.com\npadded.example.org\n10.1.2.3\n"
+    assert b"[CANDIDATE] Domain at 0-8: evil.com" in got.err and b"[CANDIDATE] IPv4 at 19-27: 10.1.2.3" in got.err  # spans index the trimmed line
     assert main(["extract", str(path), "--format", "xml"]) == 1
     assert main(["extract", str(path), "--types", "bogus"]) == 1
 
