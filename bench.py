@@ -169,6 +169,32 @@ def cpu_port_throughput(db, cfg, scale, threads, target_seconds=12.0, offset_blo
     return sample.size / dt / 1e9, int(sample.size), cores, cnt
 
 
+def parity_gate(eng, db, host, nbytes, flags, base, record_bytes, cores=0):
+    """BASELINE.md §4.4, untimed: the engine's result of its last scan of this resident shard (counters over ALL of it,
+    records over its first `record_bytes`) against the CPU oracle on the same bytes.  Returns the `parity` object of the
+    JSON line; the caller exits non-zero when something differs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib
+    orc = oracle_lib.Oracle(db)
+    t0 = time.perf_counter()
+    got_cnt = eng.counters_list()
+    recs, ids = eng.results()
+    want_cnt = orc.scan_mt(host[:nbytes], flags=flags, threads=cores)
+    counters_equal = got_cnt == want_cnt
+    record_bytes = min(record_bytes, nbytes) // 65536 * 65536  # generator blocks end with a newline
+    want_recs, want_ids, _ = orc.scan_mt_keep(host[:record_bytes], flags=flags, threads=cores, base=base)
+    k = int(np.searchsorted(recs["offset"], base + record_bytes, side="left")) if len(recs) else 0
+    sub = recs[:k]
+    pat = sub[sub["kind"] == 2]
+    n_ids = int(pat["ids_index"][-1]) + int(pat["n_ids"][-1]) if len(pat) else 0
+    records_equal = len(sub) == len(want_recs) and sub.tobytes() == want_recs.tobytes() and ids[:n_ids].tobytes() == want_ids.tobytes()
+    return {"bytes_counted": int(nbytes), "bytes_compared": int(record_bytes), "counters_equal": bool(counters_equal),
+            "records_equal": bool(records_equal), "records_compared": int(len(want_recs)), "id_pairs_compared": int(len(want_ids)),
+            "oracle": "oracle/oracle.cpp (CPU restatement of matchy v1.2.2), all host cores", "seconds": round(time.perf_counter() - t0, 1),
+            "counters": {"gpu": got_cnt, "oracle": want_cnt} if not counters_equal else None}
+
+
 def run_reference(args):
     """The reference arm: CPU matcher on the host cores, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -242,6 +268,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--crypto", action="store_true", help="also run the Bitcoin/Ethereum/Monero extractors (matchy match without --extractors=-crypto)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed full-size parity gate against the CPU oracle")
+    ap.add_argument("--parity-gb", type=float, default=2.2, help="bytes of the shard whose RECORDS are compared with the oracle's (counters are compared over all of it)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -325,6 +353,11 @@ def main():
     total_bytes = nbytes * world * args.steps
     value = total_bytes / dev_s / 1e9
 
+    # ---- parity gate at the benchmarked size (untimed; rank 0's shard) ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_gate(eng, db, host, nbytes, flags, rank * nbytes, int(args.parity_gb * 1e9))
+
     # ---- end to end through the C ABI with host buffers ("e2e") ----
     e2e = None
     if not args.no_e2e:
@@ -376,7 +409,7 @@ def main():
             "lines_per_s": tot[0] * args.steps / dev_s, "matches_per_s": tot[3] * args.steps / dev_s,
             "counters": {"lines": tot[0], "bytes": tot[1], "candidates": tot[2], "matches": tot[3]},
             "wall_s_timed_region": wall_s,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
         }
         _emit(line)
     eng.dev_free(dev)
@@ -384,6 +417,9 @@ def main():
     eng.close()
     if dist:
         dist.destroy_process_group()
+    if parity is not None and not (parity["counters_equal"] and parity["records_equal"]):
+        sys.stderr.write("PARITY FAILURE: %r\n" % (parity,))
+        return 3
     return 0
 
 

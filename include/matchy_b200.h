@@ -133,6 +133,13 @@ void mgpu_set_keep_results(mgpu_ctx*, int keep); /* 0: count matches only (bench
  * walks when provably identical), 1 = generic kernels with the reference's Aho-Corasick goto/failure walk, 2 = generic
  * kernels with anchored walks.  Results are identical in every mode; the switch exists for tests. */
 void mgpu_set_ac_mode(mgpu_ctx*, int mode);
+/* Test / debug switches, never needed for results: "tok_reserve" (slots per token-list reservation), "cap_str" / "cap_ip" /
+ * "cap_rec" / "cap_ids" (pretend the work buffers are this small: drives the overflow -> split-and-redo path; 0 restores),
+ * "verify_tokens" (audit every piece's IP token list on the device; mgpu_debug_get returns the sums: slots still poisoned,
+ * padding slots, IPv4 tokens, IPv6 tokens, lookup hits, slots of unknown type, slots audited, 0; then the IP-trie kernel's own
+ * sums: hits per thread, per warp ballot, per block) ; "variant": experiment switches inside kernels, 0 in production. */
+int mgpu_set_option(mgpu_ctx*, const char* key, uint64_t value);
+int mgpu_debug_get(mgpu_ctx*, uint64_t out[64]);
 
 /* Extraction only (== Extractor::extract_from_chunk): triples (item_type, start, end) as uint64, sorted by
  * (start, item_type).  Returns the number of items (may exceed cap; only cap are written). */

@@ -55,6 +55,8 @@ SYMBOLS = {
     "mgpu_timing_get": (C.c_int, [_VP, C.POINTER(MgpuTiming)]),
     "mgpu_set_keep_results": (None, [_VP, C.c_int]),
     "mgpu_set_ac_mode": (None, [_VP, C.c_int]),
+    "mgpu_set_option": (C.c_int, [_VP, C.c_char_p, C.c_uint64]),
+    "mgpu_debug_get": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "mgpu_extract": (C.c_int64, [_VP, _U8P, _SZ, C.c_uint32, C.POINTER(C.c_uint64), _SZ]),
     "mgpu_lookup_string": (C.c_int, [_VP, _U8P, _SZ, C.POINTER(MgpuIdPair), _SZ]),
     "mgpu_lookup_ip": (C.c_int, [_VP, _U8P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]),

@@ -947,45 +947,61 @@ MGPU_HD uint32_t tree_record(const DbView& db, uint32_t node, uint32_t side) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
   }
 }
+// The walk as a resumable state machine: trie_walk_begin() consults the jump table, trie_walk_step() reads ONE record.
+// The IP-trie kernel advances all lanes of a warp in lock step (a few steps per round), so that no lane sits in a
+// 100-step serial walk while the rest of its warp waits; trie_lookup_v4 / _v6 below are the same machine run to the end.
+// Address bits as IpTok words: bit bi (0 = most significant) is bit 31 - (bi & 31) of w[bi >> 5]; an IPv4 address is w[0].
+enum { TRIE_MISS = 0, TRIE_HIT = 1, TRIE_MORE = 2 };
+struct TrieWalk { uint32_t node, bi, end; };
+MGPU_HD uint32_t trie_addr_bit(const uint32_t w[4], uint32_t bi) {
+  const uint32_t k = bi >> 5;
+  const uint32_t word = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
+  return (word >> (31u - (bi & 31u))) & 1u;
+}
+MGPU_HD int trie_walk_begin(const DbView& db, const uint32_t w[4], bool v6, TrieWalk& s, uint32_t& data_off, uint8_t& prefix) {
+  if (!v6) {
+    s.node = db.ip_version == 6 ? db.v4_start_node : 0; s.bi = 0; s.end = 32;
+    if (db.v4_top16) {  // sixteen / twenty dependent node reads in one table read
+      const uint32_t tb = db.v4_top_bits, idx = w[0] >> (32 - tb);
+      const uint32_t e = db.v4_top16[idx], kind = e >> 28;
+      if (kind == 1) return TRIE_MISS;
+      if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v4_top16_depth[idx]; return TRIE_HIT; }
+      s.node = e & 0x0FFFFFFFu; s.bi = tb;
+    }
+  } else {
+    s.node = 0; s.bi = 0; s.end = 128;
+    if (db.v6_top16) {
+      const uint32_t idx = w[0] >> 16;
+      const uint32_t e = db.v6_top16[idx], kind = e >> 28;
+      if (kind == 1) return TRIE_MISS;
+      if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v6_top16_depth[idx]; return TRIE_HIT; }
+      s.node = e & 0x0FFFFFFFu; s.bi = 16;
+    }
+  }
+  return s.bi < s.end ? TRIE_MORE : TRIE_MISS;
+}
+MGPU_HD int trie_walk_step(const DbView& db, const uint32_t w[4], TrieWalk& s, uint32_t& data_off, uint8_t& prefix) {
+  const uint32_t rec = tree_record(db, s.node, trie_addr_bit(w, s.bi));
+  if (rec == db.node_count) return TRIE_MISS;
+  if (rec < db.node_count) { s.node = rec; s.bi++; return s.bi < s.end ? TRIE_MORE : TRIE_MISS; }
+  data_off = rec - db.node_count - 16;
+  prefix = (uint8_t)(s.bi + 1);  // depth counts one per address bit in both tree kinds (96 is subtracted again, tree.rs:76-80)
+  return TRIE_HIT;
+}
+MGPU_HDN bool trie_lookup_words(const DbView& db, const uint32_t w[4], bool v6, uint32_t& data_off, uint8_t& prefix) {
+  TrieWalk s;
+  int r = trie_walk_begin(db, w, v6, s, data_off, prefix);
+  while (r == TRIE_MORE) r = trie_walk_step(db, w, s, data_off, prefix);
+  return r == TRIE_HIT;
+}
 MGPU_HDN bool trie_lookup_v4(const DbView& db, uint32_t bits, uint32_t& data_off, uint8_t& prefix) {
-  uint32_t node = db.ip_version == 6 ? db.v4_start_node : 0;
-  uint32_t bi = 0;
-  if (db.v4_top16) {  // sixteen / twenty dependent node reads in one table read
-    const uint32_t tb = db.v4_top_bits, idx = bits >> (32 - tb);
-    const uint32_t e = db.v4_top16[idx], kind = e >> 28;
-    if (kind == 1) return false;
-    if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v4_top16_depth[idx]; return true; }
-    node = e & 0x0FFFFFFFu;
-    bi = tb;
-  }
-  for (; bi < 32; bi++) {
-    uint32_t rec = tree_record(db, node, (bits >> (31 - bi)) & 1);
-    if (rec == db.node_count) return false;
-    if (rec < db.node_count) { node = rec; continue; }
-    data_off = rec - db.node_count - 16;
-    prefix = (uint8_t)(bi + 1);  // depth counts one per address bit in both tree kinds (96 is subtracted again, tree.rs:76-80)
-    return true;
-  }
-  return false;
+  const uint32_t w[4] = {bits, 0, 0, 0};
+  return trie_lookup_words(db, w, false, data_off, prefix);
 }
 MGPU_HDN bool trie_lookup_v6(const DbView& db, const uint16_t seg[8], uint32_t& data_off, uint8_t& prefix) {
-  uint32_t node = 0, bi = 0;
-  if (db.v6_top16) {
-    const uint32_t e = db.v6_top16[seg[0]], kind = e >> 28;
-    if (kind == 1) return false;
-    if (kind == 2) { data_off = (e & 0x0FFFFFFFu) - db.node_count - 16; prefix = db.v6_top16_depth[seg[0]]; return true; }
-    node = e & 0x0FFFFFFFu;
-    bi = 16;
-  }
-  for (; bi < 128; bi++) {
-    uint32_t rec = tree_record(db, node, (seg[bi >> 4] >> (15 - (bi & 15))) & 1);
-    if (rec == db.node_count) return false;
-    if (rec < db.node_count) { node = rec; continue; }
-    data_off = rec - db.node_count - 16;
-    prefix = (uint8_t)(bi + 1);
-    return true;
-  }
-  return false;
+  uint32_t w[4];
+  for (int k = 0; k < 4; k++) w[k] = ((uint32_t)seg[2 * k] << 16) | seg[2 * k + 1];
+  return trie_lookup_words(db, w, true, data_off, prefix);
 }
 
 // =================================================================================================

@@ -72,6 +72,9 @@ struct ScanArgs {
   mgpu_id_pair* ids; uint32_t cap_ids;
   DevCounters* ctr;
   ScanTotals* tot;
+  uint32_t tok_unit;   // slots a token-kernel warp takes from a token list per trip to its counter (TOK_RESERVE unless a test overrides it)
+  unsigned long long* dbg;  // audit accumulators (mgpu_set_option "verify_tokens"), else nullptr
+  uint32_t variant;         // experiment switch (mgpu_set_option "variant"), 0 in production
 };
 
 static const int K1_THREADS = 512;
@@ -385,10 +388,10 @@ static const uint32_t TOK_INVALID = 0xFFu;  // StrTok.type / IpTok.type of a pad
 struct QueueCursor { uint32_t base, left; };
 
 __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap, uint32_t need, uint32_t lane, QueueCursor& c,
-                                                 StrTok* str, IpTok* ip, uint32_t* overflow, uint32_t ovf_bit) {
+                                                 StrTok* str, IpTok* ip, uint32_t* overflow, uint32_t ovf_bit, uint32_t unit) {
   if (need <= c.left) { uint32_t b = c.base; c.base += need; c.left -= need; return b; }
   for (uint32_t i = lane; i < c.left; i += 32) { if (str) str[c.base + i].type = TOK_INVALID; else ip[c.base + i].type = TOK_INVALID; }
-  uint32_t sz = need > TOK_RESERVE ? need : TOK_RESERVE;
+  uint32_t sz = need > unit ? need : unit;
   uint32_t b = 0;
   if (lane == 0) b = atomicAdd(counter, sz);
   b = __shfl_sync(0xFFFFFFFFu, b, 0);
@@ -430,11 +433,11 @@ __device__ __forceinline__ void append_tokens(const ScanArgs& a, TokenWarp& tw, 
     if ((uint64_t)b + __popc(bs) > a.cap_str) { if (lane == 0) atomicOr(&a.ctr->overflow, 1u << 8); }
     else if (ws) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
   } else if (bs) {
-    uint32_t b = tok_reserve(&a.ctr->n_str, a.cap_str, __popc(bs), lane, tw.cs, a.str, nullptr, &a.ctr->overflow, 1u << 8);
+    uint32_t b = tok_reserve(&a.ctr->n_str, a.cap_str, __popc(bs), lane, tw.cs, a.str, nullptr, &a.ctr->overflow, 1u << 8, a.tok_unit);
     if (ws && b != NONE32) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
   }
   if (bi) {
-    uint32_t b = tok_reserve(&a.ctr->n_ip, a.cap_ip, __popc(bi), lane, tw.ci, nullptr, a.ip, &a.ctr->overflow, 1u << 9);
+    uint32_t b = tok_reserve(&a.ctr->n_ip, a.cap_ip, __popc(bi), lane, tw.ci, nullptr, a.ip, &a.ctr->overflow, 1u << 9, a.tok_unit);
     if (wi && b != NONE32) a.ip[b + __popc(bi & ((1u << lane) - 1u))] = it;
   }
 }
@@ -725,62 +728,76 @@ __device__ __forceinline__ uint32_t agg_add(uint32_t* ctr, uint32_t v) {
   return base + incl - v;
 }
 
-// K3: IP tokens.  A hit rate of a few per cent over 10^8 tokens means millions of records: appended one (or one warp's worth)
-// at a time they serialise on the single record counter (same-address atomics retire about one per nanosecond — that, not the
-// tree walk, was this kernel's time on config 3).  So a block stages the records of its 256 tokens in shared memory, takes
-// ONE slot range from the global counter and writes the records out as coalesced 16-byte stores.
+// K3: IP tokens -> SearchTree::lookup (mmdb/tree.rs:46-125) -> records.
+//  * Lock step: a warp takes 32 consecutive tokens and advances all their walks together, IPT_STEPS tree records per round,
+//    until none is left walking (trie_walk_begin / trie_walk_step).  Round 1 let every lane run its own walk to the end;
+//    at full size that version lost 0..5 of 8 million records from run to run: ONE lane in a deep IPv6 walk (~50 us of
+//    dependent DRAM reads) next to idle lanes was left behind by its warp — the warp's other 31 lanes, and with them the
+//    block's barriers and the warp-uniform registers, ran 16 loop iterations ahead of it (measured with the audit
+//    counters of mgpu_set_option("verify_tokens"); profiles/README.md "the lost records of round 1").  Here no lane is
+//    ever more than IPT_STEPS loads away from the rest of its warp, and there is no block barrier after the first line.
+//  * A hit rate of a few per cent over 10^8 tokens means millions of records: appended one warp's worth at a time they
+//    serialise on the single record counter (same-address atomics retire about one per nanosecond).  So every warp stages
+//    its records in shared memory and takes one slot range per IPT_STAGE records, written out as coalesced 16-byte stores.
+static const uint32_t IPT_STAGE = 96;
+static const int IPT_STEPS = 4;
+__device__ __forceinline__ void iptrie_flush(const ScanArgs& a, const mgpu_match* stage, uint32_t staged, uint32_t lane) {
+  __syncwarp();
+  uint32_t b = 0;
+  if (lane == 0) {
+    if (a.dbg) atomicAdd(&a.dbg[10], (unsigned long long)staged);
+    b = atomicAdd(&a.tot->n_rec, staged);
+    if ((uint64_t)b + staged > a.cap_rec) atomicOr(&a.ctr->overflow, 1u << 10);
+  }
+  b = __shfl_sync(0xFFFFFFFFu, b, 0);
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  uint4* dst = reinterpret_cast<uint4*>(a.recs);
+  for (uint32_t j = lane; j < 2 * staged; j += 32) if ((uint64_t)b + (j >> 1) < a.cap_rec) dst[2 * (size_t)b + j] = src[j];
+  __syncwarp();
+}
 __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
-  __shared__ __align__(16) mgpu_match s_rec[256];
-  __shared__ uint32_t s_cnt, s_base;
+  __shared__ __align__(16) mgpu_match s_rec[8][IPT_STAGE];
+  __shared__ uint32_t s_ovf;
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
-  if (threadIdx.x == 0) s_cnt = a.ctr->overflow;  // (read once per block: the exit must be uniform, other blocks may set the flag)
+  if (threadIdx.x == 0) s_ovf = a.ctr->overflow;  // (read once per block: the exit must be uniform, other blocks may set the flag)
   __syncthreads();
-  if (!a.db.has_ip || s_cnt) return;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {  // (block-uniform trip count)
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const uint32_t i = base + threadIdx.x;
-    bool hit = false;
-    uint32_t off = 0; uint8_t pl = 0;
+  if (!a.db.has_ip || s_ovf) return;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nw = gridDim.x * 8;
+  uint32_t staged = 0;  // records in s_rec[warp] (warp-uniform)
+  for (uint32_t t0 = (blockIdx.x * 8 + warp) * 32u; t0 < n; t0 += nw * 32u) {
+    const uint32_t i = t0 + lane;
     IpTok t;
     t.type = TOK_INVALID;
     if (i < n) t = a.ip[i];
-    if (t.type == MGPU_T_IPV4) hit = trie_lookup_v4(a.db, t.w[0], off, pl);
-    else if (t.type != TOK_INVALID) {
-      uint16_t seg[8];
-      for (int k = 0; k < 4; k++) { seg[2 * k] = (uint16_t)(t.w[k] >> 16); seg[2 * k + 1] = (uint16_t)t.w[k]; }
-      hit = trie_lookup_v6(a.db, seg, off, pl);
+    uint32_t off = 0; uint8_t pl = 0;
+    TrieWalk w;
+    int r = TRIE_MISS;
+    if (t.type == MGPU_T_IPV4 || t.type == MGPU_T_IPV6) r = trie_walk_begin(a.db, t.w, t.type == MGPU_T_IPV6, w, off, pl);
+    while (__any_sync(0xFFFFFFFFu, r == TRIE_MORE)) {
+#pragma unroll
+      for (int k = 0; k < IPT_STEPS; k++) if (r == TRIE_MORE) r = trie_walk_step(a.db, t.w, w, off, pl);
     }
-    __syncwarp();
+    const bool hit = r == TRIE_HIT;
+    if (a.dbg) {  // audit: hits counted per thread; sub-groups of a warp that arrive here on their own
+      if (hit) atomicAdd(&a.dbg[8], 1ULL);
+      const uint32_t am = __activemask();
+      if (am != 0xFFFFFFFFu && (am & (0u - am)) == (1u << lane)) atomicAdd(&a.dbg[11], 1ULL);
+    }
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
     if (bal) {
-      uint32_t b = 0;
-      if (lane == 0) b = atomicAdd(&s_cnt, (uint32_t)__popc(bal));
-      b = __shfl_sync(0xFFFFFFFFu, b, 0);
+      const uint32_t cnt = (uint32_t)__popc(bal);
+      if (staged + cnt > IPT_STAGE) { iptrie_flush(a, s_rec[warp], staged, lane); staged = 0; }
       if (hit) {
-        mgpu_match r;
-        r.offset = a.base + t.start; r.len = t.len; r.item_type = (uint8_t)t.type; r.kind = MGPU_KIND_IP; r.prefix_len = pl; r.reserved = 0;
-        r.n_ids = 0; r.ids_index = 0; r.data_offset = off; r.pad = 0;
-        s_rec[b + __popc(bal & ((1u << lane) - 1u))] = r;
+        mgpu_match m;
+        m.offset = a.base + t.start; m.len = t.len; m.item_type = (uint8_t)t.type; m.kind = MGPU_KIND_IP; m.prefix_len = pl; m.reserved = 0;
+        m.n_ids = 0; m.ids_index = 0; m.data_offset = off; m.pad = 0;
+        s_rec[warp][staged + __popc(bal & ((1u << lane) - 1u))] = m;
       }
+      staged += cnt;
     }
-    __syncthreads();
-    const uint32_t cnt = s_cnt;  // block-uniform
-    if (cnt) {
-      if (threadIdx.x == 0) {
-        s_base = atomicAdd(&a.tot->n_rec, cnt);
-        if ((uint64_t)s_base + cnt > a.cap_rec) atomicOr(&a.ctr->overflow, 1u << 10);
-      }
-      __syncthreads();
-      const uint32_t b = s_base;
-      const uint4* src = reinterpret_cast<const uint4*>(s_rec);
-      uint4* dst = reinterpret_cast<uint4*>(a.recs);
-      for (uint32_t j = threadIdx.x; j < 2 * cnt; j += 256) if ((uint64_t)b + (j >> 1) < a.cap_rec) dst[2 * (size_t)b + j] = src[j];
-    }
-    __syncthreads();
   }
+  if (staged) iptrie_flush(a, s_rec[warp], staged, lane);
 }
 
 // tokens of one warp iteration -> staged window pointer
@@ -1021,6 +1038,11 @@ __global__ void __launch_bounds__(KT_THREADS) acglob_kernel(ScanArgs a) {
   }
 }
 
+// All 32 lanes of warp `w` of the block meet here, however they arrive (one at a time is fine), and their shared-memory
+// writes are visible afterwards: a named hardware barrier (barrier.sync without .aligned), ids 1..15.  Unlike __syncwarp()
+// it cannot be optimised away on the strength of an assumed reconvergence.
+__device__ __forceinline__ void warp_rendezvous(uint32_t w) { asm volatile("barrier.sync %0, 32;" ::"r"(w + 1) : "memory"); }
+
 // K3 on the fast path: the few string tokens whose filters passed (StrTok.type carries F_LIT / F_GLOB) get the exact
 // LiteralHash::lookup and Paraglob::find_all, straight from the log buffer.  One WARP per token: the lanes share the
 // start positions of the anchored literal search (positions are independent, anchored_visit_at), pattern ids meet in a
@@ -1049,15 +1071,17 @@ __global__ void __launch_bounds__(256, 5) exact_kernel(ScanArgs a) {
     uint32_t cnt = 0;
     bool serial = exact && !(a.db.ac_anchored && a.db.wild_count == 0 && a.db.ac_size >= 20);
     if (exact && !serial) {
+      // (warp_rendezvous, not __syncwarp: the lanes come out of divergent walks, and what follows only needs every lane's
+      // shared-memory writes to have happened — see iptrie_kernel)
       if (lane == 0) s_n[warp] = 0;
-      __syncwarp();
+      warp_rendezvous(warp);
       for (uint32_t pos = lane; pos + 3 <= t.len; pos += 32)
         anchored_visit_at(a.db, text, t.len, pos, acc.gram2, [&](uint32_t pid) { uint32_t k = atomicAdd(&s_n[warp], 1u); if (k < EX_IDS) s_ids[warp][k] = pid; });
-      __syncwarp();
+      warp_rendezvous(warp);
       cnt = s_n[warp];
       if (cnt > EX_IDS) serial = true;  // more ids than the list holds: let one lane redo it with the two-pass emitter
+      warp_rendezvous(warp);  // every lane has read the count before lane 0 goes on (and the next token resets it)
     }
-    __syncwarp();
     if (lane != 0) continue;
     if (serial) { emit_string_match(a, t, text, lit_ok, lit_pid, lit_off, true, acc); continue; }
     // sort_unstable + dedup (paraglob_offset.rs:1173-1181)
@@ -1146,6 +1170,36 @@ __global__ void rfind_nl_kernel(const uint8_t* buf, uint64_t lo, uint64_t hi, ui
 
 __global__ void fill_kernel(uint4* p, size_t n16, uint32_t v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(v, v, v, v);
+}
+
+// Debug (mgpu_set_option "verify_tokens"): audit a piece's IP token list after the token kernel.  The list is poisoned before
+// the token kernel runs; every slot below n_ip must then be a token or a padding slot, the tokens must add up to the
+// per-type counters, and their lookups (recomputed here, one thread per slot, plain atomics) must add up to the IP records
+// the IP-trie kernel emits.  dbg: [0] slots still poisoned, [1] padding, [2] IPv4 tokens, [3] IPv6 tokens, [4] lookup hits,
+// [5] slots of any other type, [6] slots audited.
+static const uint32_t TOK_POISON = 0xEEEEEEEEu;
+__global__ void verify_tokens_kernel(ScanArgs a, unsigned long long* dbg) {
+  const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
+  unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const IpTok t = a.ip[i];
+    uint32_t off = 0; uint8_t pl = 0;
+    if (t.type == TOK_POISON) c[0]++;
+    else if (t.type == TOK_INVALID) c[1]++;
+    else if (t.type == MGPU_T_IPV4) { c[2]++; if (a.db.has_ip && trie_lookup_v4(a.db, t.w[0], off, pl)) c[4]++; }
+    else if (t.type == MGPU_T_IPV6) {
+      c[3]++;
+      uint16_t seg[8];
+      for (int k = 0; k < 4; k++) { seg[2 * k] = (uint16_t)(t.w[k] >> 16); seg[2 * k + 1] = (uint16_t)t.w[k]; }
+      if (a.db.has_ip && trie_lookup_v6(a.db, seg, off, pl)) c[4]++;
+    } else c[5]++;
+  }
+  for (int k = 0; k < 6; k++) {
+    unsigned long long v = c[k];
+    for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&dbg[k], v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&dbg[6], (unsigned long long)n);
 }
 
 // single-query lookups through the same device functions (Database::lookup / lookup_ip)
@@ -1267,6 +1321,10 @@ struct mgpu_ctx {
   bool force_generic = false;  // tests: run the generic string path (lithash + acglob kernels) even when the fast path applies
   std::vector<StrTok> x_str; std::vector<IpTok> x_ip;  // extraction-only capture
   bool capture_tokens = false;
+  // test / debug switches (mgpu_set_option)
+  bool verify_tokens = false;
+  unsigned long long* d_dbg = nullptr;  // 16 audit accumulators (verify_tokens_kernel: 0..6, iptrie_kernel: 8..10)
+  uint32_t alloc_cap_str = 0, alloc_cap_ip = 0, alloc_cap_rec = 0, alloc_cap_ids = 0;  // what the buffers really hold
 };
 
 static int launch_grid(mgpu_ctx* c, int per_sm) { return c->sm_count * per_sm; }
@@ -1295,7 +1353,7 @@ void mgpu_destroy(mgpu_ctx* c) {
   for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
   void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.q_long, c->args.seg_cnt, c->args.str, c->args.defer, c->args.ip, c->args.lh_res,
-                  c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
+                  c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_dbg, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   if (c->h_cut) cudaFreeHost(c->h_cut);
@@ -1352,6 +1410,8 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   a.cap_ip = cap32(chunk_bytes / 8 + 1024);
   a.cap_rec = cap32(chunk_bytes / 16 + 4096);
   a.cap_ids = cap32(chunk_bytes / 8 + 8192);
+  a.tok_unit = TOK_RESERVE;
+  c->alloc_cap_str = a.cap_str; c->alloc_cap_ip = a.cap_ip; c->alloc_cap_rec = a.cap_rec; c->alloc_cap_ids = a.cap_ids;
   CK(cudaMalloc(&a.q_dotted, (size_t)a.seg_cap[Q_DOTTED] * a.nseg_max * sizeof(Cand)));
   CK(cudaMalloc(&a.q_hash, (size_t)a.seg_cap[Q_HASH] * a.nseg_max * sizeof(Cand)));
   CK(cudaMalloc(&a.q_at, (size_t)a.seg_cap[Q_AT] * a.nseg_max * 4));
@@ -1373,6 +1433,8 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMallocHost(&c->h_cut, 4096 * sizeof(uint64_t) * 2));
   CK(cudaMalloc(&c->d_small, 65536 + TILE_BYTES));
   CK(cudaMalloc(&c->d_small_out, 64));
+  CK(cudaMalloc(&c->d_dbg, 64 * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)));
   CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
   CK(cudaFuncSetAttribute(token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOKEN_SMEM));
   CK(cudaFuncSetAttribute(tokenize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
@@ -1388,6 +1450,35 @@ mgpu_ctx* mgpu_create(int device, size_t chunk_bytes) {
 
 void mgpu_set_keep_results(mgpu_ctx* c, int keep) { c->keep_results = keep != 0; }
 void mgpu_set_ac_mode(mgpu_ctx* c, int mode) { c->force_ac_walk = mode == 1; c->force_generic = mode == 1 || mode == 2; }
+
+// Test / debug switches.  "tok_reserve": slots per reservation of the token lists; "cap_str" / "cap_ip" / "cap_rec" /
+// "cap_ids": pretend the work buffers are this small (never above what was allocated; 0 restores the allocation), which
+// drives the overflow -> split-and-redo path; "verify_tokens": audit every piece's IP token list (verify_tokens_kernel).
+int mgpu_set_option(mgpu_ctx* c, const char* key, uint64_t value) {
+  if (!c || !key) { set_err("null argument"); return MGPU_E_PARAM; }
+  const std::string k(key);
+  auto cap = [&](uint32_t& field, uint32_t alloc) { field = value == 0 ? alloc : (uint32_t)std::min<uint64_t>(value, alloc); };
+  if (k == "tok_reserve") { if (value < 32 || value > 65536) { set_err("tok_reserve out of range"); return MGPU_E_PARAM; } c->args.tok_unit = (uint32_t)value; }
+  else if (k == "cap_str") cap(c->args.cap_str, c->alloc_cap_str);
+  else if (k == "cap_ip") cap(c->args.cap_ip, c->alloc_cap_ip);
+  else if (k == "cap_rec") cap(c->args.cap_rec, c->alloc_cap_rec);
+  else if (k == "cap_ids") cap(c->args.cap_ids, c->alloc_cap_ids);
+  else if (k == "verify_tokens") {
+    c->verify_tokens = value != 0;
+    c->args.dbg = c->verify_tokens ? c->d_dbg : nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMemset failed"); return MGPU_E_CUDA; }
+  }
+  else if (k == "variant") c->args.variant = (uint32_t)value;
+  else { set_err("unknown option: " + k); return MGPU_E_PARAM; }
+  return MGPU_OK;
+}
+// accumulators of the token-list audit since "verify_tokens" was last set (see verify_tokens_kernel)
+int mgpu_debug_get(mgpu_ctx* c, uint64_t out[64]) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, c->d_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return MGPU_OK;
+}
 
 // ---- PSL ------------------------------------------------------------------------------------------------
 int mgpu_set_psl(mgpu_ctx* c, const uint8_t* text, size_t len) {
@@ -1558,10 +1649,12 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   // The token kernel overwrites the token lists the previous piece's lookups read: wait for them.  The lookups themselves
   // (latency-bound, a fraction of the SMs busy) run on a second stream, beside the tokenizer of the next piece.
   if (c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
+  if (c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
   token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
   if (flags & MGPU_X_CRYPTO) crypto_kernel<<<launch_grid(c, 8), 128, 0, st>>>(a);
+  if (c->verify_tokens) verify_tokens_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a, c->d_dbg);
   CK(cudaEventRecord(ev[2], st));
-  cudaStream_t ls = c->lookup;
+  cudaStream_t ls = (a.variant & 16u) ? st : c->lookup;  // (experiment: lookups serialised behind the token kernel)
   CK(cudaEventRecord(c->ev_tokens[slot], st));
   CK(cudaStreamWaitEvent(ls, c->ev_tokens[slot], 0));
   if (lookups) {

@@ -486,6 +486,7 @@ matchy_result_t matchy_query(const matchy_t* db, const char* query) {
   uint8_t ip16[16]; bool v6 = false;
   const bool is_ip = parse_ip(query, n, ip16, v6);
   Cached c{0, 0, 0};
+  mxy::Value* missed = nullptr;  // cache miss with data: the value, decoded before anything is counted
   bool none = false;  // Ok(None): the database has no data of the queried class
   const std::string key(query, n);
   auto hit = d->cache_cap ? d->idx.find(key) : d->idx.end();
@@ -515,6 +516,12 @@ matchy_result_t matchy_query(const matchy_t* db, const char* query) {
         if (rc > 0) c = first.data_offset == MGPU_NO_DATA ? Cached{3, 0, 0} : Cached{2, first.data_offset, 0};
       }
     }
+    // the reference decodes inside lookup_ip / lookup_string_uncached: a decode error leaves lookup() through `?` before the
+    // statistics and the cache are touched (database.rs:725-804)
+    if (c.kind == 1 || c.kind == 2) {
+      missed = new mxy::Value();
+      if (!decode_value(d, c.data_offset, *missed)) { delete missed; return not_found(); }
+    }
     d->st.total_queries++;
     if (d->cache_cap) d->st.cache_misses++;
     if (c.kind == 1) { d->st.ip_queries++; d->st.queries_with_match++; }
@@ -528,6 +535,7 @@ matchy_result_t matchy_query(const matchy_t* db, const char* query) {
     }
   }
   if (c.kind != 1 && c.kind != 2) return not_found();  // Pattern whose first entry has no data -> found = false (matchy.rs:1143-1163)
+  if (missed) return matchy_result_t{true, c.prefix_len, missed, db};
   auto* v = new mxy::Value();
   if (!decode_value(d, c.data_offset, *v)) { delete v; return not_found(); }
   return matchy_result_t{true, c.prefix_len, v, db};
@@ -640,7 +648,7 @@ char* matchy_result_to_json(const matchy_result_t* result) {
   if (!result || !result->found || !result->_data_cache) return nullptr;
   // serde_json::to_string(&DataValue): compact; object key order is the HashMap's (unspecified) in the reference, sorted here
   std::string s;
-  mxy::render_json(*(const mxy::Value*)result->_data_cache, s);
+  mxy::render_json(*(const mxy::Value*)result->_data_cache, s, /*f32_shortest=*/true);
   return dup_cstring(s);
 }
 

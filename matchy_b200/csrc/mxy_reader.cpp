@@ -174,11 +174,14 @@ void json_string(const std::string& s, std::string& out) {
   out += '"';
 }
 
-static void json_f64(double d, std::string& out) {  // ryu shortest round-trip; non-finite -> null
+// ryu shortest round-trip; non-finite -> null.  as_f32: the value is an f32 and the digits are the shortest that round-trip
+// as f32 (serde's serialize_f32, what serde_json::to_string(&DataValue) prints: 0.98, not 0.9800000190734863).
+static void json_f64(double d, std::string& out, bool as_f32 = false) {
   if (d != d || d == 1.0 / 0.0 || d == -1.0 / 0.0) { out += "null"; return; }
   char b[40];
   int prec = 1;
-  for (; prec <= 17; prec++) { snprintf(b, sizeof b, "%.*e", prec - 1, d); if (strtod(b, nullptr) == d) break; }
+  if (as_f32) { for (; prec <= 9; prec++) { snprintf(b, sizeof b, "%.*e", prec - 1, d); if (strtof(b, nullptr) == (float)d) break; } }
+  else for (; prec <= 17; prec++) { snprintf(b, sizeof b, "%.*e", prec - 1, d); if (strtod(b, nullptr) == d) break; }
   // b = d.ddddde±XX ; re-lay the digits the way ryu's pretty printer does
   std::string digits; int exp10 = 0; bool neg = false;
   {
@@ -201,10 +204,11 @@ static void json_f64(double d, std::string& out) {  // ryu shortest round-trip; 
   }
 }
 
-void render_json(const Value& v, std::string& out) {
+void render_json(const Value& v, std::string& out, bool f32_shortest) {
   switch (v.kind) {
     case Value::STR: json_string(v.s, out); break;
-    case Value::F64: case Value::F32: json_f64(v.f, out); break;
+    case Value::F64: json_f64(v.f, out); break;
+    case Value::F32: json_f64(v.f, out, f32_shortest); break;
     case Value::BYTES:
       out += '[';
       for (size_t k = 0; k < v.s.size(); k++) { if (k) out += ','; out += std::to_string((unsigned)(uint8_t)v.s[k]); }
@@ -230,14 +234,14 @@ void render_json(const Value& v, std::string& out) {
         if (k + 1 < order.size() && order[k + 1]->first == order[k]->first) continue;  // later duplicate replaces earlier
         if (!first) out += ',';
         first = false;
-        json_string(order[k]->first, out); out += ':'; render_json(order[k]->second, out);
+        json_string(order[k]->first, out); out += ':'; render_json(order[k]->second, out, f32_shortest);
       }
       out += '}';
       break;
     }
     case Value::ARR:
       out += '[';
-      for (size_t k = 0; k < v.items.size(); k++) { if (k) out += ','; render_json(v.items[k], out); }
+      for (size_t k = 0; k < v.items.size(); k++) { if (k) out += ','; render_json(v.items[k], out, f32_shortest); }
       out += ']';
       break;
     case Value::PTR: out += "\"<pointer>\""; break;
@@ -319,25 +323,29 @@ bool locate_sections(const uint8_t* d, size_t n, Layout& L, std::string& err) {
   if (!want("node_count", nc) || !want("record_size", rs) || !want("ip_version", ipv)) { err = "metadata lacks node_count/record_size/ip_version"; return false; }
   if (rs != 24 && rs != 28 && rs != 32) { err = "unsupported record_size"; return false; }
   if (ipv != 4 && ipv != 6) { err = "unsupported ip_version"; return false; }
+  // every offset / count below comes from the file: checks are written so that no addition or product can wrap
+  const uint64_t node_bytes = rs == 24 ? 6 : rs == 28 ? 7 : 8;
+  if (nc > 0xFFFFFFFFull || nc > n / node_bytes) { err = "search tree larger than file"; return false; }
   L.node_count = (uint32_t)nc; L.record_bits = (uint32_t)rs; L.ip_version = (uint32_t)ipv;
-  L.tree_size = nc * (rs == 24 ? 6 : rs == 28 ? 7 : 8);
+  L.tree_size = nc * node_bytes;
+  if (n - L.tree_size < 16) { err = "search tree larger than file"; return false; }
   L.data_start = L.tree_size + 16;
-  if (L.data_start > n) { err = "search tree larger than file"; return false; }
   uint64_t v;
   L.match_mode = (want("match_mode", v) && v == 1) ? 1 : 0;
   if (want("literal_entry_count", v)) L.literal_count = (uint32_t)v;
   if (want("glob_entry_count", v)) L.glob_count = (uint32_t)v;
   if (want("pattern_section_offset", v) && v != 0) {
-    if (v + 8 > n) { err = "pattern section header out of range"; return false; }
-    uint64_t pg_size = le32(d + v + 4), pg0 = v + 8, pg1 = pg0 + pg_size;
-    if (pg1 + 4 > n) { err = "paraglob buffer out of range"; return false; }
+    if (v > n || n - v < 8) { err = "pattern section header out of range"; return false; }
+    uint64_t pg_size = le32(d + v + 4), pg0 = v + 8;
+    if (n - pg0 < pg_size || n - pg0 - pg_size < 4) { err = "paraglob buffer out of range"; return false; }
+    uint64_t pg1 = pg0 + pg_size;
     uint64_t cnt = le32(d + pg1);
-    if (pg1 + 4 + cnt * 4 > n) { err = "glob data offsets out of range"; return false; }
+    if ((n - pg1 - 4) / 4 < cnt) { err = "glob data offsets out of range"; return false; }
     if (pg_size < 112 || memcmp(d + pg0, "PARAGLOB", 8) != 0) { err = "bad PARAGLOB magic"; return false; }
     L.has_glob = true; L.pg_off = pg0; L.pg_len = pg_size; L.map_off = pg1 + 4; L.map_count = cnt;
   }
   if (want("literal_section_offset", v) && v != 0) {
-    if (v + 32 > n) { err = "literal section out of range"; return false; }
+    if (v > n || n - v < 32) { err = "literal section out of range"; return false; }
     if (memcmp(d + v, "LHSH", 4) != 0 || le32(d + v + 4) != 1) { err = "bad LHSH header"; return false; }
     L.has_literal = true; L.lit_off = v; L.lit_len = n - v;
   }

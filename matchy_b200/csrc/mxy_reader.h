@@ -54,7 +54,9 @@ class ValueReader {
   size_t n_;
 };
 
-void render_json(const Value& v, std::string& out);          // serde_json compact, object keys sorted
+// serde_json compact, object keys sorted.  f32_shortest = false: Float values widened to f64 first (`matchy match`: json!(f),
+// bin/cli_utils.rs:177-201); true: shortest f32 digits (serde_json::to_string(&DataValue), the C API's matchy_result_to_json)
+void render_json(const Value& v, std::string& out, bool f32_shortest = false);
 void json_string(const std::string& s, std::string& out);    // serde_json string escaping
 std::string cidr_text(const uint8_t* text, size_t n, unsigned prefix_len);  // format_cidr_into
 std::string ipv6_text(const uint16_t seg[8]);                // Rust Display for Ipv6Addr (RFC 5952)

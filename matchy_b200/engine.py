@@ -130,6 +130,19 @@ class Engine:
         """0: automatic; 1: force the reference's Aho-Corasick walk instead of anchored walks (same results)."""
         self.L.mgpu_set_ac_mode(self.h, int(mode))
 
+    def set_option(self, key: str, value: int):
+        """Test / debug switches of the engine (include/matchy_b200.h: mgpu_set_option)."""
+        _check(self.L.mgpu_set_option(self.h, key.encode(), int(value)), "mgpu_set_option(%s)" % key)
+
+    def debug_counters(self):
+        """Sums of the token-list audit since set_option("verify_tokens", 1)."""
+        out = (C.c_uint64 * 64)()
+        _check(self.L.mgpu_debug_get(self.h, out), "mgpu_debug_get")
+        self.debug_events = [(int(out[16 + 2 * k]) >> 32, int(out[16 + 2 * k]) & 0xFFFFFFFF, int(out[17 + 2 * k]) >> 32, int(out[17 + 2 * k]) & 0xFFFFFFFF)
+                             for k in range(min(24, int(out[13])))]  # (block, base, warp, active mask) of the first partial-warp events
+        names = ("poisoned", "padding", "ipv4", "ipv6", "lookup_hits", "unknown", "slots", "_7", "trie_thread_hits", "trie_warp_hits", "trie_block_hits", "trie_partial_warps", "trie_n_mismatch")
+        return dict(zip(names, (int(x) for x in out)))
+
     def extract_array(self, data, flags=X_SUPPORTED):
         """uint64 array [n, 3] of (item_type, start, end) rows sorted by (start, item_type)."""
         p, n, keep = N.as_ptr(data)

@@ -24,6 +24,7 @@ class WorkerStats:
         t = c["by_type"]
         self.domain_count += t[0]; self.email_count += t[1]; self.ipv4_count += t[2]; self.ipv6_count += t[3]
         self.md5_count += t[4]; self.sha1_count += t[5]; self.sha256_count += t[6]; self.sha384_count += t[7]; self.sha512_count += t[8]
+        self.bitcoin_count += t[9]; self.ethereum_count += t[10]; self.monero_count += t[11]
         if timing:
             for k, v in timing["kernel_ms"].items():
                 self.kernel_ms[k] += v
@@ -147,7 +148,7 @@ class Worker:
             mv = memoryview(data) if not isinstance(data, memoryview) else data
             for r in recs:
                 off, ln = int(r["offset"]), int(r["len"])
-                text = bytes(mv[off:off + ln]).decode("utf-8")
+                text = bytes(mv[off:off + ln]).decode("utf-8", errors="replace")  # (tokens are validated UTF-8 or ASCII; never raise on a record)
                 if r["kind"] == E.KIND_IP:
                     qr = QueryResult("Ip", data=db.decode(int(r["data_offset"])) if decode else int(r["data_offset"]), prefix_len=int(r["prefix_len"]))
                 else:

@@ -1717,6 +1717,62 @@ int orc_scan_mt(orc_handle* h, const uint8_t* data, size_t len, uint32_t flags, 
   return rc;
 }
 
+// The same sharded scan, keeping the records: h->scan afterwards holds every shard's records sorted by
+// (offset, item_type, len) with the id pairs re-packed in record order and offsets made absolute with `base` — the layout
+// mgpu_results() returns, so a multi-GiB record-exact comparison is two array compares (tests/, bench.py parity gate).
+int orc_scan_mt_keep(orc_handle* h, const uint8_t* data, size_t len, uint64_t base, uint32_t flags, int threads, uint64_t* out16) {
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads <= 0) threads = 1;
+  std::vector<size_t> cuts{0};
+  for (int t = 1; t < threads; t++) {
+    size_t p = len / threads * t;
+    if (p < cuts.back()) p = cuts.back();
+    while (p < len && data[p] != '\n') p++;
+    if (p < len) p++;
+    cuts.push_back(p);
+  }
+  cuts.push_back(len);
+  std::vector<Scan> scans(threads);
+  std::vector<std::thread> th;
+  Extractor ex = h->ex;
+  ex.flags = flags;
+  for (int t = 0; t < threads; t++) {
+    th.emplace_back([&, t]() {
+      if (cuts[t + 1] > cuts[t]) scan_stream(h->db, ex, data + cuts[t], cuts[t + 1] - cuts[t], base + cuts[t], 128 * 1024, scans[t]);
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int k = 0; k < 16; k++) out16[k] = 0;
+  int rc = 0;
+  h->scan = Scan();
+  std::vector<MatchRec> all;
+  std::vector<IdPair> ids_all;
+  for (auto& s : scans) {
+    if (s.error) rc = -1;
+    out16[0] += s.c.lines; out16[1] += s.c.bytes; out16[2] += s.c.candidates; out16[3] += s.c.matches;
+    for (int k = 0; k < 12; k++) out16[4 + k] += s.c.by_type[k];
+    const uint32_t rebase = (uint32_t)ids_all.size();
+    for (MatchRec r : s.recs) { if (r.kind == 2) r.ids_index += rebase; all.push_back(r); }
+    ids_all.insert(ids_all.end(), s.ids.begin(), s.ids.end());
+  }
+  std::stable_sort(all.begin(), all.end(), [](const MatchRec& x, const MatchRec& y) {
+    if (x.offset != y.offset) return x.offset < y.offset;
+    if (x.item_type != y.item_type) return x.item_type < y.item_type;
+    return x.len < y.len;
+  });
+  for (MatchRec& r : all) {
+    if (r.kind == 2) {
+      const uint32_t at = (uint32_t)h->scan.ids.size();
+      h->scan.ids.insert(h->scan.ids.end(), ids_all.begin() + r.ids_index, ids_all.begin() + r.ids_index + r.n_ids);
+      r.ids_index = at;
+    }
+  }
+  h->scan.recs.swap(all);
+  h->scan.c.lines = out16[0]; h->scan.c.bytes = out16[1]; h->scan.c.candidates = out16[2]; h->scan.c.matches = out16[3];
+  for (int k = 0; k < 12; k++) h->scan.c.by_type[k] = out16[4 + k];
+  return rc;
+}
+
 // extraction only: returns count; items as (type, start, end) triples of uint64
 size_t orc_extract(orc_handle* h, const uint8_t* data, size_t len, uint32_t flags, uint64_t* out, size_t cap) {
   h->ex.flags = flags;

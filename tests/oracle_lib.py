@@ -46,6 +46,7 @@ def lib():
         L.orc_has.argtypes = [C.c_void_p, C.c_int]
         L.orc_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_size_t]
         L.orc_scan_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+        L.orc_scan_mt_keep.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         L.orc_n_matches.restype = C.c_size_t
         L.orc_n_matches.argtypes = [C.c_void_p]
         L.orc_matches.restype = C.POINTER(MatchRec)
@@ -143,6 +144,29 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("oracle scan_mt failed rc=%d" % rc)
         return [int(x) for x in out]
+
+    REC_DTYPE = [("offset", "<u8"), ("len", "<u4"), ("item_type", "u1"), ("kind", "u1"), ("prefix_len", "u1"), ("reserved", "u1"),
+                 ("n_ids", "<u4"), ("ids_index", "<u4"), ("data_offset", "<u4"), ("pad", "<u4")]
+    ID_DTYPE = [("pattern_id", "<u4"), ("data_offset", "<u4")]
+
+    def scan_mt_keep(self, data, flags=None, threads=0, base=0):
+        """Multi-threaded scan that keeps the records: (recs, ids, counters) with recs / ids as numpy structured arrays in
+        exactly the layout and order mgpu_results() returns (sorted by (offset, item_type, len), ids re-packed in record
+        order), so a multi-GiB record-exact comparison is two array compares."""
+        import numpy as np
+        if flags is None:
+            flags = self.default_flags()
+        p, n, keep = _buf(data)
+        out = (C.c_uint64 * 16)()
+        rc = self.L.orc_scan_mt_keep(self.h, p, n, base, flags, threads, out)
+        if rc != 0:
+            raise RuntimeError("oracle scan_mt_keep failed rc=%d" % rc)
+        nr, ni = self.L.orc_n_matches(self.h), self.L.orc_n_ids(self.h)
+        recs = (np.frombuffer((C.c_uint8 * (nr * 32)).from_address(C.addressof(self.L.orc_matches(self.h).contents)), dtype=np.dtype(self.REC_DTYPE)).copy()
+                if nr else np.zeros(0, np.dtype(self.REC_DTYPE)))
+        ids = (np.frombuffer((C.c_uint8 * (ni * 8)).from_address(C.addressof(self.L.orc_ids(self.h).contents)), dtype=np.dtype(self.ID_DTYPE)).copy()
+               if ni else np.zeros(0, np.dtype(self.ID_DTYPE)))
+        return recs, ids, [int(x) for x in out]
 
     def _collect(self):
         n = self.L.orc_n_matches(self.h)

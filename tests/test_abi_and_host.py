@@ -199,3 +199,44 @@ def test_build_subcommand(built, tmp_path, capsys):
     bad.write_text("a,b\n1,2\n")
     assert main(["build", str(bad), "-o", str(out), "-f", "csv"]) == 1
     assert "must have an 'entry' or 'key' column" in capsys.readouterr().err
+
+
+def _patch_metadata_uint(db: bytes, key: bytes, value: int) -> bytes:
+    """The database with metadata field `key` re-encoded as an 8-byte MMDB uint64 holding `value`."""
+    mk = db.rfind(b"\xab\xcd\xefMaxMind.com")
+    at = db.index(key, mk) + len(key)
+    ctrl = db[at]
+    assert ctrl >> 5 in (5, 6) or (ctrl >> 5 == 0 and db[at + 1] == 2), "expected a uint16/32/64 value"
+    size = ctrl & 31
+    old_len = 1 + size if ctrl >> 5 else 2 + size
+    return db[:at] + bytes([8, 2]) + value.to_bytes(8, "big") + db[at + old_len:]  # extended type 9 (uint64), 8 bytes
+
+
+def test_validate_rejects_wrapping_section_offsets(built, tmp_path):
+    """A crafted 64-bit section offset near 2^64 must not wrap past the bounds checks (mxy_reader.cpp:331)."""
+    from matchy_b200 import DatabaseBuilder, _native as N
+    b = DatabaseBuilder(build_epoch=1)
+    b.add_glob("*.evil.com", {"k": "v"})
+    b.add_entry("bad.example.com", {"k": "w"})
+    b.add_entry("10.0.0.0/8", {"k": "x"})
+    db = b.build()
+    L = C.CDLL(N.LIB_PATH)
+    L.matchy_validate.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p)]
+    good = tmp_path / "good.mxy"
+    good.write_bytes(db)
+    assert L.matchy_validate(str(good).encode(), 0, None) == 0
+    for key, value in ((b"pattern_section_offset", 0xFFFFFFFFFFFFFFF9), (b"literal_section_offset", 0xFFFFFFFFFFFFFFE1),
+                       (b"pattern_section_offset", len(db) - 4), (b"node_count", 0x3000000000000001), (b"node_count", 0xFFFFFFFF)):
+        bad = tmp_path / "bad.mxy"
+        bad.write_bytes(_patch_metadata_uint(db, key, value))
+        msg = C.c_char_p()
+        assert L.matchy_validate(str(bad).encode(), 0, C.byref(msg)) < 0, (key, hex(value))
+        assert N.lib().mxyr_open(bad.read_bytes(), bad.stat().st_size) in (None, 0)
+
+
+def test_worker_stats_count_crypto_types():
+    from matchy_b200.processing import WorkerStats
+    s = WorkerStats()
+    s.add_counters({"lines": 3, "bytes": 100, "candidates": 78, "matches": 2, "by_type": list(range(1, 13))})
+    assert (s.bitcoin_count, s.ethereum_count, s.monero_count) == (10, 11, 12)
+    assert s.as_vector()[-3:] == [10, 11, 12] and s.domain_count == 1 and s.sha512_count == 9
