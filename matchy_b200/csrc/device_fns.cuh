@@ -416,9 +416,10 @@ __device__ __forceinline__ void load_head_words_shared(uint32_t saddr, uint32_t 
   const uint32_t w0 = lds_u32(q), w1 = lds_u32(q + 4), w2 = lds_u32(q + 8), w3 = lds_u32(q + 12), w4 = lds_u32(q + 16);
   h[0] = __funnelshift_r(w0, w1, sh); h[1] = __funnelshift_r(w1, w2, sh); h[2] = __funnelshift_r(w2, w3, sh); h[3] = __funnelshift_r(w3, w4, sh);
 }
-__device__ __forceinline__ void load_tail_words_shared(uint32_t saddr, uint32_t n, uint32_t t[4]) {
-  // the four words end at saddr + n; all share one alignment: five aligned words, the lower ones only when inside the token
-  const uint32_t e = saddr + n, q = e & ~3u, sh = (e & 3u) * 8;
+// (e = shared-space address just past the token's last byte)
+__device__ __forceinline__ void load_tail_words_shared_end(uint32_t e, uint32_t n, uint32_t t[4]) {
+  // the four words end at e; all share one alignment: five aligned words, the lower ones only when inside the token
+  const uint32_t q = e & ~3u, sh = (e & 3u) * 8;
   const uint32_t w4 = sh ? lds_u32(q) : 0u;  // (the word that holds the bytes just below an unaligned end)
   const uint32_t w3 = n >= 1 ? lds_u32(q - 4) : 0u, w2 = n >= 5 ? lds_u32(q - 8) : 0u, w1 = n >= 9 ? lds_u32(q - 12) : 0u, w0 = n >= 13 ? lds_u32(q - 16) : 0u;
   t[3] = n >= 4 ? __funnelshift_r(w3, w4, sh) : 0u;
@@ -426,6 +427,7 @@ __device__ __forceinline__ void load_tail_words_shared(uint32_t saddr, uint32_t 
   t[1] = n >= 12 ? __funnelshift_r(w1, w2, sh) : 0u;
   t[0] = n >= 16 ? __funnelshift_r(w0, w1, sh) : 0u;
 }
+__device__ __forceinline__ void load_tail_words_shared(uint32_t saddr, uint32_t n, uint32_t t[4]) { load_tail_words_shared_end(saddr + n, n, t); }
 #endif
 
 // try_parse_ipv4 (lib.rs:813-869) on a whole boundary-delimited word of n bytes held in h[0..4) (only the first n bytes count):

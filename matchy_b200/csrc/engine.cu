@@ -531,7 +531,8 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
     const bool have = idx < n;
     const Cand c = cn;
     if (idx + 32 < n) cn = ld_cand(q + idx + 32); else cn = Cand{0xFFFFFFFFu, 0};
-    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c.start, 0);
+    // (lowest start of the 32: the tokenizer's segments are sorted by position, the fused kernel's slow-path entries are not)
+    const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, have ? c.start : 0xFFFFFFFFu);
     const uint32_t alo = lo & ~15u;
     const bool fits = !have || (uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN;
     const uint32_t nf = direct ? 0u : __ballot_sync(0xFFFFFFFFu, !fits);
@@ -687,6 +688,399 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   for (int t = 0; t < 9; t++) {
     uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cnt[t]);
     if (lane == 0 && v) atomicAdd(&a.ctr->by_type[t], (unsigned long long)v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1+K2 fused: scan_kernel — ONE pass over the log (round 2).
+//
+// tokenize_kernel + token_kernel read the log twice (the token kernel through 2 KiB windows, then again for the numeric
+// queue) and pass ~0.2 candidates per log byte through queues in HBM: 3.35 DRAM bytes per log byte between them.  Here a
+// warp owns a contiguous range of 1 KiB tiles as before, but the tiles arrive in a private 4 KiB shared-memory ring by
+// bulk asynchronous copies (cp.async.bulk + mbarrier: one elected lane issues, all lanes wait on the tile's barrier;
+// UBLKCP / SYNCS in SASS), and everything that follows reads them from there:
+//   * classification: one 4-byte table entry per byte (128 rows x 32 lanes, conflict-free) holds a 4-bit byte category as
+//     four bit planes; three LOP3 per mask turn the planes into the eight class masks of tokenize.cuh;
+//   * the carry-chain word logic of tokenize_kernel, unchanged;
+//   * dotted / numeric candidates go into a 64-entry queue in shared memory instead of HBM; whenever 32 are waiting (or
+//     the tiles they lie in are about to be overwritten) one lane per candidate reads the word's first / last 16 bytes
+//     from the ring and decides: IPv4 by SWAR, domain by the PSL last-label table, then the string gate;
+//   * whatever needs a loop over the token's bytes (multi-label PSL suffixes, UTF-8 validation, words that began before
+//     the ring's reach) and the rare anchors ('@', "::", hash-length and crypto-length words) still go to the segmented
+//     queues in HBM and are handled by token_kernel / crypto_kernel afterwards, exactly as in round 1.
+// Ring discipline: while tile t is processed, tiles t-1 and t-2 are intact and t+1 is in flight; the load of t+2 (into
+// the slot of t-2) is issued at the end of tile t, after every queued candidate that ended before tile t has been
+// handled.  A candidate that ends in tile t is queued only if it starts at or after the first byte of tile t-1.
+// The 32 bytes behind the ring mirror its first 32, so a 20-byte read may start anywhere in the ring.
+// ---------------------------------------------------------------------------------------------------------
+static const int SK_WARPS = 16;
+static const int SK_THREADS = SK_WARPS * 32;
+static const uint32_t SK_RING = 4096;
+static const uint32_t SK_PAD = 32;
+static const uint32_t SK_QCAP = 64;
+static const uint32_t SK_LUT_BYTES = 128 * 32 * 4;  // byte values 0..127 (bytes >= 0x80 are mapped onto 'g' first: same category)
+struct SkWarp { uint8_t ring[SK_RING + SK_PAD]; uint2 q[SK_QCAP]; unsigned long long mbar[4]; };
+static_assert(sizeof(SkWarp) % 16 == 0, "rings must stay 16-byte aligned");
+static const size_t SCAN_SMEM = (size_t)HOT_WORDS * 4 + SK_LUT_BYTES + SK_WARPS * sizeof(SkWarp);
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar_s, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s), "r"(count) : "memory"); }
+// one lane: arm the tile's barrier with the byte count, then start the bulk copy global -> shared that completes on it
+__device__ __forceinline__ void tile_load(uint32_t dst_s, const uint8_t* src, uint32_t bytes, uint32_t mbar_s) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src), "r"(bytes), "r"(mbar_s) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_s, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SK_DONE;\n"
+      "bra SK_WAIT;\n"
+      "SK_DONE:\n"
+      "}\n" ::"r"(mbar_s), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_u64(uint32_t saddr, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(saddr), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(x) : "memory"); }
+
+// per-warp state of the fused kernel's candidate queue and its global overflow queues (all warp-uniform)
+struct SkQueues {
+  uint32_t ring_s, q_s;            // shared-space addresses of the ring and of the candidate queue
+  uint32_t qhead, qcount, q_old;   // queue cursor; q_old = entries at the head that ended before the current tile
+  uint32_t high;                   // "some byte >= 0x80 in the last three tiles"
+  Cand* qd; Cand* qn;              // this warp's segments of the dotted / numeric queues in HBM (slow path)
+  uint32_t nd, nn, ovf;
+};
+
+// Slow path: the lanes with `slow` append their word to the dotted (numeric = false) or numeric queue segment in HBM.
+__device__ __forceinline__ void sk_push_slow(const ScanArgs& a, SkQueues& k, uint32_t lane, bool slow, bool numeric, uint32_t start, uint32_t len) {
+  const uint32_t bd = __ballot_sync(0xFFFFFFFFu, slow && !numeric), bn = __ballot_sync(0xFFFFFFFFu, slow && numeric);
+  const uint32_t lt = (1u << lane) - 1u;
+  if (bd) {
+    if (k.nd + __popc(bd) <= a.seg_cap[Q_DOTTED]) { if (slow && !numeric) k.qd[k.nd + __popc(bd & lt)] = Cand{start, len}; }
+    else k.ovf |= 1u << Q_DOTTED;
+    k.nd += __popc(bd);
+  }
+  if (bn) {
+    if (k.nn + __popc(bn) <= a.seg_cap[Q_NUMERIC]) { if (slow && numeric) k.qn[k.nn + __popc(bn & lt)] = Cand{start, len}; }
+    else k.ovf |= 1u << Q_NUMERIC;
+    k.nn += __popc(bn);
+  }
+}
+
+// One lane per queued candidate, g (<= 32) of them from the head of the queue.
+__device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQueues& k, const HotShared& s_hot, uint32_t g, uint32_t lane, uint32_t xflags, bool fast) {
+  const bool have = lane < g;
+  uint2 e = make_uint2(0u, 0u);
+  if (have) e = lds_u64(k.q_s + ((k.qhead + lane) & (SK_QCAP - 1)) * 8);
+  k.qhead = (k.qhead + g) & (SK_QCAP - 1); k.qcount -= g; k.q_old = k.q_old > g ? k.q_old - g : 0u;
+  const uint32_t start = e.x, len = e.y & 0x7FFFFFFFu;
+  const bool numeric = (e.y >> 31) != 0;
+  KeyWords kw;
+  load_head_words_shared(k.ring_s + (start & (SK_RING - 1)), kw.h);
+  load_tail_words_shared_end(k.ring_s + ((start + len - 16u) & (SK_RING - 1)) + 16u, have ? len : 0u, kw.t);
+  bool wi = false;
+  IpTok it{start, len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
+  if (have && numeric && (xflags & MGPU_X_IPV4)) wi = parse_ipv4_words(kw.h, len, it.w[0]);
+  if (wi) tw.n_v4++;
+  bool ws = false, slow = false;
+  StrTok st{start, len, MGPU_T_DOMAIN};
+  if (have && !wi && (xflags & MGPU_X_DOMAINS)) {
+    // a valid IPv4 address is never a domain: its last label is numeric, and no PSL entry ends in one (checked at upload)
+    const uint64_t tail8 = len >= 8 ? (((uint64_t)kw.t[3] << 32) | kw.t[2]) : ((((uint64_t)kw.h[1] << 32) | kw.h[0]) << (8 * (8 - len)));
+    const int c = tld_class(a.db.psl_tld, tail8);
+    if (c == TLD_ACCEPT && !k.high) ws = true;
+    else if (c != TLD_REJECT) slow = true;  // multi-label suffix walk or UTF-8 validation: loops over the bytes -> token_kernel
+  }
+  __syncwarp();
+  if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, false, start, len);
+  uint32_t gate = 0;
+  if (__any_sync(0xFFFFFFFFu, ws)) {
+    if (ws) {
+      tw.n_dom++;
+      if (fast) { gate = string_gate(a.db, s_hot, kw, len); ws = false; }  // (both filter stages of a class run in defer_drain: no per-lane loops here)
+    }
+    __syncwarp();
+  }
+  append_tokens(a, tw, lane, ws, st, wi, it);
+  defer_push(a, tw, lane, gate, st, s_hot);
+}
+
+template <uint32_t FIXED>
+__global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  uint32_t* s_hot_words = reinterpret_cast<uint32_t*>(sk_smem);
+  uint32_t* lut = reinterpret_cast<uint32_t*>(sk_smem + (size_t)HOT_WORDS * 4);
+  SkWarp* sw = reinterpret_cast<SkWarp*>(sk_smem + (size_t)HOT_WORDS * 4 + SK_LUT_BYTES);
+  const HotShared s_hot{(uint32_t)__cvta_generic_to_shared(sk_smem), a.db.gen_gram2};
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const bool fast = a.fast != 0;
+  for (uint32_t i = threadIdx.x; i < 128 * 32; i += blockDim.x) lut[i] = category_planes((uint8_t)(i >> 5));
+  if (fast) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.db.hot);
+    for (uint32_t i = threadIdx.x; i < HOT_WORDS / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_hot_words)[i] = src[i];
+  }
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&sw[warp].mbar[0]);
+  if (lane == 0) { for (uint32_t j = 0; j < 4; j++) mbar_init(mbar_s + 8 * j, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const uint32_t lut_lane_s = (uint32_t)__cvta_generic_to_shared(lut) + lane * 4;
+  const uint64_t nwarps = (uint64_t)gridDim.x * SK_WARPS;  // == a.nseg
+  const uint64_t w = (uint64_t)blockIdx.x * SK_WARPS + warp;
+  const uint64_t tiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
+  const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
+  const uint64_t t0 = w * tpw;
+  uint64_t t1 = t0 + tpw;
+  if (t1 > tiles) t1 = tiles;
+  Cand* const qh = a.q_hash + w * a.seg_cap[Q_HASH];
+  uint32_t* const qa = a.q_at + w * a.seg_cap[Q_AT];
+  uint32_t* const qc = a.q_c2 + w * a.seg_cap[Q_COLON2];
+  Cand* const ql = a.q_long + w * a.seg_cap[Q_LONG];
+  SkQueues k;
+  k.ring_s = (uint32_t)__cvta_generic_to_shared(&sw[warp].ring[0]);
+  k.q_s = (uint32_t)__cvta_generic_to_shared(&sw[warp].q[0]);
+  k.qhead = 0; k.qcount = 0; k.q_old = 0; k.high = 0;
+  k.qd = a.q_dotted + w * a.seg_cap[Q_DOTTED]; k.qn = a.q_numeric + w * a.seg_cap[Q_NUMERIC];
+  k.nd = 0; k.nn = 0; k.ovf = 0;
+  uint32_t nh = 0, na = 0, nc = 0, nl = 0;
+  uint32_t lines = 0;
+  TokenWarp tw;
+  memset(&tw, 0, sizeof tw);
+  tw.defer = a.defer + (size_t)w * DEFER_CAP;
+  const uint32_t xflags = FIXED ? FIXED : a.flags;
+  if (t0 < t1) {
+    TileCarry cy = range_prologue(a.buf, a.lo, t0 * TILE_BYTES);
+    uint32_t pDOT = (cy.prev & PV_DOT) ? 0x80000000u : 0u, pDASH = (cy.prev & PV_DASH) ? 0x80000000u : 0u;
+    uint32_t pCL = ((cy.prev & PV_CL1) ? 0x80000000u : 0u) | ((cy.prev & PV_CL2) ? 0x40000000u : 0u);
+    const bool want_dot = (xflags & (MGPU_X_IPV4 | MGPU_X_DOMAINS)) != 0;
+    const bool want_hash = (xflags & MGPU_X_HASHES) != 0;
+    const bool want_at = (xflags & MGPU_X_EMAILS) != 0;
+    const bool want_c2 = (xflags & MGPU_X_IPV6) != 0;
+    const bool want_long = (xflags & MGPU_X_CRYPTO) != 0;
+    const uint32_t t_begin = (uint32_t)t0, t_end = (uint32_t)t1, t_last = (uint32_t)(tiles - 1);
+    const uint32_t range_lo = t_begin * TILE_BYTES;
+    if (lane == 0) {
+      tile_load(k.ring_s + (t_begin & 3u) * TILE_BYTES, a.buf + (size_t)t_begin * TILE_BYTES, TILE_BYTES, mbar_s + (t_begin & 3u) * 8);
+      if (t_begin + 1 < t_end) tile_load(k.ring_s + ((t_begin + 1) & 3u) * TILE_BYTES, a.buf + (size_t)(t_begin + 1) * TILE_BYTES, TILE_BYTES, mbar_s + ((t_begin + 1) & 3u) * 8);
+    }
+    uint32_t high_hist = 0;
+    for (uint32_t t = t_begin; t < t_end; t++) {
+      const uint32_t slot = t & 3u;
+      const uint32_t tile_base = t * TILE_BYTES;  // chunks are at most 2 GiB: positions fit 32 bits
+      const uint32_t p = tile_base + lane * SLICE_BYTES;
+      mbar_wait(mbar_s + slot * 8, ((t - t_begin) >> 2) & 1u);
+      if (slot == 0) {  // refresh the mirror of the ring's first bytes
+        if (lane < SK_PAD / 4) sts_u32(k.ring_s + SK_RING + lane * 4, lds_u32(k.ring_s + lane * 4));
+        __syncwarp();
+      }
+      const uint4 v0 = lds_u128(k.ring_s + slot * TILE_BYTES + lane * SLICE_BYTES), v1 = lds_u128(k.ring_s + slot * TILE_BYTES + lane * SLICE_BYTES + 16);
+      uint32_t wds[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const uint32_t hb = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) & 0x80808080u;
+      const bool tile_high = __any_sync(0xFFFFFFFFu, hb != 0);
+      high_hist = ((high_hist << 1) | (tile_high ? 1u : 0u)) & 7u;
+      k.high = high_hist;
+      if (tile_high) {  // (warp-uniform, rare) bytes >= 0x80 are domain characters of the 'g' kind: give them that row of the table
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint32_t mk = ((wds[j] & 0x80808080u) >> 7) * 0xFFu;
+          wds[j] = (wds[j] & ~mk) | (0x67676767u & mk);
+        }
+      }
+      uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const uint32_t bv = __byte_perm(wds[j], 0u, 0x4440u | (uint32_t)kk);  // byte kk of the word
+          const uint32_t ev = lds_u32(bv * 128u + lut_lane_s);
+          acc[j >> 1] += ev << ((j & 1) * 4 + kk);
+        }
+      }
+      // byte c of acc[q] = plane c of bytes 8q..8q+7: a 4x4 byte transpose gives one 32-bit mask per plane
+      LaneMasks m;
+      {
+        const uint32_t r0 = __byte_perm(acc[0], acc[1], 0x5140), r1 = __byte_perm(acc[0], acc[1], 0x7362);
+        const uint32_t r2 = __byte_perm(acc[2], acc[3], 0x5140), r3 = __byte_perm(acc[2], acc[3], 0x7362);
+        const uint32_t P0 = __byte_perm(r0, r2, 0x5410), P1 = __byte_perm(r0, r2, 0x7632);
+        const uint32_t P2 = __byte_perm(r1, r3, 0x5410), P3 = __byte_perm(r1, r3, 0x7632);
+        m.B = P3; m.NL = P3 & ~P1 & P0; m.AT = P3 & P1 & ~P0; m.CL = P3 & P1 & P0;
+        m.DM = P2; m.DOT = P2 & ~P1 & P0; m.DASH = P2 & P1 & ~P0; m.HX = P2 & P1 & P0;
+      }
+      if (t == 0 || t == t_last) {  // only the chunk's first (lo < 16) and last tile can hold bytes outside [lo, n): they behave like a boundary (chunk edge)
+        uint64_t valid = a.n > p ? a.n - p : 0;
+        uint32_t keep = valid >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)valid) - 1u);
+        if (p < a.lo) keep &= (a.lo - p >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.lo - p));
+        m.B |= ~keep; m.DOT &= keep; m.AT &= keep; m.CL &= keep; m.NL &= keep; m.DM &= keep; m.HX &= keep; m.DASH &= keep;
+      }
+      if ((int32_t)cy.prevB < 0) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
+      lines += __popc(m.NL);
+
+      const uint32_t T = ~m.B;
+      uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1), DOTp = __shfl_up_sync(0xFFFFFFFFu, m.DOT, 1);
+      uint32_t DASHp = __shfl_up_sync(0xFFFFFFFFu, m.DASH, 1), CLp = __shfl_up_sync(0xFFFFFFFFu, m.CL, 1);
+      if (lane == 0) { Bprev = cy.prevB; DOTp = pDOT; DASHp = pDASH; CLp = pCL; }
+      const uint32_t prevT = ~__funnelshift_l(Bprev, m.B, 1);  // bit i: byte i-1 is a word byte
+      const bool pT = (int32_t)Bprev >= 0;                      // the byte before my slice is a word byte
+      const uint32_t S = T & ~prevT;
+      uint32_t bad, bad_end;
+      domain_rule_masks_prev(m, S, __funnelshift_l(DOTp, m.DOT, 1), __funnelshift_l(DASHp, m.DASH, 1), bad, bad_end);
+      // "does the word contain ..." chains (tokenize.cuh): a byte that rules out a domain, a '.', a byte that is neither a hex
+      // digit nor a '.'; "a non-hex byte" is the OR of the last two
+      const uint32_t Y1 = T & (~m.DM | bad), Y2 = m.DOT, Y4 = T & ~m.HX & ~m.DOT;
+      const uint32_t g1 = chain_gen(T, Y1), g2 = chain_gen(T, Y2), g4 = chain_gen(T, Y4);
+      const uint32_t pb = __ballot_sync(0xFFFFFFFFu, T == 0xFFFFFFFFu);
+      const uint32_t G1 = __ballot_sync(0xFFFFFFFFu, g1), G2 = __ballot_sync(0xFFFFFFFFu, g2), G4 = __ballot_sync(0xFFFFFFFFu, g4);
+      uint32_t co1, co2, co4;
+      const uint32_t cv1 = carry_chain(G1, pb & ~G1, cy.cBad, co1), cv2 = carry_chain(G2, pb & ~G2, cy.cDot, co2), cv4 = carry_chain(G4, pb & ~G4, cy.cNhd, co4);
+      cy.cBad = co1; cy.cDot = co2; cy.cNhd = co4;
+      const uint32_t E = m.B & prevT;  // boundaries that end a word
+      const uint32_t hasBad = chain_ends(T, Y1, (cv1 >> lane) & 1u, m.B), hasDot = chain_ends(T, Y2, (cv2 >> lane) & 1u, m.B);
+      const uint32_t hasNhd = chain_ends(T, Y4, (cv4 >> lane) & 1u, m.B);
+      const uint32_t hasNhx = hasNhd | hasDot;
+      const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
+      uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
+      if (candHex && (Bprev >> (__ffs(candHex) - 1)) != 0) candHex = 0;
+      const uint32_t candLong = want_long ? long_word_ends(T, ~Bprev, E) : 0u;
+      const uint32_t candAt = want_at ? m.AT : 0u;
+      const uint32_t cl1 = __funnelshift_l(CLp, m.CL, 1), cl2 = __funnelshift_l(CLp, m.CL, 2);
+      const uint32_t candC2 = want_c2 ? (m.CL & cl1 & ~cl2) : 0u;
+
+      // where the word that is open at the start of my slice begins
+      const uint32_t hasB = __ballot_sync(0xFFFFFFFFu, m.B != 0);
+      const uint32_t src = lane_below_with_boundary(hasB, lane);
+      const uint32_t Bsrc = __shfl_sync(0xFFFFFFFFu, m.B, src & 31u);
+      const uint32_t lane_open = src < 32u ? tile_base + src * 32 + top_bit(Bsrc) + 1 : (uint32_t)cy.open_start;
+
+      // ---- dotted words: into the shared-memory queue, one per lane and round ----
+      {
+        const uint32_t candNum = candDot & ~hasNhd;  // hex digits and dots only: IPv4 candidates
+        const uint32_t ring_lo = tile_base >= range_lo + TILE_BYTES ? tile_base - TILE_BYTES : range_lo;  // oldest byte a queued word may start at
+        uint32_t rem = candDot;
+        while (__any_sync(0xFFFFFFFFu, rem != 0)) {
+          const bool have = rem != 0;
+          uint32_t s = 0, len = 0;
+          bool numeric = false;
+          if (have) {
+            const uint32_t low = rem & (0u - rem), bit = __ffs(rem) - 1;
+            const uint32_t below = m.B & (low - 1u);
+            s = below ? p + top_bit(below) + 1 : lane_open;
+            len = p + bit - s;
+            numeric = (candNum & low) != 0;
+            rem &= rem - 1;
+          }
+          const bool slow = have && s < ring_lo;
+          const uint32_t bq = __ballot_sync(0xFFFFFFFFu, have && !slow);
+          if (bq) {
+            if (have && !slow) sts_u64(k.q_s + ((k.qhead + k.qcount + __popc(bq & lt_mask)) & (SK_QCAP - 1)) * 8, s, len | (numeric ? 0x80000000u : 0u));
+            k.qcount += __popc(bq);
+          }
+          if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, numeric, s, len);
+          __syncwarp();
+          if (k.qcount >= 32) sk_group(a, tw, k, s_hot, 32, lane, xflags, fast);
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2 | candLong) != 0)) {  // rare in most logs: one vote covers the four
+        {
+          bool keep = false; Cand c{0, 0};
+          if (candHex) {
+            const uint32_t bit = __ffs(candHex) - 1;
+            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+            keep = is_hash_len(p + bit - s);
+            c.start = s; c.len = p + bit - s;
+          }
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+          if (bal) {
+            const uint32_t total = __popc(bal);
+            if (nh + total <= a.seg_cap[Q_HASH]) { if (keep) qh[nh + __popc(bal & lt_mask)] = c; }
+            else k.ovf |= 1u << Q_HASH;
+            nh += total;
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, candAt != 0)) {
+          const uint32_t cnt = __popc(candAt), incl = warp_incl_scan(cnt, lane);
+          const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (na + total <= a.seg_cap[Q_AT]) {
+            uint32_t idx = na + incl - cnt;
+            for (uint32_t mm = candAt; mm; mm &= mm - 1) qa[idx++] = (uint32_t)(p + __ffs(mm) - 1);
+          } else k.ovf |= 1u << Q_AT;
+          na += total;
+        }
+        if (__any_sync(0xFFFFFFFFu, candLong != 0)) {
+          Cand c2[2]; uint32_t kq = 0;
+          for (uint32_t mm = candLong; mm; mm &= mm - 1) {
+            const uint32_t bit = __ffs(mm) - 1;
+            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+            if (is_crypto_len(p + bit - s) && kq < 2) c2[kq++] = Cand{s, p + bit - s};
+          }
+          const uint32_t incl = warp_incl_scan(kq, lane), total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (total) {
+            if (nl + total <= a.seg_cap[Q_LONG]) { for (uint32_t j = 0; j < kq; j++) ql[nl + incl - kq + j] = c2[j]; }
+            else k.ovf |= 1u << Q_LONG;
+            nl += total;
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, candC2 != 0)) {
+          const uint32_t cnt = __popc(candC2), incl = warp_incl_scan(cnt, lane);
+          const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          if (nc + total <= a.seg_cap[Q_COLON2]) {
+            uint32_t idx = nc + incl - cnt;
+            for (uint32_t mm = candC2; mm; mm &= mm - 1) qc[idx++] = (uint32_t)(p + __ffs(mm) - 2);
+          } else k.ovf |= 1u << Q_COLON2;
+          nc += total;
+        }
+      }
+
+      // ---- end of the tile: candidates that ended before it must go before their bytes do; then the next load ----
+      if (k.q_old) sk_group(a, tw, k, s_hot, k.qcount < 32u ? k.qcount : 32u, lane, xflags, fast);
+      k.q_old = k.qcount;
+      __syncwarp();
+      if (lane == 0 && t + 2 < t_end) tile_load(k.ring_s + ((t + 2) & 3u) * TILE_BYTES, a.buf + (size_t)(t + 2) * TILE_BYTES, TILE_BYTES, mbar_s + ((t + 2) & 3u) * 8);
+
+      // ---- carry into the next tile ----
+      if (hasB) {
+        const uint32_t ll = top_bit(hasB);
+        const uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
+        cy.open_start = tile_base + ll * 32 + top_bit(Bl) + 1;
+      }
+      cy.prevB = __shfl_sync(0xFFFFFFFFu, m.B, 31);
+      pDOT = __shfl_sync(0xFFFFFFFFu, m.DOT, 31); pDASH = __shfl_sync(0xFFFFFFFFu, m.DASH, 31); pCL = __shfl_sync(0xFFFFFFFFu, m.CL, 31);
+    }
+    while (k.qcount) sk_group(a, tw, k, s_hot, k.qcount < 32u ? k.qcount : 32u, lane, xflags, fast);
+  }
+  if (tw.n_def) { defer_drain(a, tw, lane, tw.defer, tw.n_def, s_hot); tw.n_def = 0; }  // (n_def is warp-uniform)
+  for (uint32_t i = lane; i < tw.cs.left; i += 32) a.str[tw.cs.base + i].type = TOK_INVALID;
+  for (uint32_t i = lane; i < tw.ci.left; i += 32) a.ip[tw.ci.base + i].type = TOK_INVALID;
+  if (lane == 0) {
+    uint32_t* sc = a.seg_cnt + w;
+    sc[Q_DOTTED * a.nseg_max] = k.ovf & (1u << Q_DOTTED) ? 0u : k.nd;
+    sc[Q_HASH * a.nseg_max] = k.ovf & (1u << Q_HASH) ? 0u : nh;
+    sc[Q_AT * a.nseg_max] = k.ovf & (1u << Q_AT) ? 0u : na;
+    sc[Q_COLON2 * a.nseg_max] = k.ovf & (1u << Q_COLON2) ? 0u : nc;
+    sc[Q_NUMERIC * a.nseg_max] = k.ovf & (1u << Q_NUMERIC) ? 0u : k.nn;
+    sc[Q_LONG * a.nseg_max] = k.ovf & (1u << Q_LONG) ? 0u : nl;
+    if (k.ovf) atomicOr(&a.ctr->overflow, k.ovf);
+  }
+  for (int d = 16; d; d >>= 1) lines += __shfl_down_sync(0xFFFFFFFFu, lines, d);
+  if (lane == 0 && lines) atomicAdd(&a.ctr->lines, (unsigned long long)lines);
+  uint32_t cnt[9] = {tw.n_dom, tw.n_mail, tw.n_v4, tw.n_v6, tw.n_md5, tw.n_sha1, tw.n_sha256, tw.n_sha384, tw.n_sha512};
+#pragma unroll
+  for (int tt = 0; tt < 9; tt++) {
+    uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cnt[tt]);
+    if (lane == 0 && v) atomicAdd(&a.ctr->by_type[tt], (unsigned long long)v);
   }
 }
 
@@ -1290,6 +1684,7 @@ struct mgpu_ctx {
   cudaEvent_t ev_tokens[MAX_BATCH] = {}, ev_looked[MAX_BATCH] = {};  // token lists of the slot's piece written / consumed
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_k[MAX_BATCH][MGPU_K_COUNT + 1] = {};
+  cudaEvent_t ev_l0[MAX_BATCH] = {};  // on the lookup stream, after it has waited for the piece's tokens: where the IP-trie kernel's time starts
   cudaEvent_t ev_scan[2] = {nullptr, nullptr};
   // log staging (double buffered) and pinned bounce buffers for pageable callers
   uint8_t* d_log[2] = {nullptr, nullptr};
@@ -1322,6 +1717,7 @@ struct mgpu_ctx {
   std::vector<StrTok> x_str; std::vector<IpTok> x_ip;  // extraction-only capture
   bool capture_tokens = false;
   // test / debug switches (mgpu_set_option)
+  bool fused = true;  // scan_kernel (one pass) instead of tokenize_kernel + the word passes of token_kernel
   bool verify_tokens = false;
   unsigned long long* d_dbg = nullptr;  // 16 audit accumulators (verify_tokens_kernel: 0..6, iptrie_kernel: 8..10)
   uint32_t alloc_cap_str = 0, alloc_cap_ip = 0, alloc_cap_rec = 0, alloc_cap_ids = 0;  // what the buffers really hold
@@ -1351,6 +1747,7 @@ void mgpu_destroy(mgpu_ctx* c) {
     if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
   }
   for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_l0) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
   void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.q_long, c->args.seg_cnt, c->args.str, c->args.defer, c->args.ip, c->args.lh_res,
                   c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_dbg, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
@@ -1392,6 +1789,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
     CK(cudaMallocHost(&c->h_pin[s], std::min(chunk_bytes, (size_t)64 << 20)));
   }
   for (auto& row : c->ev_k) for (auto& e : row) CK(cudaEventCreate(&e));
+  for (auto& e : c->ev_l0) CK(cudaEventCreate(&e));
   for (auto& e : c->ev_scan) CK(cudaEventCreate(&e));
   ScanArgs& a = c->args;
   memset(&a, 0, sizeof a);
@@ -1437,6 +1835,8 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)));
   CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
   CK(cudaFuncSetAttribute(token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOKEN_SMEM));
+  CK(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
+  CK(cudaFuncSetAttribute(scan_kernel<K1_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
   CK(cudaFuncSetAttribute(tokenize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
   CK(cudaFuncSetAttribute(tokenize_kernel<K1_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
   return MGPU_OK;
@@ -1469,6 +1869,7 @@ int mgpu_set_option(mgpu_ctx* c, const char* key, uint64_t value) {
     if (cudaSetDevice(c->device) != cudaSuccess || cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMemset failed"); return MGPU_E_CUDA; }
   }
   else if (k == "variant") c->args.variant = (uint32_t)value;
+  else if (k == "fused") c->fused = value != 0;
   else { set_err("unknown option: " + k); return MGPU_E_PARAM; }
   return MGPU_OK;
 }
@@ -1632,9 +2033,23 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   if (c->force_ac_walk) a.db.ac_anchored = 0;
   cudaStream_t st = c->compute;
   cudaEvent_t* ev = c->ev_k[slot];
+  const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
+  a.fast = fast ? 1u : 0u;
+  const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
+  if (c->fused) {
+    // the fused kernel appends to the token lists the previous piece's lookups read: wait for them first
+    if (c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
+    if (c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
+    CK(cudaEventRecord(ev[0], st));
+    uint64_t want_blocks = (tiles + SK_WARPS - 1) / SK_WARPS;
+    int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 1));
+    if (grid < 1) grid = 1;
+    a.nseg = (uint32_t)grid * SK_WARPS;
+    if (flags == K1_DEFAULT_FLAGS) scan_kernel<K1_DEFAULT_FLAGS><<<grid, SK_THREADS, SCAN_SMEM, st>>>(a);
+    else scan_kernel<0><<<grid, SK_THREADS, SCAN_SMEM, st>>>(a);
+  } else {
   CK(cudaEventRecord(ev[0], st));
   {
-    uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
     uint64_t want_blocks = (tiles + K1_WARPS - 1) / K1_WARPS;
     int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 2));
     if (grid < 1) grid = 1;
@@ -1643,13 +2058,12 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     if (flags == K1_DEFAULT_FLAGS) tokenize_kernel<K1_DEFAULT_FLAGS><<<grid, K1_THREADS, smem, st>>>(a);
     else tokenize_kernel<0><<<grid, K1_THREADS, smem, st>>>(a);
   }
+  }
   CK(cudaEventRecord(ev[1], st));
-  const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
-  a.fast = fast ? 1u : 0u;
   // The token kernel overwrites the token lists the previous piece's lookups read: wait for them.  The lookups themselves
   // (latency-bound, a fraction of the SMs busy) run on a second stream, beside the tokenizer of the next piece.
-  if (c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
-  if (c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
+  if (!c->fused && c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
+  if (!c->fused && c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
   token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
   if (flags & MGPU_X_CRYPTO) crypto_kernel<<<launch_grid(c, 8), 128, 0, st>>>(a);
   if (c->verify_tokens) verify_tokens_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a, c->d_dbg);
@@ -1657,6 +2071,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   cudaStream_t ls = (a.variant & 16u) ? st : c->lookup;  // (experiment: lookups serialised behind the token kernel)
   CK(cudaEventRecord(c->ev_tokens[slot], st));
   CK(cudaStreamWaitEvent(ls, c->ev_tokens[slot], 0));
+  CK(cudaEventRecord(c->ev_l0[slot], ls));
   if (lookups) {
     iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
     CK(cudaEventRecord(ev[3], ls));
@@ -1697,7 +2112,8 @@ static int end_batch(mgpu_ctx* c, int pieces) {
   for (int p = 0; p < pieces; p++) {
     for (int k = 0; k < MGPU_K_COUNT; k++) {
       float ms = 0;
-      CK(cudaEventElapsedTime(&ms, c->ev_k[p][k], c->ev_k[p][k + 1]));
+      // (the lookup kernels run on their own stream: their span starts where that stream has finished waiting for the tokens)
+      CK(cudaEventElapsedTime(&ms, k == MGPU_K_IPTRIE ? c->ev_l0[p] : c->ev_k[p][k], c->ev_k[p][k + 1]));
       c->timing.kernel_ms[k] += ms;
     }
     float tot = 0;

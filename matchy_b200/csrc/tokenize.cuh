@@ -37,6 +37,23 @@ MGPU_HD uint32_t class_bits(uint8_t b) {
   return c;
 }
 
+// byte category as four bit planes in the four bytes of a word (bit 0 of byte c = plane c):
+//   plane 3: boundary byte; among them planes 1,0 = 00 other, 01 '\n', 10 '@', 11 ':'
+//   plane 2: domain character;       planes 1,0 = 00 other, 01 '.',  10 '-', 11 hex digit
+MGPU_HD uint32_t category_planes(uint8_t b) {
+  const uint32_t c = class_bits(b);
+  uint32_t p3 = 0, p2 = 0, lo = 0;
+  if (c & (1u << CLS_B)) { p3 = 1; lo = (c & (1u << CLS_NL)) ? 1u : (c & (1u << CLS_AT)) ? 2u : (c & (1u << CLS_CL)) ? 3u : 0u; }
+  else if (c & (1u << CLS_DM)) { p2 = 1; lo = (c & (1u << CLS_DOT)) ? 1u : (c & (1u << CLS_DASH)) ? 2u : (c & (1u << CLS_HX)) ? 3u : 0u; }
+  return (lo & 1u) | ((lo >> 1) << 8) | (p2 << 16) | (p3 << 24);
+}
+// the eight class bits back from the planes of ONE byte (what the kernel does per 32-byte mask with three LOP3 each)
+MGPU_HD uint32_t class_bits_from_planes(uint32_t e) {
+  const uint32_t P0 = e & 1u, P1 = (e >> 8) & 1u, P2 = (e >> 16) & 1u, P3 = (e >> 24) & 1u;
+  return (P3 << CLS_B) | ((P2 & ~P1 & P0) << CLS_DOT) | ((P3 & P1 & ~P0 & 1u) << CLS_AT) | ((P3 & P1 & P0) << CLS_CL) | ((P3 & ~P1 & P0 & 1u) << CLS_NL) |
+         (P2 << CLS_DM) | ((P2 & P1 & P0) << CLS_HX) | ((P2 & P1 & ~P0 & 1u) << CLS_DASH);
+}
+
 struct LaneMasks { uint32_t B, DOT, AT, CL, NL, DM, HX, DASH; };
 
 // State carried into a tile (identical in all lanes of the warp).

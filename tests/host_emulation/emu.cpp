@@ -334,6 +334,10 @@ uint32_t emu_tree_record(const uint8_t* tree, uint32_t node_count, uint32_t reco
 // the kernels' mask-arithmetic IPv6 parser on a bare run (s must be readable 8 bytes past n); 1 = parsed
 int emu_parse_ipv6_masks(const uint8_t* s, uint32_t n, uint32_t w[4]) { return parse_ipv6_run_masks(s, n, w) ? 1 : 0; }
 
+// scan_kernel's byte classification: category planes of byte b (bytes >= 0x80 take the row of 'g') -> class bits
+uint32_t emu_class_bits_via_planes(uint32_t b) { return class_bits_from_planes(category_planes((uint8_t)(b >= 0x80 ? 'g' : b))); }
+uint32_t emu_class_bits(uint32_t b) { return class_bits((uint8_t)b); }
+
 int64_t emu_tokens(emu_ctx* c, uint64_t* out, size_t cap) {
   std::vector<std::array<uint64_t, 3>> items;
   for (auto& t : c->str) items.push_back({t.type, t.start, (uint64_t)t.start + t.len});

@@ -252,3 +252,13 @@ def test_ipv6_mask_parser_equals_reference_parser():
             assert [(w[k // 2] >> (0 if k & 1 else 16)) & 0xFFFF for k in range(8)] == want, s
         checked += 1
     assert checked > 5000
+
+
+def test_byte_category_planes_reproduce_the_class_bits():
+    """scan_kernel classifies a byte through a 4-bit category (four bit planes, one table word) instead of the tokenizer's
+    eight class bits: the planes must give back exactly class_bits() for every byte value."""
+    import emu_lib
+    L = emu_lib.lib()
+    L.emu_class_bits_via_planes.restype = L.emu_class_bits.restype = __import__("ctypes").c_uint32
+    for b in range(256):
+        assert L.emu_class_bits_via_planes(b) == L.emu_class_bits(b), b
