@@ -485,6 +485,63 @@ MGPU_HDN bool parse_ipv4_words(const uint32_t h[4], uint32_t n, uint32_t& addr_o
   addr_out = addr;
   return true;
 }
+// The same parser for a word that is KNOWN to consist of hex digits and '.' only (the numeric queue's words: the tokenizer's
+// fourth carry chain established it).  Then a byte is a decimal digit iff its bit 4 is set ('0'..'9' = 0x30..0x39, '.' = 0x2E,
+// letters 0x41.. / 0x61..) and a dot iff bits 4 and 6 are both clear, the digit values are the low nibbles, and the four
+// groups are cut out of the 16 nibbles by shifts: about half the instructions of the general version.  The fused scan
+// kernel runs this one; tests/test_emulation_vs_oracle.py checks it against parse_ipv4_words on every such word it can make up.
+MGPU_HD uint32_t pack_flags4(uint32_t x) { return (x * 0x01020408u) >> 24; }  // bit 0 of each of the four bytes -> four bits
+MGPU_HDN bool parse_ipv4_hexdot(const uint32_t h[4], uint32_t n, uint32_t& addr_out) {
+  if (n < 7 || n > 15) return false;
+  const uint32_t D = pack_flags4((h[0] >> 4) & 0x01010101u) | (pack_flags4((h[1] >> 4) & 0x01010101u) << 4) | (pack_flags4((h[2] >> 4) & 0x01010101u) << 8) |
+                     (pack_flags4((h[3] >> 4) & 0x01010101u) << 12);
+  const uint32_t P = pack_flags4(~((h[0] >> 4) | (h[0] >> 6)) & 0x01010101u) | (pack_flags4(~((h[1] >> 4) | (h[1] >> 6)) & 0x01010101u) << 4) |
+                     (pack_flags4(~((h[2] >> 4) | (h[2] >> 6)) & 0x01010101u) << 8) | (pack_flags4(~((h[3] >> 4) | (h[3] >> 6)) & 0x01010101u) << 12);
+  const uint32_t all = (1u << n) - 1u;
+  if (((D | P) & all) != all) return false;  // a letter
+  const uint32_t Pn = P & all;
+#ifdef __CUDA_ARCH__
+  if (__popc(Pn) != 3) return false;
+  const uint32_t p1 = (uint32_t)__ffs((int)Pn) - 1u, P2 = Pn & (Pn - 1), p2 = (uint32_t)__ffs((int)P2) - 1u, p3 = (uint32_t)__ffs((int)(P2 & (P2 - 1))) - 1u;
+#else
+  if (__builtin_popcount(Pn) != 3) return false;
+  const uint32_t p1 = (uint32_t)__builtin_ctz(Pn), P2 = Pn & (Pn - 1), p2 = (uint32_t)__builtin_ctz(P2), p3 = (uint32_t)__builtin_ctz(P2 & (P2 - 1));
+#endif
+  // the 16 low nibbles, byte i's in nibble i
+  uint32_t nlo, nhi;
+  {
+    const uint32_t a0 = h[0] & 0x0F0F0F0Fu, a1 = h[1] & 0x0F0F0F0Fu, a2 = h[2] & 0x0F0F0F0Fu, a3 = h[3] & 0x0F0F0F0Fu;
+    const uint32_t b0 = a0 | (a0 >> 4), b1 = a1 | (a1 >> 4), b2 = a2 | (a2 >> 4), b3 = a3 | (a3 >> 4);  // bytes 0 and 2 hold two nibbles each
+#ifdef __CUDA_ARCH__
+    nlo = __byte_perm(b0, b1, 0x6420); nhi = __byte_perm(b2, b3, 0x6420);
+#else
+    nlo = (b0 & 0xFFu) | ((b0 >> 8) & 0xFF00u) | ((b1 & 0xFFu) << 16) | ((b1 & 0xFF0000u) << 8);
+    nhi = (b2 & 0xFFu) | ((b2 >> 8) & 0xFF00u) | ((b3 & 0xFFu) << 16) | ((b3 & 0xFF0000u) << 8);
+#endif
+  }
+  const uint32_t st[4] = {0u, p1 + 1, p2 + 1, p3 + 1}, ln[4] = {p1, p2 - p1 - 1, p3 - p2 - 1, n - p3 - 1};
+  uint32_t addr = 0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t l = ln[k], sh = 4 * st[k];
+    ok = ok && l >= 1 && l <= 3;
+    // the group's nibbles, first digit lowest; then right-aligned in three nibbles: (0, 0, d0) / (0, d0, d1) / (d0, d1, d2)
+#ifdef __CUDA_ARCH__
+    const uint32_t x = sh < 32 ? __funnelshift_r(nlo, nhi, sh) : (nhi >> (sh - 32));
+#else
+    const uint64_t nn = ((uint64_t)nhi << 32) | nlo;
+    const uint32_t x = (uint32_t)(nn >> sh);
+#endif
+    const uint32_t y = (x << (4 * ((3 - l) & 3))) & 0xFFFu;
+    const uint32_t v = (y & 15u) * 100u + ((y >> 4) & 15u) * 10u + (y >> 8);
+    ok = ok && v <= 255 && !(l > 1 && (x & 15u) == 0);
+    addr = (addr << 8) | (v & 0xFF);
+  }
+  if (!ok) return false;
+  addr_out = addr;
+  return true;
+}
 MGPU_HDN bool parse_ipv4_word(const uint8_t* w, uint32_t n, uint32_t& addr_out) {
   if (n < 7 || n > 15) return false;
   uint32_t h[4];

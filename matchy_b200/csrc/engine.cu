@@ -59,6 +59,7 @@ struct ScanArgs {
   uint64_t base;       // absolute log offset of buf[0]
   uint32_t flags;
   uint32_t fast;       // 1: the token kernel applies string_filters() and only flagged string tokens reach the exact kernel
+  uint32_t lookups;    // 0: extraction only (mgpu_extract): tokens are produced, nothing is looked up
   DbView db;
   Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2; Cand* q_numeric; Cand* q_long;
   uint32_t seg_cap[Q_COUNT];
@@ -385,6 +386,7 @@ __device__ __forceinline__ const uint8_t* stage_window(const uint8_t* buf, uint8
 // ---------------------------------------------------------------------------------------------------------
 static const uint32_t TOK_RESERVE = 128;
 static const uint32_t TOK_INVALID = 0xFFu;  // StrTok.type / IpTok.type of a padding slot
+static const uint32_t TOK_RAW4 = 0xFEu;     // IpTok.type: a numeric-queue word of 7..15 bytes, not parsed yet; w[] = its first 16 bytes (iptrie_kernel parses it)
 struct QueueCursor { uint32_t base, left; };
 
 __device__ __forceinline__ uint32_t tok_reserve(uint32_t* counter, uint32_t cap, uint32_t need, uint32_t lane, QueueCursor& c,
@@ -482,19 +484,21 @@ __device__ __forceinline__ void defer_drain(const ScanArgs& a, TokenWarp& tw, ui
   append_tokens(a, tw, lane, ws, t, false, IpTok{0, 0, 0, 0, {0, 0, 0, 0}});
 }
 
-// Queue the lanes' gate-passing tokens; run stage 2 with a full warp once 32 are waiting.
-__device__ __forceinline__ void defer_push(const ScanArgs& a, TokenWarp& tw, uint32_t lane, uint32_t gate, const StrTok& st, const HotShared& s_hot) {
+// Queue the lanes' gate-passing tokens; run stage 2 with a full warp once 32 are waiting (flush: with whatever is waiting).
+// (One call of defer_drain in the code: the filters are large, and the fused kernel's loop has to stay in the instruction cache.)
+__device__ __forceinline__ void defer_push(const ScanArgs& a, TokenWarp& tw, uint32_t lane, uint32_t gate, const StrTok& st, const HotShared& s_hot, bool flush = false) {
   const uint32_t bal = __ballot_sync(0xFFFFFFFFu, gate != 0);
-  if (!bal) return;
+  if (!bal && !flush) return;
   if (gate) {
     StrTok* d = tw.defer + tw.n_def + __popc(bal & ((1u << lane) - 1u));
     __stcg(&d->start, st.start); __stcg(&d->len, st.len); __stcg(&d->type, (st.type & 0xFFFFu) | (gate << 16));
   }
   tw.n_def += __popc(bal);
   __syncwarp();
-  if (tw.n_def >= 32) {
-    tw.n_def -= 32;
-    defer_drain(a, tw, lane, tw.defer + tw.n_def, 32, s_hot);
+  while (tw.n_def >= 32 || (flush && tw.n_def)) {
+    const uint32_t cnt = tw.n_def >= 32 ? 32u : tw.n_def;
+    tw.n_def -= cnt;
+    defer_drain(a, tw, lane, tw.defer + tw.n_def, cnt, s_hot);
   }
 }
 
@@ -779,7 +783,9 @@ __device__ __forceinline__ void sk_push_slow(const ScanArgs& a, SkQueues& k, uin
 }
 
 // One lane per queued candidate, g (<= 32) of them from the head of the queue.
-__device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQueues& k, const HotShared& s_hot, uint32_t g, uint32_t lane, uint32_t xflags, bool fast) {
+__device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQueues& k, const HotShared& s_hot, uint32_t g, uint32_t lane, uint32_t xflags, bool fast,
+                                         bool final) {
+  __syncwarp();  // the queue entries were written by other lanes
   const bool have = lane < g;
   uint2 e = make_uint2(0u, 0u);
   if (have) e = lds_u64(k.q_s + ((k.qhead + lane) & (SK_QCAP - 1)) * 8);
@@ -789,10 +795,12 @@ __device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQue
   KeyWords kw;
   load_head_words_shared(k.ring_s + (start & (SK_RING - 1)), kw.h);
   load_tail_words_shared_end(k.ring_s + ((start + len - 16u) & (SK_RING - 1)) + 16u, have ? len : 0u, kw.t);
-  bool wi = false;
-  IpTok it{start, len, MGPU_T_IPV4, 0, {0, 0, 0, 0}};
-  if (have && numeric && (xflags & MGPU_X_IPV4)) wi = parse_ipv4_words(kw.h, len, it.w[0]);
-  if (wi) tw.n_v4++;
+  // A word of hex digits and dots, 7..15 bytes long, may be an IPv4 address: it goes to the IP token list UNPARSED, with its
+  // first 16 bytes, and iptrie_kernel parses it (one thread per token there, every lane busy, in a kernel that waits on memory
+  // anyway; here a quarter of the lanes at best would run the parser).  Should it not be an address, iptrie_kernel gives it
+  // the domain treatment (numeric_word_as_domain).
+  const bool wi = have && numeric && len >= 7 && len <= 15 && (xflags & MGPU_X_IPV4);
+  const IpTok it{start, len, TOK_RAW4, 0, {kw.h[0], kw.h[1], kw.h[2], kw.h[3]}};
   bool ws = false, slow = false;
   StrTok st{start, len, MGPU_T_DOMAIN};
   if (have && !wi && (xflags & MGPU_X_DOMAINS)) {
@@ -813,7 +821,7 @@ __device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQue
     __syncwarp();
   }
   append_tokens(a, tw, lane, ws, st, wi, it);
-  defer_push(a, tw, lane, gate, st, s_hot);
+  defer_push(a, tw, lane, gate, st, s_hot, final);
 }
 
 template <uint32_t FIXED>
@@ -876,10 +884,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       if (t_begin + 1 < t_end) tile_load(k.ring_s + ((t_begin + 1) & 3u) * TILE_BYTES, a.buf + (size_t)(t_begin + 1) * TILE_BYTES, TILE_BYTES, mbar_s + ((t_begin + 1) & 3u) * 8);
     }
     uint32_t high_hist = 0;
-    for (uint32_t t = t_begin; t < t_end; t++) {
-      const uint32_t slot = t & 3u;
+    bool flushed = false;
+    // One iteration per tile, plus a last one (t == t_end) that only empties the queues: sk_group() is large, so it is
+    // called from ONE place and everything that has to reach it goes through the loop below.
+    for (uint32_t t = t_begin; t <= t_end; t++) {
+      const bool last = t == t_end;
       const uint32_t tile_base = t * TILE_BYTES;  // chunks are at most 2 GiB: positions fit 32 bits
       const uint32_t p = tile_base + lane * SLICE_BYTES;
+      uint32_t rem = 0, candNum = 0, rounds = 0, Bm = 0, lane_open = 0, ring_lo = 0, total_dot = 0, excl_dot = 0;
+      bool may_slow = false;
+      if (!last) {
+      const uint32_t slot = t & 3u;
       mbar_wait(mbar_s + slot * 8, ((t - t_begin) >> 2) & 1u);
       if (slot == 0) {  // refresh the mirror of the ring's first bytes
         if (lane < SK_PAD / 4) sts_u32(k.ring_s + SK_RING + lane * 4, lds_u32(k.ring_s + lane * 4));
@@ -926,6 +941,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       }
       if ((int32_t)cy.prevB < 0) cy.open_start = tile_base;  // no word is open: a word that fills the tile from its first byte starts here
       lines += __popc(m.NL);
+      // oldest byte a queued word may start at; only the word that is open at the start of the tile can begin before it
+      ring_lo = tile_base >= range_lo + TILE_BYTES ? tile_base - TILE_BYTES : range_lo;
+      may_slow = (uint32_t)cy.open_start < ring_lo;
 
       const uint32_t T = ~m.B;
       uint32_t Bprev = __shfl_up_sync(0xFFFFFFFFu, m.B, 1), DOTp = __shfl_up_sync(0xFFFFFFFFu, m.DOT, 1);
@@ -961,36 +979,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       const uint32_t hasB = __ballot_sync(0xFFFFFFFFu, m.B != 0);
       const uint32_t src = lane_below_with_boundary(hasB, lane);
       const uint32_t Bsrc = __shfl_sync(0xFFFFFFFFu, m.B, src & 31u);
-      const uint32_t lane_open = src < 32u ? tile_base + src * 32 + top_bit(Bsrc) + 1 : (uint32_t)cy.open_start;
+      lane_open = src < 32u ? tile_base + src * 32 + top_bit(Bsrc) + 1 : (uint32_t)cy.open_start;
 
-      // ---- dotted words: into the shared-memory queue, one per lane and round ----
-      {
-        const uint32_t candNum = candDot & ~hasNhd;  // hex digits and dots only: IPv4 candidates
-        const uint32_t ring_lo = tile_base >= range_lo + TILE_BYTES ? tile_base - TILE_BYTES : range_lo;  // oldest byte a queued word may start at
-        uint32_t rem = candDot;
-        while (__any_sync(0xFFFFFFFFu, rem != 0)) {
-          const bool have = rem != 0;
-          uint32_t s = 0, len = 0;
-          bool numeric = false;
-          if (have) {
-            const uint32_t low = rem & (0u - rem), bit = __ffs(rem) - 1;
-            const uint32_t below = m.B & (low - 1u);
-            s = below ? p + top_bit(below) + 1 : lane_open;
-            len = p + bit - s;
-            numeric = (candNum & low) != 0;
-            rem &= rem - 1;
-          }
-          const bool slow = have && s < ring_lo;
-          const uint32_t bq = __ballot_sync(0xFFFFFFFFu, have && !slow);
-          if (bq) {
-            if (have && !slow) sts_u64(k.q_s + ((k.qhead + k.qcount + __popc(bq & lt_mask)) & (SK_QCAP - 1)) * 8, s, len | (numeric ? 0x80000000u : 0u));
-            k.qcount += __popc(bq);
-          }
-          if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, numeric, s, len);
-          __syncwarp();
-          if (k.qcount >= 32) sk_group(a, tw, k, s_hot, 32, lane, xflags, fast);
-        }
-      }
       if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2 | candLong) != 0)) {  // rare in most logs: one vote covers the four
         {
           bool keep = false; Cand c{0, 0};
@@ -1044,13 +1034,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
         }
       }
 
-      // ---- end of the tile: candidates that ended before it must go before their bytes do; then the next load ----
-      if (k.q_old) sk_group(a, tw, k, s_hot, k.qcount < 32u ? k.qcount : 32u, lane, xflags, fast);
-      k.q_old = k.qcount;
-      __syncwarp();
-      if (lane == 0 && t + 2 < t_end) tile_load(k.ring_s + ((t + 2) & 3u) * TILE_BYTES, a.buf + (size_t)(t + 2) * TILE_BYTES, TILE_BYTES, mbar_s + ((t + 2) & 3u) * 8);
-
-      // ---- carry into the next tile ----
+      // ---- carry into the next tile (nothing below needs the class masks any more, only the boundary mask) ----
       if (hasB) {
         const uint32_t ll = top_bit(hasB);
         const uint32_t Bl = __shfl_sync(0xFFFFFFFFu, m.B, ll);
@@ -1058,10 +1042,70 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       }
       cy.prevB = __shfl_sync(0xFFFFFFFFu, m.B, 31);
       pDOT = __shfl_sync(0xFFFFFFFFu, m.DOT, 31); pDASH = __shfl_sync(0xFFFFFFFFu, m.DASH, 31); pCL = __shfl_sync(0xFFFFFFFFu, m.CL, 31);
+      Bm = m.B;
+      rem = candDot;
+      candNum = candDot & ~hasNhd;  // hex digits and dots only: IPv4 candidates
+      {
+        const uint32_t cnt = (uint32_t)__popc(candDot), incl = warp_incl_scan(cnt, lane);
+        total_dot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        excl_dot = incl - cnt;
+        rounds = total_dot ? 32u : 0u;  // (upper bound for the round-by-round path, which stops when no lane has a word left)
+      }
+      }
+
+      // ---- dotted words: into the shared-memory queue; a group of 32 whenever that many wait ----
+      // Usual case: all of the tile's words fit behind what is queued -> one prefix sum over the lanes' counts and every
+      // lane stores its own.  Otherwise (a tile full of short words, or a word that began behind the ring) one word per lane
+      // and round, with groups in between.
+      if (total_dot && !may_slow && k.qcount + total_dot <= SK_QCAP) {
+        uint32_t idx = k.qhead + k.qcount + excl_dot;
+        for (uint32_t mm = rem; mm; mm &= mm - 1) {
+          const uint32_t low = mm & (0u - mm), bit = __ffs(mm) - 1;
+          const uint32_t below = Bm & (low - 1u);
+          const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+          sts_u64(k.q_s + (idx++ & (SK_QCAP - 1)) * 8, s, (p + bit - s) | ((candNum & low) ? 0x80000000u : 0u));
+        }
+        k.qcount += total_dot;
+        rem = 0; rounds = 0;
+      }
+      for (;;) {
+        while (rounds && k.qcount < 32) {
+          if (!__any_sync(0xFFFFFFFFu, rem != 0)) { rounds = 0; break; }
+          const bool have = rem != 0;
+          uint32_t s = 0, len = 0;
+          bool numeric = false;
+          if (have) {
+            const uint32_t low = rem & (0u - rem), bit = __ffs(rem) - 1;
+            const uint32_t below = Bm & (low - 1u);
+            s = below ? p + top_bit(below) + 1 : lane_open;
+            len = p + bit - s;
+            numeric = (candNum & low) != 0;
+            rem &= rem - 1;
+          }
+          bool slow = false;
+          if (may_slow) {  // (warp-uniform) the word that was open when the tile began lies partly behind the ring
+            slow = have && s < ring_lo;
+            if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, numeric, s, len);
+          }
+          const uint32_t bq = __ballot_sync(0xFFFFFFFFu, have && !slow);
+          if (have && !slow) sts_u64(k.q_s + ((k.qhead + k.qcount + __popc(bq & lt_mask)) & (SK_QCAP - 1)) * 8, s, len | (numeric ? 0x80000000u : 0u));
+          k.qcount += __popc(bq);
+        }
+        uint32_t g;
+        if (k.qcount >= 32) g = 32;
+        else if (rounds == 0 && (last ? !flushed : k.q_old != 0)) g = k.qcount;  // what ended before this tile must go now; at the very end, everything
+        else break;
+        const bool fin = last && k.qcount == g;
+        sk_group(a, tw, k, s_hot, g, lane, xflags, fast, fin);
+        if (fin) flushed = true;
+      }
+      if (last) break;
+      // ---- the next load: tile t+2 into the slot of tile t-2, whose words have all been handled ----
+      k.q_old = k.qcount;
+      __syncwarp();
+      if (lane == 0 && t + 2 < t_end) tile_load(k.ring_s + ((t + 2) & 3u) * TILE_BYTES, a.buf + (size_t)(t + 2) * TILE_BYTES, TILE_BYTES, mbar_s + ((t + 2) & 3u) * 8);
     }
-    while (k.qcount) sk_group(a, tw, k, s_hot, k.qcount < 32u ? k.qcount : 32u, lane, xflags, fast);
   }
-  if (tw.n_def) { defer_drain(a, tw, lane, tw.defer, tw.n_def, s_hot); tw.n_def = 0; }  // (n_def is warp-uniform)
   for (uint32_t i = lane; i < tw.cs.left; i += 32) a.str[tw.cs.base + i].type = TOK_INVALID;
   for (uint32_t i = lane; i < tw.ci.left; i += 32) a.ip[tw.ci.base + i].type = TOK_INVALID;
   if (lane == 0) {
@@ -1149,21 +1193,45 @@ __device__ __forceinline__ void iptrie_flush(const ScanArgs& a, const mgpu_match
   for (uint32_t j = lane; j < 2 * staged; j += 32) if ((uint64_t)b + (j >> 1) < a.cap_rec) dst[2 * (size_t)b + j] = src[j];
   __syncwarp();
 }
+// A numeric-queue word (hex digits and dots, 7..15 bytes, all of it in t.w) that is not an IPv4 address may still be a
+// domain ("cafe.de"): PSL check, then the string path like any other domain token.  Rare; one thread, plain atomics.
+__device__ __noinline__ void numeric_word_as_domain(const ScanArgs& a, const IpTok& t) {
+  uint32_t tw[4];
+  tail_words_from_head(t.w, t.len, tw);
+  const uint64_t tail8 = t.len >= 8 ? (((uint64_t)tw[3] << 32) | tw[2]) : ((((uint64_t)t.w[1] << 32) | t.w[0]) << (8 * (8 - t.len)));
+  if (!domain_word_fast(a.db, a.db.psl_tld, a.buf + t.start, t.len, /*maybe_high=*/false, tail8)) return;
+  atomicAdd(&a.ctr->by_type[MGPU_T_DOMAIN], 1ULL);
+  uint32_t f = 0;
+  if (a.fast) { f = string_filters(a.db, a.db.hot, a.buf + t.start, t.len); if (!f) return; }
+  const uint32_t k = atomicAdd(&a.ctr->n_str, 1u);
+  if (k >= a.cap_str) { atomicOr(&a.ctr->overflow, 1u << 8); return; }
+  a.str[k] = StrTok{t.start, t.len, (uint32_t)MGPU_T_DOMAIN | f};
+}
+
 __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
   __shared__ __align__(16) mgpu_match s_rec[8][IPT_STAGE];
   __shared__ uint32_t s_ovf;
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
   if (threadIdx.x == 0) s_ovf = a.ctr->overflow;  // (read once per block: the exit must be uniform, other blocks may set the flag)
   __syncthreads();
-  if (!a.db.has_ip || s_ovf) return;
+  if (s_ovf) return;
+  const bool walk = a.lookups && a.db.has_ip;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nw = gridDim.x * 8;
   uint32_t staged = 0;  // records in s_rec[warp] (warp-uniform)
+  uint32_t n_v4 = 0;    // raw numeric words that turned out to be addresses (WorkerStats.ipv4_count)
   for (uint32_t t0 = (blockIdx.x * 8 + warp) * 32u; t0 < n; t0 += nw * 32u) {
     const uint32_t i = t0 + lane;
     IpTok t;
     t.type = TOK_INVALID;
     if (i < n) t = a.ip[i];
+    if (t.type == TOK_RAW4) {  // the fused scan kernel's numeric words: try_parse_ipv4 (lib.rs:813-869) happens here
+      uint32_t addr = 0;
+      if (parse_ipv4_hexdot(t.w, t.len, addr)) { t.type = MGPU_T_IPV4; t.w[0] = addr; n_v4++; }
+      else { t.type = TOK_INVALID; if (a.flags & MGPU_X_DOMAINS) numeric_word_as_domain(a, t); }
+      if (!a.lookups) { a.ip[i].type = t.type; a.ip[i].w[0] = t.w[0]; }  // extraction only: the list itself is the result
+    }
+    if (!walk) continue;
     uint32_t off = 0; uint8_t pl = 0;
     TrieWalk w;
     int r = TRIE_MISS;
@@ -1192,6 +1260,8 @@ __global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
     }
   }
   if (staged) iptrie_flush(a, s_rec[warp], staged, lane);
+  n_v4 = __reduce_add_sync(0xFFFFFFFFu, n_v4);
+  if (lane == 0 && n_v4) atomicAdd(&a.ctr->by_type[MGPU_T_IPV4], (unsigned long long)n_v4);
 }
 
 // tokens of one warp iteration -> staged window pointer
@@ -1576,8 +1646,12 @@ __global__ void verify_tokens_kernel(ScanArgs a, unsigned long long* dbg) {
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
   unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const IpTok t = a.ip[i];
+    IpTok t = a.ip[i];
     uint32_t off = 0; uint8_t pl = 0;
+    if (t.type == TOK_RAW4) {  // (unparsed numeric word of the fused scan kernel: count it as what iptrie_kernel will make of it)
+      uint32_t addr = 0;
+      if (parse_ipv4_hexdot(t.w, t.len, addr)) { t.type = MGPU_T_IPV4; t.w[0] = addr; } else t.type = TOK_INVALID;
+    }
     if (t.type == TOK_POISON) c[0]++;
     else if (t.type == TOK_INVALID) c[1]++;
     else if (t.type == MGPU_T_IPV4) { c[2]++; if (a.db.has_ip && trie_lookup_v4(a.db, t.w[0], off, pl)) c[4]++; }
@@ -2035,6 +2109,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   cudaEvent_t* ev = c->ev_k[slot];
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
   a.fast = fast ? 1u : 0u;
+  a.lookups = lookups ? 1u : 0u;
   const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
   if (c->fused) {
     // the fused kernel appends to the token lists the previous piece's lookups read: wait for them first
@@ -2081,6 +2156,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     else if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, ls>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
     CK(cudaEventRecord(ev[5], ls));
   } else {
+    if (c->fused) iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);  // (extraction only: parses the scan kernel's raw numeric words)
     for (int k = 3; k <= 5; k++) CK(cudaEventRecord(ev[k], ls));
   }
   piece_end_kernel<<<1, 1, 0, ls>>>(a.ctr, a.tot);

@@ -338,6 +338,15 @@ int emu_parse_ipv6_masks(const uint8_t* s, uint32_t n, uint32_t w[4]) { return p
 uint32_t emu_class_bits_via_planes(uint32_t b) { return class_bits_from_planes(category_planes((uint8_t)(b >= 0x80 ? 'g' : b))); }
 uint32_t emu_class_bits(uint32_t b) { return class_bits((uint8_t)b); }
 
+// both IPv4 parsers on one word of hex digits and dots (s readable 20 bytes past n): bit 0 = general parser accepted,
+// bit 1 = hex-dot parser accepted, *out = their addresses
+uint32_t emu_parse_ipv4_both(const uint8_t* s, uint32_t n, uint32_t out[2]) {
+  uint32_t h[4];
+  load_head_words(s, h);
+  out[0] = out[1] = 0;
+  return (parse_ipv4_words(h, n, out[0]) ? 1u : 0u) | (parse_ipv4_hexdot(h, n, out[1]) ? 2u : 0u);
+}
+
 int64_t emu_tokens(emu_ctx* c, uint64_t* out, size_t cap) {
   std::vector<std::array<uint64_t, 3>> items;
   for (auto& t : c->str) items.push_back({t.type, t.start, (uint64_t)t.start + t.len});

@@ -262,3 +262,33 @@ def test_byte_category_planes_reproduce_the_class_bits():
     L.emu_class_bits_via_planes.restype = L.emu_class_bits.restype = __import__("ctypes").c_uint32
     for b in range(256):
         assert L.emu_class_bits_via_planes(b) == L.emu_class_bits(b), b
+
+
+def test_hexdot_ipv4_parser_equals_general_parser():
+    """scan_kernel parses numeric-queue words (hex digits and dots only) with parse_ipv4_hexdot: same verdict and address as
+    parse_ipv4_words on valid addresses, every near miss, and random words over the alphabet."""
+    import ctypes as C
+    import random
+    import emu_lib
+    L = emu_lib.lib()
+    L.emu_parse_ipv4_both.restype = C.c_uint32
+    L.emu_parse_ipv4_both.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    rng = random.Random(7)
+    words = [b"1.2.3.4", b"255.255.255.255", b"256.1.1.1", b"01.2.3.4", b"1.02.3.4", b"0.0.0.0", b"1.2.3", b"1.2.3.4.5", b"1..2.3", b".1.2.3", b"1.2.3.",
+             b"a.b.c.d", b"1.2.3.4a", b"cafe.de", b"1.2.3.f", b"999.999.999.999", b"1.2.3.1000", b"10.20.30.40", b"192.168.001.1", b"192.168.1.001",
+             b"25.5.2.55", b"1.1.1.1", b"12.34.56.78", b"249.250.251.252", b"199.200.201.202", b"100.099.1.1", b"0.00.0.0", b"1234.1.1.1"]
+    for _ in range(60000):
+        kind = rng.random()
+        if kind < 0.5:
+            w = ".".join(str(rng.choice([rng.randrange(0, 300), rng.randrange(0, 30), rng.randrange(250, 260)])) for _ in range(4)).encode()
+        elif kind < 0.75:
+            w = ".".join(("%0*d" % (rng.randint(1, 4), rng.randrange(0, 400))) for _ in range(rng.randint(3, 5))).encode()
+        else:
+            w = bytes(rng.choice(b"0123456789.abcdefABCDEF..00") for _ in range(rng.randint(1, 18)))
+        words.append(w)
+    out = (C.c_uint32 * 2)()
+    for w in words:
+        for tail in (b"\0" * 24, b"9.9.9.9 zzzzzzzzzzzzzzzzzzzz", b"\xff" * 24):  # whatever follows the word must not matter
+            r = L.emu_parse_ipv4_both(w + tail, len(w), out)
+            assert r in (0, 3), (w, r)
+            assert r == 0 or out[0] == out[1], w
