@@ -147,6 +147,11 @@ struct HotShared {
   __device__ __forceinline__ uint32_t word(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + i * 4)); return v; }
   __device__ __forceinline__ uint32_t gen2(uint32_t i) const { return __ldg(g2 + i); }
 };
+struct HotGlobal {    // the hot filter in global memory, read through L1 (scan_kernel's wide block keeps no copy)
+  const uint32_t* p; const uint32_t* g2;
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(p + i); }
+  __device__ __forceinline__ uint32_t gen2(uint32_t i) const { return __ldg(g2 + i); }
+};
 struct BytesShared {  // a token in a shared-memory window
   uint32_t saddr;
   __device__ __forceinline__ uint32_t at(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr + i) : "memory"); return v; }

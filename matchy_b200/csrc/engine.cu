@@ -20,6 +20,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/matchy_b200.h"
@@ -66,7 +67,8 @@ struct ScanArgs {
   uint32_t* seg_cnt;   // [Q_COUNT][nseg_max]
   uint32_t nseg, nseg_max;
   StrTok* str; uint32_t cap_str;
-  StrTok* defer;       // token kernel: per-warp queues (DEFER_CAP slots each) of tokens that passed string_gate and owe stage 2
+  StrTok* defer;       // per-warp queues (DEFER_CAP slots each) of tokens that passed string_gate and owe stage 2 (scan_kernel / tokenize path)
+  StrTok* defer_tk;    // the same for token_kernel, which runs beside the next piece's scan_kernel
   IpTok* ip; uint32_t cap_ip;
   uint32_t* lh_res;
   mgpu_match* recs; uint32_t cap_rec;
@@ -464,7 +466,8 @@ __device__ __forceinline__ bool string_token(const ScanArgs& a, TokenWarp& tw, b
 }
 
 // Stage 2 of the string filters for `count` (<= 32) queued tokens, one per lane, read back from the log buffer.
-__device__ __forceinline__ void defer_drain(const ScanArgs& a, TokenWarp& tw, uint32_t lane, const StrTok* src, uint32_t count, const HotShared& s_hot) {
+template <typename H>
+__device__ __forceinline__ void defer_drain(const ScanArgs& a, TokenWarp& tw, uint32_t lane, const StrTok* src, uint32_t count, const H& s_hot) {
   const bool have = lane < count;
   StrTok t{0, 0, 0};
   if (have) { t.start = __ldcg(&src[lane].start); t.len = __ldcg(&src[lane].len); t.type = __ldcg(&src[lane].type); }
@@ -486,7 +489,8 @@ __device__ __forceinline__ void defer_drain(const ScanArgs& a, TokenWarp& tw, ui
 
 // Queue the lanes' gate-passing tokens; run stage 2 with a full warp once 32 are waiting (flush: with whatever is waiting).
 // (One call of defer_drain in the code: the filters are large, and the fused kernel's loop has to stay in the instruction cache.)
-__device__ __forceinline__ void defer_push(const ScanArgs& a, TokenWarp& tw, uint32_t lane, uint32_t gate, const StrTok& st, const HotShared& s_hot, bool flush = false) {
+template <typename H>
+__device__ __forceinline__ void defer_push(const ScanArgs& a, TokenWarp& tw, uint32_t lane, uint32_t gate, const StrTok& st, const H& s_hot, bool flush = false) {
   const uint32_t bal = __ballot_sync(0xFFFFFFFFu, gate != 0);
   if (!bal && !flush) return;
   if (gate) {
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   __syncthreads();
   TokenWarp tw;
   memset(&tw, 0, sizeof tw);
-  tw.defer = a.defer + (size_t)(blockIdx.x * TK_WARPS + warp) * DEFER_CAP;
+  tw.defer = a.defer_tk + (size_t)(blockIdx.x * TK_WARPS + warp) * DEFER_CAP;
   const uint32_t nwarps = gridDim.x * TK_WARPS;
   for (uint32_t seg = blockIdx.x * TK_WARPS + warp; seg < a.nseg; seg += nwarps) {
     const uint32_t* sc = a.seg_cnt + seg;
@@ -717,15 +721,16 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
 // handled.  A candidate that ends in tile t is queued only if it starts at or after the first byte of tile t-1.
 // The 32 bytes behind the ring mirror its first 32, so a 20-byte read may start anywhere in the ring.
 // ---------------------------------------------------------------------------------------------------------
-static const int SK_WARPS = 16;
-static const int SK_THREADS = SK_WARPS * 32;
+static const int SK_WARPS = 16;       // with the 128 KiB hot string filter in shared memory
+static const int SK_WARPS_NOHOT = 24; // when the database puts nothing into the hot filter (no strings, or only classes too big for it)
 static const uint32_t SK_RING = 4096;
 static const uint32_t SK_PAD = 32;
 static const uint32_t SK_QCAP = 64;
 static const uint32_t SK_LUT_BYTES = 128 * 32 * 4;  // byte values 0..127 (bytes >= 0x80 are mapped onto 'g' first: same category)
 struct SkWarp { uint8_t ring[SK_RING + SK_PAD]; uint2 q[SK_QCAP]; unsigned long long mbar[4]; };
 static_assert(sizeof(SkWarp) % 16 == 0, "rings must stay 16-byte aligned");
-static const size_t SCAN_SMEM = (size_t)HOT_WORDS * 4 + SK_LUT_BYTES + SK_WARPS * sizeof(SkWarp);
+// (the wide block has room for the PSL last-label table as well: 32 KiB)
+static constexpr size_t scan_smem(bool hot, int warps) { return (hot ? (size_t)HOT_WORDS * 4 : (size_t)TLD_SLOTS * 8) + SK_LUT_BYTES + (size_t)warps * sizeof(SkWarp); }
 
 __device__ __forceinline__ void mbar_init(uint32_t mbar_s, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s), "r"(count) : "memory"); }
 // one lane: arm the tile's barrier with the byte count, then start the bulk copy global -> shared that completes on it
@@ -762,36 +767,44 @@ struct SkQueues {
   uint32_t ring_s, q_s;            // shared-space addresses of the ring and of the candidate queue
   uint32_t qhead, qcount, q_old;   // queue cursor; q_old = entries at the head that ended before the current tile
   uint32_t high;                   // "some byte >= 0x80 in the last three tiles"
-  Cand* qd; Cand* qn;              // this warp's segments of the dotted / numeric queues in HBM (slow path)
-  uint32_t nd, nn, ovf;
+  Cand* qd; Cand* qn; Cand* qh;    // this warp's segments of the dotted / numeric / hash queues in HBM (slow path)
+  uint32_t nd, nn, nh, ovf;
 };
+enum { SK_DOTTED = 0, SK_NUMERIC = 1, SK_HASH = 2 };  // kind of a queued word (bits 31, 30 of the entry's second word: numeric, hash)
 
-// Slow path: the lanes with `slow` append their word to the dotted (numeric = false) or numeric queue segment in HBM.
-__device__ __forceinline__ void sk_push_slow(const ScanArgs& a, SkQueues& k, uint32_t lane, bool slow, bool numeric, uint32_t start, uint32_t len) {
-  const uint32_t bd = __ballot_sync(0xFFFFFFFFu, slow && !numeric), bn = __ballot_sync(0xFFFFFFFFu, slow && numeric);
+// Slow path: the lanes with `slow` append their word to the dotted / numeric / hash queue segment in HBM (token_kernel's input).
+__device__ __forceinline__ void sk_push_slow(const ScanArgs& a, SkQueues& k, uint32_t lane, bool slow, uint32_t kind, uint32_t start, uint32_t len) {
+  const uint32_t bd = __ballot_sync(0xFFFFFFFFu, slow && kind == SK_DOTTED), bn = __ballot_sync(0xFFFFFFFFu, slow && kind == SK_NUMERIC);
+  const uint32_t bh = __ballot_sync(0xFFFFFFFFu, slow && kind == SK_HASH);
   const uint32_t lt = (1u << lane) - 1u;
   if (bd) {
-    if (k.nd + __popc(bd) <= a.seg_cap[Q_DOTTED]) { if (slow && !numeric) k.qd[k.nd + __popc(bd & lt)] = Cand{start, len}; }
+    if (k.nd + __popc(bd) <= a.seg_cap[Q_DOTTED]) { if (slow && kind == SK_DOTTED) k.qd[k.nd + __popc(bd & lt)] = Cand{start, len}; }
     else k.ovf |= 1u << Q_DOTTED;
     k.nd += __popc(bd);
   }
   if (bn) {
-    if (k.nn + __popc(bn) <= a.seg_cap[Q_NUMERIC]) { if (slow && numeric) k.qn[k.nn + __popc(bn & lt)] = Cand{start, len}; }
+    if (k.nn + __popc(bn) <= a.seg_cap[Q_NUMERIC]) { if (slow && kind == SK_NUMERIC) k.qn[k.nn + __popc(bn & lt)] = Cand{start, len}; }
     else k.ovf |= 1u << Q_NUMERIC;
     k.nn += __popc(bn);
+  }
+  if (bh) {
+    if (k.nh + __popc(bh) <= a.seg_cap[Q_HASH]) { if (slow && kind == SK_HASH) k.qh[k.nh + __popc(bh & lt)] = Cand{start, len}; }
+    else k.ovf |= 1u << Q_HASH;
+    k.nh += __popc(bh);
   }
 }
 
 // One lane per queued candidate, g (<= 32) of them from the head of the queue.
-__device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQueues& k, const HotShared& s_hot, uint32_t g, uint32_t lane, uint32_t xflags, bool fast,
+template <typename H>
+__device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQueues& k, const H& s_hot, const uint64_t* tld, uint32_t g, uint32_t lane, uint32_t xflags, bool fast,
                                          bool final) {
   __syncwarp();  // the queue entries were written by other lanes
   const bool have = lane < g;
   uint2 e = make_uint2(0u, 0u);
   if (have) e = lds_u64(k.q_s + ((k.qhead + lane) & (SK_QCAP - 1)) * 8);
   k.qhead = (k.qhead + g) & (SK_QCAP - 1); k.qcount -= g; k.q_old = k.q_old > g ? k.q_old - g : 0u;
-  const uint32_t start = e.x, len = e.y & 0x7FFFFFFFu;
-  const bool numeric = (e.y >> 31) != 0;
+  const uint32_t start = e.x, len = e.y & 0x3FFFFFFFu;
+  const bool numeric = (e.y >> 31) != 0, is_hash = ((e.y >> 30) & 1u) != 0;
   KeyWords kw;
   load_head_words_shared(k.ring_s + (start & (SK_RING - 1)), kw.h);
   load_tail_words_shared_end(k.ring_s + ((start + len - 16u) & (SK_RING - 1)) + 16u, have ? len : 0u, kw.t);
@@ -803,19 +816,23 @@ __device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQue
   const IpTok it{start, len, TOK_RAW4, 0, {kw.h[0], kw.h[1], kw.h[2], kw.h[3]}};
   bool ws = false, slow = false;
   StrTok st{start, len, MGPU_T_DOMAIN};
-  if (have && !wi && (xflags & MGPU_X_DOMAINS)) {
+  if (have && is_hash) {  // a hash-length word of hex digits is a token as it stands (lib.rs:1212-1250)
+    st.type = hash_type_of(len);
+    ws = true;
+  } else if (have && !wi && (xflags & MGPU_X_DOMAINS)) {
     // a valid IPv4 address is never a domain: its last label is numeric, and no PSL entry ends in one (checked at upload)
     const uint64_t tail8 = len >= 8 ? (((uint64_t)kw.t[3] << 32) | kw.t[2]) : ((((uint64_t)kw.h[1] << 32) | kw.h[0]) << (8 * (8 - len)));
-    const int c = tld_class(a.db.psl_tld, tail8);
+    const int c = tld_class(tld, tail8);
     if (c == TLD_ACCEPT && !k.high) ws = true;
     else if (c != TLD_REJECT) slow = true;  // multi-label suffix walk or UTF-8 validation: loops over the bytes -> token_kernel
   }
   __syncwarp();
-  if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, false, start, len);
+  if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, SK_DOTTED, start, len);
   uint32_t gate = 0;
   if (__any_sync(0xFFFFFFFFu, ws)) {
     if (ws) {
-      tw.n_dom++;
+      tw.n_dom += st.type == MGPU_T_DOMAIN; tw.n_md5 += st.type == MGPU_T_MD5; tw.n_sha1 += st.type == MGPU_T_SHA1;
+      tw.n_sha256 += st.type == MGPU_T_SHA256; tw.n_sha384 += st.type == MGPU_T_SHA384; tw.n_sha512 += st.type == MGPU_T_SHA512;
       if (fast) { gate = string_gate(a.db, s_hot, kw, len); ws = false; }  // (both filter stages of a class run in defer_drain: no per-lane loops here)
     }
     __syncwarp();
@@ -824,20 +841,32 @@ __device__ __forceinline__ void sk_group(const ScanArgs& a, TokenWarp& tw, SkQue
   defer_push(a, tw, lane, gate, st, s_hot, final);
 }
 
-template <uint32_t FIXED>
-__global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
+// HOT = false: the database's string filters use no hot-filter class (DbView::hot_tags == 0, or no string lookups at all), so
+// the 128 KiB are not staged and the block runs more warps instead.
+template <uint32_t FIXED, bool HOT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(ScanArgs a) {
   extern __shared__ __align__(128) uint8_t sk_smem[];
+  constexpr size_t HOT_BYTES = HOT ? (size_t)HOT_WORDS * 4 : (size_t)TLD_SLOTS * 8;  // hot string filter, or (wide block) the PSL last-label table
   uint32_t* s_hot_words = reinterpret_cast<uint32_t*>(sk_smem);
-  uint32_t* lut = reinterpret_cast<uint32_t*>(sk_smem + (size_t)HOT_WORDS * 4);
-  SkWarp* sw = reinterpret_cast<SkWarp*>(sk_smem + (size_t)HOT_WORDS * 4 + SK_LUT_BYTES);
-  const HotShared s_hot{(uint32_t)__cvta_generic_to_shared(sk_smem), a.db.gen_gram2};
+  uint32_t* lut = reinterpret_cast<uint32_t*>(sk_smem + HOT_BYTES);
+  SkWarp* sw = reinterpret_cast<SkWarp*>(sk_smem + HOT_BYTES + SK_LUT_BYTES);
+  // the hot string filter: the block's shared-memory copy, or (wide block) the 128 KiB in global memory behind L1
+  typename std::conditional<HOT, HotShared, HotGlobal>::type s_hot;
+  if constexpr (HOT) { s_hot.base = (uint32_t)__cvta_generic_to_shared(sk_smem); s_hot.g2 = a.db.gen_gram2; }
+  else { s_hot.p = a.db.hot; s_hot.g2 = a.db.gen_gram2; }
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const bool fast = a.fast != 0;
   for (uint32_t i = threadIdx.x; i < 128 * 32; i += blockDim.x) lut[i] = category_planes((uint8_t)(i >> 5));
-  if (fast) {
+  if (HOT && fast) {
     const uint4* src = reinterpret_cast<const uint4*>(a.db.hot);
     for (uint32_t i = threadIdx.x; i < HOT_WORDS / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_hot_words)[i] = src[i];
+  }
+  const uint64_t* tld_tab = a.db.psl_tld;
+  if (!HOT && a.db.psl_tld) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.db.psl_tld);
+    for (uint32_t i = threadIdx.x; i < TLD_SLOTS / 2; i += blockDim.x) reinterpret_cast<uint4*>(sk_smem)[i] = src[i];
+    tld_tab = reinterpret_cast<const uint64_t*>(sk_smem);
   }
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&sw[warp].mbar[0]);
   if (lane == 0) { for (uint32_t j = 0; j < 4; j++) mbar_init(mbar_s + 8 * j, 1); }
@@ -845,14 +874,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
   __syncthreads();
 
   const uint32_t lut_lane_s = (uint32_t)__cvta_generic_to_shared(lut) + lane * 4;
-  const uint64_t nwarps = (uint64_t)gridDim.x * SK_WARPS;  // == a.nseg
-  const uint64_t w = (uint64_t)blockIdx.x * SK_WARPS + warp;
+  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS;  // == a.nseg
+  const uint64_t w = (uint64_t)blockIdx.x * WARPS + warp;
   const uint64_t tiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
   const uint64_t tpw = (tiles + nwarps - 1) / nwarps;
   const uint64_t t0 = w * tpw;
   uint64_t t1 = t0 + tpw;
   if (t1 > tiles) t1 = tiles;
-  Cand* const qh = a.q_hash + w * a.seg_cap[Q_HASH];
   uint32_t* const qa = a.q_at + w * a.seg_cap[Q_AT];
   uint32_t* const qc = a.q_c2 + w * a.seg_cap[Q_COLON2];
   Cand* const ql = a.q_long + w * a.seg_cap[Q_LONG];
@@ -860,9 +888,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
   k.ring_s = (uint32_t)__cvta_generic_to_shared(&sw[warp].ring[0]);
   k.q_s = (uint32_t)__cvta_generic_to_shared(&sw[warp].q[0]);
   k.qhead = 0; k.qcount = 0; k.q_old = 0; k.high = 0;
-  k.qd = a.q_dotted + w * a.seg_cap[Q_DOTTED]; k.qn = a.q_numeric + w * a.seg_cap[Q_NUMERIC];
-  k.nd = 0; k.nn = 0; k.ovf = 0;
-  uint32_t nh = 0, na = 0, nc = 0, nl = 0;
+  k.qd = a.q_dotted + w * a.seg_cap[Q_DOTTED]; k.qn = a.q_numeric + w * a.seg_cap[Q_NUMERIC]; k.qh = a.q_hash + w * a.seg_cap[Q_HASH];
+  k.nd = 0; k.nn = 0; k.nh = 0; k.ovf = 0;
+  uint32_t na = 0, nc = 0, nl = 0;
   uint32_t lines = 0;
   TokenWarp tw;
   memset(&tw, 0, sizeof tw);
@@ -891,7 +919,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       const bool last = t == t_end;
       const uint32_t tile_base = t * TILE_BYTES;  // chunks are at most 2 GiB: positions fit 32 bits
       const uint32_t p = tile_base + lane * SLICE_BYTES;
-      uint32_t rem = 0, candNum = 0, rounds = 0, Bm = 0, lane_open = 0, ring_lo = 0, total_dot = 0, excl_dot = 0;
+      uint32_t rem = 0, candNum = 0, candHashK = 0, rounds = 0, Bm = 0, lane_open = 0, ring_lo = 0, total_dot = 0, excl_dot = 0;
       bool may_slow = false;
       if (!last) {
       const uint32_t slot = t & 3u;
@@ -982,22 +1010,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       lane_open = src < 32u ? tile_base + src * 32 + top_bit(Bsrc) + 1 : (uint32_t)cy.open_start;
 
       if (__any_sync(0xFFFFFFFFu, (candHex | candAt | candC2 | candLong) != 0)) {  // rare in most logs: one vote covers the four
-        {
-          bool keep = false; Cand c{0, 0};
-          if (candHex) {
-            const uint32_t bit = __ffs(candHex) - 1;
-            const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
-            const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
-            keep = is_hash_len(p + bit - s);
-            c.start = s; c.len = p + bit - s;
-          }
-          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-          if (bal) {
-            const uint32_t total = __popc(bal);
-            if (nh + total <= a.seg_cap[Q_HASH]) { if (keep) qh[nh + __popc(bal & lt_mask)] = c; }
-            else k.ovf |= 1u << Q_HASH;
-            nh += total;
-          }
+        if (candHex) {  // an all-hex word of >= 32 bytes ends here: a hash iff its length is one of the five (joins the dotted words below)
+          const uint32_t bit = __ffs(candHex) - 1;
+          const uint32_t below = m.B & ~(0xFFFFFFFFu << bit);
+          const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
+          if (is_hash_len(p + bit - s)) candHashK = candHex;
         }
         if (__any_sync(0xFFFFFFFFu, candAt != 0)) {
           const uint32_t cnt = __popc(candAt), incl = warp_incl_scan(cnt, lane);
@@ -1043,10 +1060,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
       cy.prevB = __shfl_sync(0xFFFFFFFFu, m.B, 31);
       pDOT = __shfl_sync(0xFFFFFFFFu, m.DOT, 31); pDASH = __shfl_sync(0xFFFFFFFFu, m.DASH, 31); pCL = __shfl_sync(0xFFFFFFFFu, m.CL, 31);
       Bm = m.B;
-      rem = candDot;
+      rem = candDot | candHashK;    // (disjoint: a hash word holds no '.')
       candNum = candDot & ~hasNhd;  // hex digits and dots only: IPv4 candidates
       {
-        const uint32_t cnt = (uint32_t)__popc(candDot), incl = warp_incl_scan(cnt, lane);
+        const uint32_t cnt = (uint32_t)__popc(rem), incl = warp_incl_scan(cnt, lane);
         total_dot = __shfl_sync(0xFFFFFFFFu, incl, 31);
         excl_dot = incl - cnt;
         rounds = total_dot ? 32u : 0u;  // (upper bound for the round-by-round path, which stops when no lane has a word left)
@@ -1063,7 +1080,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
           const uint32_t low = mm & (0u - mm), bit = __ffs(mm) - 1;
           const uint32_t below = Bm & (low - 1u);
           const uint32_t s = below ? p + top_bit(below) + 1 : lane_open;
-          sts_u64(k.q_s + (idx++ & (SK_QCAP - 1)) * 8, s, (p + bit - s) | ((candNum & low) ? 0x80000000u : 0u));
+          sts_u64(k.q_s + (idx++ & (SK_QCAP - 1)) * 8, s, (p + bit - s) | ((candNum & low) ? 0x80000000u : 0u) | ((candHashK & low) ? 0x40000000u : 0u));
         }
         k.qcount += total_dot;
         rem = 0; rounds = 0;
@@ -1072,23 +1089,22 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
         while (rounds && k.qcount < 32) {
           if (!__any_sync(0xFFFFFFFFu, rem != 0)) { rounds = 0; break; }
           const bool have = rem != 0;
-          uint32_t s = 0, len = 0;
-          bool numeric = false;
+          uint32_t s = 0, len = 0, kind = SK_DOTTED;
           if (have) {
             const uint32_t low = rem & (0u - rem), bit = __ffs(rem) - 1;
             const uint32_t below = Bm & (low - 1u);
             s = below ? p + top_bit(below) + 1 : lane_open;
             len = p + bit - s;
-            numeric = (candNum & low) != 0;
+            kind = (candNum & low) ? (uint32_t)SK_NUMERIC : ((candHashK & low) ? (uint32_t)SK_HASH : (uint32_t)SK_DOTTED);
             rem &= rem - 1;
           }
           bool slow = false;
           if (may_slow) {  // (warp-uniform) the word that was open when the tile began lies partly behind the ring
             slow = have && s < ring_lo;
-            if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, numeric, s, len);
+            if (__any_sync(0xFFFFFFFFu, slow)) sk_push_slow(a, k, lane, slow, kind, s, len);
           }
           const uint32_t bq = __ballot_sync(0xFFFFFFFFu, have && !slow);
-          if (have && !slow) sts_u64(k.q_s + ((k.qhead + k.qcount + __popc(bq & lt_mask)) & (SK_QCAP - 1)) * 8, s, len | (numeric ? 0x80000000u : 0u));
+          if (have && !slow) sts_u64(k.q_s + ((k.qhead + k.qcount + __popc(bq & lt_mask)) & (SK_QCAP - 1)) * 8, s, len | (kind == SK_NUMERIC ? 0x80000000u : 0u) | (kind == SK_HASH ? 0x40000000u : 0u));
           k.qcount += __popc(bq);
         }
         uint32_t g;
@@ -1096,7 +1112,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
         else if (rounds == 0 && (last ? !flushed : k.q_old != 0)) g = k.qcount;  // what ended before this tile must go now; at the very end, everything
         else break;
         const bool fin = last && k.qcount == g;
-        sk_group(a, tw, k, s_hot, g, lane, xflags, fast, fin);
+        sk_group(a, tw, k, s_hot, tld_tab, g, lane, xflags, fast, fin);
         if (fin) flushed = true;
       }
       if (last) break;
@@ -1111,7 +1127,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) scan_kernel(ScanArgs a) {
   if (lane == 0) {
     uint32_t* sc = a.seg_cnt + w;
     sc[Q_DOTTED * a.nseg_max] = k.ovf & (1u << Q_DOTTED) ? 0u : k.nd;
-    sc[Q_HASH * a.nseg_max] = k.ovf & (1u << Q_HASH) ? 0u : nh;
+    sc[Q_HASH * a.nseg_max] = k.ovf & (1u << Q_HASH) ? 0u : k.nh;
     sc[Q_AT * a.nseg_max] = k.ovf & (1u << Q_AT) ? 0u : na;
     sc[Q_COLON2 * a.nseg_max] = k.ovf & (1u << Q_COLON2) ? 0u : nc;
     sc[Q_NUMERIC * a.nseg_max] = k.ovf & (1u << Q_NUMERIC) ? 0u : k.nn;
@@ -1780,6 +1796,8 @@ struct mgpu_ctx {
   void* d_psl_keys = nullptr; void* d_psl_vals = nullptr; void* d_psl_pool = nullptr; void* d_psl_tld = nullptr;
   // results of the last scan
   PinnedVec<mgpu_match> recs;
+  PinnedVec<mgpu_match> stage;  // where the device writes a batch's records: pinned HOST memory, written over PCIe by the lookup kernels
+                                // while later pieces are still being scanned (no device-side record buffer, no D2H copy at the end)
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
   mgpu_counters counters{};
@@ -1792,6 +1810,15 @@ struct mgpu_ctx {
   bool capture_tokens = false;
   // test / debug switches (mgpu_set_option)
   bool fused = true;  // scan_kernel (one pass) instead of tokenize_kernel + the word passes of token_kernel
+  bool serial = false;  // everything on one stream (MATCHY_B200_SERIAL=1): per-kernel times without scheduling waits
+  int wide_warps = SK_WARPS_NOHOT;
+  bool wide_scan = false;  // scan_kernel always as the 24-warp block that reads the hot filter through L1 (MATCHY_B200_WIDE_SCAN=1)
+  // Working sets: the candidate queues and token lists of piece i are read by its lookups while piece i+1 is scanned, so
+  // there are two of each (fused mode) and a piece uses set (slot & 1); set_slot[s] = batch slot of the piece that used set s last.
+  struct BufSet { Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2; Cand* q_numeric; Cand* q_long; uint32_t* seg_cnt; StrTok* str; IpTok* ip; };
+  BufSet sets[2] = {};
+  int nsets = 1;
+  bool set_pending[2] = {false, false}; int set_slot[2] = {0, 0};
   bool verify_tokens = false;
   unsigned long long* d_dbg = nullptr;  // 16 audit accumulators (verify_tokens_kernel: 0..6, iptrie_kernel: 8..10)
   uint32_t alloc_cap_str = 0, alloc_cap_ip = 0, alloc_cap_rec = 0, alloc_cap_ids = 0;  // what the buffers really hold
@@ -1823,8 +1850,9 @@ void mgpu_destroy(mgpu_ctx* c) {
   for (auto& row : c->ev_k) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_l0) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_scan) if (e) cudaEventDestroy(e);
-  void* bufs[] = {c->args.q_dotted, c->args.q_hash, c->args.q_at, c->args.q_c2, c->args.q_numeric, c->args.q_long, c->args.seg_cnt, c->args.str, c->args.defer, c->args.ip, c->args.lh_res,
-                  c->args.recs, c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_dbg, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
+  for (auto& b : c->sets) { void* q[] = {b.q_dotted, b.q_hash, b.q_at, b.q_c2, b.q_numeric, b.q_long, b.seg_cnt, b.str, b.ip}; for (void* p : q) if (p) cudaFree(p); }
+  void* bufs[] = {c->args.defer, c->args.defer_tk, c->args.lh_res,
+                  c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_dbg, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   if (c->h_cut) cudaFreeHost(c->h_cut);
@@ -1868,34 +1896,71 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   ScanArgs& a = c->args;
   memset(&a, 0, sizeof a);
   auto cap32 = [](size_t v) { return (uint32_t)std::min<size_t>(v, 0x7FFFFFFFu); };
-  // candidate queue segments: one per tokenizer warp; capacity = its share of the density budget (1 dotted word per 8 log
-  // bytes, ...), but never less than the worst case of a single 1 KiB tile, so that splitting a piece always ends overflows
-  a.nseg_max = (uint32_t)launch_grid(c, 2) * K1_WARPS;
-  const size_t share = chunk_bytes / a.nseg_max;
-  a.seg_cap[Q_DOTTED] = cap32(std::max<size_t>(share / 8 + 32, 256));
-  a.seg_cap[Q_HASH] = cap32(std::max<size_t>(share / 33 + 8, 32));
-  a.seg_cap[Q_AT] = cap32(std::max<size_t>(share / 16 + 32, 1024));
-  a.seg_cap[Q_COLON2] = cap32(std::max<size_t>(share / 16 + 32, 512));
-  a.seg_cap[Q_NUMERIC] = cap32(std::max<size_t>(share / 8 + 32, 256));
-  a.seg_cap[Q_LONG] = cap32(std::max<size_t>(share / 27 + 8, 40));
-  a.cap_str = cap32(chunk_bytes / 8 + 1024);
-  a.cap_ip = cap32(chunk_bytes / 8 + 1024);
-  a.cap_rec = cap32(chunk_bytes / 16 + 4096);
-  a.cap_ids = cap32(chunk_bytes / 8 + 8192);
+  // Which first stage: tokenize_kernel + token_kernel (two passes over the log, 32 warps per SM each — the faster pair on the
+  // BASELINE configs, measured: DESIGN.md §4) or the single-pass scan_kernel (MATCHY_B200_FUSED=1; one pass, 1.2 DRAM bytes per
+  // log byte, but 16..28 warps per SM).  The work buffers differ, so the choice is made when the context is created.
+  c->fused = getenv("MATCHY_B200_FUSED") != nullptr && getenv("MATCHY_B200_UNFUSED") == nullptr;
+  c->nsets = c->fused ? 2 : 1;
+  c->wide_scan = getenv("MATCHY_B200_HOT_SMEM") == nullptr;  // (28-warp block reading the hot filter through L1: measured 15 % faster than 16 warps + shared-memory copy)
+  c->wide_warps = 28;
+  c->serial = getenv("MATCHY_B200_SERIAL") != nullptr;
+  if (const char* ww = getenv("MATCHY_B200_WIDE_WARPS")) { int v = atoi(ww); if (v == 24 || v == 28 || v == 32) c->wide_warps = v; }
+  // Candidate queue segments in HBM: one per scanning warp.  Capacities follow what a log can plausibly hold; a piece that
+  // needs more sets its overflow flag and is split at newlines and redone (scan_piece), so exactness never depends on them.
+  // No segment is smaller than the worst case of a single 1 KiB tile, so that splitting always ends overflows.
+  if (c->fused) {
+    // scan_kernel keeps dotted / numeric / hash words in shared memory; HBM sees the slow path and the rare anchors only
+    a.nseg_max = (uint32_t)launch_grid(c, 1) * 32;
+    const size_t share = chunk_bytes / a.nseg_max;
+    a.seg_cap[Q_DOTTED] = cap32(std::max<size_t>(share / 64 + 64, 288));
+    a.seg_cap[Q_HASH] = cap32(std::max<size_t>(share / 1024 + 32, 64));
+    a.seg_cap[Q_AT] = cap32(std::max<size_t>(share / 64 + 64, 1024));
+    a.seg_cap[Q_COLON2] = cap32(std::max<size_t>(share / 64 + 64, 512));
+    a.seg_cap[Q_NUMERIC] = cap32(std::max<size_t>(share / 1024 + 32, 64));
+    a.seg_cap[Q_LONG] = cap32(std::max<size_t>(share / 128 + 8, 40));
+    a.cap_str = cap32(chunk_bytes / 32 + 65536);
+    a.cap_ip = cap32(chunk_bytes / 32 + 65536);
+    a.cap_rec = cap32(chunk_bytes / 64 + 65536);
+    a.cap_ids = cap32(chunk_bytes / 64 + 65536);
+  } else {
+    a.nseg_max = (uint32_t)launch_grid(c, 2) * K1_WARPS;
+    const size_t share = chunk_bytes / a.nseg_max;
+    a.seg_cap[Q_DOTTED] = cap32(std::max<size_t>(share / 8 + 32, 256));
+    a.seg_cap[Q_HASH] = cap32(std::max<size_t>(share / 33 + 8, 32));
+    a.seg_cap[Q_AT] = cap32(std::max<size_t>(share / 16 + 32, 1024));
+    a.seg_cap[Q_COLON2] = cap32(std::max<size_t>(share / 16 + 32, 512));
+    a.seg_cap[Q_NUMERIC] = cap32(std::max<size_t>(share / 8 + 32, 256));
+    a.seg_cap[Q_LONG] = cap32(std::max<size_t>(share / 27 + 8, 40));
+    a.cap_str = cap32(chunk_bytes / 8 + 1024);
+    a.cap_ip = cap32(chunk_bytes / 8 + 1024);
+    a.cap_rec = cap32(chunk_bytes / 64 + 65536);
+    a.cap_ids = cap32(chunk_bytes / 8 + 8192);
+  }
   a.tok_unit = TOK_RESERVE;
   c->alloc_cap_str = a.cap_str; c->alloc_cap_ip = a.cap_ip; c->alloc_cap_rec = a.cap_rec; c->alloc_cap_ids = a.cap_ids;
-  CK(cudaMalloc(&a.q_dotted, (size_t)a.seg_cap[Q_DOTTED] * a.nseg_max * sizeof(Cand)));
-  CK(cudaMalloc(&a.q_hash, (size_t)a.seg_cap[Q_HASH] * a.nseg_max * sizeof(Cand)));
-  CK(cudaMalloc(&a.q_at, (size_t)a.seg_cap[Q_AT] * a.nseg_max * 4));
-  CK(cudaMalloc(&a.q_c2, (size_t)a.seg_cap[Q_COLON2] * a.nseg_max * 4));
-  CK(cudaMalloc(&a.q_numeric, (size_t)a.seg_cap[Q_NUMERIC] * a.nseg_max * sizeof(Cand)));
-  CK(cudaMalloc(&a.q_long, (size_t)a.seg_cap[Q_LONG] * a.nseg_max * sizeof(Cand)));
-  CK(cudaMalloc(&a.seg_cnt, (size_t)Q_COUNT * a.nseg_max * 4));
-  CK(cudaMalloc(&a.str, (size_t)a.cap_str * sizeof(StrTok)));
+  for (int k = 0; k < c->nsets; k++) {
+    mgpu_ctx::BufSet& b = c->sets[k];
+    CK(cudaMalloc(&b.q_dotted, (size_t)a.seg_cap[Q_DOTTED] * a.nseg_max * sizeof(Cand)));
+    CK(cudaMalloc(&b.q_hash, (size_t)a.seg_cap[Q_HASH] * a.nseg_max * sizeof(Cand)));
+    CK(cudaMalloc(&b.q_at, (size_t)a.seg_cap[Q_AT] * a.nseg_max * 4));
+    CK(cudaMalloc(&b.q_c2, (size_t)a.seg_cap[Q_COLON2] * a.nseg_max * 4));
+    CK(cudaMalloc(&b.q_numeric, (size_t)a.seg_cap[Q_NUMERIC] * a.nseg_max * sizeof(Cand)));
+    CK(cudaMalloc(&b.q_long, (size_t)a.seg_cap[Q_LONG] * a.nseg_max * sizeof(Cand)));
+    CK(cudaMalloc(&b.seg_cnt, (size_t)Q_COUNT * a.nseg_max * 4));
+    CK(cudaMalloc(&b.str, (size_t)a.cap_str * sizeof(StrTok)));
+    CK(cudaMalloc(&b.ip, (size_t)a.cap_ip * sizeof(IpTok)));
+  }
+  {
+    const mgpu_ctx::BufSet& b = c->sets[0];
+    a.q_dotted = b.q_dotted; a.q_hash = b.q_hash; a.q_at = b.q_at; a.q_c2 = b.q_c2; a.q_numeric = b.q_numeric; a.q_long = b.q_long; a.seg_cnt = b.seg_cnt;
+    a.str = b.str; a.ip = b.ip;
+  }
   CK(cudaMalloc(&a.defer, (size_t)launch_grid(c, 1) * TK_WARPS * DEFER_CAP * sizeof(StrTok)));
-  CK(cudaMalloc(&a.ip, (size_t)a.cap_ip * sizeof(IpTok)));
+  CK(cudaMalloc(&a.defer_tk, (size_t)launch_grid(c, 1) * TK_WARPS * DEFER_CAP * sizeof(StrTok)));
   CK(cudaMalloc(&a.lh_res, (size_t)a.cap_str * 4));
-  CK(cudaMalloc(&a.recs, (size_t)a.cap_rec * sizeof(mgpu_match)));
+  // match records go straight to pinned host memory (unified addressing: the host pointer is the device pointer)
+  if (!c->stage.reserve(a.cap_rec) || !c->recs.reserve(a.cap_rec)) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
+  a.recs = c->stage.p;
   CK(cudaMalloc(&a.ids, (size_t)a.cap_ids * sizeof(mgpu_id_pair)));
   CK(cudaMalloc(&a.ctr, sizeof(DevCounters) * mgpu_ctx::MAX_BATCH));
   CK(cudaMalloc(&c->d_tot, sizeof(ScanTotals)));
@@ -1909,8 +1974,14 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   CK(cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)));
   CK(cudaFuncSetAttribute(acglob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACGLOB_SMEM));
   CK(cudaFuncSetAttribute(token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOKEN_SMEM));
-  CK(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
-  CK(cudaFuncSetAttribute(scan_kernel<K1_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
+  CK(cudaFuncSetAttribute(scan_kernel<0, true, SK_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(true, SK_WARPS)));
+  CK(cudaFuncSetAttribute(scan_kernel<K1_DEFAULT_FLAGS, true, SK_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(true, SK_WARPS)));
+  CK(cudaFuncSetAttribute(scan_kernel<0, false, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(false, 28)));
+  CK(cudaFuncSetAttribute(scan_kernel<K1_DEFAULT_FLAGS, false, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(false, 28)));
+  CK(cudaFuncSetAttribute(scan_kernel<0, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(false, 32)));
+  CK(cudaFuncSetAttribute(scan_kernel<K1_DEFAULT_FLAGS, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(false, 32)));
+  CK(cudaFuncSetAttribute(scan_kernel<0, false, SK_WARPS_NOHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(false, SK_WARPS_NOHOT)));
+  CK(cudaFuncSetAttribute(scan_kernel<K1_DEFAULT_FLAGS, false, SK_WARPS_NOHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem(false, SK_WARPS_NOHOT)));
   CK(cudaFuncSetAttribute(tokenize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
   CK(cudaFuncSetAttribute(tokenize_kernel<K1_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 8));
   return MGPU_OK;
@@ -1943,7 +2014,9 @@ int mgpu_set_option(mgpu_ctx* c, const char* key, uint64_t value) {
     if (cudaSetDevice(c->device) != cudaSuccess || cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMemset failed"); return MGPU_E_CUDA; }
   }
   else if (k == "variant") c->args.variant = (uint32_t)value;
-  else if (k == "fused") c->fused = value != 0;
+  else if (k == "fused") {
+    if ((value != 0) != (c->nsets == 2)) { set_err("the first-stage kernels are chosen when the context is created (MATCHY_B200_FUSED=1): the work buffers differ"); return MGPU_E_PARAM; }
+  }
   else { set_err("unknown option: " + k); return MGPU_E_PARAM; }
   return MGPU_OK;
 }
@@ -2105,48 +2178,75 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   a.buf = d_buf; a.lo = lo; a.n = n; a.base = base; a.flags = flags;
   a.ctr = c->args.ctr + slot;
   if (c->force_ac_walk) a.db.ac_anchored = 0;
-  cudaStream_t st = c->compute;
+  const int set = c->nsets == 2 ? (slot & 1) : 0;
+  {
+    const mgpu_ctx::BufSet& b = c->sets[set];
+    a.q_dotted = b.q_dotted; a.q_hash = b.q_hash; a.q_at = b.q_at; a.q_c2 = b.q_c2; a.q_numeric = b.q_numeric; a.q_long = b.q_long; a.seg_cnt = b.seg_cnt;
+    a.str = b.str; a.ip = b.ip;
+  }
+  cudaStream_t st = c->compute, ls = c->serial ? c->compute : c->lookup;
   cudaEvent_t* ev = c->ev_k[slot];
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
   a.fast = fast ? 1u : 0u;
   a.lookups = lookups ? 1u : 0u;
   const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
   if (c->fused) {
-    // the fused kernel appends to the token lists the previous piece's lookups read: wait for them first
-    if (c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
+    // compute stream: scan_kernel of piece i.  It fills working set (i & 1), which the lookups of piece i-2 may still read.
+    if (c->set_pending[set]) { CK(cudaStreamWaitEvent(st, c->ev_looked[c->set_slot[set]], 0)); c->set_pending[set] = false; }
     if (c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
     CK(cudaEventRecord(ev[0], st));
-    uint64_t want_blocks = (tiles + SK_WARPS - 1) / SK_WARPS;
+    const bool hot = fast && a.db.hot_tags != 0 && !c->wide_scan;
+    const int warps = hot ? SK_WARPS : c->wide_warps;
+    uint64_t want_blocks = (tiles + warps - 1) / warps;
     int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 1));
     if (grid < 1) grid = 1;
-    a.nseg = (uint32_t)grid * SK_WARPS;
-    if (flags == K1_DEFAULT_FLAGS) scan_kernel<K1_DEFAULT_FLAGS><<<grid, SK_THREADS, SCAN_SMEM, st>>>(a);
-    else scan_kernel<0><<<grid, SK_THREADS, SCAN_SMEM, st>>>(a);
+    a.nseg = (uint32_t)grid * warps;
+    if (hot) {
+      if (flags == K1_DEFAULT_FLAGS) scan_kernel<K1_DEFAULT_FLAGS, true, SK_WARPS><<<grid, SK_WARPS * 32, scan_smem(true, SK_WARPS), st>>>(a);
+      else scan_kernel<0, true, SK_WARPS><<<grid, SK_WARPS * 32, scan_smem(true, SK_WARPS), st>>>(a);
+    } else if (warps == 28) {
+      if (flags == K1_DEFAULT_FLAGS) scan_kernel<K1_DEFAULT_FLAGS, false, 28><<<grid, 28 * 32, scan_smem(false, 28), st>>>(a);
+      else scan_kernel<0, false, 28><<<grid, 28 * 32, scan_smem(false, 28), st>>>(a);
+    } else if (warps == 32) {
+      if (flags == K1_DEFAULT_FLAGS) scan_kernel<K1_DEFAULT_FLAGS, false, 32><<<grid, 32 * 32, scan_smem(false, 32), st>>>(a);
+      else scan_kernel<0, false, 32><<<grid, 32 * 32, scan_smem(false, 32), st>>>(a);
+    } else {
+      if (flags == K1_DEFAULT_FLAGS) scan_kernel<K1_DEFAULT_FLAGS, false, SK_WARPS_NOHOT><<<grid, SK_WARPS_NOHOT * 32, scan_smem(false, SK_WARPS_NOHOT), st>>>(a);
+      else scan_kernel<0, false, SK_WARPS_NOHOT><<<grid, SK_WARPS_NOHOT * 32, scan_smem(false, SK_WARPS_NOHOT), st>>>(a);
+    }
+    CK(cudaEventRecord(ev[1], st));
+    CK(cudaEventRecord(c->ev_tokens[slot], st));
+    // lookup stream, beside the scan of piece i+1: the anchors and slow-path words (token_kernel), then the lookups
+    CK(cudaStreamWaitEvent(ls, c->ev_tokens[slot], 0));
+    CK(cudaEventRecord(c->ev_l0[slot], ls));
+    token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, ls>>>(a);
+    if (flags & MGPU_X_CRYPTO) crypto_kernel<<<launch_grid(c, 8), 128, 0, ls>>>(a);
+    if (c->verify_tokens) verify_tokens_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a, c->d_dbg);
+    CK(cudaEventRecord(ev[2], ls));
   } else {
-  CK(cudaEventRecord(ev[0], st));
-  {
-    uint64_t want_blocks = (tiles + K1_WARPS - 1) / K1_WARPS;
-    int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 2));
-    if (grid < 1) grid = 1;
-    a.nseg = (uint32_t)grid * K1_WARPS;
-    size_t smem = 256 * 32 * 8;
-    if (flags == K1_DEFAULT_FLAGS) tokenize_kernel<K1_DEFAULT_FLAGS><<<grid, K1_THREADS, smem, st>>>(a);
-    else tokenize_kernel<0><<<grid, K1_THREADS, smem, st>>>(a);
+    CK(cudaEventRecord(ev[0], st));
+    {
+      uint64_t want_blocks = (tiles + K1_WARPS - 1) / K1_WARPS;
+      int grid = (int)std::min<uint64_t>(want_blocks, (uint64_t)launch_grid(c, 2));
+      if (grid < 1) grid = 1;
+      a.nseg = (uint32_t)grid * K1_WARPS;
+      size_t smem = 256 * 32 * 8;
+      if (flags == K1_DEFAULT_FLAGS) tokenize_kernel<K1_DEFAULT_FLAGS><<<grid, K1_THREADS, smem, st>>>(a);
+      else tokenize_kernel<0><<<grid, K1_THREADS, smem, st>>>(a);
+    }
+    CK(cudaEventRecord(ev[1], st));
+    // The token kernel overwrites the token lists the previous piece's lookups read: wait for them.  The lookups themselves
+    // (latency-bound, a fraction of the SMs busy) run on a second stream, beside the tokenizer of the next piece.
+    if (c->set_pending[0]) { CK(cudaStreamWaitEvent(st, c->ev_looked[c->set_slot[0]], 0)); c->set_pending[0] = false; }
+    if (c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
+    token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
+    if (flags & MGPU_X_CRYPTO) crypto_kernel<<<launch_grid(c, 8), 128, 0, st>>>(a);
+    if (c->verify_tokens) verify_tokens_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a, c->d_dbg);
+    CK(cudaEventRecord(ev[2], st));
+    CK(cudaEventRecord(c->ev_tokens[slot], st));
+    CK(cudaStreamWaitEvent(ls, c->ev_tokens[slot], 0));
+    CK(cudaEventRecord(c->ev_l0[slot], ls));
   }
-  }
-  CK(cudaEventRecord(ev[1], st));
-  // The token kernel overwrites the token lists the previous piece's lookups read: wait for them.  The lookups themselves
-  // (latency-bound, a fraction of the SMs busy) run on a second stream, beside the tokenizer of the next piece.
-  if (!c->fused && c->looked_pending) CK(cudaStreamWaitEvent(st, c->ev_looked[c->looked_slot], 0));
-  if (!c->fused && c->verify_tokens) fill_kernel<<<launch_grid(c, 8), 256, 0, st>>>((uint4*)a.ip, (size_t)c->alloc_cap_ip * sizeof(IpTok) / 16, TOK_POISON);
-  token_kernel<<<launch_grid(c, 1), TK_THREADS, TOKEN_SMEM, st>>>(a);
-  if (flags & MGPU_X_CRYPTO) crypto_kernel<<<launch_grid(c, 8), 128, 0, st>>>(a);
-  if (c->verify_tokens) verify_tokens_kernel<<<launch_grid(c, 8), 256, 0, st>>>(a, c->d_dbg);
-  CK(cudaEventRecord(ev[2], st));
-  cudaStream_t ls = (a.variant & 16u) ? st : c->lookup;  // (experiment: lookups serialised behind the token kernel)
-  CK(cudaEventRecord(c->ev_tokens[slot], st));
-  CK(cudaStreamWaitEvent(ls, c->ev_tokens[slot], 0));
-  CK(cudaEventRecord(c->ev_l0[slot], ls));
   if (lookups) {
     iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
     CK(cudaEventRecord(ev[3], ls));
@@ -2161,6 +2261,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   }
   piece_end_kernel<<<1, 1, 0, ls>>>(a.ctr, a.tot);
   CK(cudaEventRecord(c->ev_looked[slot], ls));
+  c->set_pending[set] = true; c->set_slot[set] = slot;
   c->looked_pending = true; c->looked_slot = slot;
   CK(cudaGetLastError());
   c->timing.launches[MGPU_K_TOKENIZE]++; c->timing.launches[MGPU_K_TOKEN]++;
@@ -2182,14 +2283,18 @@ static int begin_batch(mgpu_ctx* c, int pieces) {
 }
 // Finish a batch: counters to the host, one synchronisation, kernel times.
 static int end_batch(mgpu_ctx* c, int pieces) {
-  if (c->looked_pending) { CK(cudaStreamWaitEvent(c->compute, c->ev_looked[c->looked_slot], 0)); c->looked_pending = false; }
+  if (c->looked_pending) { CK(cudaStreamWaitEvent(c->compute, c->ev_looked[c->looked_slot], 0)); c->looked_pending = false; }  // (one lookup stream: the latest event covers all)
+  c->set_pending[0] = c->set_pending[1] = false;
   CK(cudaMemcpyAsync(c->h_ctr, c->args.ctr, sizeof(DevCounters) * pieces, cudaMemcpyDeviceToHost, c->compute));
   CK(cudaStreamSynchronize(c->compute));
   for (int p = 0; p < pieces; p++) {
     for (int k = 0; k < MGPU_K_COUNT; k++) {
       float ms = 0;
       // (the lookup kernels run on their own stream: their span starts where that stream has finished waiting for the tokens)
-      CK(cudaEventElapsedTime(&ms, k == MGPU_K_IPTRIE ? c->ev_l0[p] : c->ev_k[p][k], c->ev_k[p][k + 1]));
+      // (whichever kernel opens the lookup stream's part of the piece — token_kernel when scan_kernel did the first pass, else
+      // iptrie_kernel — is timed from ev_l0, recorded after that stream's wait for the tokens)
+      const int first_on_lookup = c->fused ? MGPU_K_TOKEN : MGPU_K_IPTRIE;
+      CK(cudaEventElapsedTime(&ms, k == first_on_lookup ? c->ev_l0[p] : c->ev_k[p][k], c->ev_k[p][k + 1]));
       c->timing.kernel_ms[k] += ms;
     }
     float tot = 0;
@@ -2198,17 +2303,25 @@ static int end_batch(mgpu_ctx* c, int pieces) {
   }
   return MGPU_OK;
 }
-// Copy the records [r_lo, r_hi) / id pairs [i_lo, i_hi) of the shared device buffers behind the host vectors.
-static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_lo, uint32_t i_hi) {
+// Put the records [r_lo, r_hi) of the batch's record buffer (pinned host memory the device wrote into) and the id pairs
+// [i_lo, i_hi) of the device buffer behind the host vectors.  whole = these are all the records the batch produced and nothing
+// is waiting to be redone: then the two pinned buffers simply change places.
+static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_lo, uint32_t i_hi, bool whole = false) {
   if (!c->keep_results || r_hi <= r_lo) return MGPU_OK;
   size_t r0 = c->recs.size(), i0 = c->ids.size();
-  if (!c->recs.resize(r0 + (r_hi - r_lo))) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
-  CK(cudaMemcpyAsync(c->recs.data() + r0, c->args.recs + r_lo, (size_t)(r_hi - r_lo) * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->compute));
+  if (whole && r0 == 0 && r_lo == 0 && c->recs.cap == c->stage.cap) {
+    std::swap(c->recs.p, c->stage.p);
+    c->recs.n = r_hi;
+    c->args.recs = c->stage.p;
+  } else {
+    if (!c->recs.resize(r0 + (r_hi - r_lo))) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
+    memcpy(c->recs.data() + r0, c->stage.p + r_lo, (size_t)(r_hi - r_lo) * sizeof(mgpu_match));
+  }
   if (i_hi > i_lo) {
     if (!c->ids.resize(i0 + (i_hi - i_lo))) { set_err("out of pinned host memory for match ids"); return MGPU_E_CUDA; }
     CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids + i_lo, (size_t)(i_hi - i_lo) * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
+    CK(cudaStreamSynchronize(c->compute));
   }
-  CK(cudaStreamSynchronize(c->compute));
   if ((size_t)i_lo != i0)  // (the first run of a scan lands at the same indices: nothing to rebase — 8 M records per step on config 3)
     for (size_t k = r0; k < c->recs.size(); k++) if (c->recs[k].kind == MGPU_KIND_PATTERN) c->recs[k].ids_index = (uint32_t)(c->recs[k].ids_index - i_lo + i0);
   return MGPU_OK;
@@ -2275,7 +2388,7 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
     for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);
     for (size_t k = i0; k < c->x_ip.size(); k++) c->x_ip[k].start += (uint32_t)(base + al);
   }
-  return fetch_results(c, 0, h.n_rec, 0, h.n_ids);
+  return fetch_results(c, 0, h.n_rec, 0, h.n_ids, /*whole=*/true);
 }
 
 static void begin_scan(mgpu_ctx* c) {
@@ -2397,6 +2510,8 @@ static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_
     // gather: runs of pieces without overflow share one copy; overflowed pieces are redone afterwards
     std::vector<DevCounters> h(c->h_ctr, c->h_ctr + nb);  // (scan_piece below reuses the pinned block)
     std::vector<int> redo;
+    bool any_overflow = false;
+    for (int k = 0; k < nb; k++) any_overflow |= h[k].overflow != 0;
     uint32_t r_prev = 0, i_prev = 0, run_r = 0, run_i = 0;
     bool in_run = false;
     for (int k = 0; k <= nb; k++) {
@@ -2405,7 +2520,7 @@ static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_
         if (!in_run) { run_r = r_prev; run_i = i_prev; in_run = true; }
         add_counters(c, h[k], cuts[p0 + k + 1] - cuts[p0 + k], h[k].n_rec - r_prev);
       } else {
-        if (in_run) { rc = fetch_results(c, run_r, r_prev, run_i, i_prev); if (rc) return rc; in_run = false; }
+        if (in_run) { rc = fetch_results(c, run_r, r_prev, run_i, i_prev, !any_overflow); if (rc) return rc; in_run = false; }
         if (k < nb) redo.push_back(k);
       }
       if (k < nb) { r_prev = std::min(h[k].n_rec, c->args.cap_rec); i_prev = std::min(h[k].n_ids, c->args.cap_ids); }

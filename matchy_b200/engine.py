@@ -25,9 +25,23 @@ def _check(rc, what):
 
 
 class Engine:
-    def __init__(self, device=0, chunk_bytes=0, psl_path=None):
+    def __init__(self, device=0, chunk_bytes=0, psl_path=None, fused=None):
+        """fused: None = the library's default first stage (tokenize_kernel + token_kernel unless MATCHY_B200_FUSED is set);
+        True / False = the single-pass scan_kernel / the kernel pair for this engine (the choice is fixed at creation)."""
+        import os
         self.L = N.lib()
-        self.h = self.L.mgpu_create(int(device), int(chunk_bytes))
+        saved = {k: os.environ.get(k) for k in ("MATCHY_B200_FUSED", "MATCHY_B200_UNFUSED")}
+        try:
+            if fused is not None:
+                os.environ.pop("MATCHY_B200_FUSED", None); os.environ.pop("MATCHY_B200_UNFUSED", None)
+                os.environ["MATCHY_B200_FUSED" if fused else "MATCHY_B200_UNFUSED"] = "1"
+            self.h = self.L.mgpu_create(int(device), int(chunk_bytes))
+        finally:
+            if fused is not None:
+                for k, v in saved.items():
+                    os.environ.pop(k, None)
+                    if v is not None:
+                        os.environ[k] = v
         if not self.h:
             raise EngineError("mgpu_create(device=%d) failed: %s (matchy_b200 has no CPU fallback)" % (device, N.last_error()))
         self.device = device

