@@ -1,13 +1,20 @@
 #!/usr/bin/env python
 """bench.py — `matchy match` log-scan throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
-A "step" is one pass of the whole hot path (tokenize → token validation + string filters → IP-trie / exact string
-lookups → records) over one batch of synthetic log resident in HBM.  At N=1 the workload is BASELINE.json configs[1]
-(100 K globs + 1 M literal domains over 10 GB of DNS/proxy log lines).  With N>1 every rank scans its own
-10 GB shard of the same deterministic stream (byte-range sharding, database replicated per GPU, no data-path
-collective; only the summary counters are all-reduced over NCCL) — weak scaling.
+A "step" is one pass of the whole hot path (tokenize -> token validation + string filters -> IP-trie / exact string
+lookups -> records) over one batch of synthetic log resident in HBM.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C] [--gb G]
+  N = 1   BASELINE.json configs[1]: 100 K globs + 1 M literal domains over 10 GB of DNS/proxy log lines.  The line also
+          carries `per_config` (configs 1, 3, 4 measured and parity-checked in the same run) and `alt_path` (the single-pass
+          scan_kernel on the same workload).
+  N > 1   BASELINE.json configs[4]: the mixed 5 M-indicator database over a 200 GB multi-source log, sharded by byte range
+          over the ranks (100 / 50 / 25 GB per GPU, generated in HBM by the device generator), database replicated per GPU,
+          no data-path collective; the summary counters are all-reduced over NCCL — strong scaling.  `--config C` with
+          several GPUs gives every rank its own `--gb` shard of config C instead (weak scaling).
+
+Every line carries `parity`: the device's counters and records against the CPU oracle on the same bytes (untimed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C] [--gb G] [--total-gb T]
 
 `--impl reference` times the CPU restatement of the reference matcher (oracle/, kind "port": the Rust reference
 cannot be compiled in this environment) on the box's host cores over a bounded sample of the same workload.
@@ -98,12 +105,14 @@ class ClockSampler(threading.Thread):
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per log byte of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return float(json.load(f)["kernels"][kernel]["dram_bytes_per_log_byte"])
-    except Exception:
-        return None
+    """DRAM bytes per log byte of `kernel` from the committed ncu --set full capture (profiles/r2_traffic.json, else r1), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["kernels"][kernel]["dram_bytes_per_log_byte"])
+        except Exception:
+            continue
+    return None
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -254,6 +263,66 @@ def _emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def measure_resident(eng, dev, nbytes, flags, base, steps, warmup, sync_all, sampler=None):
+    """`steps` timed scans of the resident shard after `warmup` untimed ones.  Returns device seconds (sum of the per-scan CUDA
+    event spans), wall seconds, per-kernel [ms, launches], kernel launches, counters of the last scan."""
+    for _ in range(warmup):
+        eng.scan_device(dev, nbytes, flags, base=base)
+    sync_all()
+    if sampler:
+        sampler.start()
+    step_ms, kern, launches, counters = [], {}, 0, None
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.scan_device(dev, nbytes, flags, base=base)  # inputs are far larger than the 126 MB L2
+        t = eng.timing()
+        step_ms.append(t["scan_ms"])
+        for k, v in t["kernel_ms"].items():
+            kern.setdefault(k, [0.0, 0])
+            kern[k][0] += v; kern[k][1] += t["launches"][k]
+        launches += sum(t["launches"].values()) + t["aux_launches"]
+        counters = eng.counters()
+    sync_all()
+    return sum(step_ms) / 1000.0, time.perf_counter() - t0, kern, launches, counters
+
+
+def dominant(kern, nbytes, steps, peak):
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms, dom_launches = kern[dom]
+    bytes_per_launch = nbytes * steps / max(dom_launches, 1)  # 1 algorithmic byte per log byte scanned (SURVEY §8(d))
+    achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    return dom, achieved, bytes_per_launch
+
+
+def per_config_block(local_rank, args, peak):
+    """Configs 1, 3 and 4 (BASELINE.json configs[0], [2], [3]) in the driver's own run: value, dominant kernel, its roofline
+    fraction and the parity flags — 4 GB resident each (generated on the device), records compared on the first 1 GB."""
+    import numpy as np
+    from matchy_b200 import Engine, synth
+    out = {}
+    nbytes = int(args.per_config_gb * 1e9) // 65536 * 65536
+    pbytes = min(nbytes, (1 << 30))
+    for cfg in (1, 3, 4):
+        db = synth.build_db(cfg, args.scale)
+        eng = Engine(local_rank, chunk_bytes=args.chunk_mb << 20)
+        eng.upload(db)
+        flags = eng.default_flags()
+        dev = eng.dev_alloc(nbytes)
+        synth.gen_log_device(local_rank, cfg, dev, nbytes, args.scale)
+        dev_s, wall_s, kern, _, counters = measure_resident(eng, dev, nbytes, flags, 0, 3, 3, lambda: None)
+        dom, achieved, _ = dominant(kern, nbytes, 3, peak)
+        host = synth.gen_log(cfg, pbytes, args.scale)
+        eng.scan_device(dev, pbytes, flags)
+        par = parity_gate(eng, db, host, pbytes, flags, 0, pbytes)
+        out["cfg%d" % cfg] = {"workload": WORKLOADS[cfg], "log_bytes": nbytes, "value": nbytes * 3 / dev_s / 1e9, "unit": "GB/s", "ms_per_step": 1000 * dev_s / 3,
+                              "whole_path_frac": nbytes * 3 / dev_s / 1e9 / peak, "dominant_kernel": dom, "dominant_kernel_frac": achieved / peak,
+                              "kernel_ms_per_step": {k: v[0] / 3 for k, v in kern.items()}, "matches": counters["matches"], "lines": counters["lines"],
+                              "parity": {k: par[k] for k in ("bytes_compared", "counters_equal", "records_equal", "records_compared")}}
+        eng.dev_free(dev)
+        eng.close()
+    return out
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -261,17 +330,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--config", type=int, default=2)
-    ap.add_argument("--gb", type=float, default=10.0, help="log bytes per GPU per step, in GB (1e9)")
+    ap.add_argument("--config", type=int, default=0, help="BASELINE.json config 1-5; default: 2 on one GPU, 5 (200 GB sharded by byte range) on several")
+    ap.add_argument("--gb", type=float, default=10.0, help="one GPU / explicit --config: log bytes per GPU per step, in GB (1e9)")
+    ap.add_argument("--total-gb", type=float, default=200.0, help="several GPUs, config 5: total log bytes, split evenly over the ranks")
     ap.add_argument("--scale", type=float, default=1.0, help="database size scale (1.0 = the BASELINE.json counts)")
     ap.add_argument("--chunk-mb", type=int, default=2040, help="scan piece size (MiB, < 2048); pieces of a resident scan are launched back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the per_config block (configs 1, 3, 4 at 4 GB each)")
+    ap.add_argument("--per-config-gb", type=float, default=4.0)
     ap.add_argument("--crypto", action="store_true", help="also run the Bitcoin/Ethereum/Monero extractors (matchy match without --extractors=-crypto)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed full-size parity gate against the CPU oracle")
     ap.add_argument("--parity-gb", type=float, default=2.2, help="bytes of the shard whose RECORDS are compared with the oracle's (counters are compared over all of it)")
     args = ap.parse_args()
     if args.impl == "reference":
+        if not args.config:
+            args.config = 2 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 5
         return run_reference(args)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,10 +362,21 @@ def main():
         g.build()
     if dist:
         dist.barrier()
+    import ctypes as C
+    import numpy as np
     from matchy_b200 import Engine, synth
+    from matchy_b200 import _native as N
 
-    cfg, scale = args.config, args.scale
-    nbytes = int(args.gb * 1e9) // 65536 * 65536
+    # One GPU: BASELINE.json configs[1], 10 GB resident (weak: a rank's own shard).  Several GPUs: configs[4], the 200 GB stream
+    # split by byte range — strong scaling, every shard generated in its GPU's HBM.
+    sharded = world > 1 and args.config in (0, 5)
+    cfg = args.config or (5 if world > 1 else 2)
+    scale = args.scale
+    if sharded:
+        nbytes = int(args.total_gb * 1e9 / world) // 65536 * 65536
+    else:
+        nbytes = int(args.gb * 1e9) // 65536 * 65536
+    base = rank * nbytes
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     db = synth.build_db(cfg, scale)
     eng = Engine(local_rank, chunk_bytes=args.chunk_mb << 20)
@@ -299,17 +384,17 @@ def main():
     info = eng.db_info()
     flags = eng.default_flags() | (0xE0 if args.crypto else 0)  # configs run with --extractors=-crypto semantics unless --crypto
 
-    # this rank's shard of the stream: blocks [rank*nblocks, (rank+1)*nblocks); generated on the host into pinned memory
-    import ctypes as C
-    import numpy as np
-    from matchy_b200 import _native as N
-    pinned = N.lib().mgpu_host_alloc_pinned(nbytes)
+    # host copy (pinned) of what the parity gate and the e2e leg need: the whole shard on one GPU, its first part otherwise
+    host_bytes = nbytes if not sharded else min(nbytes, max(int(args.parity_gb * 1e9), 4 << 30) // 65536 * 65536)
+    pinned = N.lib().mgpu_host_alloc_pinned(host_bytes)
     if not pinned:
         raise RuntimeError("pinned allocation failed")
-    host = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint8)), shape=(nbytes,))
-    synth.gen_log(cfg, nbytes, scale, offset=rank * nbytes, out=host)
+    host = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint8)), shape=(host_bytes,))
+    synth.gen_log(cfg, host_bytes, scale, offset=base, out=host)
     dev = eng.dev_alloc(nbytes)
-    eng.dev_upload(dev, host)
+    t_gen = time.perf_counter()
+    synth.gen_log_device(local_rank, cfg, dev, nbytes, scale, offset=base)  # (same bytes as gen_log: tests/test_gpu_parity.py)
+    t_gen = time.perf_counter() - t_gen
 
     def sync_all():
         if dist:
@@ -318,28 +403,9 @@ def main():
 
     # ---- HBM-resident timing ("value") ----
     eng.set_keep_results(True)
-    for _ in range(args.warmup):
-        eng.scan_device(dev, nbytes, flags, base=rank * nbytes)
     sampler = ClockSampler(local_rank)
-    sync_all()
-    sampler.start()
-    step_ms, kern = [], {}
-    launches = 0
-    counters = None
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.scan_device(dev, nbytes, flags, base=rank * nbytes)  # inputs (10 GB) are far larger than the 126 MB L2
-        t = eng.timing()
-        step_ms.append(t["scan_ms"])
-        for k, v in t["kernel_ms"].items():
-            kern.setdefault(k, [0.0, 0])
-            kern[k][0] += v; kern[k][1] += t["launches"][k]
-        launches += sum(t["launches"].values()) + t["aux_launches"]
-        counters = eng.counters()
-    sync_all()
-    wall_s = time.perf_counter() - t_wall0
+    dev_s, wall_s, kern, launches, counters = measure_resident(eng, dev, nbytes, flags, base, args.steps, args.warmup, sync_all, sampler)
     clocks = sampler.stop()
-    dev_s = sum(step_ms) / 1000.0
     if dist:
         tt = torch.tensor([dev_s, wall_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -356,17 +422,22 @@ def main():
     # ---- parity gate at the benchmarked size (untimed; rank 0's shard) ----
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = parity_gate(eng, db, host, nbytes, flags, rank * nbytes, int(args.parity_gb * 1e9))
+        if host_bytes == nbytes:  # counters over the whole shard, records over its first part
+            parity = parity_gate(eng, db, host, nbytes, flags, base, int(args.parity_gb * 1e9))
+        else:                     # the shard exists on the device only: counters and records over its first host_bytes
+            eng.scan_device(dev, host_bytes, flags, base=base)
+            parity = parity_gate(eng, db, host, host_bytes, flags, base, host_bytes)
+            parity["note"] = "shard generated on the device; its first %d bytes regenerated on the host for the oracle" % host_bytes
 
     # ---- end to end through the C ABI with host buffers ("e2e") ----
     e2e = None
     if not args.no_e2e:
-        eng.scan(host, flags, base=rank * nbytes)  # warm-up
+        eng.scan(host, flags, base=base)  # warm-up
         sync_all()
         t0 = time.perf_counter()
         d2h = 0
         for _ in range(args.steps):
-            recs, ids = eng.scan(host, flags, base=rank * nbytes)
+            recs, ids = eng.scan(host, flags, base=base)
             d2h += recs.nbytes + ids.nbytes + 192
         sync_all()
         e_s = time.perf_counter() - t0
@@ -374,51 +445,72 @@ def main():
             tt = torch.tensor([e_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e_s = float(tt[0])
-        e2e = {"value": total_bytes / e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h // args.steps,
-               "timed": "wall clock around mgpu_scan (pinned host buffer -> double-buffered H2D -> kernels -> D2H of records), max over ranks"}
+        e2e = {"value": host_bytes * world * args.steps / e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": host_bytes, "d2h_bytes_per_step": d2h // args.steps,
+               "timed": "wall clock around mgpu_scan (pinned host buffer -> double-buffered H2D -> kernels -> records written to pinned host memory), max over ranks",
+               "sample": None if host_bytes == nbytes else "the first %d bytes of every rank's shard per step (the 200 GB stream does not fit host memory)" % host_bytes}
 
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peak()
-    dom = max(kern, key=lambda k: kern[k][0])
-    dom_ms, dom_launches = kern[dom]
-    bytes_per_launch = nbytes * args.steps / max(dom_launches, 1)  # 1 algorithmic byte per log byte scanned
-    achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    dom, achieved, bytes_per_launch = dominant(kern, nbytes, args.steps, peak)
     per_byte = ncu_traffic(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": per_byte * bytes_per_launch if per_byte is not None else None,
-                "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per log byte of this kernel (ncu --set full, cfg2), scaled to this launch size",
+                "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per log byte of this kernel (ncu --set full, cfg2), scaled to this launch size",
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
-                "whole_path_frac": (nbytes * args.steps / dev_s / 1e9) / peak if world == 1 else None}
+                "whole_path_frac": (nbytes * args.steps / dev_s / 1e9) / peak if world == 1 else (value / world) / peak}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         gbs, sample_bytes, cores, _ = cpu_port_throughput(db, cfg, scale, 0)
-        cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+        cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "mb_per_s_per_core": 1000 * gbs / cores,
+               "reference_published": "200-500 MB/s sequential, 400-2000 MB/s parallel (book/src/commands/matchy-match.md:343-350, hardware unspecified)",
                "sample": "%d MiB of the same stream, one thread per newline-aligned shard, 128 KiB reads" % (sample_bytes >> 20)}
+
+    eng.dev_free(dev)
+    N.lib().mgpu_host_free_pinned(C.c_void_p(pinned))
+    eng.close()
+
+    # ---- the other single-GPU configs and the single-pass kernel, in the same run (one GPU only) ----
+    per_config = alt = None
+    if rank == 0 and world == 1 and cfg == 2 and not args.no_per_config:
+        per_config = per_config_block(local_rank, args, peak)
+        e2 = Engine(local_rank, chunk_bytes=args.chunk_mb << 20, fused=True)
+        e2.upload(db)
+        n2 = min(nbytes, int(8e9) // 65536 * 65536)
+        d2 = e2.dev_alloc(n2)
+        synth.gen_log_device(local_rank, cfg, d2, n2, scale)
+        a_s, _, a_kern, _, a_cnt = measure_resident(e2, d2, n2, flags, 0, 3, 3, lambda: None)
+        alt = {"what": "scan_kernel (MATCHY_B200_FUSED=1): one pass over the log, 1 KiB tiles by cp.async.bulk into per-warp shared-memory rings; not the default: see DESIGN.md §4",
+               "log_bytes": n2, "value": n2 * 3 / a_s / 1e9, "unit": "GB/s", "kernel_ms_per_step": {k: v[0] / 3 for k, v in a_kern.items()}, "matches": a_cnt["matches"]}
+        e2.dev_free(d2)
+        e2.close()
 
     if rank == 0:
         line = {
             "metric": "log_scan_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "log_bytes_per_gpu": nbytes, "chunk_bytes": args.chunk_mb << 20, "extractor_flags": flags,
+            "config": {"workload": WORKLOADS[cfg], "config": cfg, "db_scale": scale, "log_bytes_per_gpu": nbytes, "log_bytes_total": nbytes * world,
+                       "chunk_bytes": args.chunk_mb << 20, "extractor_flags": flags,
                        "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (nbytes / 1e9),
                        "db": {k: info[k] for k in ("node_count", "literal_count", "glob_count", "ac_node_count", "file_bytes")},
-                       "parallelism": "byte-range shards x%d, database replicated" % world, "rank0_numa_binding": numa},
+                       "parallelism": "byte-range shards x%d, database replicated" % world, "rank0_numa_binding": numa,
+                       "generated": "on the device (csrc/synth_device.cu), %.2f s for %.1f GB on rank 0" % (t_gen, nbytes / 1e9)},
             "lines_per_s": tot[0] * args.steps / dev_s, "matches_per_s": tot[3] * args.steps / dev_s,
-            "counters": {"lines": tot[0], "bytes": tot[1], "candidates": tot[2], "matches": tot[3]},
-            "wall_s_timed_region": wall_s,
+            "counters": {"lines": tot[0], "bytes": tot[1], "candidates": tot[2], "matches": tot[3], "by_type": tot[4:]},
+            "wall_s_timed_region": wall_s, "value_wall": total_bytes / wall_s / 1e9,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
+            "per_config": per_config, "alt_path": alt,
         }
         _emit(line)
-    eng.dev_free(dev)
-    N.lib().mgpu_host_free_pinned(C.c_void_p(pinned))
-    eng.close()
     if dist:
         dist.destroy_process_group()
-    if parity is not None and not (parity["counters_equal"] and parity["records_equal"]):
-        sys.stderr.write("PARITY FAILURE: %r\n" % (parity,))
+    bad = parity is not None and not (parity["counters_equal"] and parity["records_equal"])
+    if per_config:
+        bad = bad or any(not (v["parity"]["counters_equal"] and v["parity"]["records_equal"]) for v in per_config.values())
+    if bad:
+        sys.stderr.write("PARITY FAILURE: %r %r\n" % (parity, per_config))
         return 3
     return 0
 

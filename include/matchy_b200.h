@@ -154,6 +154,7 @@ int mgpu_lookup_ip(mgpu_ctx*, const uint8_t ip16[16], int is_v6, uint32_t* data_
 void* mgpu_dev_alloc(mgpu_ctx*, size_t bytes);
 void mgpu_dev_free(mgpu_ctx*, void*);
 int mgpu_dev_upload(mgpu_ctx*, void* dst, const void* src, size_t bytes);
+int mgpu_dev_download(mgpu_ctx*, void* dst, const void* src, size_t bytes);
 void* mgpu_host_alloc_pinned(size_t bytes);
 void mgpu_host_free_pinned(void*);
 int mgpu_flush_l2(mgpu_ctx*);
@@ -198,6 +199,9 @@ mxyb_builder* mgen_db(int config, double scale);
 /* Fills out[0..len) with the config's log lines for byte range [offset, offset+len) of the infinite
  * deterministic stream (block-addressable); the last line is cut at len and padded with '\n'. */
 int mgen_log(int config, double scale, uint64_t offset, uint8_t* out, size_t len, int threads);
+/* The same bytes, generated in the HBM of `device` (offset and len multiples of 64 KiB): config 5's 100 / 50 / 25 GB shards
+ * never cross PCIe.  The same integer code runs on both sides (csrc/synth_gen.h). */
+int mgen_log_device(int device, int config, double scale, uint64_t offset, void* dev_out, size_t len);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ SYMBOLS = {
     "mgpu_dev_alloc": (_VP, [_VP, _SZ]),
     "mgpu_dev_free": (None, [_VP, _VP]),
     "mgpu_dev_upload": (C.c_int, [_VP, _VP, _VP, _SZ]),
+    "mgpu_dev_download": (C.c_int, [_VP, _VP, _VP, _SZ]),
     "mgpu_host_alloc_pinned": (_VP, [_SZ]),
     "mgpu_host_free_pinned": (None, [_VP]),
     "mgpu_flush_l2": (C.c_int, [_VP]),
@@ -93,6 +94,7 @@ SYMBOLS = {
     "mxyb_xxh64": (C.c_uint64, [C.c_char_p, _SZ]),
     "mgen_db": (_VP, [C.c_int, C.c_double]),
     "mgen_log": (C.c_int, [C.c_int, C.c_double, C.c_uint64, _VP, _SZ, C.c_int]),
+    "mgen_log_device": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_uint64, _VP, _SZ]),
 }
 
 _lib = None

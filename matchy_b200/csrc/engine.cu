@@ -2315,7 +2315,17 @@ static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_l
     c->args.recs = c->stage.p;
   } else {
     if (!c->recs.resize(r0 + (r_hi - r_lo))) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
-    memcpy(c->recs.data() + r0, c->stage.p + r_lo, (size_t)(r_hi - r_lo) * sizeof(mgpu_match));
+    // (later batches of a long resident scan: tens of millions of records — copy with several threads)
+    const size_t nrec = r_hi - r_lo;
+    const unsigned nt = nrec < (1u << 20) ? 1u : std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    mgpu_match* dst = c->recs.data() + r0;
+    const mgpu_match* src = c->stage.p + r_lo;
+    if (nt == 1) memcpy(dst, src, nrec * sizeof(mgpu_match));
+    else {
+      std::vector<std::thread> th;
+      for (unsigned k = 0; k < nt; k++) th.emplace_back([=] { const size_t a = nrec * k / nt, b = nrec * (k + 1) / nt; memcpy(dst + a, src + a, (b - a) * sizeof(mgpu_match)); });
+      for (auto& t : th) t.join();
+    }
   }
   if (i_hi > i_lo) {
     if (!c->ids.resize(i0 + (i_hi - i_lo))) { set_err("out of pinned host memory for match ids"); return MGPU_E_CUDA; }
@@ -2692,6 +2702,11 @@ void mgpu_dev_free(mgpu_ctx* c, void* p) { cudaSetDevice(c->device); cudaFree(p)
 int mgpu_dev_upload(mgpu_ctx* c, void* dst, const void* src, size_t bytes) {
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return MGPU_OK;
+}
+int mgpu_dev_download(mgpu_ctx* c, void* dst, const void* src, size_t bytes) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
   return MGPU_OK;
 }
 void* mgpu_host_alloc_pinned(size_t bytes) {

@@ -33,3 +33,11 @@ def gen_log(config: int, nbytes: int, scale: float = 1.0, offset: int = 0, threa
     if rc != 0:
         raise ValueError("mgen_log failed: %d" % rc)
     return out
+
+
+def gen_log_device(device: int, config: int, dev_ptr: int, nbytes: int, scale: float = 1.0, offset: int = 0) -> None:
+    """Fill device memory [dev_ptr, dev_ptr + nbytes) on GPU `device` with the same bytes gen_log() would produce (offset and
+    nbytes multiples of 64 KiB).  Raises without a CUDA device: the generator runs as a kernel (csrc/synth_device.cu)."""
+    rc = N.lib().mgen_log_device(int(device), int(config), float(scale), int(offset), C.c_void_p(dev_ptr), int(nbytes))
+    if rc != 0:
+        raise ValueError("mgen_log_device failed: %d" % rc)

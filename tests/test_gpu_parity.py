@@ -459,3 +459,25 @@ def test_paraglob_integration_vectors_on_device(built):
         for t in texts:
             assert eng.lookup_string(t.encode()) == orc.lookup_string(t.encode()), (patterns[:3], t)
     eng.close()
+
+
+def test_device_generator_equals_host_generator(built):
+    """mgen_log_device (csrc/synth_device.cu) writes the bytes mgen_log (csrc/synth.cpp) writes: same integer code
+    (csrc/synth_gen.h) on both sides, every config / line family, several offsets, full and 1 % database scale."""
+    import ctypes as C
+    from matchy_b200 import Engine, synth, _native as N
+    eng = Engine(0, chunk_bytes=1 << 20)
+    nbytes = 48 * 65536
+    dev = eng.dev_alloc(nbytes)
+    got = np.empty(nbytes, dtype=np.uint8)
+    try:
+        for cfg in (1, 2, 3, 4, 5):
+            for scale in (1.0, 0.01):
+                for off in (0, 5 * 65536, 123457 * 65536):
+                    synth.gen_log_device(0, cfg, dev, nbytes, scale, offset=off)
+                    assert N.lib().mgpu_dev_download(C.c_void_p(eng.h), C.c_void_p(got.ctypes.data), C.c_void_p(dev), nbytes) == 0
+                    want = synth.gen_log(cfg, nbytes, scale, offset=off)
+                    assert np.array_equal(got, want), (cfg, scale, off)
+    finally:
+        eng.dev_free(dev)
+    eng.close()
