@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -215,18 +216,17 @@ __global__ void __launch_bounds__(K1_THREADS) tokenize_kernel(ScanArgs a) {
 
       // four "does the word contain ..." chains: a byte that rules out a domain, a '.', a non-hex byte, a byte that is
       // neither a hex digit nor a '.'
-      const uint32_t Y1 = T & (~m.DM | bad), Y2 = m.DOT, Y3 = T & ~m.HX, Y4 = Y3 & ~m.DOT;
-      const uint32_t g1 = chain_gen(T, Y1), g2 = chain_gen(T, Y2), g3 = chain_gen(T, Y3), g4 = chain_gen(T, Y4);
+      // (three chains: "the word holds a non-hex byte" is "it holds a '.' or a byte that is neither hex nor '.'")
+      const uint32_t Y1 = T & (~m.DM | bad), Y2 = m.DOT, Y4 = T & ~m.HX & ~m.DOT;
+      const uint32_t g1 = chain_gen(T, Y1), g2 = chain_gen(T, Y2), g4 = chain_gen(T, Y4);
       const uint32_t pb = __ballot_sync(0xFFFFFFFFu, T == 0xFFFFFFFFu);
-      const uint32_t G1 = __ballot_sync(0xFFFFFFFFu, g1), G2 = __ballot_sync(0xFFFFFFFFu, g2), G3 = __ballot_sync(0xFFFFFFFFu, g3);
-      const uint32_t G4 = __ballot_sync(0xFFFFFFFFu, g4);
-      uint32_t co1, co2, co3, co4;
-      const uint32_t cv1 = carry_chain(G1, pb & ~G1, cy.cBad, co1), cv2 = carry_chain(G2, pb & ~G2, cy.cDot, co2), cv3 = carry_chain(G3, pb & ~G3, cy.cNhx, co3);
-      const uint32_t cv4 = carry_chain(G4, pb & ~G4, cy.cNhd, co4);
-      cy.cBad = co1; cy.cDot = co2; cy.cNhx = co3; cy.cNhd = co4;
+      const uint32_t G1 = __ballot_sync(0xFFFFFFFFu, g1), G2 = __ballot_sync(0xFFFFFFFFu, g2), G4 = __ballot_sync(0xFFFFFFFFu, g4);
+      uint32_t co1, co2, co4;
+      const uint32_t cv1 = carry_chain(G1, pb & ~G1, cy.cBad, co1), cv2 = carry_chain(G2, pb & ~G2, cy.cDot, co2), cv4 = carry_chain(G4, pb & ~G4, cy.cNhd, co4);
+      cy.cBad = co1; cy.cDot = co2; cy.cNhd = co4;
       const uint32_t E = m.B & prevT;  // boundaries that end a word
       const uint32_t hasBad = chain_ends(T, Y1, (cv1 >> lane) & 1u, m.B), hasDot = chain_ends(T, Y2, (cv2 >> lane) & 1u, m.B);
-      const uint32_t hasNhx = chain_ends(T, Y3, (cv3 >> lane) & 1u, m.B), hasNhd = chain_ends(T, Y4, (cv4 >> lane) & 1u, m.B);
+      const uint32_t hasNhd = chain_ends(T, Y4, (cv4 >> lane) & 1u, m.B), hasNhx = hasNhd | hasDot;
       const uint32_t candDot = want_dot ? (hasDot & ~hasBad & ~bad_end) : 0u;
       // a word of >= 32 bytes that ends in my slice started in an earlier one: only my first boundary qualifies
       uint32_t candHex = (want_hash && pT) ? (E & ~hasNhx & (m.B & (0u - m.B))) : 0u;
@@ -1800,6 +1800,10 @@ struct mgpu_ctx {
                                 // while later pieces are still being scanned (no device-side record buffer, no D2H copy at the end)
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
+  // record index where each gathered piece ends: pieces arrive in log order and hold disjoint offset ranges, so the final
+  // sort is one small sort per piece, in parallel (pieces_in_order = false after a redo, whose records arrive late)
+  std::vector<size_t> piece_ends;
+  bool pieces_in_order = true;
   mgpu_counters counters{};
   mgpu_timing timing{};
   bool keep_results = true;
@@ -2398,11 +2402,13 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
     for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);
     for (size_t k = i0; k < c->x_ip.size(); k++) c->x_ip[k].start += (uint32_t)(base + al);
   }
+  if (c->keep_results) c->piece_ends.push_back((c->piece_ends.empty() ? 0 : c->piece_ends.back()) + h.n_rec);
   return fetch_results(c, 0, h.n_rec, 0, h.n_ids, /*whole=*/true);
 }
 
 static void begin_scan(mgpu_ctx* c) {
   c->recs.clear(); c->ids.clear();
+  c->piece_ends.clear(); c->pieces_in_order = true;
   c->x_str.clear(); c->x_ip.clear();
   memset(&c->counters, 0, sizeof c->counters);
   memset(&c->timing, 0, sizeof c->timing);
@@ -2422,7 +2428,16 @@ static void finish_scan(mgpu_ctx* c) {
   };
   const size_t nrec = c->recs.size();
   unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-  if (nrec < 65536 || nt < 2) std::sort(c->recs.begin(), c->recs.end(), less);
+  if (c->pieces_in_order && !c->piece_ends.empty() && c->piece_ends.back() == nrec && nrec >= 65536 && nt >= 2) {
+    // every piece's records lie in its own offset range and the pieces are in log order: sort piece by piece, in parallel
+    mgpu_match* r = c->recs.data();
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < nt; k++) th.emplace_back([&] {
+      for (size_t p = next.fetch_add(1); p < c->piece_ends.size(); p = next.fetch_add(1)) std::sort(r + (p ? c->piece_ends[p - 1] : 0), r + c->piece_ends[p], less);
+    });
+    for (auto& t : th) t.join();
+  } else if (nrec < 65536 || nt < 2) std::sort(c->recs.begin(), c->recs.end(), less);
   else {
     // large result sets: sort nt slices in parallel, then merge pairwise (the sort was ~10 % of an end-to-end 10 GB scan)
     while (nt & (nt - 1)) nt &= nt - 1;  // power of two
@@ -2529,12 +2544,14 @@ static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_
       if (ok) {
         if (!in_run) { run_r = r_prev; run_i = i_prev; in_run = true; }
         add_counters(c, h[k], cuts[p0 + k + 1] - cuts[p0 + k], h[k].n_rec - r_prev);
+        if (c->keep_results) c->piece_ends.push_back((c->piece_ends.empty() ? 0 : c->piece_ends.back()) + (h[k].n_rec - r_prev));
       } else {
         if (in_run) { rc = fetch_results(c, run_r, r_prev, run_i, i_prev, !any_overflow); if (rc) return rc; in_run = false; }
         if (k < nb) redo.push_back(k);
       }
       if (k < nb) { r_prev = std::min(h[k].n_rec, c->args.cap_rec); i_prev = std::min(h[k].n_ids, c->args.cap_ids); }
     }
+    if (!redo.empty()) c->pieces_in_order = false;
     for (int k : redo) {
       rc = scan_piece(c, dev, cuts[p0 + k], cuts[p0 + k + 1], base, flags, lookups, 0);
       if (rc) return rc;

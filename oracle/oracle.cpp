@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <list>
 #include <string>
 #include <unordered_map>
 #include <thread>
@@ -960,7 +961,8 @@ struct Extractor {
     if (flags & (X_HASHES | X_BITCOIN | X_MONERO)) find_word_boundaries(c, n, bounds);
     // dots: the reference collects once if both ipv4+domains, else lazily; identical positions either way
     if (flags & (X_IPV4 | X_DOMAINS)) {
-      for (size_t i = 0; i < n; i++) if (c[i] == '.') dots.push_back(i);
+      // memchr_iter(b'.', chunk) (lib.rs:432-447)
+      for (const uint8_t* q = c; (q = (const uint8_t*)memchr(q, '.', (size_t)(c + n - q))) != nullptr; q++) dots.push_back((size_t)(q - c));
     }
     if (flags & X_IPV6) extract_ipv6_chunk(c, n, out);
     if (flags & X_IPV4) extract_ipv4_chunk(c, n, dots, out);
@@ -1275,7 +1277,7 @@ struct Db {
   }
 
   // run_ac_matching_into_static :1186-1266
-  void run_ac(const uint8_t* ac, size_t acn, const uint8_t* text, size_t n, std::unordered_set<uint32_t>& lits) const {
+  void run_ac(const uint8_t* ac, size_t acn, const uint8_t* text, size_t n, std::vector<uint32_t>& lits) const {
     if (acn == 0 || n == 0) return;
     std::string lowered;
     if (match_mode == 1) { lowered = ascii_lower(text, n); text = (const uint8_t*)lowered.data(); }
@@ -1294,7 +1296,7 @@ struct Db {
       uint8_t pc = nd[3];
       if (pc > 0) {
         size_t po = rd32(nd + 16);
-        if (po + (size_t)pc * 4 <= acn) for (size_t k = 0; k < pc; k++) lits.insert(rd32(ac + po + k * 4));
+        if (po + (size_t)pc * 4 <= acn) for (size_t k = 0; k < pc; k++) lits.push_back(rd32(ac + po + k * 4));
       }
     }
   }
@@ -1420,14 +1422,21 @@ struct Db {
     result.clear();
     if (pg_len < 112) return;
     size_t ac_start = rd32(pg + 20), ac_size = rd32(pg + 24);
-    std::unordered_set<uint32_t> lits, cands;
+    // (the reference collects literal ids and candidate patterns in hash sets, :1046-1095; per-thread vectors that are sorted
+    //  and deduplicated give the same sets without an allocation per token)
+    static thread_local std::vector<uint32_t> lits, cands;
+    lits.clear(); cands.clear();
     if (ac_size > 0 && ac_start + ac_size <= pg_len) {
       run_ac(pg + ac_start, ac_size, text, tn, lits);
+      std::sort(lits.begin(), lits.end());
+      lits.erase(std::unique(lits.begin(), lits.end()), lits.end());
       for (uint32_t lit : lits) {
         auto it = aclh.find(lit);
         if (it == aclh.end()) continue;
-        for (uint32_t k = 0; k < it->second.second; k++) cands.insert(rd32(pg + it->second.first + (size_t)k * 4));
+        for (uint32_t k = 0; k < it->second.second; k++) cands.push_back(rd32(pg + it->second.first + (size_t)k * 4));
       }
+      std::sort(cands.begin(), cands.end());
+      cands.erase(std::unique(cands.begin(), cands.end()), cands.end());
     }
     size_t unaligned = (size_t)rd32(pg + 40) + rd32(pg + 44);
     size_t wild_off = unaligned + ((8 - (unaligned % 8)) % 8);
@@ -1505,8 +1514,32 @@ struct Scan {
   bool error = false;
 };
 
-static void process_bytes(const Db& db, const Extractor& ex, const uint8_t* d, size_t n, uint64_t base, Scan& out) {
-  for (size_t i = 0; i < n; i++) out.c.lines += d[i] == '\n';
+// The reference's thread-local LRU query cache (database.rs:32-37; lookup() :725-804, lookup_ip() :837-886): every Some(result),
+// NotFound included, is stored under the query text (IP lookups: under the address).  `matchy match` opens its database with
+// --cache-size 10000 by default (bin/matchy.rs).  Results are what the uncached lookups return, so only the time changes.
+struct LruCache {
+  struct Val { uint8_t kind; uint8_t prefix_len; uint32_t data_offset; std::vector<IdPair> ids; };  // kind 0 NotFound, 1 Ip, 2 Pattern
+  size_t cap;
+  std::list<std::pair<std::string, Val>> order;  // most recent first
+  std::unordered_map<std::string, std::list<std::pair<std::string, Val>>::iterator> index;
+  explicit LruCache(size_t c) : cap(c) {}
+  const Val* get(const std::string& key) {
+    auto it = index.find(key);
+    if (it == index.end()) return nullptr;
+    order.splice(order.begin(), order, it->second);
+    return &it->second->second;
+  }
+  void put(const std::string& key, Val v) {
+    auto it = index.find(key);
+    if (it != index.end()) { it->second->second = std::move(v); order.splice(order.begin(), order, it->second); return; }
+    order.emplace_front(key, std::move(v));
+    index[key] = order.begin();
+    if (order.size() > cap) { index.erase(order.back().first); order.pop_back(); }
+  }
+};
+
+static void process_bytes(const Db& db, const Extractor& ex, const uint8_t* d, size_t n, uint64_t base, Scan& out, LruCache* cache = nullptr) {
+  for (const uint8_t* q = d; (q = (const uint8_t*)memchr(q, '\n', (size_t)(d + n - q))) != nullptr; q++) out.c.lines++;  // memchr::memchr_iter(b'\n', data).count() (mod.rs:357)
   out.c.bytes += n;
   std::vector<Item> items;
   ex.extract_from_chunk(d, n, items);
@@ -1519,8 +1552,19 @@ static void process_bytes(const Db& db, const Extractor& ex, const uint8_t* d, s
     if (it.type == T_IPV4 || it.type == T_IPV6) {  // lookup_extracted database.rs:889-901 → lookup_ip
       if (!db.has_ip_header) continue;
       uint32_t off = 0; uint8_t pl = 0;
-      int rc = it.type == T_IPV4 ? db.lookup_v4(it.v4, off, pl) : db.lookup_v6(it.v6, off, pl);
-      if (rc < 0) { out.error = true; return; }  // Err aborts the chunk (mod.rs:414-416)
+      int rc;
+      std::string key;
+      const LruCache::Val* hit = nullptr;
+      if (cache) {  // (keyed by the address: one-to-one with the canonical text the reference keys on, database.rs:839)
+        key = it.type == T_IPV4 ? std::string((const char*)&it.v4, 4) : std::string((const char*)it.v6, 16);
+        hit = cache->get(key);
+      }
+      if (hit) { rc = hit->kind == 1; off = hit->data_offset; pl = hit->prefix_len; }
+      else {
+        rc = it.type == T_IPV4 ? db.lookup_v4(it.v4, off, pl) : db.lookup_v6(it.v6, off, pl);
+        if (rc < 0) { out.error = true; return; }  // Err aborts the chunk (mod.rs:414-416)
+        if (cache) cache->put(key, LruCache::Val{(uint8_t)(rc ? 1 : 0), pl, off, {}});
+      }
       if (rc == 0) continue;
       r.kind = 1; r.prefix_len = pl; r.data_offset = off; r.n_ids = 0; r.ids_index = 0;
     } else {
@@ -1535,7 +1579,17 @@ static void process_bytes(const Db& db, const Extractor& ex, const uint8_t* d, s
         r.kind = 1; r.prefix_len = pl; r.data_offset = off;
       } else {
         if (!db.has_literal && !db.has_glob) continue;  // Ok(None)
-        if (!db.lookup_string(d + it.start, it.end - it.start, ids)) continue;
+        if (cache) {
+          const std::string key((const char*)d + it.start, it.end - it.start);
+          if (const LruCache::Val* hit = cache->get(key)) {
+            if (hit->kind != 2) continue;
+            ids = hit->ids;
+          } else {
+            const bool found = db.lookup_string(d + it.start, it.end - it.start, ids);
+            cache->put(key, LruCache::Val{(uint8_t)(found ? 2 : 0), 0, 0, found ? ids : std::vector<IdPair>()});
+            if (!found) continue;
+          }
+        } else if (!db.lookup_string(d + it.start, it.end - it.start, ids)) continue;
         r.kind = 2; r.n_ids = (uint32_t)ids.size(); r.ids_index = (uint32_t)out.ids.size();
         r.data_offset = NO_DATA;
         out.ids.insert(out.ids.end(), ids.begin(), ids.end());
@@ -1548,13 +1602,13 @@ static void process_bytes(const Db& db, const Extractor& ex, const uint8_t* d, s
 
 // FileReader::next_batch — processing/mod.rs:206-251, driven over an in-memory "file"
 static void scan_stream(const Db& db, const Extractor& ex, const uint8_t* d, size_t n, uint64_t base, size_t chunk_size,
-                        Scan& out) {
+                        Scan& out, LruCache* cache = nullptr) {
   size_t rd = 0;           // bytes "read" so far
   size_t left_start = 0;   // leftover = d[left_start..rd)
   for (;;) {
     size_t got = std::min(chunk_size, n - rd);
     if (got == 0) {
-      if (left_start < rd) process_bytes(db, ex, d + left_start, rd - left_start, base + left_start, out);
+      if (left_start < rd) process_bytes(db, ex, d + left_start, rd - left_start, base + left_start, out, cache);
       return;
     }
     rd += got;
@@ -1563,7 +1617,7 @@ static void scan_stream(const Db& db, const Extractor& ex, const uint8_t* d, siz
     bool found = false;
     while (pos > left_start) { if (d[pos - 1] == '\n') { found = true; break; } pos--; }
     if (!found) continue;  // leftover = combined; read more
-    process_bytes(db, ex, d + left_start, pos - left_start, base + left_start, out);
+    process_bytes(db, ex, d + left_start, pos - left_start, base + left_start, out, cache);
     if (out.error) return;
     left_start = pos;
   }
@@ -1632,6 +1686,7 @@ struct orc_handle {
   Extractor ex;
   Scan scan;
   std::string ndjson;
+  size_t cache_capacity = 10000;  // `matchy match --cache-size` default; 0 = no cache (orc_set_cache)
 };
 
 extern "C" {
@@ -1653,6 +1708,8 @@ int orc_cryptoaddr(int what, const uint8_t* s, size_t n) {
   switch (what) { case 0: return cryptoaddr::bitcoin_base58(s, n); case 1: return cryptoaddr::bitcoin_bech32(s, n); case 2: return n == 42 && cryptoaddr::ethereum(s); default: return cryptoaddr::monero(s, n); }
 }
 void orc_close(orc_handle* h) { delete h; }
+// per-thread LRU query cache of the multi-threaded scans (0 disables it), like `matchy match --cache-size N`
+void orc_set_cache(orc_handle* h, size_t capacity) { h->cache_capacity = capacity; }
 
 // default extractor flags as `matchy match` derives them from DB capabilities (match_cmd.rs:277-303),
 // with the crypto extractors off (--extractors=-crypto)
@@ -1703,7 +1760,8 @@ int orc_scan_mt(orc_handle* h, const uint8_t* data, size_t len, uint32_t flags, 
   ex.flags = flags;
   for (int t = 0; t < threads; t++) {
     th.emplace_back([&, t]() {
-      if (cuts[t + 1] > cuts[t]) scan_stream(h->db, ex, data + cuts[t], cuts[t + 1] - cuts[t], cuts[t], 128 * 1024, scans[t]);
+      LruCache cache(h->cache_capacity);
+      if (cuts[t + 1] > cuts[t]) scan_stream(h->db, ex, data + cuts[t], cuts[t + 1] - cuts[t], cuts[t], 128 * 1024, scans[t], h->cache_capacity ? &cache : nullptr);
     });
   }
   for (auto& x : th) x.join();
@@ -1738,7 +1796,8 @@ int orc_scan_mt_keep(orc_handle* h, const uint8_t* data, size_t len, uint64_t ba
   ex.flags = flags;
   for (int t = 0; t < threads; t++) {
     th.emplace_back([&, t]() {
-      if (cuts[t + 1] > cuts[t]) scan_stream(h->db, ex, data + cuts[t], cuts[t + 1] - cuts[t], base + cuts[t], 128 * 1024, scans[t]);
+      LruCache cache(h->cache_capacity);
+      if (cuts[t + 1] > cuts[t]) scan_stream(h->db, ex, data + cuts[t], cuts[t + 1] - cuts[t], base + cuts[t], 128 * 1024, scans[t], h->cache_capacity ? &cache : nullptr);
     });
   }
   for (auto& x : th) x.join();

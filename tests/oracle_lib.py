@@ -19,7 +19,7 @@ TYPE_NAMES = ["Domain", "Email", "IPv4", "IPv6", "MD5", "SHA1", "SHA256", "SHA38
 
 def build_oracle(force=False):
     if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(ORACLE_SRC):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", ORACLE_SO, ORACLE_SRC])
+        subprocess.check_call(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", ORACLE_SO, ORACLE_SRC])
     return ORACLE_SO
 
 
@@ -47,6 +47,7 @@ def lib():
         L.orc_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_size_t]
         L.orc_scan_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         L.orc_scan_mt_keep.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+        L.orc_set_cache.argtypes = [C.c_void_p, C.c_size_t]
         L.orc_n_matches.restype = C.c_size_t
         L.orc_n_matches.argtypes = [C.c_void_p]
         L.orc_matches.restype = C.POINTER(MatchRec)
@@ -111,6 +112,10 @@ class Oracle:
 
     def default_flags(self):
         return self.L.orc_default_flags(self.h)
+
+    def set_cache(self, capacity: int):
+        """Per-thread LRU query cache of scan_mt / scan_mt_keep (`matchy match --cache-size`, default 10000; 0 = off)."""
+        self.L.orc_set_cache(self.h, int(capacity))
 
     def extract(self, data, flags=X_DEFAULT):
         p, n, keep = _buf(data)
