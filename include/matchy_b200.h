@@ -168,6 +168,10 @@ size_t mxyr_data_json(mxyr_db*, uint32_t data_offset, const char** out);
 /* `matchy match` NDJSON lines (parallel mode) for recs[0..n); log/base locate matched_text. */
 size_t mxyr_ndjson(mxyr_db*, const mgpu_match* recs, size_t n, const mgpu_id_pair* ids, const uint8_t* log, uint64_t base,
                    const char* source, const char** out);
+/* The same lines as `matchy match --threads 1` / --follow print them (bin/match_processor/sequential.rs:205-390): `timestamp` is
+ * the caller's text (wall clock, "%.3f"), matched_text and cidr use the canonical text of an address (Ipv6Addr Display). */
+size_t mxyr_ndjson_sequential(mxyr_db*, const mgpu_match* recs, size_t n, const mgpu_id_pair* ids, const uint8_t* log, uint64_t base,
+                              const char* source, const char* timestamp, const char** out);
 
 /* ---- .mxy writer -------------------------------------------------------------------------------- */
 typedef struct mxyb_builder mxyb_builder;

@@ -2,9 +2,11 @@
 `python -m matchy_b200 extract LOG [LOG...]` — the `matchy extract` output contract (bin/commands/extract_cmd.rs).
 
 Prints one JSON object per match, in the reference's parallel-mode format (bin/match_processor/parallel.rs:297-369: keys
-sorted, `timestamp` "0.000", `source` = the file path), and with `--stats` the WorkerStats counters on stderr.  Only what the
-scan path needs: `.gz` inputs are inflated on the host, "-" is stdin; no follow mode, no `--format`; the CLI proper is out of scope
-(DESIGN.md)."""
+sorted, `timestamp` "0.000", `source` = the file path), and with `--stats` the WorkerStats counters on stderr.  `--threads 1`
+gives the sequential-mode output instead (line order, wall-clock timestamps, canonical address text:
+bin/match_processor/sequential.rs:205-390), `--follow` keeps reading what is appended to the files (follow.rs) and
+`--watch-db` reloads the database when its file changes (watching_database.rs).  `.gz` inputs are inflated on the host, "-"
+is stdin.  The CLI proper (progress bars, `--format summary`) is out of scope."""
 import argparse
 import json
 import sys
@@ -198,6 +200,10 @@ def main(argv=None):
     m.add_argument("--extractors", default="", help="comma list; '-crypto' drops the Bitcoin/Ethereum/Monero extractors (match_cmd.rs)")
     m.add_argument("--stats", action="store_true")
     m.add_argument("--chunk-mb", type=int, default=512)
+    m.add_argument("-j", "--threads", default=None, help="1 = sequential mode (line order, real timestamps); anything else: the parallel-mode output")
+    m.add_argument("--follow", action="store_true", help="after the existing content, keep processing what is appended to the files")
+    m.add_argument("--follow-idle-exit", type=float, default=None, help="(follow mode) stop after this many seconds without new data; default: run until interrupted")
+    m.add_argument("--watch-db", action="store_true", help="reload the database into the engine when its file changes")
     x = sub.add_parser("extract", help="extract IoC tokens from log files, one JSON / CSV / text line per item on stdout")
     x.add_argument("inputs", nargs="+", help='log files, or "-" for stdin')
     x.add_argument("--format", default="json")
@@ -224,31 +230,56 @@ def main(argv=None):
     if a.cmd == "build":
         return cmd_build(a)
     from . import Engine, RecordFormatter
-    db = open(a.database, "rb").read()
-    eng = Engine(a.device, chunk_bytes=a.chunk_mb << 20)
-    eng.upload(db)
-    flags = eng.default_flags()
+    from . import match_modes as M
+    sequential = str(a.threads) == "1" or a.follow  # (follow mode prints sequential-mode lines, follow.rs:209-262)
+    watch = None
+    if a.watch_db:
+        watch = M.WatchingDatabase.from_(a.database).device(a.device).chunk_bytes(a.chunk_mb << 20).on_reload(
+            lambda gen, path: print("[INFO] database reloaded (generation %d): %s" % (gen, path), file=sys.stderr)).open()
+        eng = watch.engine
+    else:
+        db = open(a.database, "rb").read()
+        eng = Engine(a.device, chunk_bytes=a.chunk_mb << 20)
+        eng.upload(db)
+        fmt = RecordFormatter(db)
     info = eng.db_info()
-    if (info["has_literal"] or info["has_glob"]) and "-crypto" not in a.extractors.split(","):
-        flags |= 0xE0  # crypto extractors are on by default when the database has strings (match_cmd.rs:290-292)
-    fmt = RecordFormatter(db)
-    tot = None
+    crypto = (info["has_literal"] or info["has_glob"]) and "-crypto" not in a.extractors.split(",")
+    tot = [None]
     t0 = time.perf_counter()
-    nbytes = 0
+    nbytes = [0]
     out = sys.stdout.buffer
-    for path in a.inputs:
-        data = read_input(path)
-        nbytes += data.size
-        recs, ids = eng.scan(data, flags)
-        out.write(fmt.ndjson(recs, ids, data, 0, path))
-        c = eng.counters_list()
-        tot = c if tot is None else [x + y for x, y in zip(tot, c)]
+
+    def scan_batch(data, path):
+        """One buffer through the device scan, rendered in the selected mode."""
+        import contextlib
+        with (watch.lock() if watch else contextlib.nullcontext()):
+            f = watch.formatter() if watch else fmt
+            flags = eng.default_flags() | (0xE0 if crypto else 0)  # crypto extractors are on by default when the database has strings (match_cmd.rs:290-292)
+            nbytes[0] += data.size
+            recs, ids = eng.scan(data, flags)
+            c = eng.counters_list()
+            tot[0] = c if tot[0] is None else [x + y for x, y in zip(tot[0], c)]
+            return M.render_sequential(f, recs, ids, data, path) if sequential else f.ndjson(recs, ids, data, 0, path)
+
+    try:
+        if a.follow:
+            M.follow_files(a.inputs, scan_batch, out, idle_exit=a.follow_idle_exit)
+        else:
+            for path in a.inputs:
+                out.write(scan_batch(read_input(path), path))
+    except (KeyboardInterrupt, ValueError) as e:
+        if isinstance(e, ValueError):
+            print("Error: %s" % e, file=sys.stderr)
+            return 1
     out.flush()
-    if a.stats and tot is not None:
+    if a.stats and tot[0] is not None:
         dt = time.perf_counter() - t0
         names = ["lines", "bytes", "candidates", "matches"]
-        print(json.dumps({"stats": dict(zip(names, tot[:4])), "seconds": round(dt, 3), "MB_per_s": round(nbytes / dt / 1e6, 1)}), file=sys.stderr)
-    eng.close()
+        print(json.dumps({"stats": dict(zip(names, tot[0][:4])), "seconds": round(dt, 3), "MB_per_s": round(nbytes[0] / dt / 1e6, 1)}), file=sys.stderr)
+    if watch:
+        watch.close()
+    else:
+        eng.close()
     return 0
 
 

@@ -71,6 +71,7 @@ SYMBOLS = {
     "mxyr_close": (None, [_VP]),
     "mxyr_data_json": (_SZ, [_VP, C.c_uint32, C.POINTER(C.c_char_p)]),
     "mxyr_ndjson": (_SZ, [_VP, C.POINTER(MgpuMatch), _SZ, C.POINTER(MgpuIdPair), _U8P, C.c_uint64, C.c_char_p, C.POINTER(_VP)]),
+    "mxyr_ndjson_sequential": (_SZ, [_VP, C.POINTER(MgpuMatch), _SZ, C.POINTER(MgpuIdPair), _U8P, C.c_uint64, C.c_char_p, C.c_char_p, C.POINTER(_VP)]),
     "mxyb_new": (_VP, [C.c_int]),
     "mxyb_free": (None, [_VP]),
     "mxyb_error": (C.c_char_p, [_VP]),

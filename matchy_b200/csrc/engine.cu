@@ -2069,10 +2069,11 @@ static int dev_copy(mgpu_ctx* c, const void* src, size_t len, size_t align_off, 
 
 int mgpu_db_upload(mgpu_ctx* c, const uint8_t* d, size_t n) {
   CK(cudaSetDevice(c->device));
-  free_db(c);
   std::string err;
   PreparedDb P;
-  if (!prepare_db(d, n, P, err)) { set_err(err); return MGPU_E_FORMAT; }
+  if (!prepare_db(d, n, P, err)) { set_err(err); return MGPU_E_FORMAT; }  // (a bad file leaves the database in place: hot reload)
+  CK(cudaDeviceSynchronize());  // nothing may still be reading the tables that are about to be freed
+  free_db(c);
   const mxy::Layout& L = P.L;
   DbView db = P.view;  // scalar fields filled; pointers below
   db.psl_keys = c->args.db.psl_keys; db.psl_vals = c->args.db.psl_vals; db.psl_pool = c->args.db.psl_pool;

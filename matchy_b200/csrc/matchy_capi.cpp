@@ -28,6 +28,7 @@
 #include "../../include/matchy/matchy.h"
 #include "mxy_builder.h"
 #include "mxy_reader.h"
+#include "db_prepare.h"
 
 using namespace matchy;
 
@@ -660,8 +661,14 @@ int32_t matchy_validate(const char* filename, int32_t level, char** error_messag
   std::ifstream f(filename, std::ios::binary);
   if (!f) { if (error_message) *error_message = dup_cstring(std::string("cannot open ") + filename); return MATCHY_ERROR_FILE_NOT_FOUND; }
   std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  // validate_database (crates/matchy/src/validation.rs:256-): metadata marker and required fields, section bounds, then the
+  // structural pass the device upload runs anyway (db_prepare.h::prepare_db): every tree record is a node, the empty marker or
+  // an in-range data pointer; LHSH / PARAGLOB / ACLH headers, every automaton offset in range and aligned, glob segments sane.
   mxy::Layout L; std::string err;
   if (!mxy::locate_sections(bytes.data(), bytes.size(), L, err)) { if (error_message) *error_message = dup_cstring(err); return MATCHY_ERROR_CORRUPT_DATA; }
+  bytes.resize(bytes.size() + 64, 0);  // (the preparer reads whole words at the very end of sections)
+  mgpu::PreparedDb P;
+  if (!mgpu::prepare_db(bytes.data(), bytes.size() - 64, P, err)) { if (error_message) *error_message = dup_cstring(err); return MATCHY_ERROR_CORRUPT_DATA; }
   return MATCHY_SUCCESS;
 }
 

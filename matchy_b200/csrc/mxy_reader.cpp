@@ -384,22 +384,32 @@ size_t mxyr_data_json(mxyr_db* h, uint32_t off, const char** out) {
   return h->text.size();
 }
 
-size_t mxyr_ndjson(mxyr_db* h, const mgpu_match* recs, size_t n, const mgpu_id_pair* ids, const uint8_t* log, uint64_t base,
-                   const char* source, const char** out) {
+// One renderer for the two modes of `matchy match`:
+//   parallel   (bin/match_processor/parallel.rs:297-369)   timestamp "0.000", matched_text = the raw bytes of the span
+//   sequential (bin/match_processor/sequential.rs:205-390) timestamp = wall clock ("%.3f"), matched_text = item.as_value():
+//              the canonical text of an address (Ipv4Addr / Ipv6Addr Display), the token itself for everything else
+static size_t render_ndjson(mxyr_db* h, const mgpu_match* recs, size_t n, const mgpu_id_pair* ids, const uint8_t* log, uint64_t base,
+                            const char* source, const char* timestamp, bool canonical, const char** out) {
   std::string& o = h->text;
   o.clear();
   ValueReader r(h->d + h->L.data_start, h->n - h->L.data_start);
   std::string src = source ? source : "";
+  const std::string ts = timestamp ? timestamp : "0.000";
   for (size_t k = 0; k < n; k++) {
     const mgpu_match& m = recs[k];
     const uint8_t* t = log + (m.offset - base);
+    std::string text((const char*)t, m.len);
+    if (canonical && m.item_type == MGPU_T_IPV6) {
+      uint16_t v6[8];
+      if (parse_ipv6_text((const char*)t, m.len, v6)) text = ipv6_text(v6);
+    }
     std::string line = "{";
     if (m.kind == MGPU_KIND_IP) {
       Value v;
       if (!r.read(m.data_offset, v)) continue;  // decode error: the reference drops the chunk; cannot occur on valid DBs
-      line += "\"cidr\":"; json_string(cidr_text(t, m.len, m.prefix_len), line);
+      line += "\"cidr\":"; json_string(cidr_text((const uint8_t*)text.data(), text.size(), m.prefix_len), line);
       line += ",\"data\":"; render_json(v, line);
-      line += ",\"match_type\":\"ip\",\"matched_text\":"; json_string(std::string((const char*)t, m.len), line);
+      line += ",\"match_type\":\"ip\",\"matched_text\":"; json_string(text, line);
       line += ",\"prefix_len\":" + std::to_string((unsigned)m.prefix_len);
     } else {
       std::string arr; bool any = false, bad = false;
@@ -414,15 +424,24 @@ size_t mxyr_ndjson(mxyr_db* h, const mgpu_match* recs, size_t n, const mgpu_id_p
       }
       if (bad) continue;
       if (any) line += "\"data\":[" + arr + "],";
-      line += "\"match_type\":\"pattern\",\"matched_text\":"; json_string(std::string((const char*)t, m.len), line);
+      line += "\"match_type\":\"pattern\",\"matched_text\":"; json_string(text, line);
       line += ",\"pattern_count\":" + std::to_string(m.n_ids);
     }
     line += ",\"source\":"; json_string(src, line);
-    line += ",\"timestamp\":\"0.000\"}\n";
+    line += ",\"timestamp\":\"" + ts + "\"}\n";
     o += line;
   }
   *out = o.c_str();
   return o.size();
+}
+
+size_t mxyr_ndjson(mxyr_db* h, const mgpu_match* recs, size_t n, const mgpu_id_pair* ids, const uint8_t* log, uint64_t base,
+                   const char* source, const char** out) {
+  return render_ndjson(h, recs, n, ids, log, base, source, nullptr, false, out);
+}
+size_t mxyr_ndjson_sequential(mxyr_db* h, const mgpu_match* recs, size_t n, const mgpu_id_pair* ids, const uint8_t* log, uint64_t base,
+                              const char* source, const char* timestamp, const char** out) {
+  return render_ndjson(h, recs, n, ids, log, base, source, timestamp, true, out);
 }
 
 }  // extern "C"

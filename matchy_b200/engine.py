@@ -233,13 +233,19 @@ class RecordFormatter:
         n = self.L.mxyr_data_json(self.h, int(data_offset), C.byref(out))
         return C.string_at(out, n).decode("utf-8")
 
-    def ndjson(self, recs: np.ndarray, ids: np.ndarray, log, base=0, source="") -> bytes:
+    def ndjson(self, recs: np.ndarray, ids: np.ndarray, log, base=0, source="", timestamp=None) -> bytes:
+        """`matchy match` lines for these records.  timestamp=None: parallel mode ("0.000", raw matched_text); a string:
+        sequential / follow mode (that timestamp, canonical address text — bin/match_processor/sequential.rs:205-390)."""
         if len(recs) == 0:
             return b""
         p, n, keep = N.as_ptr(log)
         recs = np.ascontiguousarray(recs)
         ids = np.ascontiguousarray(ids) if len(ids) else np.zeros(1, Engine.ID_DTYPE)
         out = C.c_void_p()
-        ln = self.L.mxyr_ndjson(self.h, C.cast(C.c_void_p(recs.ctypes.data), C.POINTER(N.MgpuMatch)), len(recs),
-                                C.cast(C.c_void_p(ids.ctypes.data), C.POINTER(N.MgpuIdPair)), p, int(base), source.encode(), C.byref(out))
+        rp = C.cast(C.c_void_p(recs.ctypes.data), C.POINTER(N.MgpuMatch))
+        ip = C.cast(C.c_void_p(ids.ctypes.data), C.POINTER(N.MgpuIdPair))
+        if timestamp is None:
+            ln = self.L.mxyr_ndjson(self.h, rp, len(recs), ip, p, int(base), source.encode(), C.byref(out))
+        else:
+            ln = self.L.mxyr_ndjson_sequential(self.h, rp, len(recs), ip, p, int(base), source.encode(), str(timestamp).encode(), C.byref(out))
         return C.string_at(out, ln)

@@ -240,3 +240,48 @@ def test_worker_stats_count_crypto_types():
     s.add_counters({"lines": 3, "bytes": 100, "candidates": 78, "matches": 2, "by_type": list(range(1, 13))})
     assert (s.bitcoin_count, s.ethereum_count, s.monero_count) == (10, 11, 12)
     assert s.as_vector()[-3:] == [10, 11, 12] and s.domain_count == 1 and s.sha512_count == 9
+
+
+def test_sequential_order_is_line_then_extractor_group_then_position():
+    """match_modes.sequential_order: the order `matchy match --threads 1` prints matches in (sequential.rs:205-390 over
+    extract_from_line, lib.rs:1472-1521: domains, IPv4, e-mails, IPv6, hashes, crypto)."""
+    import numpy as np
+    from matchy_b200 import match_modes as M
+    from matchy_b200.engine import Engine
+    data = b"a 1.2.3.4 evil.com\nx@evil.org 2001:db8::1 evil.net\n\n5d41402abc4b2a76b9719d911017c592 9.9.9.9\n"
+    rows = [(36, 8, 0), (2, 7, 2), (10, 8, 0), (19, 10, 1), (21, 8, 0), (30, 11, 3), (52, 32, 4), (85, 7, 2)]  # (offset, len, item type), shuffled
+    recs = np.zeros(len(rows), Engine.REC_DTYPE)
+    for k, (o, l, t) in enumerate(rows):
+        recs[k]["offset"], recs[k]["len"], recs[k]["item_type"] = o + 1000, l, t
+    got = [tuple(int(x) for x in (recs[i]["offset"] - 1000, recs[i]["item_type"])) for i in M.sequential_order(recs, data, base=1000)]
+    # line 0: domain evil.com, then IPv4; line 1: domains (evil.org inside the e-mail at 21, evil.net at 36), e-mail, IPv6; line 3: IPv4 before the hash
+    assert got == [(10, 0), (2, 2), (21, 0), (36, 0), (19, 1), (30, 3), (85, 2), (52, 4)]
+
+
+def test_follow_files_batches_and_rotation(tmp_path):
+    """match_modes.follow_files: existing content first, appended bytes next, a truncated file starts over (follow.rs:209-262)."""
+    import threading
+    import time
+    from matchy_b200 import match_modes as M
+    p = tmp_path / "a.log"
+    p.write_bytes(b"one\ntwo\n")
+    seen, out = [], __import__("io").BytesIO()
+
+    def scan_batch(data, source):
+        seen.append((bytes(data), source))
+        return b"%d\n" % len(data)
+
+    def writer():
+        time.sleep(0.4)
+        with open(p, "ab") as f:
+            f.write(b"three\n")
+        time.sleep(0.4)
+        p.write_bytes(b"new\n")  # rotation: the file is shorter than what was read
+    th = threading.Thread(target=writer)
+    th.start()
+    total = M.follow_files([str(p)], scan_batch, out, poll=0.05, idle_exit=1.0)
+    th.join()
+    assert [d for d, _ in seen] == [b"one\ntwo\n", b"three\n", b"new\n"] and total == 18
+    assert out.getvalue() == b"8\n6\n4\n"
+    with pytest.raises(ValueError):
+        M.follow_files(["-"], scan_batch, out)

@@ -248,3 +248,16 @@ def test_data_codec_round_trips_of_the_reference(built):
     assert data_of(6)[1] == {"a": {"b": {"c": {"d": [1, [2, [3, {"e": "deep"}]]]}}}}
     assert data_of(7)[1] == {"u16max": 65535, "u32min": 65536, "u32max": 4294967295, "u64min": 4294967296, "u64max": 18446744073709551615,
                              "i32min": -2147483648, "m1": -1}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test_c_api", "test_c_api_extensions"])
+def test_reference_c_test_programs_pass(built, name, tmp_path):
+    """The reference's OWN C test programs (crates/matchy/tests/test_c_api.c, test_c_api_extensions.c), compiled unchanged
+    against the reference's own header by __graft_entry__.build_reference_c_tests() and linked against libmatchy_b200.so,
+    run to completion on the GPU.  (The sources stay in /root/reference; on a box without them the prebuilt binaries run.)"""
+    exe = os.path.join(ROOT, "tests", "capi", "_ref", name)
+    if not os.path.exists(exe):
+        pytest.skip("reference C tests were not built (no /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])

@@ -481,3 +481,96 @@ def test_device_generator_equals_host_generator(built):
     finally:
         eng.dev_free(dev)
     eng.close()
+
+
+def _canon(line):
+    """A `matchy match` JSON line without its timestamp, IPv6 matched_text in canonical form (what sequential mode prints)."""
+    import json
+    d = json.loads(line)
+    d.pop("timestamp")
+    if ":" in d["matched_text"]:
+        d["matched_text"] = O.ipv6_display(O.parse_ipv6(d["matched_text"].encode()))
+    return json.dumps(d, sort_keys=True)
+
+
+def test_sequential_mode_and_follow_mode_cli(small_dbs, tmp_path):
+    """`match --threads 1`: the oracle's match set, in line order, with wall-clock timestamps and canonical address text;
+    `match --follow`: the same lines for content that arrives while the command runs."""
+    import json
+    import subprocess
+    import sys
+    import time
+    db, log = small_dbs[5]
+    log = log[: log.rfind(b"\n", 0, 400_000) + 1] + b"v6 2001:0DB8:0000:0000:0000:0000:0000:0001 and 2001:db8::0:1 end\n"
+    dbp, lp = tmp_path / "t.mxy", tmp_path / "a.log"
+    dbp.write_bytes(db)
+    lp.write_bytes(log)
+    root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    orc = O.Oracle(db)
+    orc.scan(log, flags=orc.default_flags() | 0xE0, chunk_size=128 * 1024)
+    want = sorted(_canon(l) for l in orc.ndjson(log, str(lp)).splitlines())
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-m", "matchy_b200", "match", str(dbp), str(lp), "--threads", "1"], capture_output=True, cwd=root)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = r.stdout.splitlines()
+    assert sorted(_canon(l) for l in lines) == want and len(want) > 50
+    stamps = [float(json.loads(l)["timestamp"]) for l in lines]
+    assert all(t0 - 1 <= s <= time.time() + 1 for s in stamps)
+    # line order: the position of each match's line in the log never decreases
+    starts, pos = [0] + [i + 1 for i, b in enumerate(log) if b == 10], 0
+    import bisect
+    prev = -1
+    for l in lines:
+        text = json.loads(l)["matched_text"].encode()
+        at = log.find(text, starts[max(prev, 0)]) if ":" not in text.decode() else -1
+        if at >= 0:
+            ln = bisect.bisect_right(starts, at) - 1
+            assert ln >= prev
+            prev = ln
+    # follow mode: half of the log is there at the start, the rest arrives later
+    cut = log.rfind(b"\n", 0, len(log) // 2) + 1
+    lp.write_bytes(log[:cut])
+    proc = subprocess.Popen([sys.executable, "-m", "matchy_b200", "match", str(dbp), str(lp), "--follow", "--follow-idle-exit", "4"],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=root)
+    time.sleep(8)  # (engine start-up: the existing half is processed before the rest is appended, or together with it — both are valid)
+    with open(lp, "ab") as f:
+        f.write(log[cut:])
+    out, err = proc.communicate(timeout=120)
+    assert proc.returncode == 0, err[-500:]
+    assert sorted(_canon(l) for l in out.splitlines()) == want
+
+
+def test_watching_database_reloads_into_the_same_engine(built, tmp_path):
+    """WatchingDatabase (watching_database.rs:103-191): a changed database file is uploaded into the running engine, the
+    generation counter moves, scans see the new indicators; a corrupt file is refused and the old database stays."""
+    from matchy_b200 import DatabaseBuilder
+    from matchy_b200.match_modes import WatchingDatabase
+    from matchy_b200.database import DatabaseError
+
+    def make(entries):
+        b = DatabaseBuilder(build_epoch=1)
+        for e in entries:
+            b.add_entry(e, {"e": e})
+        return b.build()
+    p = tmp_path / "w.mxy"
+    p.write_bytes(make(["evil.com", "10.0.0.0/8"]))
+    seen = []
+    db = WatchingDatabase.from_(str(p)).no_thread().on_reload(lambda gen, path: seen.append(gen)).open()
+    data = b"a evil.com b bad.org c 10.1.2.3 d 192.168.1.1\n"
+    recs, _ = db.engine.scan(data)
+    assert sorted(bytes(data[int(r["offset"]):int(r["offset"]) + int(r["len"])]) for r in recs) == [b"10.1.2.3", b"evil.com"]
+    assert db.generation() == 1 and not db.check()
+    os_stat = p.stat()
+    p.write_bytes(make(["bad.org", "192.168.0.0/16"]))
+    __import__("os").utime(p, ns=(os_stat.st_atime_ns, os_stat.st_mtime_ns + 10_000_000))
+    assert db.check() and db.generation() == 2 and seen == [2]
+    recs, _ = db.engine.scan(data)
+    assert sorted(bytes(data[int(r["offset"]):int(r["offset"]) + int(r["len"])]) for r in recs) == [b"192.168.1.1", b"bad.org"]
+    assert db.lookup("bad.org").kind == "Pattern" and db.lookup("evil.com").is_not_found()
+    p.write_bytes(b"not a database" * 100)
+    with pytest.raises(DatabaseError):
+        db.check()
+    assert db.generation() == 2
+    recs, _ = db.engine.scan(data)
+    assert len(recs) == 2  # the old tables are still there
+    db.close()
