@@ -150,12 +150,11 @@ def cmd_extract(a):
 
 def cmd_build(a):
     """`matchy build` (bin/commands/build_cmd.rs): text / csv / json inputs -> one .mxy file, written read-only (0444) like the
-    reference does.  MISP import and schema validation (the `-t <known schema>` case) are off the scan path and not provided."""
+    reference does.  `-f misp` goes through misp_importer.py; schema validation (the `-t <known schema>` case) is not provided."""
     import os
     from . import builder as B
-    if a.format not in ("text", "csv", "json"):
-        print("Error: %s" % ("MISP import is not provided by this build" if a.format == "misp" else
-                             "Unknown format: %s. Use 'text', 'csv', 'json', or 'misp'" % a.format), file=sys.stderr)
+    if a.format not in ("text", "csv", "json", "misp"):
+        print("Error: Unknown format: %s. Use 'text', 'csv', 'json', or 'misp'" % a.format, file=sys.stderr)
         return 1
     b = B.DatabaseBuilder(B.MatchMode.CaseInsensitive if a.case_insensitive else B.MatchMode.CaseSensitive)
     if a.database_type:
@@ -165,11 +164,19 @@ def cmd_build(a):
         b.set_database_type(a.database_type)
     if a.description:
         b.set_description(a.desc_lang, a.description)
-    add = {"text": B.add_text_file, "csv": B.add_csv_file, "json": B.add_json_file}[a.format]
     total = 0
     try:
-        for path in a.inputs:
-            total += add(b, path)
+        if a.format == "misp":
+            from .misp_importer import add_misp_files
+            total = add_misp_files(b, a.inputs)
+            if a.database_type:
+                b.set_database_type(a.database_type)
+            if a.description:
+                b.set_description(a.desc_lang, a.description)
+        else:
+            add = {"text": B.add_text_file, "csv": B.add_csv_file, "json": B.add_json_file}[a.format]
+            for path in a.inputs:
+                total += add(b, path)
         st = b.stats()
         if a.verbose or a.debug:
             print("\nBuilding database:\n  Total entries:   %d\n  IP entries:      %d\n  Literal entries: %d\n  Glob entries:    %d"

@@ -154,12 +154,13 @@ class WatchingDatabase:
         self._db.close()
 
 
-def follow_files(paths, scan_batch, out, poll=0.2, idle_exit=None, stop=None, warn=sys.stderr):
+def follow_files(paths, scan_batch, out, poll=0.2, idle_exit=None, stop=None, warn=None):
     """`matchy match --follow`: process what the files hold, then every batch of appended bytes, until `stop` is set (or nothing
     has arrived for `idle_exit` seconds — tests).  scan_batch(data: np.ndarray, source: str) -> bytes renders one batch.
     A file that shrank was rotated: it starts again at offset 0 (follow.rs:223-226).  Returns total bytes processed."""
     if any(p == "-" for p in paths):
         raise ValueError("--follow mode not supported with stdin")
+    warn = warn or sys.stderr
     pos = {p: 0 for p in paths}
     total = 0
     last_activity = time.monotonic()

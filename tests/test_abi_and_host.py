@@ -201,6 +201,66 @@ def test_build_subcommand(built, tmp_path, capsys):
     assert "must have an 'entry' or 'key' column" in capsys.readouterr().err
 
 
+def test_build_from_misp_events(built, tmp_path, capsys):
+    """`matchy build -f misp` (misp_importer.rs): event + attribute + object metadata, composite values split, ignored types,
+    non-event files skipped, malformed events refused."""
+    from matchy_b200.__main__ import main
+    from matchy_b200.misp_importer import domain_of_url
+    # the reference's own unit vectors (misp_importer.rs:1158-1177)
+    assert domain_of_url("http://example.com/path") == "example.com"
+    assert domain_of_url("https://test.org:8080/") == "test.org"
+    assert domain_of_url("example.net") == "example.net"
+    assert domain_of_url("http://evil.com?param=value") == "evil.com"
+    ev = {"Event": {"uuid": "u-1", "info": "Test Event", "threat_level_id": "2", "analysis": 1, "date": "2024-05-06", "Orgc": {"name": "CIRCL"},
+                    "Tag": [{"name": "tlp:green"}, {"name": "apt"}],
+                    "Attribute": [{"type": "ip-src", "value": "192.168.1.1", "category": "Network activity", "to_ids": True, "comment": "", "Tag": [{"name": "c2"}]},
+                                  {"type": "ip-dst|port", "value": "10.1.2.3|443"},
+                                  {"type": "domain|ip", "value": "bad.example|172.16.0.9", "comment": "pair"},
+                                  {"type": "url", "value": "https://dl.evil.test:8080/a.exe"},
+                                  {"type": "filename|sha256", "value": "x.exe|" + "ab" * 32},
+                                  {"type": "ip-src/netmask", "value": "203.0.113.0/24"},
+                                  {"type": "comment", "value": "never.added.example"},
+                                  {"type": "port", "value": 8080},
+                                  {"type": "md5", "value": None},
+                                  {"type": "brand-new-type", "value": "odd-value"},
+                                  {"type": "brand-new-type", "value": "z" * 1000}],
+                    "Object": [{"name": "file", "comment": "dropper", "Attribute": [{"type": "sha1", "value": "cd" * 20, "object_relation": "sha1"}]}]}}
+    f1 = tmp_path / "event1.json"
+    f1.write_text(json.dumps(ev))
+    (tmp_path / "manifest.json").write_text(json.dumps({"u-1": {"info": "x"}}))
+    (tmp_path / "notes.json").write_text("[1, 2, 3]")
+    out = tmp_path / "m.mxy"
+    assert main(["build", str(f1), str(tmp_path / "manifest.json"), str(tmp_path / "notes.json"), "-o", str(out), "-f", "misp", "-v"]) == 0
+    cap = capsys.readouterr()
+    assert "Skipped 2 non-MISP file(s)" in cap.err and "manifest.json: metadata file" in cap.err and "notes.json: not a MISP event" in cap.err
+    assert "IP entries:      4" in cap.out and "Glob entries:    0" in cap.out
+    db = out.read_bytes()
+    assert b"MISP-ThreatIntel" in db[-600:]
+    o = O.Oracle(db)
+    base = {"event_info": "Test Event", "event_uuid": "u-1", "threat_level": "Medium", "analysis": "Ongoing", "event_date": "2024-05-06", "org_name": "CIRCL"}
+    f, off, pl = o.lookup_ip4(0xC0A80101)
+    assert f and pl == 32 and json.loads(o.data_json(off)) == dict(base, type="ip-src", category="Network activity", to_ids=True, tags="tlp:green,apt,c2")
+    f, off, pl = o.lookup_ip4(0x0A010203)
+    assert f and json.loads(o.data_json(off)) == dict(base, type="ip-dst|port", tags="tlp:green,apt")
+    assert o.lookup_ip4(0xAC100009)[0] and o.lookup_ip4(0xCB007142)[2] == 24
+    hit = o.lookup_string(b"bad.example")
+    assert hit and json.loads(o.data_json(hit[0][1])) == dict(base, type="domain|ip", comment="pair", tags="tlp:green,apt")
+    for lit in (b"dl.evil.test", b"https://dl.evil.test:8080/a.exe", b"x.exe", b"ab" * 32, b"odd-value"):
+        assert o.lookup_string(lit), lit
+    hit = o.lookup_string(b"cd" * 20)
+    assert hit and json.loads(o.data_json(hit[0][1])) == dict(base, type="sha1", object_type="file", object_comment="dropper", tags="tlp:green,apt")
+    for lit in (b"never.added.example", b"8080", b"z" * 1000):
+        assert not o.lookup_string(lit), lit
+    # something that claims to be an event but is not one is an error, not a skip
+    f2 = tmp_path / "broken.json"
+    f2.write_text('{"Event": {"threat_level_id": 999, "Attribute": []}}')
+    assert main(["build", str(f1), str(f2), "-o", str(out), "-f", "misp"]) == 1
+    assert "Failed to parse MISP JSON in broken.json" in capsys.readouterr().err
+    f3 = tmp_path / "badip.json"
+    f3.write_text(json.dumps({"Event": {"Attribute": [{"type": "ip-src", "value": "not-an-ip"}]}}))
+    assert main(["build", str(f3), "-o", str(out), "-f", "misp"]) == 1
+
+
 def _patch_metadata_uint(db: bytes, key: bytes, value: int) -> bytes:
     """The database with metadata field `key` re-encoded as an 8-byte MMDB uint64 holding `value`."""
     mk = db.rfind(b"\xab\xcd\xefMaxMind.com")
@@ -232,6 +292,32 @@ def test_validate_rejects_wrapping_section_offsets(built, tmp_path):
         msg = C.c_char_p()
         assert L.matchy_validate(str(bad).encode(), 0, C.byref(msg)) < 0, (key, hex(value))
         assert N.lib().mxyr_open(bad.read_bytes(), bad.stat().st_size) in (None, 0)
+
+
+def test_validate_rejects_corrupt_tree_records(built, tmp_path):
+    """matchy_validate runs the device-side preparation too (db_prepare.h): a tree record that is neither a node, the empty
+    marker nor a pointer into the data section is refused, and so is the upload of such a file (validation.rs:256 walks the
+    tree the same way)."""
+    from matchy_b200 import DatabaseBuilder, _native as N
+    b = DatabaseBuilder(build_epoch=1)
+    for k in range(50):
+        b.add_entry("10.%d.0.0/16" % k, {"n": k})
+    db = bytearray(b.build())
+    L = C.CDLL(N.LIB_PATH)
+    L.matchy_validate.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p)]
+    path = tmp_path / "t.mxy"
+    path.write_bytes(db)
+    assert L.matchy_validate(str(path).encode(), 0, None) == 0
+    at = db.rfind(b"node_count") + len(b"node_count")
+    assert db[at] == 0xC4  # uint32, 4 bytes
+    nodes = int.from_bytes(db[at + 1:at + 5], "big")
+    for bad_record in (b"\xff\xff\xf0", (nodes + 5).to_bytes(3, "big")):  # far past the data section; inside the 16-byte separator
+        d = bytearray(db)
+        d[3:6] = bad_record  # right record of node 0
+        path.write_bytes(d)
+        msg = C.c_char_p()
+        assert L.matchy_validate(str(path).encode(), 0, C.byref(msg)) < 0
+        assert b"tree" in (msg.value or b"").lower()
 
 
 def test_worker_stats_count_crypto_types():

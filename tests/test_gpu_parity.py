@@ -530,9 +530,10 @@ def test_sequential_mode_and_follow_mode_cli(small_dbs, tmp_path):
     # follow mode: half of the log is there at the start, the rest arrives later
     cut = log.rfind(b"\n", 0, len(log) // 2) + 1
     lp.write_bytes(log[:cut])
-    proc = subprocess.Popen([sys.executable, "-m", "matchy_b200", "match", str(dbp), str(lp), "--follow", "--follow-idle-exit", "4"],
+    proc = subprocess.Popen([sys.executable, "-m", "matchy_b200", "match", str(dbp), str(lp), "--follow", "--follow-idle-exit", "12"],
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=root)
-    time.sleep(8)  # (engine start-up: the existing half is processed before the rest is appended, or together with it — both are valid)
+    time.sleep(6)  # (the existing half is processed before the rest is appended, or — slow engine start-up — together with it: both are valid;
+    #                 the idle limit is longer than this wait, so the command cannot leave before the second half arrives)
     with open(lp, "ab") as f:
         f.write(log[cut:])
     out, err = proc.communicate(timeout=120)
