@@ -136,9 +136,11 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
                                                  : (((uint32_t)(b[3] & 15) << 24) | ((uint32_t)b[4] << 16) | ((uint32_t)b[5] << 8) | b[6]);
       b += side * 4; return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
     };
+    bool any_data = false;
     for (uint32_t i = 0; i < L.node_count; i++)
       for (int s = 0; s < 2; s++) {
         uint32_t r = rec(i, s);
+        any_data |= r > L.node_count;
         if (r > L.node_count && ((uint64_t)r < (uint64_t)L.node_count + 16 || (uint64_t)r - L.node_count - 16 >= data_len)) {
           err = "corrupt IP search tree: record is neither a node, the empty marker nor a data pointer";
           return false;
@@ -150,6 +152,7 @@ inline bool prepare_db(const uint8_t* d, size_t n, PreparedDb& P, std::string& e
     }
     db.v4_start_node = node;
     if (L.node_count == 0) db.has_ip = 0;
+    db.ip_empty = any_data ? 0 : 1;
     // Walk state after the first TB address bits, by depth-first expansion from the start node (2^TB leaves): IPv4 queries
     // (TB = 16, or 20 for trees with more than 2^16 nodes, where a /16 bucket still holds a subtree) and, in IPv6 trees, IPv6
     // queries (16 bits from the root).

@@ -37,6 +37,7 @@ struct DbView {
   const uint8_t* tree;
   uint32_t node_count, record_bits, ip_version, has_ip;
   uint32_t v4_start_node;  // derived: result of find_ipv4_start_node (tree.rs:258-277), identical for every query
+  uint32_t ip_empty;       // derived: no record of the tree points into the data section — every lookup is a miss (string-only databases)
   // derived: the state of the IPv4 walk after its first v4_top_bits (16 or 20) address bits, for every such prefix:
   // bits 0..27 value, bits 28..31 kind — 0: continue at node `value`; 1: not found; 2: data record `value` found at depth
   // v4_top16_depth[prefix] (1..v4_top_bits).  Exact: the entry is what the bit-by-bit walk of tree.rs:46-90 reaches.

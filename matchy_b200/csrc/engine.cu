@@ -62,6 +62,7 @@ struct ScanArgs {
   uint32_t flags;
   uint32_t fast;       // 1: the token kernel applies string_filters() and only flagged string tokens reach the exact kernel
   uint32_t lookups;    // 0: extraction only (mgpu_extract): tokens are produced, nothing is looked up
+  uint32_t ip_skip;    // 1: the database has no IP entry (DbView::ip_empty): addresses are validated and counted, not listed, and iptrie_kernel is not launched
   DbView db;
   Cand* q_dotted; Cand* q_hash; uint32_t* q_at; uint32_t* q_c2; Cand* q_numeric; Cand* q_long;
   uint32_t seg_cap[Q_COUNT];
@@ -440,7 +441,7 @@ __device__ __forceinline__ void append_tokens(const ScanArgs& a, TokenWarp& tw, 
     uint32_t b = tok_reserve(&a.ctr->n_str, a.cap_str, __popc(bs), lane, tw.cs, a.str, nullptr, &a.ctr->overflow, 1u << 8, a.tok_unit);
     if (ws && b != NONE32) a.str[b + __popc(bs & ((1u << lane) - 1u))] = st;
   }
-  if (bi) {
+  if (bi && !a.ip_skip) {
     uint32_t b = tok_reserve(&a.ctr->n_ip, a.cap_ip, __popc(bi), lane, tw.ci, nullptr, a.ip, &a.ctr->overflow, 1u << 9, a.tok_unit);
     if (wi && b != NONE32) a.ip[b + __popc(bi & ((1u << lane) - 1u))] = it;
   }
@@ -2194,6 +2195,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
   a.fast = fast ? 1u : 0u;
   a.lookups = lookups ? 1u : 0u;
+  a.ip_skip = lookups && a.db.ip_empty && !c->fused && !c->verify_tokens ? 1u : 0u;  // (scan_kernel leaves numeric words to iptrie_kernel's parser; the audit wants the list)
   const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
   if (c->fused) {
     // compute stream: scan_kernel of piece i.  It fills working set (i & 1), which the lookups of piece i-2 may still read.
@@ -2253,7 +2255,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     CK(cudaEventRecord(c->ev_l0[slot], ls));
   }
   if (lookups) {
-    iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
+    if (!a.ip_skip) iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
     CK(cudaEventRecord(ev[3], ls));
     if (a.db.has_literal && !fast) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, ls>>>(a);
     CK(cudaEventRecord(ev[4], ls));
