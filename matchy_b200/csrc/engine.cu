@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -29,6 +30,7 @@
 #include "mxy_reader.h"
 #include "tokenize.cuh"
 #include "crypto_addr.cuh"
+#include "host_sort.h"
 
 namespace cg = cooperative_groups;
 
@@ -1801,10 +1803,8 @@ struct mgpu_ctx {
                                 // while later pieces are still being scanned (no device-side record buffer, no D2H copy at the end)
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
-  // record index where each gathered piece ends: pieces arrive in log order and hold disjoint offset ranges, so the final
-  // sort is one small sort per piece, in parallel (pieces_in_order = false after a redo, whose records arrive late)
-  std::vector<size_t> piece_ends;
-  bool pieces_in_order = true;
+  std::vector<mgpu_match> sort_tmp;   // sort_records' scratch
+  std::unique_ptr<WorkerPool> pool;   // host threads of the result sort, started by the first scan that returns >= 4096 records
   mgpu_counters counters{};
   mgpu_timing timing{};
   bool keep_results = true;
@@ -2405,13 +2405,11 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
     for (size_t k = s0; k < c->x_str.size(); k++) c->x_str[k].start += (uint32_t)(base + al);
     for (size_t k = i0; k < c->x_ip.size(); k++) c->x_ip[k].start += (uint32_t)(base + al);
   }
-  if (c->keep_results) c->piece_ends.push_back((c->piece_ends.empty() ? 0 : c->piece_ends.back()) + h.n_rec);
   return fetch_results(c, 0, h.n_rec, 0, h.n_ids, /*whole=*/true);
 }
 
 static void begin_scan(mgpu_ctx* c) {
   c->recs.clear(); c->ids.clear();
-  c->piece_ends.clear(); c->pieces_in_order = true;
   c->x_str.clear(); c->x_ip.clear();
   memset(&c->counters, 0, sizeof c->counters);
   memset(&c->timing, 0, sizeof c->timing);
@@ -2424,37 +2422,12 @@ static void finish_scan(mgpu_ctx* c) {
   cudaEventElapsedTime(&c->timing.scan_ms, c->ev_scan[0], c->ev_scan[1]);
   // deterministic output: records by (offset, item_type, len), id pairs re-packed in record order (the device appends
   // both with atomics, so their raw order varies from run to run)
-  auto less = [](const mgpu_match& x, const mgpu_match& y) {
-    if (x.offset != y.offset) return x.offset < y.offset;
-    if (x.item_type != y.item_type) return x.item_type < y.item_type;
-    return x.len < y.len;
-  };
   const size_t nrec = c->recs.size();
-  unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-  if (c->pieces_in_order && !c->piece_ends.empty() && c->piece_ends.back() == nrec && nrec >= 65536 && nt >= 2) {
-    // every piece's records lie in its own offset range and the pieces are in log order: sort piece by piece, in parallel
-    mgpu_match* r = c->recs.data();
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> th;
-    for (unsigned k = 0; k < nt; k++) th.emplace_back([&] {
-      for (size_t p = next.fetch_add(1); p < c->piece_ends.size(); p = next.fetch_add(1)) std::sort(r + (p ? c->piece_ends[p - 1] : 0), r + c->piece_ends[p], less);
-    });
-    for (auto& t : th) t.join();
-  } else if (nrec < 65536 || nt < 2) std::sort(c->recs.begin(), c->recs.end(), less);
-  else {
-    // large result sets: sort nt slices in parallel, then merge pairwise (the sort was ~10 % of an end-to-end 10 GB scan)
-    while (nt & (nt - 1)) nt &= nt - 1;  // power of two
-    mgpu_match* r = c->recs.data();
-    auto cut = [&](unsigned k) { return nrec * k / nt; };
-    std::vector<std::thread> th;
-    for (unsigned k = 0; k < nt; k++) th.emplace_back([&, k] { std::sort(r + cut(k), r + cut(k + 1), less); });
-    for (auto& t : th) t.join();
-    for (unsigned w = 1; w < nt; w *= 2) {
-      th.clear();
-      for (unsigned k = 0; k + w < nt; k += 2 * w) th.emplace_back([&, k, w] { std::inplace_merge(r + cut(k), r + cut(k + w), r + cut(std::min(k + 2 * w, nt)), less); });
-      for (auto& t : th) t.join();
-    }
+  if (nrec >= 4096 && !c->pool) {
+    const unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (nt >= 2) c->pool.reset(new WorkerPool(nt));
   }
+  sort_records(c->recs.data(), nrec, c->sort_tmp, c->pool.get());
   if (!c->ids.empty()) {
     std::vector<mgpu_id_pair>& packed = c->ids_tmp;
     packed.clear();
@@ -2547,14 +2520,12 @@ static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_
       if (ok) {
         if (!in_run) { run_r = r_prev; run_i = i_prev; in_run = true; }
         add_counters(c, h[k], cuts[p0 + k + 1] - cuts[p0 + k], h[k].n_rec - r_prev);
-        if (c->keep_results) c->piece_ends.push_back((c->piece_ends.empty() ? 0 : c->piece_ends.back()) + (h[k].n_rec - r_prev));
       } else {
         if (in_run) { rc = fetch_results(c, run_r, r_prev, run_i, i_prev, !any_overflow); if (rc) return rc; in_run = false; }
         if (k < nb) redo.push_back(k);
       }
       if (k < nb) { r_prev = std::min(h[k].n_rec, c->args.cap_rec); i_prev = std::min(h[k].n_ids, c->args.cap_ids); }
     }
-    if (!redo.empty()) c->pieces_in_order = false;
     for (int k : redo) {
       rc = scan_piece(c, dev, cuts[p0 + k], cuts[p0 + k + 1], base, flags, lookups, 0);
       if (rc) return rc;

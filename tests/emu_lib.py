@@ -29,7 +29,7 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(p) for p in DEPS):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", SO] + SRC)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", SO] + SRC)
         L = C.CDLL(SO)
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_char_p, C.c_size_t]
@@ -49,6 +49,8 @@ def lib():
         L.emu_counters_get.argtypes = [C.c_void_p, C.POINTER(Counters)]
         L.emu_tokens.restype = C.c_int64
         L.emu_tokens.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t]
+        L.emu_sort_records.restype = C.c_double
+        L.emu_sort_records.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_int]
         _lib = L
     return _lib
 

@@ -8,6 +8,8 @@
 // and the product has no CPU execution path: libmatchy_b200.so fails without a CUDA device.
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <memory>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +20,7 @@
 #include "../../matchy_b200/csrc/db_prepare.h"
 #include "../../matchy_b200/csrc/tokenize.cuh"
 #include "../../matchy_b200/csrc/crypto_addr.cuh"
+#include "../../matchy_b200/csrc/host_sort.h"
 
 using namespace mgpu;
 
@@ -345,6 +348,20 @@ uint32_t emu_parse_ipv4_both(const uint8_t* s, uint32_t n, uint32_t out[2]) {
   load_head_words(s, h);
   out[0] = out[1] = 0;
   return (parse_ipv4_words(h, n, out[0]) ? 1u : 0u) | (parse_ipv4_hexdot(h, n, out[1]) ? 2u : 0u);
+}
+
+// the engine's result sort (host_sort.h) on n records, with `threads` pool workers (0: no pool); returns microseconds
+double emu_sort_records(mgpu_match* r, size_t n, unsigned threads, int repeat) {
+  std::vector<mgpu_match> tmp, copy(r, r + n);
+  std::unique_ptr<mgpu::WorkerPool> pool(threads ? new mgpu::WorkerPool(threads) : nullptr);
+  double best = 1e30;
+  for (int k = 0; k < repeat; k++) {
+    std::copy(copy.begin(), copy.end(), r);
+    auto t0 = std::chrono::steady_clock::now();
+    mgpu::sort_records(r, n, tmp, pool.get());
+    best = std::min(best, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  }
+  return best;
 }
 
 int64_t emu_tokens(emu_ctx* c, uint64_t* out, size_t cap) {

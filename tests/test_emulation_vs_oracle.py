@@ -292,3 +292,34 @@ def test_hexdot_ipv4_parser_equals_general_parser():
             r = L.emu_parse_ipv4_both(w + tail, len(w), out)
             assert r in (0, 3), (w, r)
             assert r == 0 or out[0] == out[1], w
+
+
+def test_result_sort_equals_a_plain_sort():
+    """host_sort.h (offset-range partition + per-bucket sorts on a thread pool) against numpy's lexsort: spread-out offsets,
+    clustered offsets, ties on offset decided by (item_type, len), sizes around the thresholds."""
+    import numpy as np
+    import emu_lib
+    L = emu_lib.lib()
+    dt = np.dtype([("offset", "<u8"), ("len", "<u4"), ("item_type", "u1"), ("kind", "u1"), ("prefix_len", "u1"), ("reserved", "u1"),
+                   ("n_ids", "<u4"), ("ids_index", "<u4"), ("data_offset", "<u4"), ("pad", "<u4")])
+    rng = np.random.default_rng(7)
+    for n, threads, shape in ((0, 4, "spread"), (1, 4, "spread"), (4095, 4, "spread"), (4096, 4, "spread"), (60000, 8, "spread"), (300000, 16, "spread"),
+                              (100000, 8, "cluster"), (50000, 3, "ties"), (50000, 0, "spread"), (70000, 8, "one")):
+        r = np.zeros(n, dtype=dt)
+        if shape == "spread":
+            r["offset"] = rng.integers(5_000_000_000, 15_000_000_000, n)
+        elif shape == "cluster":
+            r["offset"] = np.where(rng.random(n) < 0.9, rng.integers(10**9, 10**9 + 4000, n), rng.integers(0, 2**40, n))
+        elif shape == "ties":
+            r["offset"] = rng.integers(0, 3000, n)
+        else:
+            r["offset"] = 12345
+        r["item_type"] = rng.integers(0, 12, n)
+        r["len"] = rng.integers(1, 300, n)
+        r["ids_index"] = np.arange(n)  # payload: every record must survive
+        want = r[np.lexsort((r["len"], r["item_type"], r["offset"]))]
+        got = r.copy()
+        L.emu_sort_records(got.ctypes.data, n, threads, 1)
+        key = lambda a: (a["offset"].tolist(), a["item_type"].tolist(), a["len"].tolist())
+        assert key(got) == key(want), (n, threads, shape)
+        assert sorted(got["ids_index"].tolist()) == list(range(n)), (n, threads, shape)
