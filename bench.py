@@ -109,10 +109,10 @@ def ncu_traffic(kernel):
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                return float(json.load(f)["kernels"][kernel]["dram_bytes_per_log_byte"])
+                return float(json.load(f)["kernels"][kernel]["dram_bytes_per_log_byte"]), name
         except Exception:
             continue
-    return None
+    return None, None
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -421,6 +421,8 @@ def main():
     eng.set_keep_results(True)
     sampler = ClockSampler(local_rank)
     dev_s, wall_s, kern, launches, counters = measure_resident(eng, dev, nbytes, flags, base, args.steps, args.warmup, sync_all, sampler)
+    eng.debug_counters()
+    host_us = dict(eng.host_us)  # host side of the last timed step: the whole mgpu_scan_device call, of which result sort / id re-pack / launches + gather
     clocks = sampler.stop()
     if dist:
         tt = torch.tensor([dev_s, wall_s], dtype=torch.float64, device="cuda")
@@ -468,10 +470,10 @@ def main():
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peak()
     dom, achieved, bytes_per_launch = dominant(kern, nbytes, args.steps, peak)
-    per_byte = ncu_traffic(dom)
+    per_byte, traffic_file = ncu_traffic(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": per_byte * bytes_per_launch if per_byte is not None else None,
-                "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per log byte of this kernel (ncu --set full, cfg2), scaled to this launch size",
+                "traffic_source": None if per_byte is None else "profiles/%s: dram__bytes_read.sum + dram__bytes_write.sum per log byte of this kernel (ncu --set full, one 500 MB piece), scaled to this launch size" % traffic_file,
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
                 "whole_path_frac": (nbytes * args.steps / dev_s / 1e9) / peak if world == 1 else (value / world) / peak}
@@ -516,7 +518,7 @@ def main():
                        "generated": "on the device (csrc/synth_device.cu), %.2f s for %.1f GB on rank 0" % (t_gen, nbytes / 1e9)},
             "lines_per_s": tot[0] * args.steps / dev_s, "matches_per_s": tot[3] * args.steps / dev_s,
             "counters": {"lines": tot[0], "bytes": tot[1], "candidates": tot[2], "matches": tot[3], "by_type": tot[4:]},
-            "wall_s_timed_region": wall_s, "value_wall": total_bytes / wall_s / 1e9,
+            "wall_s_timed_region": wall_s, "value_wall": total_bytes / wall_s / 1e9, "host_us_last_step": host_us,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
             "per_config": per_config, "alt_path": alt,
         }

@@ -1227,7 +1227,10 @@ __device__ __noinline__ void numeric_word_as_domain(const ScanArgs& a, const IpT
   a.str[k] = StrTok{t.start, t.len, (uint32_t)MGPU_T_DOMAIN | f};
 }
 
-__global__ void __launch_bounds__(256) iptrie_kernel(ScanArgs a) {
+// (MINB: resident blocks per SM the register budget is cut for — measured, more warps at the price of spills do not pay;
+//  grid constant: the out-of-line fallback takes &a without a per-thread copy of the 0.7 KB of arguments)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) iptrie_kernel(const __grid_constant__ ScanArgs a) {
   __shared__ __align__(16) mgpu_match s_rec[8][IPT_STAGE];
   __shared__ uint32_t s_ovf;
   const uint32_t n = min(a.ctr->n_ip, a.cap_ip);
@@ -1804,6 +1807,9 @@ struct mgpu_ctx {
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
   std::vector<mgpu_match> sort_tmp;   // sort_records' scratch
+  int iptrie_minb = 4;                // iptrie_kernel instance: 4 = 64 registers, 5 = 48, 6 = 40 (MATCHY_B200_IPTRIE_MINB; config 3 at 8 GB: 588 / 577 / 526 GB/s — the spills cost more than the warps bring)
+  uint64_t scan_lo = 0, scan_hi = ~0ull;  // absolute offsets the current scan can report (the range of sort_records' partition)
+  uint64_t host_us[4] = {0, 0, 0, 0}; // microseconds of the last mgpu_scan_device on the host: whole call, sort, id re-pack, launches + gather
   std::unique_ptr<WorkerPool> pool;   // host threads of the result sort, started by the first scan that returns >= 4096 records
   mgpu_counters counters{};
   mgpu_timing timing{};
@@ -1909,6 +1915,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   c->wide_scan = getenv("MATCHY_B200_HOT_SMEM") == nullptr;  // (28-warp block reading the hot filter through L1: measured 15 % faster than 16 warps + shared-memory copy)
   c->wide_warps = 28;
   c->serial = getenv("MATCHY_B200_SERIAL") != nullptr;
+  if (const char* mb = getenv("MATCHY_B200_IPTRIE_MINB")) c->iptrie_minb = atoi(mb);
   if (const char* ww = getenv("MATCHY_B200_WIDE_WARPS")) { int v = atoi(ww); if (v == 24 || v == 28 || v == 32) c->wide_warps = v; }
   // Candidate queue segments in HBM: one per scanning warp.  Capacities follow what a log can plausibly hold; a piece that
   // needs more sets its overflow flag and is split at newlines and redone (scan_piece), so exactness never depends on them.
@@ -2030,6 +2037,7 @@ int mgpu_debug_get(mgpu_ctx* c, uint64_t out[64]) {
   CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, c->d_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; k++) out[60 + k] = c->host_us[k];  // host time of the last resident scan: whole call, result sort, id re-pack, launch + gather
   return MGPU_OK;
 }
 
@@ -2255,7 +2263,11 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     CK(cudaEventRecord(c->ev_l0[slot], ls));
   }
   if (lookups) {
-    if (!a.ip_skip) iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);
+    if (!a.ip_skip) {
+      if (c->iptrie_minb == 5) iptrie_kernel<5><<<launch_grid(c, 8), 256, 0, ls>>>(a);
+      else if (c->iptrie_minb == 6) iptrie_kernel<6><<<launch_grid(c, 8), 256, 0, ls>>>(a);
+      else iptrie_kernel<4><<<launch_grid(c, 8), 256, 0, ls>>>(a);
+    }
     CK(cudaEventRecord(ev[3], ls));
     if (a.db.has_literal && !fast) lithash_kernel<<<launch_grid(c, 6), KT_THREADS, 0, ls>>>(a);
     CK(cudaEventRecord(ev[4], ls));
@@ -2263,7 +2275,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     else if (a.db.has_literal || a.db.has_glob) acglob_kernel<<<launch_grid(c, 4), KT_THREADS, ACGLOB_SMEM, ls>>>(a);  // 4 blocks/SM: register- and shared-memory-limited
     CK(cudaEventRecord(ev[5], ls));
   } else {
-    if (c->fused) iptrie_kernel<<<launch_grid(c, 8), 256, 0, ls>>>(a);  // (extraction only: parses the scan kernel's raw numeric words)
+    if (c->fused) iptrie_kernel<4><<<launch_grid(c, 8), 256, 0, ls>>>(a);  // (extraction only: parses the scan kernel's raw numeric words)
     for (int k = 3; k <= 5; k++) CK(cudaEventRecord(ev[k], ls));
   }
   piece_end_kernel<<<1, 1, 0, ls>>>(a.ctr, a.tot);
@@ -2427,20 +2439,17 @@ static void finish_scan(mgpu_ctx* c) {
     const unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
     if (nt >= 2) c->pool.reset(new WorkerPool(nt));
   }
-  sort_records(c->recs.data(), nrec, c->sort_tmp, c->pool.get());
+  const auto t_sort = std::chrono::steady_clock::now();
+  sort_records(c->recs.data(), nrec, c->scan_lo, c->scan_hi, c->sort_tmp, c->pool.get());
+  const auto t_ids = std::chrono::steady_clock::now();
   if (!c->ids.empty()) {
-    std::vector<mgpu_id_pair>& packed = c->ids_tmp;
-    packed.clear();
-    packed.reserve(c->ids.size());
-    for (auto& r : c->recs) {
-      if (r.kind != MGPU_KIND_PATTERN) continue;
-      uint32_t at = (uint32_t)packed.size();
-      packed.insert(packed.end(), c->ids.begin() + r.ids_index, c->ids.begin() + r.ids_index + r.n_ids);
-      r.ids_index = at;
-    }
-    c->ids.n = packed.size();
-    if (!packed.empty()) memcpy(c->ids.data(), packed.data(), packed.size() * sizeof(mgpu_id_pair));
+    const size_t np = repack_ids(c->recs.data(), nrec, c->ids.data(), c->ids_tmp, c->pool.get());
+    c->ids.n = np;
+    if (np) memcpy(c->ids.data(), c->ids_tmp.data(), np * sizeof(mgpu_id_pair));
   }
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+  c->host_us[1] = us(t_sort, t_ids);
+  c->host_us[2] = us(t_ids, std::chrono::steady_clock::now());
 }
 
 static int check_ready(mgpu_ctx* c, uint32_t flags) {
@@ -2538,10 +2547,15 @@ int mgpu_scan_device(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_t base,
   int rc = check_ready(c, flags);
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
+  const auto t0 = std::chrono::steady_clock::now();
   begin_scan(c);
+  c->scan_lo = base; c->scan_hi = base + len;
   rc = scan_device_impl(c, dev, len, base, flags, true);
   if (rc) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   finish_scan(c);
+  c->host_us[3] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+  c->host_us[0] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
   return MGPU_OK;
 }
 
@@ -2612,6 +2626,7 @@ int mgpu_scan(mgpu_ctx* c, const uint8_t* host, size_t len, uint64_t base, uint3
   const bool trace = getenv("MGPU_TRACE") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
   begin_scan(c);
+  c->scan_lo = base; c->scan_hi = base + len;
   rc = scan_host_impl(c, host, len, base, flags, true);
   if (rc) return rc;
   auto t1 = std::chrono::steady_clock::now();

@@ -19,7 +19,9 @@
 
 namespace mgpu {
 
-// n workers, each runs job(worker index) once per parallel() call; parallel() returns when all are done.
+// n workers, each runs job(worker index) once per parallel() call; parallel() returns when all are done.  The phases of one
+// sort follow each other within microseconds, so a worker spins on the generation counter for a short while after a job
+// before it goes to sleep on the condition variable (a sleeping pool costs a futex wake per worker and phase).
 class WorkerPool {
  public:
   explicit WorkerPool(unsigned n) {
@@ -32,33 +34,40 @@ class WorkerPool {
   }
   unsigned size() const { return (unsigned)th_.size(); }
   void parallel(const std::function<void(unsigned)>& f) {
-    std::unique_lock<std::mutex> l(m_);
-    job_ = &f; pending_ = (unsigned)th_.size(); gen_++;
-    cv_.notify_all();
-    done_.wait(l, [&] { return pending_ == 0; });
-    job_ = nullptr;
+    job_ = &f;
+    pending_.store((unsigned)th_.size(), std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> l(m_);  // (pairs with the sleepers' predicate check: no lost wake-up)
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    if (sleepers_.load(std::memory_order_acquire)) cv_.notify_all();
+    for (unsigned spin = 0; pending_.load(std::memory_order_acquire) != 0; spin++)
+      if (spin > 2000) std::this_thread::yield();
   }
 
  private:
   void run(unsigned k) {
     unsigned seen = 0;
-    std::unique_lock<std::mutex> l(m_);
     for (;;) {
-      cv_.wait(l, [&] { return stop_ || gen_ != seen; });
-      if (stop_) return;
-      seen = gen_;
-      const std::function<void(unsigned)>* j = job_;
-      l.unlock();
-      (*j)(k);
-      l.lock();
-      if (--pending_ == 0) done_.notify_one();
+      bool have = false;
+      for (unsigned spin = 0; spin < 20000 && !have; spin++) have = gen_.load(std::memory_order_acquire) != seen;  // ~20-50 us
+      if (!have) {
+        std::unique_lock<std::mutex> l(m_);
+        sleepers_.fetch_add(1, std::memory_order_release);
+        cv_.wait(l, [&] { return stop_ || gen_.load(std::memory_order_acquire) != seen; });
+        sleepers_.fetch_sub(1, std::memory_order_release);
+        if (stop_) return;
+      }
+      seen = gen_.load(std::memory_order_acquire);
+      (*job_)(k);
+      pending_.fetch_sub(1, std::memory_order_release);
     }
   }
   std::vector<std::thread> th_;
   std::mutex m_;
-  std::condition_variable cv_, done_;
+  std::condition_variable cv_;
   const std::function<void(unsigned)>* job_ = nullptr;
-  unsigned gen_ = 0, pending_ = 0;
+  std::atomic<unsigned> gen_{0}, pending_{0}, sleepers_{0};
   bool stop_ = false;
 };
 
@@ -68,19 +77,12 @@ inline bool record_less(const mgpu_match& x, const mgpu_match& y) {
   return x.len < y.len;
 }
 
-// r[0..n) sorted by (offset, item_type, len).  tmp: scratch the caller keeps between calls; pool may be null (one thread).
-inline void sort_records(mgpu_match* r, size_t n, std::vector<mgpu_match>& tmp, WorkerPool* pool) {
+// r[0..n) sorted by (offset, item_type, len).  Every offset lies in [lo, hi] (the scanned byte range).  tmp: scratch the caller
+// keeps between calls; pool may be null (one thread).
+inline void sort_records(mgpu_match* r, size_t n, uint64_t lo, uint64_t hi, std::vector<mgpu_match>& tmp, WorkerPool* pool) {
   if (n < 4096 || !pool || pool->size() < 2) { std::sort(r, r + n, record_less); return; }
   const unsigned T = pool->size();
-  // offset range (one slice per worker)
-  std::vector<uint64_t> lo_s(T, ~0ull), hi_s(T, 0);
   auto slice = [&](unsigned k) { return n * k / T; };
-  pool->parallel([&](unsigned k) {
-    uint64_t lo = ~0ull, hi = 0;
-    for (size_t i = slice(k); i < slice(k + 1); i++) { lo = std::min(lo, r[i].offset); hi = std::max(hi, r[i].offset); }
-    lo_s[k] = lo; hi_s[k] = hi;
-  });
-  const uint64_t lo = *std::min_element(lo_s.begin(), lo_s.end()), hi = *std::max_element(hi_s.begin(), hi_s.end());
   // bucket = (offset - lo) >> shift, about 512 records per bucket when matches are spread evenly
   const uint64_t span = hi - lo;
   size_t want = std::min<size_t>(std::max<size_t>(n / 512, 16), (size_t)1 << 16);
@@ -88,10 +90,15 @@ inline void sort_records(mgpu_match* r, size_t n, std::vector<mgpu_match>& tmp, 
   while ((span >> shift) >= want) shift++;
   const size_t B = (size_t)(span >> shift) + 1;
   std::vector<uint32_t> hist((size_t)T * B, 0);  // (n < 2^32: a batch holds at most cap_rec < 2^31 records per piece... sums below are 64-bit)
+  std::atomic<bool> outside{false};
   pool->parallel([&](unsigned k) {
     uint32_t* h = hist.data() + (size_t)k * B;
-    for (size_t i = slice(k); i < slice(k + 1); i++) h[(r[i].offset - lo) >> shift]++;
+    for (size_t i = slice(k); i < slice(k + 1); i++) {
+      if (r[i].offset < lo || r[i].offset > hi) { outside.store(true, std::memory_order_relaxed); return; }
+      h[(r[i].offset - lo) >> shift]++;
+    }
   });
+  if (outside.load()) { std::sort(r, r + n, record_less); return; }  // (a caller that got the range wrong still gets sorted records)
   std::vector<size_t> start((size_t)T * B), bucket_at(B + 1);
   size_t run = 0;
   for (size_t b = 0; b < B; b++) {
@@ -115,6 +122,33 @@ inline void sort_records(mgpu_match* r, size_t n, std::vector<mgpu_match>& tmp, 
       memcpy(r + bucket_at[g], t + bucket_at[g], (bucket_at[g1] - bucket_at[g]) * sizeof(mgpu_match));
     }
   });
+}
+
+// The id pairs of pattern records, gathered in record order into `packed` (ids_index rewritten to match); the device appends
+// them in whatever order its warps finish.  Returns the number of pairs.  Random reads of `ids`: latency-bound, so in parallel.
+inline size_t repack_ids(mgpu_match* r, size_t n, const mgpu_id_pair* ids, std::vector<mgpu_id_pair>& packed, WorkerPool* pool) {
+  const unsigned T = (pool && n >= 4096) ? pool->size() : 1;
+  auto slice = [&](unsigned k) { return n * k / T; };
+  std::vector<size_t> first(T + 1, 0);
+  auto count = [&](unsigned k) {
+    size_t c = 0;
+    for (size_t i = slice(k); i < slice(k + 1); i++) if (r[i].kind == MGPU_KIND_PATTERN) c += r[i].n_ids;
+    first[k + 1] = c;
+  };
+  auto gather = [&](unsigned k) {
+    size_t at = first[k];
+    for (size_t i = slice(k); i < slice(k + 1); i++) {
+      if (r[i].kind != MGPU_KIND_PATTERN) continue;
+      memcpy(packed.data() + at, ids + r[i].ids_index, (size_t)r[i].n_ids * sizeof(mgpu_id_pair));
+      r[i].ids_index = (uint32_t)at;
+      at += r[i].n_ids;
+    }
+  };
+  if (T == 1) count(0); else pool->parallel(count);
+  for (unsigned k = 0; k < T; k++) first[k + 1] += first[k];
+  if (packed.size() < first[T]) packed.resize(first[T]);
+  if (T == 1) gather(0); else pool->parallel(gather);
+  return first[T];
 }
 
 }  // namespace mgpu

@@ -351,17 +351,26 @@ uint32_t emu_parse_ipv4_both(const uint8_t* s, uint32_t n, uint32_t out[2]) {
 }
 
 // the engine's result sort (host_sort.h) on n records, with `threads` pool workers (0: no pool); returns microseconds
-double emu_sort_records(mgpu_match* r, size_t n, unsigned threads, int repeat) {
+double emu_sort_records(mgpu_match* r, size_t n, uint64_t lo, uint64_t hi, unsigned threads, int repeat) {
   std::vector<mgpu_match> tmp, copy(r, r + n);
   std::unique_ptr<mgpu::WorkerPool> pool(threads ? new mgpu::WorkerPool(threads) : nullptr);
   double best = 1e30;
   for (int k = 0; k < repeat; k++) {
     std::copy(copy.begin(), copy.end(), r);
     auto t0 = std::chrono::steady_clock::now();
-    mgpu::sort_records(r, n, tmp, pool.get());
+    mgpu::sort_records(r, n, lo, hi, tmp, pool.get());
     best = std::min(best, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
   }
   return best;
+}
+
+// the engine's id re-pack on n sorted records; out must hold every pair; returns the number of pairs
+size_t emu_repack_ids(mgpu_match* r, size_t n, const mgpu_id_pair* ids, mgpu_id_pair* out, unsigned threads) {
+  std::vector<mgpu_id_pair> packed;
+  std::unique_ptr<mgpu::WorkerPool> pool(threads ? new mgpu::WorkerPool(threads) : nullptr);
+  const size_t np = mgpu::repack_ids(r, n, ids, packed, pool.get());
+  std::copy(packed.begin(), packed.begin() + np, out);
+  return np;
 }
 
 int64_t emu_tokens(emu_ctx* c, uint64_t* out, size_t cap) {

@@ -318,8 +318,31 @@ def test_result_sort_equals_a_plain_sort():
         r["len"] = rng.integers(1, 300, n)
         r["ids_index"] = np.arange(n)  # payload: every record must survive
         want = r[np.lexsort((r["len"], r["item_type"], r["offset"]))]
-        got = r.copy()
-        L.emu_sort_records(got.ctypes.data, n, threads, 1)
         key = lambda a: (a["offset"].tolist(), a["item_type"].tolist(), a["len"].tolist())
-        assert key(got) == key(want), (n, threads, shape)
-        assert sorted(got["ids_index"].tolist()) == list(range(n)), (n, threads, shape)
+        lo, hi = (int(r["offset"].min()), int(r["offset"].max())) if n else (0, 0)
+        for rng_lo, rng_hi in ((lo, hi), (0, 2**41), (lo + 1, hi)):  # exact range, generous range, WRONG range (falls back to a plain sort)
+            got = r.copy()
+            L.emu_sort_records(got.ctypes.data, n, rng_lo, rng_hi, threads, 1)
+            assert key(got) == key(want), (n, threads, shape, rng_lo)
+            assert sorted(got["ids_index"].tolist()) == list(range(n)), (n, threads, shape)
+    # id pairs gathered in record order
+    idt = np.dtype([("pattern_id", "<u4"), ("data_offset", "<u4")])
+    for n, threads in ((10, 4), (5000, 4), (40000, 8), (40000, 0)):
+        r = np.zeros(n, dtype=dt)
+        r["kind"] = rng.integers(1, 3, n)  # 1 = IP record (no ids), 2 = pattern record
+        r["n_ids"] = np.where(r["kind"] == 2, rng.integers(1, 5, n), 0)
+        total = int(r["n_ids"].sum())
+        ids = np.zeros(total + 7, dtype=idt)
+        ids["pattern_id"] = rng.permutation(total + 7)
+        starts = np.concatenate(([0], np.cumsum(r["n_ids"])[:-1]))
+        order = rng.permutation(n)  # the device's arrival order: record k's pairs sit at a random place
+        where = np.zeros(n, dtype=np.int64)
+        where[order] = np.concatenate(([0], np.cumsum(r["n_ids"][order])[:-1]))
+        r["ids_index"] = where
+        want_ids = np.concatenate([ids["pattern_id"][where[k]:where[k] + r["n_ids"][k]] for k in range(n)]) if total else np.zeros(0)
+        out = np.zeros(total, dtype=idt)
+        got_r = r.copy()
+        assert L.emu_repack_ids(got_r.ctypes.data, n, ids.ctypes.data, out.ctypes.data, threads) == total
+        assert out["pattern_id"].tolist() == want_ids.tolist(), (n, threads)
+        pat = got_r["kind"] == 2
+        assert got_r["ids_index"][pat].tolist() == starts[pat].tolist(), (n, threads)
