@@ -1188,7 +1188,7 @@ __device__ __forceinline__ uint32_t agg_add(uint32_t* ctr, uint32_t v) {
 // K3: IP tokens -> SearchTree::lookup (mmdb/tree.rs:46-125) -> records.
 //  * Lock step: a warp takes 32 consecutive tokens and advances all their walks together, IPT_STEPS tree records per round,
 //    until none is left walking (trie_walk_begin / trie_walk_step).  Round 1 let every lane run its own walk to the end;
-//    at full size that version lost 0..5 of 8 million records from run to run: ONE lane in a deep IPv6 walk (~50 us of
+//    at full size, with larger token reservation units, that version lost 0..5 of 8 million records from run to run: ONE lane in a deep IPv6 walk (~50 us of
 //    dependent DRAM reads) next to idle lanes was left behind by its warp — the warp's other 31 lanes, and with them the
 //    block's barriers and the warp-uniform registers, ran 16 loop iterations ahead of it (measured with the audit
 //    counters of mgpu_set_option("verify_tokens"); profiles/README.md "the lost records of round 1").  Here no lane is
@@ -2305,6 +2305,9 @@ static int end_batch(mgpu_ctx* c, int pieces) {
   if (c->looked_pending) { CK(cudaStreamWaitEvent(c->compute, c->ev_looked[c->looked_slot], 0)); c->looked_pending = false; }  // (one lookup stream: the latest event covers all)
   c->set_pending[0] = c->set_pending[1] = false;
   CK(cudaMemcpyAsync(c->h_ctr, c->args.ctr, sizeof(DevCounters) * pieces, cudaMemcpyDeviceToHost, c->compute));
+  // The scan's device span (mgpu_timing.scan_ms) ends with the last device operation, not with the host's gathering of the
+  // results: re-recorded after every batch and after every copy of id pairs, the last record stands.
+  CK(cudaEventRecord(c->ev_scan[1], c->compute));
   CK(cudaStreamSynchronize(c->compute));
   for (int p = 0; p < pieces; p++) {
     for (int k = 0; k < MGPU_K_COUNT; k++) {
@@ -2349,6 +2352,7 @@ static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_l
   if (i_hi > i_lo) {
     if (!c->ids.resize(i0 + (i_hi - i_lo))) { set_err("out of pinned host memory for match ids"); return MGPU_E_CUDA; }
     CK(cudaMemcpyAsync(c->ids.data() + i0, c->args.ids + i_lo, (size_t)(i_hi - i_lo) * sizeof(mgpu_id_pair), cudaMemcpyDeviceToHost, c->compute));
+    CK(cudaEventRecord(c->ev_scan[1], c->compute));
     CK(cudaStreamSynchronize(c->compute));
   }
   if ((size_t)i_lo != i0)  // (the first run of a scan lands at the same indices: nothing to rebase — 8 M records per step on config 3)
@@ -2426,10 +2430,10 @@ static void begin_scan(mgpu_ctx* c) {
   memset(&c->counters, 0, sizeof c->counters);
   memset(&c->timing, 0, sizeof c->timing);
   cudaEventRecord(c->ev_scan[0], c->compute);
+  cudaEventRecord(c->ev_scan[1], c->compute);  // (stands only for an empty input: every batch records it again)
 }
 
 static void finish_scan(mgpu_ctx* c) {
-  cudaEventRecord(c->ev_scan[1], c->compute);
   cudaEventSynchronize(c->ev_scan[1]);
   cudaEventElapsedTime(&c->timing.scan_ms, c->ev_scan[0], c->ev_scan[1]);
   // deterministic output: records by (offset, item_type, len), id pairs re-packed in record order (the device appends

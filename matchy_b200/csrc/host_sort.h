@@ -19,20 +19,21 @@
 
 namespace mgpu {
 
-// n workers, each runs job(worker index) once per parallel() call; parallel() returns when all are done.  The phases of one
+// n workers — n - 1 threads and the caller itself, so that a pool as wide as the machine does not oversubscribe it —, each runs
+// job(worker index) once per parallel() call; parallel() returns when all are done.  The phases of one
 // sort follow each other within microseconds, so a worker spins on the generation counter for a short while after a job
 // before it goes to sleep on the condition variable (a sleeping pool costs a futex wake per worker and phase).
 class WorkerPool {
  public:
   explicit WorkerPool(unsigned n) {
-    for (unsigned k = 0; k < n; k++) th_.emplace_back([this, k] { run(k); });
+    for (unsigned k = 0; k + 1 < n; k++) th_.emplace_back([this, k] { run(k); });
   }
   ~WorkerPool() {
     { std::lock_guard<std::mutex> l(m_); stop_ = true; }
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
-  unsigned size() const { return (unsigned)th_.size(); }
+  unsigned size() const { return (unsigned)th_.size() + 1; }
   void parallel(const std::function<void(unsigned)>& f) {
     job_ = &f;
     pending_.store((unsigned)th_.size(), std::memory_order_relaxed);
@@ -41,6 +42,7 @@ class WorkerPool {
       gen_.fetch_add(1, std::memory_order_release);
     }
     if (sleepers_.load(std::memory_order_acquire)) cv_.notify_all();
+    f((unsigned)th_.size());  // the caller is the last worker
     for (unsigned spin = 0; pending_.load(std::memory_order_acquire) != 0; spin++)
       if (spin > 2000) std::this_thread::yield();
   }

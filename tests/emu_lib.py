@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "host_emulation", "emu.cpp"),
        os.path.join(ROOT, "matchy_b200", "csrc", "mxy_reader.cpp"),
        os.path.join(ROOT, "matchy_b200", "csrc", "mxy_builder.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "matchy_b200", "csrc", f) for f in ("device_fns.cuh", "tokenize.cuh", "crypto_addr.cuh", "db_prepare.h", "mxy_reader.h", "mxy_builder.h")]
+DEPS = SRC + [os.path.join(ROOT, "matchy_b200", "csrc", f) for f in ("device_fns.cuh", "tokenize.cuh", "crypto_addr.cuh", "db_prepare.h", "mxy_reader.h", "mxy_builder.h", "host_sort.h", "synth_gen.h")]
 SO = os.path.join(ROOT, "tests", "host_emulation", "libemu.so")
 PSL_PATH = os.path.join(ROOT, "matchy_b200", "data", "public_suffix_list.dat")
 
