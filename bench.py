@@ -389,7 +389,10 @@ def main():
     cfg = args.config or (5 if world > 1 else 2)
     scale = args.scale
     if sharded:
-        nbytes = int(args.total_gb * 1e9 / world) // 65536 * 65536
+        # the SAME stream for every N: the total is a whole number of 64 KiB generator blocks divisible by 840 (= lcm(1..8)), so
+        # that the all-reduced counters of N = 2, 4, 8 (or any N up to 8) must be identical — blocks end at newlines
+        total_blocks = int(args.total_gb * 1e9) // 65536 // 840 * 840
+        nbytes = (total_blocks // world if total_blocks % world == 0 else int(args.total_gb * 1e9 / world) // 65536) * 65536
     else:
         nbytes = int(args.gb * 1e9) // 65536 * 65536
     base = rank * nbytes

@@ -82,6 +82,7 @@ struct ScanArgs {
   uint32_t tok_unit;   // slots a token-kernel warp takes from a token list per trip to its counter (TOK_RESERVE unless a test overrides it)
   unsigned long long* dbg;  // audit accumulators (mgpu_set_option "verify_tokens"), else nullptr
   uint32_t variant;         // experiment switch (mgpu_set_option "variant"), 0 in production
+  uint32_t sub_block;       // token_kernel: bytes of a segment handled per dotted / numeric round (0: whole segment; must be 0 when the queues are not sorted)
 };
 
 static const int K1_THREADS = 512;
@@ -527,26 +528,31 @@ __device__ __forceinline__ Cand ld_cand(const Cand* p) {
 // many consecutive candidates (at most 32) as fit in the warp's window, stages the window with coalesced 16-byte loads and
 // lets one lane handle one candidate.
 enum { W_DOTTED = 0, W_NUMERIC = 1, W_HASH = 2 };
+// Resumable: starts at candidate i0 and stops in front of the first candidate whose start is >= limit (the segment being sorted,
+// that is a prefix); returns the index it stopped at.  token_kernel alternates the dotted and the numeric queue in sub-blocks of
+// a warp's range, so that the numeric pass finds its bytes still in L2.
 template <int MODE>
-__device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t n, uint8_t* s_win,
-                                            const HotShared& s_hot, bool fast, uint32_t lane) {
+__device__ __forceinline__ uint32_t token_words(const ScanArgs& a, TokenWarp& tw, const Cand* q, uint32_t i0, uint32_t n, uint32_t limit, uint8_t* s_win,
+                                                const HotShared& s_hot, bool fast, uint32_t lane) {
   const bool want_dom = (a.flags & MGPU_X_DOMAINS) != 0, want_v4 = (a.flags & MGPU_X_IPV4) != 0;
-  if (MODE == W_DOTTED && !want_dom) return;
+  if (MODE == W_DOTTED && !want_dom) return n;
   // IPv4 candidates are sparse in most logs (a 2 KiB window would hold a handful): 32 per iteration straight from the log
   // buffer — all that is needed of each is its first 16 bytes.  (Choosing per segment at run time cost 4 % on every config.)
   constexpr bool direct = MODE == W_NUMERIC;
   Cand cn{0xFFFFFFFFu, 0};  // prefetched: candidate i0 + lane of the NEXT iteration (assuming a full group of 32)
-  if (lane < n) cn = ld_cand(q + lane);
-  for (uint32_t i0 = 0; i0 < n;) {
+  if (i0 + lane < n) cn = ld_cand(q + i0 + lane);
+  while (i0 < n) {
     const uint32_t idx = i0 + lane;
-    const bool have = idx < n;
     const Cand c = cn;
+    const bool have = idx < n && c.start < limit;
+    const uint32_t hv = __ballot_sync(0xFFFFFFFFu, have);
+    if (hv == 0) break;  // the next candidate belongs to a later sub-block
     if (idx + 32 < n) cn = ld_cand(q + idx + 32); else cn = Cand{0xFFFFFFFFu, 0};
     // (lowest start of the 32: the tokenizer's segments are sorted by position, the fused kernel's slow-path entries are not)
     const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, have ? c.start : 0xFFFFFFFFu);
     const uint32_t alo = lo & ~15u;
     const bool fits = !have || (uint64_t)c.start + c.len + 16 <= (uint64_t)alo + TK_WIN;
-    const uint32_t nf = direct ? 0u : __ballot_sync(0xFFFFFFFFu, !fits);
+    const uint32_t nf = (direct ? 0u : __ballot_sync(0xFFFFFFFFu, !fits)) | ~hv;  // (lanes past the limit or the end do not "fit")
     uint32_t g = nf ? (uint32_t)__ffs((int)nf) - 1u : 32u;  // candidates of this iteration: lanes [0, g)
     const uint8_t* p = a.buf;
     bool high = true;  // "the token bytes may hold bytes >= 0x80"
@@ -626,6 +632,7 @@ __device__ __forceinline__ void token_words(const ScanArgs& a, TokenWarp& tw, co
     }
     i0 += g;
   }
+  return i0;
 }
 
 __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
@@ -653,9 +660,26 @@ __global__ void __launch_bounds__(TK_THREADS, 1) token_kernel(ScanArgs a) {
   const uint32_t nwarps = gridDim.x * TK_WARPS;
   for (uint32_t seg = blockIdx.x * TK_WARPS + warp; seg < a.nseg; seg += nwarps) {
     const uint32_t* sc = a.seg_cnt + seg;
-    token_words<W_DOTTED>(a, tw, a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED], sc[Q_DOTTED * a.nseg_max], s_win, s_hot, fast, lane);
-    token_words<W_NUMERIC>(a, tw, a.q_numeric + (size_t)seg * a.seg_cap[Q_NUMERIC], sc[Q_NUMERIC * a.nseg_max], s_win, s_hot, fast, lane);
-    token_words<W_HASH>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], sc[Q_HASH * a.nseg_max], s_win, s_hot, fast, lane);
+    // Dotted and numeric words can alternate in sub-blocks of a.sub_block bytes of the segment: the numeric pass reads its words
+    // straight from the log buffer, and after a dotted pass over the WHOLE segment (all warps together: the whole piece) those
+    // bytes have left L2 again — the top stall of the kernel and one DRAM byte per log byte.  Built, measured, and off by
+    // default (sub_block = 0: one round): see mgpu_ctx::sub_block.
+    {
+      const Cand* qD = a.q_dotted + (size_t)seg * a.seg_cap[Q_DOTTED];
+      const Cand* qN = a.q_numeric + (size_t)seg * a.seg_cap[Q_NUMERIC];
+      const uint32_t nD = (a.flags & MGPU_X_DOMAINS) ? sc[Q_DOTTED * a.nseg_max] : 0u, nN = sc[Q_NUMERIC * a.nseg_max];
+      uint32_t iD = 0, iN = 0;
+      while (iD < nD || iN < nN) {
+        uint32_t limit = 0xFFFFFFFFu;
+        if (a.sub_block) {
+          const uint32_t sD = iD < nD ? ld_cand(qD + iD).start : 0xFFFFFFFFu, sN = iN < nN ? ld_cand(qN + iN).start : 0xFFFFFFFFu;
+          limit = min(sD, sN) + a.sub_block;  // (positions inside a piece are < 2^31)
+        }
+        iD = token_words<W_DOTTED>(a, tw, qD, iD, nD, limit, s_win, s_hot, fast, lane);
+        iN = token_words<W_NUMERIC>(a, tw, qN, iN, nN, limit, s_win, s_hot, fast, lane);
+      }
+    }
+    token_words<W_HASH>(a, tw, a.q_hash + (size_t)seg * a.seg_cap[Q_HASH], 0u, sc[Q_HASH * a.nseg_max], 0xFFFFFFFFu, s_win, s_hot, fast, lane);
     // '@' and "::" anchors: rare, straight from the log buffer
     const uint32_t nA = sc[Q_AT * a.nseg_max], nC = sc[Q_COLON2 * a.nseg_max];
     const uint32_t* qa = a.q_at + (size_t)seg * a.seg_cap[Q_AT];
@@ -1807,6 +1831,8 @@ struct mgpu_ctx {
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
   std::vector<mgpu_match> sort_tmp;   // sort_records' scratch
+  uint32_t sub_block = 0;             // ScanArgs::sub_block of the two-kernel path (option "sub_block"; MATCHY_B200_SUB_BLOCK).  Measured, config 2 at 8 GB:
+                                      // token_kernel 4.29 ms with 0, 5.61 / 4.89 / 4.63 ms with 8 / 16 / 32 KiB — the short groups at every sub-block edge cost more than the L2 hits bring
   int iptrie_minb = 4;                // iptrie_kernel instance: 4 = 64 registers, 5 = 48, 6 = 40 (MATCHY_B200_IPTRIE_MINB; config 3 at 8 GB: 588 / 577 / 526 GB/s — the spills cost more than the warps bring)
   uint64_t scan_lo = 0, scan_hi = ~0ull;  // absolute offsets the current scan can report (the range of sort_records' partition)
   uint64_t host_us[4] = {0, 0, 0, 0}; // microseconds of the last mgpu_scan_device on the host: whole call, sort, id re-pack, launches + gather
@@ -1916,6 +1942,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   c->wide_warps = 28;
   c->serial = getenv("MATCHY_B200_SERIAL") != nullptr;
   if (const char* mb = getenv("MATCHY_B200_IPTRIE_MINB")) c->iptrie_minb = atoi(mb);
+  if (const char* sb = getenv("MATCHY_B200_SUB_BLOCK")) c->sub_block = (uint32_t)atoi(sb);
   if (const char* ww = getenv("MATCHY_B200_WIDE_WARPS")) { int v = atoi(ww); if (v == 24 || v == 28 || v == 32) c->wide_warps = v; }
   // Candidate queue segments in HBM: one per scanning warp.  Capacities follow what a log can plausibly hold; a piece that
   // needs more sets its overflow flag and is split at newlines and redone (scan_piece), so exactness never depends on them.
@@ -2026,6 +2053,7 @@ int mgpu_set_option(mgpu_ctx* c, const char* key, uint64_t value) {
     if (cudaSetDevice(c->device) != cudaSuccess || cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMemset failed"); return MGPU_E_CUDA; }
   }
   else if (k == "variant") c->args.variant = (uint32_t)value;
+  else if (k == "sub_block") c->sub_block = (uint32_t)value;
   else if (k == "fused") {
     if ((value != 0) != (c->nsets == 2)) { set_err("the first-stage kernels are chosen when the context is created (MATCHY_B200_FUSED=1): the work buffers differ"); return MGPU_E_PARAM; }
   }
@@ -2203,6 +2231,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
   const bool fast = lookups && a.db.fast_ok && !c->force_generic && (a.db.has_literal || a.db.has_glob);
   a.fast = fast ? 1u : 0u;
   a.lookups = lookups ? 1u : 0u;
+  a.sub_block = c->fused ? 0u : c->sub_block;  // (scan_kernel's slow-path entries are not sorted by position)
   a.ip_skip = lookups && a.db.ip_empty && !c->fused && !c->verify_tokens ? 1u : 0u;  // (scan_kernel leaves numeric words to iptrie_kernel's parser; the audit wants the list)
   const uint64_t tiles = (n + TILE_BYTES - 1) / TILE_BYTES;
   if (c->fused) {
