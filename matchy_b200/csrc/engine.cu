@@ -390,7 +390,7 @@ __device__ __forceinline__ const uint8_t* stage_window(const uint8_t* buf, uint8
 // one 2 KiB log window per warp.  Tokens are appended through per-warp reservations of TOK_RESERVE slots (unused slots
 // are marked invalid), so a warp's tokens stay in log order for the generic lookup kernels.
 // ---------------------------------------------------------------------------------------------------------
-static const uint32_t TOK_RESERVE = 128;
+static const uint32_t TOK_RESERVE = 256;  // (config 3 at 8 GB: 578 GB/s with 128, 619 with 256, 618 with 512 — the wait for the counter's atomic was 10 % of the token kernel's stalls)
 static const uint32_t TOK_INVALID = 0xFFu;  // StrTok.type / IpTok.type of a padding slot
 static const uint32_t TOK_RAW4 = 0xFEu;     // IpTok.type: a numeric-queue word of 7..15 bytes, not parsed yet; w[] = its first 16 bytes (iptrie_kernel parses it)
 struct QueueCursor { uint32_t base, left; };
@@ -1976,6 +1976,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
     a.cap_ids = cap32(chunk_bytes / 8 + 8192);
   }
   a.tok_unit = TOK_RESERVE;
+  if (const char* tu = getenv("MATCHY_B200_TOK_RESERVE")) { const int v = atoi(tu); if (v >= 32 && v <= 65536) a.tok_unit = (uint32_t)v; }
   c->alloc_cap_str = a.cap_str; c->alloc_cap_ip = a.cap_ip; c->alloc_cap_rec = a.cap_rec; c->alloc_cap_ids = a.cap_ids;
   for (int k = 0; k < c->nsets; k++) {
     mgpu_ctx::BufSet& b = c->sets[k];
@@ -2065,7 +2066,8 @@ int mgpu_debug_get(mgpu_ctx* c, uint64_t out[64]) {
   CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, c->d_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  for (int k = 0; k < 4; k++) out[60 + k] = c->host_us[k];  // host time of the last resident scan: whole call, result sort, id re-pack, launch + gather
+  for (int k = 0; k < 4; k++) out[60 + k] = c->host_us[k];
+  // host time of the last resident scan: whole call, result sort, id re-pack, launch + gather
   return MGPU_OK;
 }
 
@@ -2468,11 +2470,11 @@ static void finish_scan(mgpu_ctx* c) {
   // deterministic output: records by (offset, item_type, len), id pairs re-packed in record order (the device appends
   // both with atomics, so their raw order varies from run to run)
   const size_t nrec = c->recs.size();
+  const auto t_sort = std::chrono::steady_clock::now();
   if (nrec >= 4096 && !c->pool) {
     const unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
     if (nt >= 2) c->pool.reset(new WorkerPool(nt));
   }
-  const auto t_sort = std::chrono::steady_clock::now();
   sort_records(c->recs.data(), nrec, c->scan_lo, c->scan_hi, c->sort_tmp, c->pool.get());
   const auto t_ids = std::chrono::steady_clock::now();
   if (!c->ids.empty()) {

@@ -84,7 +84,8 @@ inline bool record_less(const mgpu_match& x, const mgpu_match& y) {
 inline void sort_records(mgpu_match* r, size_t n, uint64_t lo, uint64_t hi, std::vector<mgpu_match>& tmp, WorkerPool* pool) {
   if (n < 4096 || !pool || pool->size() < 2) { std::sort(r, r + n, record_less); return; }
   const unsigned T = pool->size();
-  auto slice = [&](unsigned k) { return n * k / T; };
+  auto slice = [&](unsigned k) { return n * k / T; };  // (every worker takes part even for small n: the workers that find nothing
+                                                        //  to do are awake for the next phase either way)
   // bucket = (offset - lo) >> shift, about 512 records per bucket when matches are spread evenly
   const uint64_t span = hi - lo;
   size_t want = std::min<size_t>(std::max<size_t>(n / 512, 16), (size_t)1 << 16);

@@ -11,5 +11,12 @@ $B3 > gpurun_out/plain_${TAG}_c3.log 2>&1 && ncu --set full --clock-control none
 MATCHY_B200_FUSED=1 $B > gpurun_out/plain_${TAG}_f.log 2>&1 && MATCHY_B200_FUSED=1 ncu --set full --clock-control none --import-source on -k regex:'scan_kernel' -c 2 -f -o gpurun_out/prof_${TAG}_fused $B > gpurun_out/ncu_${TAG}_f.log 2>&1; tail -2 gpurun_out/ncu_${TAG}_f.log
 BL="python bench.py --gb 4 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-parity --no-per-config"
 $BL > gpurun_out/plain_${TAG}_l.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $BL > gpurun_out/ncu_${TAG}_l.log 2>&1; tail -2 gpurun_out/ncu_${TAG}_l.log
-for r in c2 c3 fused; do ncu -i gpurun_out/prof_${TAG}_$r.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_${r}_raw.csv 2>/dev/null; done
+# the reports themselves (25 MB each) would push gpurun_out/ past what travels back: keep the raw and source pages as CSV
+for r in c2 c3 fused; do
+  ncu -i gpurun_out/prof_${TAG}_$r.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_${r}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/prof_${TAG}_$r.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/prof_${TAG}_${r}_source.csv 2>/dev/null
+  python profiles/ncu_lines.py gpurun_out/prof_${TAG}_${r}_source.csv 60 > gpurun_out/prof_${TAG}_${r}_lines.txt 2>/dev/null
+  gzip -f gpurun_out/prof_${TAG}_${r}_source.csv
+  rm -f gpurun_out/prof_${TAG}_$r.ncu-rep
+done
 ls -la gpurun_out | grep $TAG

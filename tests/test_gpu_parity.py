@@ -575,3 +575,4 @@ def test_watching_database_reloads_into_the_same_engine(built, tmp_path):
     recs, _ = db.engine.scan(data)
     assert len(recs) == 2  # the old tables are still there
     db.close()
+
