@@ -1624,7 +1624,12 @@ __global__ void __launch_bounds__(256, 5) exact_kernel(ScanArgs a) {
 }
 
 // end of a piece: snapshot the running totals into the piece's counter block
-__global__ void piece_end_kernel(DevCounters* ctr, const ScanTotals* tot) { ctr->n_rec = tot->n_rec; ctr->n_ids = tot->n_ids; }
+// (h_nrec: the same snapshot in pinned host memory — the host reads it as soon as the piece's event has fired and starts the
+//  copy of the piece's records while later pieces are still being scanned, see drain_records)
+__global__ void piece_end_kernel(DevCounters* ctr, const ScanTotals* tot, uint32_t* h_nrec) {
+  ctr->n_rec = tot->n_rec; ctr->n_ids = tot->n_ids;
+  if (h_nrec) *h_nrec = tot->n_rec;
+}
 
 // Cut points of a resident buffer, all at once: out[k] = position just after the last '\n' in [at[k] - span, at[k]), or
 // NONE64 when that window holds none.  One block per cut.
@@ -1826,8 +1831,18 @@ struct mgpu_ctx {
   void* d_psl_keys = nullptr; void* d_psl_vals = nullptr; void* d_psl_pool = nullptr; void* d_psl_tld = nullptr;
   // results of the last scan
   PinnedVec<mgpu_match> recs;
-  PinnedVec<mgpu_match> stage;  // where the device writes a batch's records: pinned HOST memory, written over PCIe by the lookup kernels
-                                // while later pieces are still being scanned (no device-side record buffer, no D2H copy at the end)
+  PinnedVec<mgpu_match> stage;  // a batch's records in pinned HOST memory, in the order the device appended them
+  // How they get there.  Until the round's last session the lookup kernels stored them straight into `stage` over PCIe (no device-side
+  // record buffer).  ncu then showed what that costs when a database matches often: iptrie_kernel on config 3 ran for 403 us per
+  // 500 MB piece at pcie__write_bytes = 46 GB/s — the kernel's length WAS the 15 MB of records crossing the link, with its blocks
+  // holding registers the next piece's tokenizer was waiting for.  Now the kernels append to d_recs in HBM, piece_end_kernel leaves
+  // the running record count in pinned memory, and the host — idle while a batch runs — copies every piece's records with the
+  // copy engine (stream d2h) as soon as the piece's lookups are done, beside the kernels of the pieces behind it.
+  // MATCHY_B200_RECS_ZEROCOPY=1 restores the direct stores (d_recs stays null).
+  mgpu_match* d_recs = nullptr;
+  uint32_t* h_nrec = nullptr;   // pinned, MAX_BATCH entries
+  cudaStream_t d2h = nullptr;
+  cudaEvent_t ev_d2h = nullptr;
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
   std::vector<mgpu_match> sort_tmp;   // sort_records' scratch
@@ -1892,6 +1907,10 @@ void mgpu_destroy(mgpu_ctx* c) {
                   c->args.ids, c->args.ctr, c->d_tot, c->d_cut, c->d_small, c->d_small_out, c->d_dbg, c->d_flush, c->d_psl_keys, c->d_psl_vals, c->d_psl_pool, c->d_psl_tld};
   for (void* p : bufs) if (p) cudaFree(p);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  if (c->h_nrec) cudaFreeHost(c->h_nrec);
+  if (c->d_recs) cudaFree(c->d_recs);
+  if (c->d2h) cudaStreamDestroy(c->d2h);
+  if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
   if (c->h_cut) cudaFreeHost(c->h_cut);
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->copy) cudaStreamDestroy(c->copy);
@@ -1942,6 +1961,7 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   c->wide_warps = 28;
   c->serial = getenv("MATCHY_B200_SERIAL") != nullptr;
   if (const char* mb = getenv("MATCHY_B200_IPTRIE_MINB")) c->iptrie_minb = atoi(mb);
+  if (const char* vv = getenv("MATCHY_B200_VARIANT")) a.variant = (uint32_t)atoi(vv);  // (experiment switch, see ScanArgs::variant)
   if (const char* sb = getenv("MATCHY_B200_SUB_BLOCK")) c->sub_block = (uint32_t)atoi(sb);
   if (const char* ww = getenv("MATCHY_B200_WIDE_WARPS")) { int v = atoi(ww); if (v == 24 || v == 28 || v == 32) c->wide_warps = v; }
   // Candidate queue segments in HBM: one per scanning warp.  Capacities follow what a log can plausibly hold; a piece that
@@ -2001,6 +2021,13 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   // match records go straight to pinned host memory (unified addressing: the host pointer is the device pointer)
   if (!c->stage.reserve(a.cap_rec) || !c->recs.reserve(a.cap_rec)) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
   a.recs = c->stage.p;
+  if (getenv("MATCHY_B200_RECS_ZEROCOPY") == nullptr) {
+    CK(cudaMalloc(&c->d_recs, (size_t)a.cap_rec * sizeof(mgpu_match)));
+    CK(cudaMallocHost(&c->h_nrec, sizeof(uint32_t) * mgpu_ctx::MAX_BATCH));
+    CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming));
+    a.recs = c->d_recs;
+  }
   CK(cudaMalloc(&a.ids, (size_t)a.cap_ids * sizeof(mgpu_id_pair)));
   CK(cudaMalloc(&a.ctr, sizeof(DevCounters) * mgpu_ctx::MAX_BATCH));
   CK(cudaMalloc(&c->d_tot, sizeof(ScanTotals)));
@@ -2309,7 +2336,7 @@ static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo
     if (c->fused) iptrie_kernel<4><<<launch_grid(c, 8), 256, 0, ls>>>(a);  // (extraction only: parses the scan kernel's raw numeric words)
     for (int k = 3; k <= 5; k++) CK(cudaEventRecord(ev[k], ls));
   }
-  piece_end_kernel<<<1, 1, 0, ls>>>(a.ctr, a.tot);
+  piece_end_kernel<<<1, 1, 0, ls>>>(a.ctr, a.tot, c->d_recs ? c->h_nrec + slot : nullptr);
   CK(cudaEventRecord(c->ev_looked[slot], ls));
   c->set_pending[set] = true; c->set_slot[set] = slot;
   c->looked_pending = true; c->looked_slot = slot;
@@ -2356,6 +2383,24 @@ static int end_batch(mgpu_ctx* c, int pieces) {
   }
   return MGPU_OK;
 }
+// The records of the batch's pieces 0..nb-1, device -> `stage`, piece by piece as their lookups finish (the kernels of later
+// pieces keep running meanwhile; the ranges are disjoint: the record counter only grows).  The compute stream then waits for the
+// last copy, so that end_batch's synchronisation — and the scan's device span — covers it.
+static int drain_records(mgpu_ctx* c, int nb) {
+  if (!c->d_recs) return MGPU_OK;
+  uint32_t r_prev = 0;
+  for (int k = 0; k < nb; k++) {
+    CK(cudaEventSynchronize(c->ev_looked[k]));
+    const uint32_t r_now = std::min(c->h_nrec[k], c->args.cap_rec);
+    if (r_now > r_prev) {
+      if (c->keep_results) CK(cudaMemcpyAsync(c->stage.p + r_prev, c->d_recs + r_prev, (size_t)(r_now - r_prev) * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->d2h));
+      r_prev = r_now;
+    }
+  }
+  CK(cudaEventRecord(c->ev_d2h, c->d2h));
+  CK(cudaStreamWaitEvent(c->compute, c->ev_d2h, 0));
+  return MGPU_OK;
+}
 // Put the records [r_lo, r_hi) of the batch's record buffer (pinned host memory the device wrote into) and the id pairs
 // [i_lo, i_hi) of the device buffer behind the host vectors.  whole = these are all the records the batch produced and nothing
 // is waiting to be redone: then the two pinned buffers simply change places.
@@ -2365,7 +2410,7 @@ static int fetch_results(mgpu_ctx* c, uint32_t r_lo, uint32_t r_hi, uint32_t i_l
   if (whole && r0 == 0 && r_lo == 0 && c->recs.cap == c->stage.cap) {
     std::swap(c->recs.p, c->stage.p);
     c->recs.n = r_hi;
-    c->args.recs = c->stage.p;
+    if (!c->d_recs) c->args.recs = c->stage.p;
   } else {
     if (!c->recs.resize(r0 + (r_hi - r_lo))) { set_err("out of pinned host memory for match records"); return MGPU_E_CUDA; }
     // (later batches of a long resident scan: tens of millions of records — copy with several threads)
@@ -2419,6 +2464,8 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
   int rc = begin_batch(c, 1);
   if (rc) return rc;
   rc = launch_piece(c, 0, dev + al, pos - al, end - al, base + al, flags, lookups);
+  if (rc) return rc;
+  rc = drain_records(c, 1);
   if (rc) return rc;
   rc = end_batch(c, 1);
   if (rc) return rc;
@@ -2550,6 +2597,8 @@ static int scan_device_impl(mgpu_ctx* c, const uint8_t* dev, size_t len, uint64_
       rc = launch_piece(c, k, dev + al, pos - al, end - al, base + al, flags, lookups);
       if (rc) return rc;
     }
+    rc = drain_records(c, nb);
+    if (rc) return rc;
     rc = end_batch(c, nb);
     if (rc) return rc;
     // gather: runs of pieces without overflow share one copy; overflowed pieces are redone afterwards

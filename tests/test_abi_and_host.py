@@ -371,3 +371,93 @@ def test_follow_files_batches_and_rotation(tmp_path):
     assert out.getvalue() == b"8\n6\n4\n"
     with pytest.raises(ValueError):
         M.follow_files(["-"], scan_batch, out)
+
+
+def _repr_c_offsets(fields):
+    """Offsets of a #[repr(C)] struct from (name, size, align) in declaration order."""
+    off, out = 0, {}
+    for name, size, align in fields:
+        off = (off + align - 1) // align * align
+        out[name] = off
+        off += size
+    return out, off
+
+
+def test_mxy_section_headers_follow_the_reference_struct_layouts(built):
+    """the byte layout of what mxy_builder.cpp writes, pinned against the reference's #[repr(C)] declarations
+    field by field — ParaglobHeader (matchy-paraglob/src/offset_format.rs:73-178, 112 bytes, asserted there at :464),
+    PatternEntry 16 / SingleWildcard 8 / GlobSegmentIndex 8 / GlobSegmentHeader 12 (:470-475), LiteralHashHeader + HashEntry +
+    PatternMapping (matchy-literal-hash/src/lib.rs:80-136)."""
+    import struct
+    from matchy_b200 import DatabaseBuilder
+    u32 = lambda n: (n, 4, 4)
+    pg_fields = [("magic", 8, 1)] + [u32(n) for n in (
+        "version", "match_mode", "ac_node_count", "ac_nodes_offset", "ac_edges_size", "ac_patterns_size", "pattern_count", "patterns_offset",
+        "pattern_strings_offset", "pattern_strings_size", "meta_word_mapping_count", "meta_word_mappings_offset", "pattern_refs_size",
+        "wildcard_count", "total_buffer_size")] + [("endianness", 1, 1), ("reserved", 3, 1)] + [u32(n) for n in (
+        "data_section_offset", "data_section_size", "mapping_table_offset", "mapping_count", "data_flags", "reserved_v2",
+        "ac_literal_map_offset", "ac_literal_map_count", "glob_segments_offset", "glob_segments_size")]
+    po, psize = _repr_c_offsets(pg_fields)
+    assert psize == 112
+    lh_fields = [("magic", 4, 1)] + [u32(n) for n in ("version", "entry_count", "table_size", "strings_offset", "strings_size", "num_shards", "shard_bits")]
+    lo, lsize = _repr_c_offsets(lh_fields)
+    assert lsize == 32
+    he, hesize = _repr_c_offsets([("hash", 8, 8), ("string_offset", 4, 4), ("pattern_id", 4, 4)])
+    assert hesize == 16 and he["string_offset"] == 8
+
+    b = DatabaseBuilder(build_epoch=1700000000)
+    globs = ["*.evil-%d.com" % i for i in range(5)] + ["mal-*", "*[0-9].*.bad-attack.org"]
+    lits = ["lit-%d.example.com" % i for i in range(40)]
+    for g in globs:
+        b.add_glob(g, {"k": 1})
+    b.add_glob("*", {"k": 2})  # a pure wildcard (SingleWildcard entry)
+    for s in lits:
+        b.add_literal(s, {"k": 3})
+    db = b.build()
+
+    # ---- PARAGLOB ----
+    p0 = db.index(b"PARAGLOB")
+    f = lambda name: struct.unpack_from("<I", db, p0 + po[name])[0]
+    assert f("version") == 5 and f("match_mode") == 0 and db[p0 + po["endianness"]] == 1
+    assert struct.unpack_from("<I", db, p0 - 4)[0] == f("total_buffer_size")  # [total][paraglob_size][paraglob]... (mmdb_builder.rs:529-550)
+    assert f("pattern_count") == len(globs) + 1 and f("wildcard_count") == 1
+    assert f("ac_nodes_offset") % 64 == 0 and f("ac_nodes_offset") >= 112 and f("ac_node_count") > 0
+    assert f("patterns_offset") % 8 == 0 and f("patterns_offset") >= f("ac_nodes_offset") + f("ac_edges_size")
+    assert f("pattern_strings_offset") == f("patterns_offset") + 16 * f("pattern_count")  # PatternEntry = 16 bytes
+    for i, g in enumerate(globs + ["*"]):  # PatternEntry {pattern_id u32, pattern_type u8, pad[3], string_offset u32, string_len u32}
+        pid, ptype, soff, slen = struct.unpack_from("<IB3xII", db, p0 + f("patterns_offset") + 16 * i)
+        assert pid == i and slen == len(g) and db[p0 + soff:p0 + soff + slen + 1] == g.encode() + b"\0"
+    assert f("data_section_offset") == 0 and f("mapping_count") == 0
+    ao = f("ac_literal_map_offset")
+    assert db[p0 + ao:p0 + ao + 4] == b"ACLH" and f("ac_literal_map_count") > 0
+    go, gsz = f("glob_segments_offset"), f("glob_segments_size")
+    assert go % 8 == 0 and go + gsz == f("total_buffer_size")
+    first_hdr = None
+    for i in range(f("pattern_count")):  # GlobSegmentIndex {first_segment_offset u32, segment_count u16, reserved u16} = 8 bytes
+        first, cnt = struct.unpack_from("<IH", db, p0 + go + 8 * i)
+        if first_hdr is None:
+            first_hdr = first
+        assert first >= go + 8 * f("pattern_count") and (first - first_hdr) % 12 == 0  # GlobSegmentHeader = 12 bytes
+        assert cnt >= 1
+    assert first_hdr == go + 8 * f("pattern_count")
+
+    # ---- LHSH ----  header 32 B, shard offset table (num_shards + 1) x u32, slot table, string pool, [count][PatternMapping x count]
+    # (matchy-literal-hash/src/lib.rs:236-330)
+    l0 = db.index(b"LHSH")
+    g = lambda name: struct.unpack_from("<I", db, l0 + lo[name])[0]
+    assert g("version") == 1 and g("entry_count") == len(lits)
+    assert g("num_shards") == 1 << g("shard_bits") and g("table_size") >= g("entry_count")
+    table0 = 32 + 4 * (g("num_shards") + 1)
+    assert g("strings_offset") == table0 + 16 * g("table_size")
+    shard_off = struct.unpack_from("<%dI" % (g("num_shards") + 1), db, l0 + 32)
+    assert shard_off[0] == 0 and shard_off[-1] == g("table_size") and list(shard_off) == sorted(shard_off)
+    seen = set()
+    for s_ in range(g("table_size")):  # HashEntry {hash u64, string_offset u32, pattern_id u32}; empty = string_offset 0xFFFFFFFF
+        h, so, pid = struct.unpack_from("<QII", db, l0 + table0 + 16 * s_)
+        if so != 0xFFFFFFFF:
+            assert pid < len(lits) and so < g("strings_size")
+            seen.add(pid)
+    assert seen == set(range(len(lits)))
+    m0 = l0 + g("strings_offset") + g("strings_size")
+    assert struct.unpack_from("<I", db, m0)[0] == len(lits)  # PatternMapping {pattern_id u32, data_offset u32} = 8 bytes each
+    assert sorted(struct.unpack_from("<II", db, m0 + 4 + 8 * k)[0] for k in range(len(lits))) == list(range(len(lits)))
