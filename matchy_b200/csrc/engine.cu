@@ -25,6 +25,7 @@
 #include <type_traits>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>  // (the result sort below: library code, off the scan path)
 #include "../../include/matchy_b200.h"
 #include "db_prepare.h"
 #include "mxy_reader.h"
@@ -1624,6 +1625,25 @@ __global__ void __launch_bounds__(256, 5) exact_kernel(ScanArgs a) {
 }
 
 // end of a piece: snapshot the running totals into the piece's counter block
+// Result order.  The C ABI hands out records sorted by (offset, item_type, len); the kernels append them with atomics.  A piece's
+// records are sorted on the device before they leave it (pieces follow each other in offset order, so the batch arrives sorted):
+// 64-bit key = (offset - piece start) << 4 | item_type (a position yields at most one token per type, so len never decides),
+// value = record index, cub::DeviceRadixSort over the <= 35 bits in use, then the 32-byte records gathered in that order.  The host only checks the order (host_sort.h: records_sorted)
+// and keeps its own sort for what did not come this way (pieces redone after an overflow).
+__global__ void sort_keys_kernel(const mgpu_match* recs, uint32_t n, uint64_t lo, uint64_t* keys, uint32_t* vals) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 h = reinterpret_cast<const uint4*>(recs)[2 * (size_t)i];  // offset (8 bytes), len, item_type | kind << 8 | ...
+    const uint64_t off = ((uint64_t)h.y << 32) | h.x;
+    keys[i] = ((off - lo) << 4) | (uint64_t)(h.w & 0xFu);
+    vals[i] = i;
+  }
+}
+__global__ void sort_gather_kernel(const mgpu_match* recs, uint32_t n, const uint32_t* vals, mgpu_match* out) {
+  const uint4* src = reinterpret_cast<const uint4*>(recs);
+  uint4* dst = reinterpret_cast<uint4*>(out);
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < 2 * (size_t)n; j += (size_t)gridDim.x * blockDim.x)
+    dst[j] = src[2 * (size_t)vals[j >> 1] + (j & 1)];
+}
 // (h_nrec: the same snapshot in pinned host memory — the host reads it as soon as the piece's event has fired and starts the
 //  copy of the piece's records while later pieces are still being scanned, see drain_records)
 __global__ void piece_end_kernel(DevCounters* ctr, const ScanTotals* tot, uint32_t* h_nrec) {
@@ -1843,6 +1863,19 @@ struct mgpu_ctx {
   uint32_t* h_nrec = nullptr;   // pinned, MAX_BATCH entries
   cudaStream_t d2h = nullptr;
   cudaEvent_t ev_d2h = nullptr;
+  // device-side result sort (see sort_keys_kernel): key / index double buffers, the sorted records, cub's scratch
+  uint64_t* d_keys[2] = {nullptr, nullptr};
+  uint32_t* d_vals[2] = {nullptr, nullptr};
+  mgpu_match* d_sorted = nullptr;   // null: records leave the device in append order (MATCHY_B200_HOST_SORT=1) and the host sorts
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  // A piece is sorted on the device when it produced at least this many records (option "device_sort_min", MATCHY_B200_DEVICE_SORT_MIN).
+  // Measured (scripts/gpu_r2am.sh, device-timed / wall-clock GB/s): config 3, 2 M records per piece: 696 / 206 with the host sort,
+  // 572 / 484 with the device sort; config 5: 539 / 274 -> 514 / 422; config 2, 10 K records per piece: 928 / 758 -> 840 / 772 — the
+  // sort's kernels take SM slots from the single-wave scan kernels, which a 1 ms host sort of 53 K records is not worth.
+  uint32_t dev_sort_min = 131072;
+  bool arrived_sorted = false;  // the last scan's records were in order when the host looked (no host sort ran)
+  uint64_t piece_base[MAX_BATCH] = {}, piece_len[MAX_BATCH] = {};  // absolute offset of the slot's piece buffer and its length (the sort keys are relative to it)
   PinnedVec<mgpu_id_pair> ids;
   std::vector<mgpu_id_pair> ids_tmp;
   std::vector<mgpu_match> sort_tmp;   // sort_records' scratch
@@ -1910,6 +1943,7 @@ void mgpu_destroy(mgpu_ctx* c) {
   if (c->h_nrec) cudaFreeHost(c->h_nrec);
   if (c->d_recs) cudaFree(c->d_recs);
   if (c->d2h) cudaStreamDestroy(c->d2h);
+  { void* sb[] = {c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_sorted, c->d_sort_tmp}; for (void* p : sb) if (p) cudaFree(p); }
   if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
   if (c->h_cut) cudaFreeHost(c->h_cut);
   if (c->compute) cudaStreamDestroy(c->compute);
@@ -2024,9 +2058,23 @@ static int create_impl(mgpu_ctx* c, int device, size_t chunk_bytes) {
   if (getenv("MATCHY_B200_RECS_ZEROCOPY") == nullptr) {
     CK(cudaMalloc(&c->d_recs, (size_t)a.cap_rec * sizeof(mgpu_match)));
     CK(cudaMallocHost(&c->h_nrec, sizeof(uint32_t) * mgpu_ctx::MAX_BATCH));
-    CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    // (highest priority: the sort's short kernels take the first SM slots a kernel boundary of the scan frees — at default
+    //  priority they starved behind the single-wave scan kernels until the batch ended, and the copies with them)
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->d2h, cudaStreamNonBlocking, getenv("MATCHY_B200_D2H_PRIO0") ? prio_lo : prio_hi));
     CK(cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming));
     a.recs = c->d_recs;
+    if (getenv("MATCHY_B200_HOST_SORT") == nullptr) {
+      for (int k = 0; k < 2; k++) { CK(cudaMalloc(&c->d_keys[k], (size_t)a.cap_rec * 8)); CK(cudaMalloc(&c->d_vals[k], (size_t)a.cap_rec * 4)); }
+      CK(cudaMalloc(&c->d_sorted, (size_t)a.cap_rec * sizeof(mgpu_match)));
+      cub::DoubleBuffer<uint64_t> dk(c->d_keys[0], c->d_keys[1]);
+      cub::DoubleBuffer<uint32_t> dv(c->d_vals[0], c->d_vals[1]);
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, c->sort_tmp_bytes, dk, dv, (int)a.cap_rec, 0, 64, c->d2h));
+      c->sort_tmp_bytes += 4096;
+      if (const char* m = getenv("MATCHY_B200_DEVICE_SORT_MIN")) c->dev_sort_min = (uint32_t)strtoul(m, nullptr, 10);
+      CK(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+    }
   }
   CK(cudaMalloc(&a.ids, (size_t)a.cap_ids * sizeof(mgpu_id_pair)));
   CK(cudaMalloc(&a.ctr, sizeof(DevCounters) * mgpu_ctx::MAX_BATCH));
@@ -2065,7 +2113,8 @@ void mgpu_set_ac_mode(mgpu_ctx* c, int mode) { c->force_ac_walk = mode == 1; c->
 
 // Test / debug switches.  "tok_reserve": slots per reservation of the token lists; "cap_str" / "cap_ip" / "cap_rec" /
 // "cap_ids": pretend the work buffers are this small (never above what was allocated; 0 restores the allocation), which
-// drives the overflow -> split-and-redo path; "verify_tokens": audit every piece's IP token list (verify_tokens_kernel).
+// drives the overflow -> split-and-redo path; "verify_tokens": audit every piece's IP token list (verify_tokens_kernel);
+// "device_sort_min": records a piece must produce to be sorted on the device (1: always — the tests; see mgpu_ctx::dev_sort_min).
 int mgpu_set_option(mgpu_ctx* c, const char* key, uint64_t value) {
   if (!c || !key) { set_err("null argument"); return MGPU_E_PARAM; }
   const std::string k(key);
@@ -2081,6 +2130,7 @@ int mgpu_set_option(mgpu_ctx* c, const char* key, uint64_t value) {
     if (cudaSetDevice(c->device) != cudaSuccess || cudaMemset(c->d_dbg, 0, 64 * sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMemset failed"); return MGPU_E_CUDA; }
   }
   else if (k == "variant") c->args.variant = (uint32_t)value;
+  else if (k == "device_sort_min") c->dev_sort_min = (uint32_t)std::min<uint64_t>(value, 0xFFFFFFFFu);
   else if (k == "sub_block") c->sub_block = (uint32_t)value;
   else if (k == "fused") {
     if ((value != 0) != (c->nsets == 2)) { set_err("the first-stage kernels are chosen when the context is created (MATCHY_B200_FUSED=1): the work buffers differ"); return MGPU_E_PARAM; }
@@ -2094,6 +2144,7 @@ int mgpu_debug_get(mgpu_ctx* c, uint64_t out[64]) {
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, c->d_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   for (int k = 0; k < 4; k++) out[60 + k] = c->host_us[k];
+  out[59] = c->arrived_sorted ? 1 : 0;  // the last scan's records came off the device in (offset, item_type, len) order
   // host time of the last resident scan: whole call, result sort, id re-pack, launch + gather
   return MGPU_OK;
 }
@@ -2247,6 +2298,7 @@ uint32_t mgpu_default_flags(mgpu_ctx* c) {
 static int launch_piece(mgpu_ctx* c, int slot, const uint8_t* d_buf, uint64_t lo, uint64_t n, uint64_t base, uint32_t flags, bool lookups) {
   ScanArgs a = c->args;
   a.buf = d_buf; a.lo = lo; a.n = n; a.base = base; a.flags = flags;
+  c->piece_base[slot] = base; c->piece_len[slot] = n;
   a.ctr = c->args.ctr + slot;
   if (c->force_ac_walk) a.db.ac_anchored = 0;
   const int set = c->nsets == 2 ? (slot & 1) : 0;
@@ -2393,7 +2445,28 @@ static int drain_records(mgpu_ctx* c, int nb) {
     CK(cudaEventSynchronize(c->ev_looked[k]));
     const uint32_t r_now = std::min(c->h_nrec[k], c->args.cap_rec);
     if (r_now > r_prev) {
-      if (c->keep_results) CK(cudaMemcpyAsync(c->stage.p + r_prev, c->d_recs + r_prev, (size_t)(r_now - r_prev) * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->d2h));
+      if (c->keep_results) {
+        const uint32_t n = r_now - r_prev;
+        const mgpu_match* src = c->d_recs + r_prev;
+        if (c->d_sorted && n > 1 && n >= c->dev_sort_min) {
+          cub::DoubleBuffer<uint64_t> dk(c->d_keys[0], c->d_keys[1]);
+          cub::DoubleBuffer<uint32_t> dv(c->d_vals[0], c->d_vals[1]);
+          int end_bit = 5;
+          while (end_bit < 64 && (c->piece_len[k] >> (end_bit - 4)) != 0) end_bit++;
+          size_t need = 0;
+          CK(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)n, 0, end_bit, c->d2h));
+          if (need <= c->sort_tmp_bytes) {
+            const int grid = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)launch_grid(c, 4));
+            sort_keys_kernel<<<grid, 256, 0, c->d2h>>>(src, n, c->piece_base[k], c->d_keys[0], c->d_vals[0]);
+            need = c->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, need, dk, dv, (int)n, 0, end_bit, c->d2h));
+            sort_gather_kernel<<<(int)std::min<uint32_t>((2 * n + 255) / 256, (uint32_t)launch_grid(c, 8)), 256, 0, c->d2h>>>(src, n, dv.Current(), c->d_sorted + r_prev);
+            src = c->d_sorted + r_prev;
+            c->timing.aux_launches += 2;  // (sort_keys_kernel, sort_gather_kernel; cub's own kernels are library launches and not counted)
+          }
+        }
+        CK(cudaMemcpyAsync(c->stage.p + r_prev, src, (size_t)n * sizeof(mgpu_match), cudaMemcpyDeviceToHost, c->d2h));
+      }
       r_prev = r_now;
     }
   }
@@ -2522,7 +2595,8 @@ static void finish_scan(mgpu_ctx* c) {
     const unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
     if (nt >= 2) c->pool.reset(new WorkerPool(nt));
   }
-  sort_records(c->recs.data(), nrec, c->scan_lo, c->scan_hi, c->sort_tmp, c->pool.get());
+  c->arrived_sorted = c->d_sorted && records_sorted(c->recs.data(), nrec, c->pool.get());
+  if (!c->arrived_sorted) sort_records(c->recs.data(), nrec, c->scan_lo, c->scan_hi, c->sort_tmp, c->pool.get());
   const auto t_ids = std::chrono::steady_clock::now();
   if (!c->ids.empty()) {
     const size_t np = repack_ids(c->recs.data(), nrec, c->ids.data(), c->ids_tmp, c->pool.get());

@@ -127,6 +127,20 @@ inline void sort_records(mgpu_match* r, size_t n, uint64_t lo, uint64_t hi, std:
   });
 }
 
+// Are r[0..n) in (offset, item_type, len) order already?  (The device sorts every piece's records before they leave it; this is
+// the host's check, and what decides whether sort_records still has to run.)
+inline bool records_sorted(const mgpu_match* r, size_t n, WorkerPool* pool) {
+  if (n < 2) return true;
+  if (n < 65536 || !pool || pool->size() < 2) { for (size_t i = 1; i < n; i++) if (record_less(r[i], r[i - 1])) return false; return true; }
+  const unsigned T = pool->size();
+  std::atomic<bool> bad{false};
+  pool->parallel([&](unsigned k) {
+    const size_t a = std::max<size_t>(1, n * k / T), b = n * (k + 1) / T;  // (slice k also compares its first element with the one before it)
+    for (size_t i = a; i < b; i++) if (record_less(r[i], r[i - 1])) { bad.store(true, std::memory_order_relaxed); return; }
+  });
+  return !bad.load();
+}
+
 // The id pairs of pattern records, gathered in record order into `packed` (ids_index rewritten to match); the device appends
 // them in whatever order its warps finish.  Returns the number of pairs.  Random reads of `ids`: latency-bound, so in parallel.
 inline size_t repack_ids(mgpu_match* r, size_t n, const mgpu_id_pair* ids, std::vector<mgpu_id_pair>& packed, WorkerPool* pool) {

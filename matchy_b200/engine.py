@@ -155,6 +155,7 @@ class Engine:
         self.debug_events = [(int(out[16 + 2 * k]) >> 32, int(out[16 + 2 * k]) & 0xFFFFFFFF, int(out[17 + 2 * k]) >> 32, int(out[17 + 2 * k]) & 0xFFFFFFFF)
                              for k in range(min(21, int(out[13])))]  # (block, base, warp, active mask) of the first partial-warp events
         self.host_us = dict(zip(("scan_call", "sort", "id_repack", "launch_and_gather"), (int(out[60 + k]) for k in range(4))))  # last resident scan, host side
+        self.arrived_sorted = bool(out[59])  # the last scan's records came off the device already in (offset, item_type, len) order
         names = ("poisoned", "padding", "ipv4", "ipv6", "lookup_hits", "unknown", "slots", "_7", "trie_thread_hits", "trie_warp_hits", "trie_block_hits", "trie_partial_warps", "trie_n_mismatch")
         return dict(zip(names, (int(x) for x in out)))
 

@@ -51,6 +51,8 @@ def lib():
         L.emu_tokens.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t]
         L.emu_sort_records.restype = C.c_double
         L.emu_sort_records.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint, C.c_int]
+        L.emu_records_sorted.restype = C.c_int
+        L.emu_records_sorted.argtypes = [C.c_void_p, C.c_size_t, C.c_uint]
         L.emu_repack_ids.restype = C.c_size_t
         L.emu_repack_ids.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint]
         _lib = L

@@ -364,6 +364,12 @@ double emu_sort_records(mgpu_match* r, size_t n, uint64_t lo, uint64_t hi, unsig
   return best;
 }
 
+// the engine's order check (what decides whether the host still sorts after the device has)
+int emu_records_sorted(const mgpu_match* r, size_t n, unsigned threads) {
+  std::unique_ptr<mgpu::WorkerPool> pool(threads ? new mgpu::WorkerPool(threads) : nullptr);
+  return mgpu::records_sorted(r, n, pool.get()) ? 1 : 0;
+}
+
 // the engine's id re-pack on n sorted records; out must hold every pair; returns the number of pairs
 size_t emu_repack_ids(mgpu_match* r, size_t n, const mgpu_id_pair* ids, mgpu_id_pair* out, unsigned threads) {
   std::vector<mgpu_id_pair> packed;

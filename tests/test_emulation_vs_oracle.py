@@ -325,6 +325,30 @@ def test_result_sort_equals_a_plain_sort():
             L.emu_sort_records(got.ctypes.data, n, rng_lo, rng_hi, threads, 1)
             assert key(got) == key(want), (n, threads, shape, rng_lo)
             assert sorted(got["ids_index"].tolist()) == list(range(n)), (n, threads, shape)
+    # the order check that lets the host skip its sort when the device has sorted: true on sorted input, false for ONE swapped
+    # neighbour pair anywhere (slice edges of the pool included), ties in offset decided by item_type, then len
+    for n, threads in ((0, 4), (1, 4), (2, 0), (70000, 4), (200000, 16), (200000, 0)):
+        r = np.zeros(n, dtype=dt)
+        r["offset"] = np.sort(rng.integers(0, 2**38, n)) if n else 0
+        r["item_type"] = 3
+        r["len"] = 7
+        assert L.emu_records_sorted(r.ctypes.data, n, threads) == 1
+        if n >= 2:
+            for at in {1, n // 2, n - 1} | ({n * k // threads for k in range(1, threads)} if threads else set()):
+                b = r.copy()
+                b[[at - 1, at]] = b[[at, at - 1]]
+                if b["offset"][at - 1] != b["offset"][at]:
+                    assert L.emu_records_sorted(b.ctypes.data, n, threads) == 0, (n, threads, at)
+            t = r.copy()
+            t["offset"][:] = 5
+            t["item_type"][n // 2:] = 4
+            assert L.emu_records_sorted(t.ctypes.data, n, threads) == 1
+            if n >= 4:  # (the last two records share offset and item_type: len decides)
+                t["len"][n - 1] = 6
+                assert L.emu_records_sorted(t.ctypes.data, n, threads) == 0
+                t["len"][n - 1] = 7
+            t["item_type"][0] = 5
+            assert L.emu_records_sorted(t.ctypes.data, n, threads) == 0
     # id pairs gathered in record order
     idt = np.dtype([("pattern_id", "<u4"), ("data_offset", "<u4")])
     for n, threads in ((10, 4), (5000, 4), (40000, 8), (40000, 0)):

@@ -31,6 +31,38 @@ def test_config_parity(engines, cfg):
 
 
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_device_result_sort(small_dbs, cfg):
+    """The per-piece result sort on the device (cub radix sort of (offset, item_type) keys + gather, engine.cu: drain_records):
+    forced for every piece ("device_sort_min" = 1; by default only pieces with >= 128 K records take it), over several pieces per
+    scan, resident and from host memory — the records equal the oracle's AND arrive in order (the host's own sort does not run)."""
+    import oracle_lib as O
+    from matchy_b200 import Engine
+    db, log = small_dbs[cfg]
+    orc = O.Oracle(db)
+    want, wcnt = orc.scan(log, chunk_size=128 * 1024)
+    eng = Engine(0, chunk_bytes=192 << 10)  # ~6 pieces per MiB
+    eng.upload(db)
+    eng.set_option("device_sort_min", 1)
+    eng.scan(log)
+    assert eng.counters_list() == wcnt and eng.records_as_tuples() == want
+    eng.debug_counters()
+    assert eng.arrived_sorted
+    dev = eng.dev_alloc(len(log))
+    eng.dev_upload(dev, log)
+    eng.scan_device(dev, len(log), eng.default_flags())
+    assert eng.counters_list() == wcnt and eng.records_as_tuples() == want
+    eng.debug_counters()
+    assert eng.arrived_sorted
+    eng.set_option("device_sort_min", 1 << 30)  # never: the host sorts
+    eng.scan_device(dev, len(log), eng.default_flags())
+    assert eng.records_as_tuples() == want
+    eng.debug_counters()
+    assert not eng.arrived_sorted or len(want) < 2
+    eng.dev_free(dev)
+    eng.close()
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 def test_ndjson_parity(engines, small_dbs, cfg):
     """sorted NDJSON of the GPU path == sorted NDJSON of the oracle (the `matchy match` output contract)."""
     from matchy_b200 import RecordFormatter
