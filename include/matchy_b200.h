@@ -137,7 +137,10 @@ void mgpu_set_ac_mode(mgpu_ctx*, int mode);
  * "cap_rec" / "cap_ids" (pretend the work buffers are this small: drives the overflow -> split-and-redo path; 0 restores),
  * "verify_tokens" (audit every piece's IP token list on the device; mgpu_debug_get returns the sums: slots still poisoned,
  * padding slots, IPv4 tokens, IPv6 tokens, lookup hits, slots of unknown type, slots audited, 0; then the IP-trie kernel's own
- * sums: hits per thread, per warp ballot, per block) ; "variant": experiment switches inside kernels, 0 in production. */
+ * sums: hits per thread, per warp ballot, per block) ; "variant": experiment switches inside kernels, 0 in production;
+ * "device_sort_min" (records a piece must produce for its records to be sorted on the device before they are copied out;
+ * default 131072, 1 = always; results are identical either way — mgpu_debug_get()[59] tells whether the last scan's records
+ * arrived in order). */
 int mgpu_set_option(mgpu_ctx*, const char* key, uint64_t value);
 int mgpu_debug_get(mgpu_ctx*, uint64_t out[64]);
 
