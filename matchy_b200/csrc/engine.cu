@@ -1874,6 +1874,8 @@ struct mgpu_ctx {
   // 572 / 484 with the device sort; config 5: 539 / 274 -> 514 / 422; config 2, 10 K records per piece: 928 / 758 -> 840 / 772 — the
   // sort's kernels take SM slots from the single-wave scan kernels, which a 1 ms host sort of 53 K records is not worth.
   uint32_t dev_sort_min = 131072;
+  bool dev_sorting = false;     // a piece of the current scan reached dev_sort_min: the pieces behind it are sorted on the device too, whatever
+                                // their size (a short last piece in append order would send the whole result through the host's sort)
   bool arrived_sorted = false;  // the last scan's records were in order when the host looked (no host sort ran)
   uint64_t piece_base[MAX_BATCH] = {}, piece_len[MAX_BATCH] = {};  // absolute offset of the slot's piece buffer and its length (the sort keys are relative to it)
   PinnedVec<mgpu_id_pair> ids;
@@ -2448,7 +2450,8 @@ static int drain_records(mgpu_ctx* c, int nb) {
       if (c->keep_results) {
         const uint32_t n = r_now - r_prev;
         const mgpu_match* src = c->d_recs + r_prev;
-        if (c->d_sorted && n > 1 && n >= c->dev_sort_min) {
+        if (n >= c->dev_sort_min) c->dev_sorting = true;
+        if (c->d_sorted && n > 1 && c->dev_sorting) {
           cub::DoubleBuffer<uint64_t> dk(c->d_keys[0], c->d_keys[1]);
           cub::DoubleBuffer<uint32_t> dv(c->d_vals[0], c->d_vals[1]);
           int end_bit = 5;
@@ -2577,6 +2580,7 @@ static int scan_piece(mgpu_ctx* c, const uint8_t* dev, uint64_t pos, uint64_t en
 
 static void begin_scan(mgpu_ctx* c) {
   c->recs.clear(); c->ids.clear();
+  c->dev_sorting = false;
   c->x_str.clear(); c->x_ip.clear();
   memset(&c->counters, 0, sizeof c->counters);
   memset(&c->timing, 0, sizeof c->timing);

@@ -43,6 +43,9 @@ def test_full_scale_parity(built, cfg):
         _compare(eng, recs, ids, want_recs, want_ids, want_cnt, "resident, first scan")
         recs, ids = eng.scan_device(dev, nbytes)  # same buffers, same answer
         _compare(eng, recs, ids, want_recs, want_ids, want_cnt, "resident, second scan")
+        if cfg in (3, 5):  # match-heavy: every piece is sorted on the device (>= 128 K records per piece), the host only checks the order
+            eng.debug_counters()
+            assert eng.arrived_sorted
     finally:
         eng.dev_free(dev)
     if cfg in (2, 3):  # the host-buffer entry point (double-buffered H2D, memrchr pieces) at the same size
