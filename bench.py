@@ -467,7 +467,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e_s = float(tt[0])
         e2e = {"value": host_bytes * world * args.steps / e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": host_bytes, "d2h_bytes_per_step": d2h // args.steps,
-               "timed": "wall clock around mgpu_scan (pinned host buffer -> double-buffered H2D -> kernels -> records written to pinned host memory), max over ranks",
+               "timed": "wall clock around mgpu_scan (pinned host buffer -> double-buffered H2D -> kernels -> records copied per piece to pinned host memory), max over ranks",
                "sample": None if host_bytes == nbytes else "the first %d bytes of every rank's shard per step (the 200 GB stream does not fit host memory)" % host_bytes}
 
     # ---- roofline of the dominant kernel ----
