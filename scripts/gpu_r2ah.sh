@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the parked / refill iptrie_kernel variants these runs compared were measured and then removed — profiles/README.md "last session"; MATCHY_B200_VARIANT=1 and MATCHY_B200_IPTRIE_MINB=3 select nothing in the committed library)
 # r2ah: iptrie_kernel with parked walks (per-warp queue of unfinished walks) vs the r2f kernel (MATCHY_B200_VARIANT=1), configs 3 and 5
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r2ah_tests.log 2>&1; echo "tests exit $?"; tail -3 gpurun_out/r2ah_tests.log

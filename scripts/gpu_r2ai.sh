@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the parked / refill iptrie_kernel variants these runs compared were measured and then removed — profiles/README.md "last session"; MATCHY_B200_VARIANT=1 and MATCHY_B200_IPTRIE_MINB=3 select nothing in the committed library)
 # r2ai: iptrie_kernel with persistent per-lane walks refilled from a per-warp queue of parked walks: 64 registers (spills) vs 80
 # registers (3 blocks per SM) vs the r2f kernel (MATCHY_B200_VARIANT=1), configs 3 and 5
 mkdir -p gpurun_out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the parked / refill iptrie_kernel variants these runs compared were measured and then removed — profiles/README.md "last session"; MATCHY_B200_VARIANT=1 and MATCHY_B200_IPTRIE_MINB=3 select nothing in the committed library)
 # r2aj: stand-alone kernel times (MATCHY_B200_SERIAL=1: lookups on the compute stream, nothing overlaps) of the refill iptrie kernel vs r2f on config 3,
 # then ncu --set full of the refill kernel on one 500 MB piece
 mkdir -p gpurun_out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the parked / refill iptrie_kernel variants these runs compared were measured and then removed — profiles/README.md "last session"; MATCHY_B200_VARIANT=1 and MATCHY_B200_IPTRIE_MINB=3 select nothing in the committed library)
 # r2ak: match records appended in HBM and copied per piece by the copy engine (default) vs stored straight into pinned host memory
 # (MATCHY_B200_RECS_ZEROCOPY=1), with the refill and the r2f iptrie kernels; whole GPU suite first
 mkdir -p gpurun_out
