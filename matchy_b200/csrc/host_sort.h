@@ -147,15 +147,18 @@ inline size_t repack_ids(mgpu_match* r, size_t n, const mgpu_id_pair* ids, std::
   const unsigned T = (pool && n >= 4096) ? pool->size() : 1;
   auto slice = [&](unsigned k) { return n * k / T; };
   std::vector<size_t> first(T + 1, 0);
+  // Pattern records are a few per cent of a match-heavy result (config 5: 1 M of 41 M per 100 GB): the first pass notes where
+  // they are, the second only visits those (one read of the records instead of two).
+  std::vector<std::vector<size_t>> where(T);
   auto count = [&](unsigned k) {
     size_t c = 0;
-    for (size_t i = slice(k); i < slice(k + 1); i++) if (r[i].kind == MGPU_KIND_PATTERN) c += r[i].n_ids;
+    std::vector<size_t>& w = where[k];
+    for (size_t i = slice(k); i < slice(k + 1); i++) if (r[i].kind == MGPU_KIND_PATTERN) { c += r[i].n_ids; w.push_back(i); }
     first[k + 1] = c;
   };
   auto gather = [&](unsigned k) {
     size_t at = first[k];
-    for (size_t i = slice(k); i < slice(k + 1); i++) {
-      if (r[i].kind != MGPU_KIND_PATTERN) continue;
+    for (size_t i : where[k]) {
       memcpy(packed.data() + at, ids + r[i].ids_index, (size_t)r[i].n_ids * sizeof(mgpu_id_pair));
       r[i].ids_index = (uint32_t)at;
       at += r[i].n_ids;

@@ -351,9 +351,9 @@ def test_result_sort_equals_a_plain_sort():
             assert L.emu_records_sorted(t.ctypes.data, n, threads) == 0
     # id pairs gathered in record order
     idt = np.dtype([("pattern_id", "<u4"), ("data_offset", "<u4")])
-    for n, threads in ((10, 4), (5000, 4), (40000, 8), (40000, 0)):
+    for n, threads, p_pattern in ((10, 4, 0.5), (5000, 4, 0.5), (40000, 8, 0.5), (40000, 0, 0.5), (120000, 8, 0.02), (50000, 16, 0.0), (50000, 5, 1.0)):
         r = np.zeros(n, dtype=dt)
-        r["kind"] = rng.integers(1, 3, n)  # 1 = IP record (no ids), 2 = pattern record
+        r["kind"] = np.where(rng.random(n) < p_pattern, 2, 1)  # 1 = IP record (no ids), 2 = pattern record
         r["n_ids"] = np.where(r["kind"] == 2, rng.integers(1, 5, n), 0)
         total = int(r["n_ids"].sum())
         ids = np.zeros(total + 7, dtype=idt)
